@@ -1,0 +1,312 @@
+/*
+ * ref_shim.cpp — TEST INFRASTRUCTURE ONLY.  C shim around the UNMODIFIED reference.
+ *
+ * Built by oracle/Makefile into oracle/_ref/libpomref.so from this file plus the
+ * reference's own src/bboard/{bboard,step,step_utility}.cpp, compiled where they lie
+ * under /root/reference (never copied into this repo).  Everything except the
+ * `ref_*` C functions below has hidden visibility, so the reference's bboard::*
+ * symbols never meet the product's in one link scope (SURVEY §8b ODR warning).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library.  The product (libpom_b200.so) never does.
+ *
+ * The shim also fences the reference's defects that bound the parity domain
+ * (SURVEY §8c):
+ *   D1  step.cpp:39-46 walks roots[]/moves[]/agents[]/dependency[] at index -1 when an
+ *       agent is unreachable in the dependency walk -> moves are passed inside a padded
+ *       buffer holding Move::IDLE at [-1]; ref_precheck() reports how many agents are
+ *       unreachable (>=2 makes the reference read a stack word: oracle output advisory).
+ *   D3  step.cpp:167 dereferences GetBomb()==nullptr when a kicker walks onto a BOMB cell
+ *       that has no queue entry -> ref_precheck() flags the tick, the caller skips the env.
+ *   D4  step.cpp:191 Position bombDestinations[20] overflows when bombs.count > 20.
+ */
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <thread>
+#include <vector>
+#include <chrono>
+#include <atomic>
+
+#include "bboard.hpp"
+#include "step_utility.hpp"
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+using bboard::State;
+using bboard::Move;
+
+static_assert(sizeof(State) == 1004, "reference State layout changed");
+
+namespace
+{
+
+inline void PaddedStep(State* s, const uint8_t* mv)
+{
+    // moves[-1] must read as Move::IDLE (defect D1)
+    Move buf[8];
+    for(int i = 0; i < 8; i++) buf[i] = Move::IDLE;
+    for(int i = 0; i < 4; i++) buf[4 + i] = Move(int(mv[i]));
+    bboard::Step(s, buf + 4);
+}
+
+// Environment::Step semantics (reference environment.cpp:125-128,149-168) on a bare State
+// + status byte (bit0 done, bit1 draw, bits2-3 winner).
+inline void EnvStep(State* s, uint8_t* status, const uint8_t* mv)
+{
+    if(*status & 0x01) return;
+    PaddedStep(s, mv);
+    s->timeStep++;
+    if(s->aliveAgents == 1)
+    {
+        int w = 0;
+        for(int i = 0; i < bboard::AGENT_COUNT; i++)
+        {
+            if(!s->agents[i].dead) w = i;
+        }
+        *status = uint8_t(0x01 | (w << 2));
+    }
+    if(s->aliveAgents == 0)
+    {
+        *status = uint8_t(0x01 | 0x02);
+    }
+}
+
+}
+
+REF_API int ref_sizeof_state()
+{
+    return int(sizeof(State));
+}
+
+REF_API void ref_zero_state(void* st)
+{
+    // what std::make_unique<State>() yields: zero bytes, then the default member initialisers
+    std::memset(st, 0, sizeof(State));
+    new(st) State();
+}
+
+REF_API void ref_step(void* st, const uint8_t* moves4)
+{
+    PaddedStep(static_cast<State*>(st), moves4);
+}
+
+REF_API void ref_env_step(void* st, uint8_t* status, const uint8_t* moves4)
+{
+    EnvStep(static_cast<State*>(st), status, moves4);
+}
+
+REF_API void ref_init_board_items(void* st, int seed)
+{
+    bboard::InitBoardItems(*static_cast<State*>(st), seed);
+}
+
+REF_API void ref_init_state(void* st, int a0, int a1, int a2, int a3)
+{
+    bboard::InitState(static_cast<State*>(st), a0, a1, a2, a3);
+}
+
+REF_API void ref_put_agents_in_corners(void* st, int a0, int a1, int a2, int a3)
+{
+    static_cast<State*>(st)->PutAgentsInCorners(a0, a1, a2, a3);
+}
+
+REF_API void ref_put_agent(void* st, int x, int y, int id)
+{
+    static_cast<State*>(st)->PutAgent(x, y, id);
+}
+
+REF_API void ref_put_item(void* st, int x, int y, int item)
+{
+    static_cast<State*>(st)->board[y][x] = item;
+}
+
+REF_API void ref_kill(void* st, int id)
+{
+    static_cast<State*>(st)->Kill(id);
+}
+
+REF_API void ref_plant_bomb(void* st, int x, int y, int id, int setItem)
+{
+    static_cast<State*>(st)->PlantBomb(x, y, id, setItem != 0);
+}
+
+REF_API void ref_spawn_flame(void* st, int x, int y, int strength)
+{
+    static_cast<State*>(st)->SpawnFlame(x, y, strength);
+}
+
+REF_API void ref_set_bomb_direction(void* st, int logicalIndex, int dir)
+{
+    State* s = static_cast<State*>(st);
+    bboard::SetBombDirection(s->bombs[logicalIndex], bboard::Direction(dir));
+}
+
+REF_API void ref_fill_dest_pos(void* st, const uint8_t* moves4, int* out8)
+{
+    Move m[4];
+    for(int i = 0; i < 4; i++) m[i] = Move(int(moves4[i]));
+    bboard::Position p[4];
+    bboard::util::FillDestPos(static_cast<State*>(st), m, p);
+    for(int i = 0; i < 4; i++) { out8[2 * i] = p[i].x; out8[2 * i + 1] = p[i].y; }
+}
+
+REF_API void ref_fix_switch_move(void* st, int* pos8)
+{
+    bboard::Position p[4];
+    for(int i = 0; i < 4; i++) { p[i].x = pos8[2 * i]; p[i].y = pos8[2 * i + 1]; }
+    bboard::util::FixSwitchMove(static_cast<State*>(st), p);
+    for(int i = 0; i < 4; i++) { pos8[2 * i] = p[i].x; pos8[2 * i + 1] = p[i].y; }
+}
+
+REF_API int ref_resolve_dependencies(void* st, const int* pos8, int* dependency4, int* roots4)
+{
+    bboard::Position p[4];
+    for(int i = 0; i < 4; i++) { p[i].x = pos8[2 * i]; p[i].y = pos8[2 * i + 1]; }
+    for(int i = 0; i < 4; i++) { dependency4[i] = -1; roots4[i] = -1; }
+    return bboard::util::ResolveDependencies(static_cast<State*>(st), p, dependency4, roots4);
+}
+
+/*
+ * Parity-domain pre-check for one tick.  Returns a bit mask:
+ *   bits 0-2 : number of agents the dependency walk cannot reach (D1)
+ *   bit  4   : D3 risk (a kicker targets a BOMB cell that has no queue entry)
+ *   bit  5   : D4 risk (bomb queue could exceed 20 entries)
+ *   bit  6   : flame queue could exceed 20 entries (FixedQueue has no guard)
+ *   bit  7   : a move byte is outside 0..5
+ */
+REF_API int ref_precheck(const void* st, const uint8_t* mv)
+{
+    State s = *static_cast<const State*>(st);
+    int flags = 0;
+    Move m[4];
+    for(int i = 0; i < 4; i++)
+    {
+        if(mv[i] > 5) flags |= 0x80;
+        m[i] = Move(int(mv[i]));
+    }
+
+    // D1: restate the walk with bounds and count visited agents
+    bboard::Position dest[4];
+    bboard::util::FillDestPos(&s, m, dest);
+    bboard::util::FixSwitchMove(&s, dest);
+    int dependency[4] = {-1, -1, -1, -1};
+    int roots[4] = {-1, -1, -1, -1};
+    int rootNumber = bboard::util::ResolveDependencies(&s, dest, dependency, roots);
+    int visited = 0, rootIdx = 0;
+    int i = rootNumber == 0 ? 0 : roots[0];
+    for(int k = 0; k < 4; k++)
+    {
+        if(i == -1)
+        {
+            rootIdx++;
+            if(rootIdx > 3 || roots[rootIdx] == -1) break;
+            i = roots[rootIdx];
+        }
+        visited++;
+        i = dependency[i];
+    }
+    flags |= (4 - visited) & 7;
+
+    // D3: kicker -> BOMB cell without queue entry (conservative, evaluated on the pre-tick board)
+    int planters = 0;
+    for(int a = 0; a < 4; a++)
+    {
+        if(s.agents[a].dead) continue;
+        if(m[a] == Move::BOMB)
+        {
+            if(s.agents[a].bombCount < s.agents[a].maxBombCount) planters++;
+            continue;
+        }
+        if(m[a] == Move::IDLE) continue;
+        bboard::Position d = bboard::util::DesiredPosition(s.agents[a].x, s.agents[a].y, m[a]);
+        if(bboard::util::IsOutOfBounds(d)) continue;
+        if(s.agents[a].canKick && s.board[d.y][d.x] == bboard::Item::BOMB && !s.HasBomb(d.x, d.y))
+        {
+            flags |= 0x10;
+        }
+    }
+    if(s.bombs.count + planters > bboard::MAX_BOMBS) flags |= 0x20;
+    // every bomb present after movement can explode this tick, each adding one flame
+    if(s.flames.count + s.bombs.count + planters > bboard::MAX_BOMBS) flags |= 0x40;
+    return flags;
+}
+
+/*
+ * CPU baseline: the reference's Step over a host AoS State[] partitioned
+ * contiguously over `nthreads` threads; `moves` is [ticks][n][4].  Environment semantics
+ * (skip finished envs, timeStep++, done/winner).  When `reset_templates` is non-null a
+ * finished env is replaced by template[(env + episode) % n_templates] at the end of the
+ * finishing tick (the engine's auto-reset rule), so all envs stay live.
+ * Returns the wall time of the step loop in seconds; *steps_out = env-steps executed.
+ */
+REF_API double ref_bench_steps(void* states, uint8_t* status, long n, const uint8_t* moves,
+                               int ticks, int nthreads, const void* reset_templates,
+                               int n_templates, unsigned long long* steps_out)
+{
+    State* S = static_cast<State*>(states);
+    const State* T = static_cast<const State*>(reset_templates);
+    if(nthreads < 1) nthreads = 1;
+    std::vector<std::thread> th;
+    std::vector<unsigned long long> counts(size_t(nthreads), 0ull);
+    auto t0 = std::chrono::steady_clock::now();
+    for(int t = 0; t < nthreads; t++)
+    {
+        long lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+        th.emplace_back([=, &counts]()
+        {
+            unsigned long long c = 0;
+            std::vector<uint32_t> episode(size_t(hi - lo), 0u);
+            for(int k = 0; k < ticks; k++)
+            {
+                const uint8_t* mv = moves + (size_t(k) * size_t(n)) * 4;
+                for(long e = lo; e < hi; e++)
+                {
+                    if(status[e] & 0x01) continue;
+                    EnvStep(&S[e], &status[e], mv + 4 * e);
+                    c++;
+                    if(T && (status[e] & 0x01))
+                    {
+                        uint32_t ep = ++episode[size_t(e - lo)];
+                        S[e] = T[(uint64_t(e) + ep) % uint64_t(n_templates)];
+                        status[e] = 0;
+                    }
+                }
+            }
+            counts[size_t(t)] = c;
+        });
+    }
+    for(auto& x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
+    unsigned long long tot = 0;
+    for(auto c : counts) tot += c;
+    if(steps_out) *steps_out = tot;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+/* Batch Environment::Step for the harness: pre[e] receives ref_precheck(); envs whose pre-check
+ * shows D3/D4/flame-overflow/bad-move risk are NOT stepped and get status |= 0x10 (excluded from
+ * comparison from then on). */
+REF_API void ref_env_step_batch(void* states, uint8_t* status, long n, const uint8_t* moves, uint8_t* pre)
+{
+    State* S = static_cast<State*>(states);
+    for(long e = 0; e < n; e++)
+    {
+        if(status[e] & 0x11) { if(pre) pre[e] = 0; continue; }
+        int f = ref_precheck(&S[e], moves + 4 * e);
+        if(pre) pre[e] = uint8_t(f);
+        if(f & 0xF0) { status[e] |= 0x10; continue; }
+        EnvStep(&S[e], &status[e], moves + 4 * e);
+    }
+}
+
+REF_API void ref_step_batch(void* states, long n, const uint8_t* moves)
+{
+    State* S = static_cast<State*>(states);
+    for(long e = 0; e < n; e++) PaddedStep(&S[e], moves + 4 * e);
+}
+
+REF_API int ref_hardware_concurrency()
+{
+    return int(std::thread::hardware_concurrency());
+}
