@@ -1,0 +1,150 @@
+/*
+ * pom_batch.h — C ABI of the B200-native batched Pommerman step path (libpom_b200.so).
+ *
+ * The reference (dist1ll/pomcpp) has no FFI layer: consumers include include/bboard.hpp and link
+ * lib/pomlib.a (README.md:58-60, Makefile:34-38).  These entry points are what a binding of the
+ * step path replaces; each one cites the reference interface it stands for.  All states live on
+ * ONE GPU per handle as packed 292-byte records (pomcpp_b200/csrc/pom_record.h); host buffers use
+ * the AoS `pom_state` of pom_state.h, which is layout-identical to the reference's bboard::State.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative POM_E_* code; nothing throws across the ABI;
+ *     pom_last_error() returns a thread-local description of the last failure.
+ *   - a handle owns its device buffers and one CUDA stream; calls on one handle are stream-ordered
+ *     and NOT thread-safe; different handles (e.g. one per GPU) may be driven from different threads.
+ *   - functions taking host pointers synchronise before returning; pom_batch_step / _rollout /
+ *     _clone / _expand_step only enqueue work (use pom_batch_sync, or CUDA events on pom_batch_stream).
+ *   - there is no CPU fallback: without a CUDA device pom_batch_init fails with POM_E_CUDA.
+ */
+#ifndef POM_BATCH_H_
+#define POM_BATCH_H_
+
+#include <stdint.h>
+#include "pom_state.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pom_batch pom_batch;
+
+enum {
+    POM_OK        =  0,
+    POM_E_ARG     = -1,   /* bad argument                                   */
+    POM_E_CUDA    = -2,   /* CUDA runtime error (see pom_last_error)         */
+    POM_E_NOMEM   = -3,   /* device or host allocation failed                */
+    POM_E_RANGE   = -4,   /* env index / count outside the batch             */
+    POM_E_STATE   = -5    /* an uploaded state cannot be represented (envs marked POM_STATUS_INVALID) */
+};
+
+/* flags of pom_batch_step / pom_batch_expand_step */
+enum {
+    POM_STEP_RAW       = 0x1, /* bare bboard::Step (step.cpp:9): no timeStep++, no done/winner, finished envs are stepped too */
+    POM_STEP_AUTORESET = 0x2, /* an env that finishes is counted in the stats and re-initialised from the
+                                 template pool at the end of the finishing tick (not in the reference)  */
+    POM_STEP_COUNT     = 0x4  /* add the number of envs stepped to stats.env_steps                       */
+};
+
+/* flags of pom_batch_rollout: actions per agent come from the shared stateless RNG
+ * (see pom_rng_moves); POM_ROLL_HARMLESS draws from {0..4} (HarmlessAgent, basic_agents.cpp:28-38),
+ * default is {0..5} (RandomAgent, basic_agents.cpp:12-22). */
+enum {
+    POM_ROLL_HARMLESS  = 0x1,
+    POM_ROLL_NO_RESET  = 0x2  /* finished envs freeze (Environment::Step, environment.cpp:125-128) instead of auto-resetting */
+};
+
+/* How pom_batch_init fills the batch.  Replaces InitState / InitBoardItems / PutAgentsInCorners
+ * (bboard.hpp:651,661; bboard.cpp:322-382) and Environment::MakeGame (environment.cpp:53-66). */
+typedef struct pom_init_desc {
+    uint64_t         env_offset;      /* global index of this handle's env 0 (sharding over GPUs)            */
+    uint32_t         n_templates;     /* size of the template pool kept on the device (>= 1)                 */
+    int32_t          first_seed;      /* pool = InitState(s, 0,1,2,3) for the first n_templates seeds >= first_seed that
+                                         are free of the reference's uninitialised-read defect (bboard.cpp:351,367,372),
+                                         generated ON THE DEVICE (mt19937_64 + libstdc++ uniform_int_distribution)   */
+    const pom_state* host_templates;  /* if non-NULL: n_templates AoS states to use as the pool instead             */
+    uint32_t         max_ticks;       /* rollout truncation (Pommerman: 800); 0 = never                      */
+    uint32_t         flags;           /* POM_INIT_*                                                            */
+} pom_init_desc;
+
+enum {
+    POM_INIT_EMPTY = 0x1   /* do not fill the envs (they will be uploaded); the pool is still built */
+};
+
+/* episode counters accumulated on the device (Environment::IsDone/IsDraw/GetWinner, bboard.hpp:617-631) */
+typedef struct pom_stats {
+    uint64_t env_steps;        /* Steps executed (finished/frozen envs not counted) */
+    uint64_t episodes;         /* episodes finished (won + draw + truncated)        */
+    uint64_t wins[4];          /* episodes won by agent 0..3                         */
+    uint64_t draws;            /* aliveAgents == 0                                   */
+    uint64_t truncated;        /* timeStep reached max_ticks                         */
+    uint64_t sum_episode_len;  /* sum of timeStep over finished episodes             */
+    uint64_t invalid;          /* envs that left the reference's defined domain      */
+} pom_stats;
+#define POM_STATS_WORDS 10
+
+/* ---- lifetime ---- */
+int  pom_device_count(void);
+int  pom_batch_init(pom_batch** out, int device, uint64_t n_envs, const pom_init_desc* desc);
+int  pom_batch_destroy(pom_batch* b);
+int  pom_batch_sync(pom_batch* b);
+const char* pom_last_error(void);
+
+/* ---- AoS <-> packed exchange (there is no reference call: State is passed by pointer) ---- */
+int  pom_batch_upload(pom_batch* b, uint64_t first, uint64_t count, const pom_state* states, const uint8_t* status /* may be NULL */);
+int  pom_batch_download(pom_batch* b, uint64_t first, uint64_t count, pom_state* states /* may be NULL */, uint8_t* status /* may be NULL */);
+int  pom_batch_reset(pom_batch* b);   /* all envs back to their template, counters and episode numbers cleared */
+int  pom_batch_templates(pom_batch* b, pom_state* out /* n_templates */, int32_t* seeds_out /* may be NULL */);
+
+/* ---- the hot path ---- */
+/* bboard::Step(State*, Move*) (bboard.hpp:668, step.cpp:9-284) wrapped in Environment::Step's
+ * bookkeeping (environment.cpp:125-128,149-168) for every env.  moves_dev: DEVICE pointer to
+ * n_envs x 4 bytes, byte a of env e = Move of agent a (bboard.hpp:35-43), values 0..5.         */
+int  pom_batch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags);
+/* same with HOST buffers: copies moves in, steps, copies the status bytes out (may be NULL), synchronises */
+int  pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags);
+/* `ticks` fused ticks with the boards resident in shared memory; actions from pom_rng_moves(rng_seed,
+ * global env index, tick0 + k); auto-reset unless POM_ROLL_NO_RESET.  Replaces the loop of
+ * Environment::StartGame (environment.cpp:68-88) with RandomAgent/HarmlessAgent::act (bboard.hpp:517-533). */
+int  pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t tick0, uint32_t flags);
+/* state copy for tree search (the reference copies the POD State by assignment, README.md:4):
+ * dst env first_dst + i <- src env src_idx[i] (HOST array of n_dst indices).  dst may equal src.    */
+int  pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_dst);
+/* tree-search expansion: child c = i * fanout + j of root src_idx[i] gets joint action j with
+ * a_k = (j / 6^k) % 6 and is stepped once (clone + Step fused, one HBM write per child).
+ * fanout <= 1296; dst needs n_roots * fanout envs.                                                  */
+int  pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_roots, uint32_t fanout, uint32_t flags);
+
+/* ---- State::SpawnFlame (bboard.cpp:198-263) on one env, used by fixtures ---- */
+int  pom_batch_spawn_flame(pom_batch* b, uint64_t env, int x, int y, int strength);
+
+/* ---- results ---- */
+int  pom_batch_status(pom_batch* b, uint64_t first, uint64_t count, uint8_t* status_host);
+int  pom_batch_stats(pom_batch* b, pom_stats* out);            /* synchronises */
+int  pom_batch_clear_stats(pom_batch* b);
+
+/* ---- action source shared by host and device ---- */
+/* four moves packed little-endian, each mulhi16(x, n_actions), from splitmix64(seed, env, tick) */
+uint32_t pom_rng_moves(uint64_t seed, uint64_t env, uint32_t tick, uint32_t n_actions);
+/* fills a DEVICE buffer of n_envs x 4 bytes with pom_rng_moves(seed, env_offset + e, tick, n_actions) */
+int  pom_batch_generate_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_t tick, uint32_t n_actions);
+
+/* ---- plumbing for callers that own CUDA objects (bench, NCCL reduce) ---- */
+uint64_t pom_batch_size(const pom_batch* b);
+int      pom_batch_device(const pom_batch* b);
+void*    pom_batch_stream(const pom_batch* b);          /* cudaStream_t                           */
+void*    pom_batch_stats_device_ptr(const pom_batch* b);/* POM_STATS_WORDS x uint64 on the device  */
+void*    pom_batch_records_device_ptr(const pom_batch* b);
+int      pom_device_alloc(int device, uint64_t bytes, void** out);
+int      pom_device_free(int device, void* p);
+/* timing helper: runs fn-less CUDA-event brackets on the handle's stream */
+int      pom_batch_event_record(pom_batch* b, int which /* 0 = start, 1 = stop */);
+int      pom_batch_event_elapsed_ms(pom_batch* b, float* ms);   /* synchronises on the stop event */
+/* writes `bytes` of zeros to a scratch buffer larger than L2 (between timed iterations)          */
+int      pom_batch_flush_l2(pom_batch* b);
+/* number of kernels this library has launched on the handle (for bench.py's gpu_launches)        */
+uint64_t pom_batch_launch_count(const pom_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POM_BATCH_H_ */

@@ -1,0 +1,557 @@
+/*
+ * pom_batch.cu — implementation of the C ABI in include/pom_batch.h (libpom_b200.so).
+ *
+ * Host side of the product: owns device memory, streams and launches; every simulation step runs
+ * in the sm_100a kernels of pom_kernels.cuh.  There is deliberately no host stepping path here:
+ * without a CUDA device every entry point fails with POM_E_CUDA.
+ */
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "pom_batch.h"
+#include "pom_kernels.cuh"
+
+namespace
+{
+
+thread_local std::string g_err;
+
+int fail(int code, const char* what, cudaError_t ce = cudaSuccess)
+{
+    g_err = what;
+    if(ce != cudaSuccess)
+    {
+        g_err += ": ";
+        g_err += cudaGetErrorString(ce);
+    }
+    return code;
+}
+
+#define CK(expr) do { cudaError_t ce_ = (expr); if(ce_ != cudaSuccess) return fail(POM_E_CUDA, #expr, ce_); } while(0)
+
+constexpr uint64_t TILE_ALIGN = 256;           /* records are allocated in whole tiles of the largest TPB */
+constexpr uint64_t XFER_CHUNK = 65536;         /* envs per AoS staging chunk (66 MB)                      */
+constexpr size_t   FLUSH_BYTES = size_t(256) << 20;
+
+}
+
+struct pom_batch {
+    int       device = 0;
+    uint64_t  n_envs = 0;
+    uint64_t  n_alloc = 0;                     /* n_envs rounded up to TILE_ALIGN */
+    uint64_t  env_offset = 0;
+    uint32_t  n_templates = 0;
+    uint32_t  max_ticks = 0;
+    int       tpb = 128;
+    uint8_t*  recs = nullptr;
+    uint8_t*  templates = nullptr;
+    uint32_t* episodes = nullptr;
+    unsigned long long* stats = nullptr;
+    uint32_t* moves_buf = nullptr;             /* n_envs x 4 bytes, for pom_batch_step_host */
+    uint8_t*  status_buf = nullptr;            /* n_envs bytes                               */
+    pom_state* aos_stage = nullptr;            /* XFER_CHUNK states                          */
+    uint8_t*  st_stage = nullptr;
+    uint32_t* bad_count = nullptr;
+    void*     flush_buf = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = { nullptr, nullptr };
+    std::vector<int32_t> seeds;
+    uint64_t  launches = 0;
+
+    pomk::BatchParams params() const
+    {
+        pomk::BatchParams P;
+        P.recs = recs; P.n_envs = n_envs; P.env_offset = env_offset; P.templates = templates;
+        P.n_templates = n_templates; P.max_ticks = max_ticks; P.episodes = episodes; P.stats = stats;
+        return P;
+    }
+};
+
+namespace
+{
+
+int use(const pom_batch* b)
+{
+    if(!b) return fail(POM_E_ARG, "null handle");
+    CK(cudaSetDevice(b->device));
+    return POM_OK;
+}
+
+template<int TPB, typename K>
+int set_smem(K kernel)
+{
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * POM_REC_BYTES + 16));
+    return POM_OK;
+}
+
+int ensure_stage(pom_batch* b)
+{
+    if(!b->aos_stage)
+    {
+        CK(cudaMalloc(&b->aos_stage, XFER_CHUNK * sizeof(pom_state)));
+        CK(cudaMalloc(&b->st_stage, XFER_CHUNK));
+        CK(cudaMalloc(&b->bad_count, sizeof(uint32_t)));
+    }
+    return POM_OK;
+}
+
+int fill_from_templates(pom_batch* b)
+{
+    const uint64_t words = b->n_envs * POM_REC_WORDS;
+    pomk::k_fill_from_templates<<<unsigned((words + 255) / 256), 256, 0, b->stream>>>(b->params());
+    b->launches++;
+    CK(cudaGetLastError());
+    return POM_OK;
+}
+
+/* builds the template pool on the device: InitState for the first n clean seeds >= first_seed */
+int build_templates_from_seeds(pom_batch* b, int32_t first_seed)
+{
+    const uint32_t n = b->n_templates;
+    uint32_t ncand = uint32_t(n * 2.2) + 64;
+    for(int attempt = 0; attempt < 6; attempt++, ncand *= 2)
+    {
+        uint8_t* cand = nullptr; uint8_t* dirty = nullptr; uint32_t* pick = nullptr;
+        CK(cudaMalloc(&cand, size_t(ncand) * POM_REC_BYTES));
+        CK(cudaMalloc(&dirty, ncand));
+        pomk::k_make_templates<<<(ncand + 63) / 64, 64, 0, b->stream>>>(cand, dirty, first_seed, ncand);
+        b->launches++;
+        CK(cudaGetLastError());
+        std::vector<uint8_t> h(ncand);
+        CK(cudaMemcpyAsync(h.data(), dirty, ncand, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        std::vector<uint32_t> idx;
+        for(uint32_t i = 0; i < ncand && idx.size() < n; i++) if(!h[i]) idx.push_back(i);
+        if(idx.size() == n)
+        {
+            CK(cudaMalloc(&pick, n * sizeof(uint32_t)));
+            CK(cudaMemcpyAsync(pick, idx.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+            const uint64_t words = uint64_t(n) * POM_REC_WORDS;
+            pomk::k_gather_records<<<unsigned((words + 255) / 256), 256, 0, b->stream>>>(
+                reinterpret_cast<uint32_t*>(b->templates), reinterpret_cast<const uint32_t*>(cand), pick, n, 0);
+            b->launches++;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(b->stream));
+            b->seeds.resize(n);
+            for(uint32_t k = 0; k < n; k++) b->seeds[k] = first_seed + int32_t(idx[k]);
+        }
+        cudaFree(cand); cudaFree(dirty); if(pick) cudaFree(pick);
+        if(idx.size() == n) return POM_OK;
+    }
+    return fail(POM_E_ARG, "could not find enough clean seeds");
+}
+
+int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, const pom_state* states, const uint8_t* status, uint32_t* bad_total)
+{
+    int rc = ensure_stage(b);
+    if(rc) return rc;
+    for(uint64_t done = 0; done < count; done += XFER_CHUNK)
+    {
+        const uint64_t c = count - done < XFER_CHUNK ? count - done : XFER_CHUNK;
+        CK(cudaMemcpyAsync(b->aos_stage, states + done, c * sizeof(pom_state), cudaMemcpyHostToDevice, b->stream));
+        if(status) CK(cudaMemcpyAsync(b->st_stage, status + done, c, cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemsetAsync(b->bad_count, 0, sizeof(uint32_t), b->stream));
+        pomk::k_pack<<<unsigned((c + 127) / 128), 128, 0, b->stream>>>(b->aos_stage, status ? b->st_stage : nullptr, dst_recs, first + done, c, b->bad_count);
+        b->launches++;
+        CK(cudaGetLastError());
+        uint32_t bad = 0;
+        CK(cudaMemcpyAsync(&bad, b->bad_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        *bad_total += bad;
+    }
+    return POM_OK;
+}
+
+template<int TPB>
+int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
+{
+    static bool once = false;
+    if(!once) { int rc = set_smem<TPB>(pomk::k_step<TPB>); if(rc) return rc; once = true; }
+    const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
+    pomk::k_step<TPB><<<grid, TPB, TPB * POM_REC_BYTES + 16, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags);
+    b->launches++;
+    CK(cudaGetLastError());
+    return POM_OK;
+}
+
+template<int TPB>
+int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, uint32_t flags)
+{
+    static bool once = false;
+    if(!once) { int rc = set_smem<TPB>(pomk::k_rollout<TPB>); if(rc) return rc; once = true; }
+    const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
+    pomk::k_rollout<TPB><<<grid, TPB, TPB * POM_REC_BYTES + 16, b->stream>>>(
+        b->params(), ticks, seed, tick0, (flags & POM_ROLL_HARMLESS) ? 5u : 6u, (flags & POM_ROLL_NO_RESET) ? 1u : 0u);
+    b->launches++;
+    CK(cudaGetLastError());
+    return POM_OK;
+}
+
+template<int TPB>
+int launch_expand(pom_batch* dst, const pom_batch* src, const uint32_t* idx_dev, uint64_t n_children, uint32_t fanout, uint32_t flags)
+{
+    static bool once = false;
+    if(!once) { int rc = set_smem<TPB>(pomk::k_expand_step<TPB>); if(rc) return rc; once = true; }
+    const unsigned grid = unsigned((n_children + TPB - 1) / TPB);
+    pomk::k_expand_step<TPB><<<grid, TPB, TPB * POM_REC_BYTES + 16, dst->stream>>>(dst->recs, src->recs, idx_dev, n_children, fanout, flags);
+    dst->launches++;
+    CK(cudaGetLastError());
+    return POM_OK;
+}
+
+}
+
+extern "C" {
+
+const char* pom_last_error(void) { return g_err.c_str(); }
+
+int pom_device_count(void)
+{
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pom_batch_init(pom_batch** out, int device, uint64_t n_envs, const pom_init_desc* desc)
+{
+    if(!out || !desc || n_envs == 0 || desc->n_templates == 0) return fail(POM_E_ARG, "pom_batch_init: bad argument");
+    if(n_envs > (uint64_t(1) << 31)) return fail(POM_E_ARG, "pom_batch_init: too many envs for one handle");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if(ce != cudaSuccess || ndev == 0) return fail(POM_E_CUDA, "no CUDA device: the step path has no CPU fallback", ce);
+    if(device < 0 || device >= ndev) return fail(POM_E_ARG, "pom_batch_init: no such device");
+    CK(cudaSetDevice(device));
+    pom_batch* b = new(std::nothrow) pom_batch();
+    if(!b) return fail(POM_E_NOMEM, "host allocation failed");
+    b->device = device;
+    b->n_envs = n_envs;
+    b->n_alloc = (n_envs + TILE_ALIGN - 1) / TILE_ALIGN * TILE_ALIGN;
+    b->env_offset = desc->env_offset;
+    b->n_templates = desc->n_templates;
+    b->max_ticks = desc->max_ticks;
+    if(const char* e = std::getenv("POM_TPB"))
+    {
+        const int t = std::atoi(e);
+        if(t == 64 || t == 128 || t == 256) b->tpb = t;
+    }
+    int rc = POM_OK;
+    do {
+        if(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
+           cudaEventCreate(&b->ev[0]) != cudaSuccess || cudaEventCreate(&b->ev[1]) != cudaSuccess)
+        { rc = fail(POM_E_CUDA, "stream/event creation failed", cudaGetLastError()); break; }
+        if(cudaMalloc(&b->recs, b->n_alloc * POM_REC_BYTES) != cudaSuccess ||
+           cudaMalloc(&b->templates, size_t(b->n_templates) * POM_REC_BYTES) != cudaSuccess ||
+           cudaMalloc(&b->episodes, b->n_alloc * sizeof(uint32_t)) != cudaSuccess ||
+           cudaMalloc(&b->stats, POM_STATS_WORDS * sizeof(unsigned long long)) != cudaSuccess ||
+           cudaMalloc(&b->moves_buf, b->n_alloc * 4) != cudaSuccess ||
+           cudaMalloc(&b->status_buf, b->n_alloc) != cudaSuccess)
+        { rc = fail(POM_E_NOMEM, "device allocation failed", cudaGetLastError()); break; }
+        if(cudaMemsetAsync(b->recs, 0, b->n_alloc * POM_REC_BYTES, b->stream) != cudaSuccess ||
+           cudaMemsetAsync(b->episodes, 0, b->n_alloc * sizeof(uint32_t), b->stream) != cudaSuccess ||
+           cudaMemsetAsync(b->stats, 0, POM_STATS_WORDS * sizeof(unsigned long long), b->stream) != cudaSuccess)
+        { rc = fail(POM_E_CUDA, "memset failed", cudaGetLastError()); break; }
+        if(desc->host_templates)
+        {
+            uint32_t bad = 0;
+            rc = pack_into(b, b->templates, 0, b->n_templates, desc->host_templates, nullptr, &bad);
+            if(rc) break;
+            if(bad) { rc = fail(POM_E_STATE, "a host template cannot be represented in the packed record"); break; }
+        }
+        else
+        {
+            rc = build_templates_from_seeds(b, desc->first_seed);
+            if(rc) break;
+        }
+        if(!(desc->flags & POM_INIT_EMPTY))
+        {
+            rc = fill_from_templates(b);
+            if(rc) break;
+        }
+        if(cudaStreamSynchronize(b->stream) != cudaSuccess) { rc = fail(POM_E_CUDA, "init sync failed", cudaGetLastError()); break; }
+    } while(0);
+    if(rc) { pom_batch_destroy(b); return rc; }
+    *out = b;
+    return POM_OK;
+}
+
+int pom_batch_destroy(pom_batch* b)
+{
+    if(!b) return POM_OK;
+    cudaSetDevice(b->device);
+    if(b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->recs); cudaFree(b->templates); cudaFree(b->episodes); cudaFree(b->stats);
+    cudaFree(b->moves_buf); cudaFree(b->status_buf); cudaFree(b->aos_stage); cudaFree(b->st_stage);
+    cudaFree(b->bad_count); cudaFree(b->flush_buf);
+    if(b->ev[0]) cudaEventDestroy(b->ev[0]);
+    if(b->ev[1]) cudaEventDestroy(b->ev[1]);
+    if(b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return POM_OK;
+}
+
+int pom_batch_sync(pom_batch* b)
+{
+    int rc = use(b); if(rc) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    return POM_OK;
+}
+
+int pom_batch_upload(pom_batch* b, uint64_t first, uint64_t count, const pom_state* states, const uint8_t* status)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!states) return fail(POM_E_ARG, "pom_batch_upload: null states");
+    if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_upload: range outside the batch");
+    uint32_t bad = 0;
+    rc = pack_into(b, b->recs, first, count, states, status, &bad);
+    if(rc) return rc;
+    if(bad) return fail(POM_E_STATE, "pom_batch_upload: some states cannot be represented (marked POM_STATUS_INVALID)");
+    return POM_OK;
+}
+
+int pom_batch_download(pom_batch* b, uint64_t first, uint64_t count, pom_state* states, uint8_t* status)
+{
+    int rc = use(b); if(rc) return rc;
+    if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_download: range outside the batch");
+    rc = ensure_stage(b); if(rc) return rc;
+    for(uint64_t done = 0; done < count; done += XFER_CHUNK)
+    {
+        const uint64_t c = count - done < XFER_CHUNK ? count - done : XFER_CHUNK;
+        pomk::k_unpack<<<unsigned((c + 127) / 128), 128, 0, b->stream>>>(b->recs, states ? b->aos_stage : nullptr, b->st_stage, first + done, c);
+        b->launches++;
+        CK(cudaGetLastError());
+        if(states) CK(cudaMemcpyAsync(states + done, b->aos_stage, c * sizeof(pom_state), cudaMemcpyDeviceToHost, b->stream));
+        if(status) CK(cudaMemcpyAsync(status + done, b->st_stage, c, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    return POM_OK;
+}
+
+int pom_batch_reset(pom_batch* b)
+{
+    int rc = use(b); if(rc) return rc;
+    CK(cudaMemsetAsync(b->episodes, 0, b->n_alloc * sizeof(uint32_t), b->stream));
+    CK(cudaMemsetAsync(b->stats, 0, POM_STATS_WORDS * sizeof(unsigned long long), b->stream));
+    return fill_from_templates(b);
+}
+
+int pom_batch_templates(pom_batch* b, pom_state* out, int32_t* seeds_out)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!out) return fail(POM_E_ARG, "pom_batch_templates: null output");
+    rc = ensure_stage(b); if(rc) return rc;
+    for(uint64_t done = 0; done < b->n_templates; done += XFER_CHUNK)
+    {
+        const uint64_t c = b->n_templates - done < XFER_CHUNK ? b->n_templates - done : XFER_CHUNK;
+        pomk::k_unpack<<<unsigned((c + 127) / 128), 128, 0, b->stream>>>(b->templates, b->aos_stage, b->st_stage, done, c);
+        b->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out + done, b->aos_stage, c * sizeof(pom_state), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    if(seeds_out)
+    {
+        for(uint32_t k = 0; k < b->n_templates; k++) seeds_out[k] = k < b->seeds.size() ? b->seeds[k] : 0;
+    }
+    return POM_OK;
+}
+
+int pom_batch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!moves_dev) return fail(POM_E_ARG, "pom_batch_step: null moves");
+    if(b->tpb == 64) return launch_step<64>(b, moves_dev, flags);
+    if(b->tpb == 256) return launch_step<256>(b, moves_dev, flags);
+    return launch_step<128>(b, moves_dev, flags);
+}
+
+int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!moves_host) return fail(POM_E_ARG, "pom_batch_step_host: null moves");
+    CK(cudaMemcpyAsync(b->moves_buf, moves_host, b->n_envs * 4, cudaMemcpyHostToDevice, b->stream));
+    rc = pom_batch_step(b, reinterpret_cast<const uint8_t*>(b->moves_buf), flags);
+    if(rc) return rc;
+    if(status_host)
+    {
+        pomk::k_unpack<<<unsigned((b->n_envs + 255) / 256), 256, 0, b->stream>>>(b->recs, nullptr, b->status_buf, 0, b->n_envs);
+        b->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(status_host, b->status_buf, b->n_envs, cudaMemcpyDeviceToHost, b->stream));
+    }
+    CK(cudaStreamSynchronize(b->stream));
+    return POM_OK;
+}
+
+int pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t tick0, uint32_t flags)
+{
+    int rc = use(b); if(rc) return rc;
+    if(b->tpb == 64) return launch_rollout<64>(b, ticks, rng_seed, tick0, flags);
+    if(b->tpb == 256) return launch_rollout<256>(b, ticks, rng_seed, tick0, flags);
+    return launch_rollout<128>(b, ticks, rng_seed, tick0, flags);
+}
+
+int pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_dst)
+{
+    int rc = use(dst); if(rc) return rc;
+    if(!src || !src_idx) return fail(POM_E_ARG, "pom_batch_clone: null argument");
+    if(src->device != dst->device) return fail(POM_E_ARG, "pom_batch_clone: handles live on different devices");
+    if(first_dst + n_dst > dst->n_envs) return fail(POM_E_RANGE, "pom_batch_clone: destination range outside the batch");
+    for(uint64_t i = 0; i < n_dst; i++) if(src_idx[i] >= src->n_envs) return fail(POM_E_RANGE, "pom_batch_clone: source index outside the batch");
+    if(n_dst == 0) return POM_OK;
+    uint32_t* idx_dev = nullptr;
+    CK(cudaMalloc(&idx_dev, n_dst * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(idx_dev, src_idx, n_dst * sizeof(uint32_t), cudaMemcpyHostToDevice, dst->stream));
+    if(src != dst) cudaStreamSynchronize(src->stream);
+    const uint8_t* from = src->recs;
+    uint8_t* tmp = nullptr;
+    if(src == dst)
+    {
+        /* in-place gather: read from a snapshot so overlapping ranges are well defined */
+        CK(cudaMalloc(&tmp, dst->n_alloc * POM_REC_BYTES));
+        CK(cudaMemcpyAsync(tmp, dst->recs, dst->n_alloc * POM_REC_BYTES, cudaMemcpyDeviceToDevice, dst->stream));
+        from = tmp;
+    }
+    const uint64_t words = n_dst * POM_REC_WORDS;
+    pomk::k_gather_records<<<unsigned((words + 255) / 256), 256, 0, dst->stream>>>(
+        reinterpret_cast<uint32_t*>(dst->recs), reinterpret_cast<const uint32_t*>(from), idx_dev, n_dst, first_dst);
+    dst->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(dst->stream));
+    cudaFree(idx_dev);
+    if(tmp) cudaFree(tmp);
+    return POM_OK;
+}
+
+int pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_roots, uint32_t fanout, uint32_t flags)
+{
+    int rc = use(dst); if(rc) return rc;
+    if(!src || !src_idx || src == dst) return fail(POM_E_ARG, "pom_batch_expand_step: bad argument");
+    if(src->device != dst->device) return fail(POM_E_ARG, "pom_batch_expand_step: handles live on different devices");
+    if(fanout == 0 || fanout > 1296) return fail(POM_E_ARG, "pom_batch_expand_step: fanout must be 1..1296");
+    const uint64_t n_children = n_roots * fanout;
+    if(n_children > dst->n_envs) return fail(POM_E_RANGE, "pom_batch_expand_step: destination too small");
+    for(uint64_t i = 0; i < n_roots; i++) if(src_idx[i] >= src->n_envs) return fail(POM_E_RANGE, "pom_batch_expand_step: root index outside the batch");
+    if(n_roots == 0) return POM_OK;
+    uint32_t* idx_dev = nullptr;
+    CK(cudaMalloc(&idx_dev, n_roots * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(idx_dev, src_idx, n_roots * sizeof(uint32_t), cudaMemcpyHostToDevice, dst->stream));
+    cudaStreamSynchronize(src->stream);
+    if(dst->tpb == 64) rc = launch_expand<64>(dst, src, idx_dev, n_children, fanout, flags);
+    else if(dst->tpb == 256) rc = launch_expand<256>(dst, src, idx_dev, n_children, fanout, flags);
+    else rc = launch_expand<128>(dst, src, idx_dev, n_children, fanout, flags);
+    cudaError_t ce = cudaStreamSynchronize(dst->stream);
+    cudaFree(idx_dev);
+    if(rc) return rc;
+    if(ce != cudaSuccess) return fail(POM_E_CUDA, "pom_batch_expand_step", ce);
+    return POM_OK;
+}
+
+int pom_batch_spawn_flame(pom_batch* b, uint64_t env, int x, int y, int strength)
+{
+    int rc = use(b); if(rc) return rc;
+    if(env >= b->n_envs) return fail(POM_E_RANGE, "pom_batch_spawn_flame: env outside the batch");
+    if(x < 0 || x > 10 || y < 0 || y > 10 || strength < 0 || strength > 255) return fail(POM_E_ARG, "pom_batch_spawn_flame: bad argument");
+    pomk::k_spawn_flame<<<1, 1, 0, b->stream>>>(b->recs, env, uint32_t(x) | (uint32_t(y) << 4), uint32_t(strength));
+    b->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(b->stream));
+    return POM_OK;
+}
+
+int pom_batch_status(pom_batch* b, uint64_t first, uint64_t count, uint8_t* status_host)
+{
+    return pom_batch_download(b, first, count, nullptr, status_host);
+}
+
+int pom_batch_stats(pom_batch* b, pom_stats* out)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!out) return fail(POM_E_ARG, "pom_batch_stats: null output");
+    unsigned long long h[POM_STATS_WORDS];
+    CK(cudaMemcpyAsync(h, b->stats, sizeof(h), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    out->env_steps = h[pomk::ST_STEPS]; out->episodes = h[pomk::ST_EPISODES];
+    for(int a = 0; a < 4; a++) out->wins[a] = h[pomk::ST_WIN0 + a];
+    out->draws = h[pomk::ST_DRAWS]; out->truncated = h[pomk::ST_TRUNC];
+    out->sum_episode_len = h[pomk::ST_SUMLEN]; out->invalid = h[pomk::ST_INVALID];
+    return POM_OK;
+}
+
+int pom_batch_clear_stats(pom_batch* b)
+{
+    int rc = use(b); if(rc) return rc;
+    CK(cudaMemsetAsync(b->stats, 0, POM_STATS_WORDS * sizeof(unsigned long long), b->stream));
+    return POM_OK;
+}
+
+uint32_t pom_rng_moves(uint64_t seed, uint64_t env, uint32_t tick, uint32_t n_actions)
+{
+    return pomcore::rng_moves(seed, env, tick, n_actions);
+}
+
+int pom_batch_generate_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_t tick, uint32_t n_actions)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!moves_dev || n_actions == 0 || n_actions > 6) return fail(POM_E_ARG, "pom_batch_generate_moves: bad argument");
+    pomk::k_generate_moves<<<unsigned((b->n_envs + 255) / 256), 256, 0, b->stream>>>(
+        reinterpret_cast<uint32_t*>(moves_dev), b->n_envs, b->env_offset, seed, tick, n_actions);
+    b->launches++;
+    CK(cudaGetLastError());
+    return POM_OK;
+}
+
+uint64_t pom_batch_size(const pom_batch* b) { return b ? b->n_envs : 0; }
+int      pom_batch_device(const pom_batch* b) { return b ? b->device : -1; }
+void*    pom_batch_stream(const pom_batch* b) { return b ? (void*)b->stream : nullptr; }
+void*    pom_batch_stats_device_ptr(const pom_batch* b) { return b ? (void*)b->stats : nullptr; }
+void*    pom_batch_records_device_ptr(const pom_batch* b) { return b ? (void*)b->recs : nullptr; }
+uint64_t pom_batch_launch_count(const pom_batch* b) { return b ? b->launches : 0; }
+
+int pom_device_alloc(int device, uint64_t bytes, void** out)
+{
+    if(!out) return fail(POM_E_ARG, "pom_device_alloc: null output");
+    CK(cudaSetDevice(device));
+    if(cudaMalloc(out, bytes) != cudaSuccess) return fail(POM_E_NOMEM, "pom_device_alloc", cudaGetLastError());
+    return POM_OK;
+}
+
+int pom_device_free(int device, void* p)
+{
+    CK(cudaSetDevice(device));
+    CK(cudaFree(p));
+    return POM_OK;
+}
+
+int pom_batch_event_record(pom_batch* b, int which)
+{
+    int rc = use(b); if(rc) return rc;
+    if(which < 0 || which > 1) return fail(POM_E_ARG, "pom_batch_event_record: which must be 0 or 1");
+    CK(cudaEventRecord(b->ev[which], b->stream));
+    return POM_OK;
+}
+
+int pom_batch_event_elapsed_ms(pom_batch* b, float* ms)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!ms) return fail(POM_E_ARG, "pom_batch_event_elapsed_ms: null output");
+    CK(cudaEventSynchronize(b->ev[1]));
+    CK(cudaEventElapsedTime(ms, b->ev[0], b->ev[1]));
+    return POM_OK;
+}
+
+int pom_batch_flush_l2(pom_batch* b)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!b->flush_buf) CK(cudaMalloc(&b->flush_buf, FLUSH_BYTES));
+    const uint64_t n16 = FLUSH_BYTES / 16;
+    pomk::k_fill_zero<<<unsigned((n16 + 255) / 256), 256, 0, b->stream>>>(reinterpret_cast<uint4*>(b->flush_buf), n16);
+    CK(cudaGetLastError());
+    return POM_OK;
+}
+
+}

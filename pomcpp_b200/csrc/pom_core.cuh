@@ -1,0 +1,928 @@
+/*
+ * pom_core.cuh — one tick of one env on the packed record (pom_record.h).
+ *
+ * This is the body every kernel runs: the per-tick kernel on a record staged in shared memory,
+ * the fused rollout kernel K times on a resident record.  One thread owns one env; the record
+ * pointer `r` addresses shared memory on the device.  The four agents live in five packed
+ * registers (`Agents`) for the whole tick; board, bomb ring and flame ring are read and written
+ * in place.
+ *
+ * Semantics follow the reference tick exactly (src/bboard/step.cpp:9-284 and the helpers it
+ * calls); each function cites the lines it re-states.  The reference's recursion
+ * (SpawnFlame <-> SpawnFlameItem <-> ExplodeBombAt, bboard.cpp:24-57,111-118,198-263) is run
+ * by an explicit stack of 16-bit frames (`explode`), its tail recursion
+ * (AgentBombChainReversion, step_utility.cpp:62-128) by a loop (`revert_chain`).
+ *
+ * The header also compiles as plain C++ (POM_HD expands to `inline`); tests/hostsim builds it
+ * that way to differential-test the tick logic on the CPU.  That build is test-only: the
+ * product library contains device code only and has no CPU stepping path.
+ */
+#ifndef POM_CORE_CUH_
+#define POM_CORE_CUH_
+
+#include <stdint.h>
+#include "pom_record.h"
+#include "pom_state.h"
+
+#if defined(__CUDACC__)
+#define POM_HD __host__ __device__ inline
+#else
+#define POM_HD inline
+#endif
+
+namespace pomcore
+{
+
+/* flags returned by step(): same bits as oracle/pom_oracle.h POM_ORC_* */
+enum {
+    F_D1_UNREACHABLE = 0x01,
+    F_D3_NULL_BOMB   = 0x02,
+    F_D4_BOMB_OVF    = 0x04,
+    F_FLAME_OVF      = 0x08,
+    F_BAD_MOVE       = 0x10,
+    F_LOOP_GUARD     = 0x20,
+    F_INVALID_MASK   = 0x3E
+};
+
+/* the four agents, one byte per agent in each word */
+struct Agents {
+    uint32_t pos;    /* x | y<<4                     */
+    uint32_t bcnt;   /* bombCount (signed byte)      */
+    uint32_t amax;   /* maxBombCount                 */
+    uint32_t astr;   /* bombStrength                 */
+    uint32_t flg;    /* AF_CANKICK | AF_DEAD         */
+    int      alive;  /* aliveAgents                  */
+};
+
+POM_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+POM_HD uint32_t with_byte(uint32_t w, int i, uint32_t v)
+{
+    const int s = 8 * i;
+    return (w & ~(0xFFu << s)) | ((v & 0xFFu) << s);
+}
+POM_HD uint32_t ring20(uint32_t a) { return a % 20u; }
+
+POM_HD uint32_t& bomb_slot(uint8_t* r, uint32_t slot) { return reinterpret_cast<uint32_t*>(r + R_BOMBS)[slot]; }
+POM_HD uint32_t& bomb_at(uint8_t* r, uint32_t logical) { return bomb_slot(r, ring20(r[R_BINDEX] + logical)); }
+
+/* positions: p = x | y<<4 (0..10 each).  "Biased" q = p + 0x11 keeps -1 and 11 representable. */
+POM_HD int cell_of(uint32_t p) { return int(p & 15u) + 11 * int(p >> 4); }
+POM_HD bool oob_biased(uint32_t q)
+{
+    const uint32_t x = q & 15u, y = (q >> 4) & 15u;
+    return x == 0u || x == 12u || y == 0u || y == 12u;
+}
+/* DesiredPosition, step_utility.cpp:9-31: UP y-1, DOWN y+1, LEFT x-1, RIGHT x+1, anything else stays */
+POM_HD int move_delta(uint32_t m)
+{
+    return (m - 1u < 4u) ? int(int8_t(0x01FF10F0u >> (8u * (m - 1u)))) : 0;
+}
+
+/* Item predicates on cell codes, bboard.hpp:73-109 */
+POM_HD bool c_is_flame(uint32_t c)   { return (c & 0x80u) != 0u; }
+POM_HD bool c_is_wood(uint32_t c)    { return c - 2u < 5u; }
+POM_HD bool c_is_powerup(uint32_t c) { return c - 9u < 3u; }
+POM_HD bool c_is_walkable(uint32_t c) { return c == 0u || c_is_powerup(c); }
+POM_HD bool c_is_agent(uint32_t c)   { return c - 13u < 4u; }
+POM_HD bool c_is_static(uint32_t c)  { return c - 1u < 6u || c_is_powerup(c); }
+
+POM_HD bool ag_dead(const Agents& A, int i) { return (byte_of(A.flg, i) & AF_DEAD) != 0u; }
+
+POM_HD void ag_kill(Agents& A, int i)                                 /* State::Kill, bboard.hpp:474-481 */
+{
+    if(!ag_dead(A, i))
+    {
+        A.flg |= uint32_t(AF_DEAD) << (8 * i);
+        A.alive--;
+    }
+}
+
+POM_HD int get_agent(const Agents& A, uint32_t p)                    /* State::GetAgent, bboard.cpp:289-299 */
+{
+    for(int i = 0; i < 4; i++)
+    {
+        if(!ag_dead(A, i) && byte_of(A.pos, i) == p) return i;
+    }
+    return -1;
+}
+
+POM_HD int bomb_index(uint8_t* r, uint32_t p)                        /* GetBombIndex / GetBomb / HasBomb, bboard.cpp:265-311 */
+{
+    const int n = r[R_BCOUNT];
+    for(int i = 0; i < n; i++)
+    {
+        if((bomb_at(r, i) & 0xFFu) == p) return i;
+    }
+    return -1;
+}
+
+POM_HD void bombs_remove_at(uint8_t* r, int at)                      /* FixedQueue::RemoveAt, bboard.hpp:151-160 */
+{
+    const int n = r[R_BCOUNT];
+    const uint32_t bi = r[R_BINDEX];
+    for(int i = at + 1; i < n; i++)
+    {
+        const uint32_t t = ring20(bi + i);
+        bomb_slot(r, (t + 19u) % 20u) = bomb_slot(r, t);
+    }
+    r[R_BCOUNT] = uint8_t(n - 1);
+}
+
+/* origin position of a flame cell code (FLAME_ID, bboard.hpp:98-101, through the slot indirection) */
+POM_HD uint32_t flame_origin(const uint8_t* r, uint32_t c)
+{
+    const uint32_t slot = (c >> 2) & 31u;
+    return slot == uint32_t(C_FLAME_ORPHAN_SLOT) ? 0u : r[R_FPOS + (slot % 20u)];
+}
+
+POM_HD void pop_flame(uint8_t* r)                                    /* State::PopFlame, bboard.cpp:148-180 */
+{
+    const uint32_t fi = r[R_FINDEX];
+    const uint32_t p = r[R_FPOS + fi];
+    int s = r[R_FSTR + fi];
+    if(s > 10) s = 10;
+    const int x = int(p & 15u), y = int(p >> 4);
+    for(int i = -s; i <= s; i++)
+    {
+        const int cx = x + i, cy = y + i;
+        if(cx >= 0 && cx < 11)
+        {
+            uint8_t* cell = r + R_BOARD + cx + 11 * y;
+            const uint32_t c = *cell;
+            if(c_is_flame(c) && flame_origin(r, c) == p)
+            {
+                const uint32_t pw = c & 3u;                          /* FlagItem, bboard.cpp:182-189 */
+                *cell = uint8_t(pw ? 8u + pw : 0u);
+            }
+        }
+        if(cy >= 0 && cy < 11)
+        {
+            uint8_t* cell = r + R_BOARD + x + 11 * cy;
+            const uint32_t c = *cell;
+            if(c_is_flame(c) && flame_origin(r, c) == p)
+            {
+                const uint32_t pw = c & 3u;
+                *cell = uint8_t(pw ? 8u + pw : 0u);
+            }
+        }
+    }
+    r[R_FINDEX] = uint8_t(ring20(fi + 1u));                          /* PopElem, bboard.hpp:131-137 */
+    r[R_FCOUNT] = uint8_t(r[R_FCOUNT] - 1);
+}
+
+POM_HD void tick_flames(uint8_t* r)                                  /* util::TickFlames, step_utility.cpp:208-222 */
+{
+    const int n = r[R_FCOUNT];
+    if(n == 0) return;
+    const uint32_t fi = r[R_FINDEX];
+    for(int i = 0; i < n; i++)
+    {
+        uint8_t* t = r + R_FTIME + ring20(fi + i);
+        *t = uint8_t(*t - 1);
+    }
+    for(int i = 0; i < n; i++)
+    {
+        if(r[R_FTIME + r[R_FINDEX]] == 0) pop_flame(r);
+        else break;   /* flames[0] unchanged => no later iteration can pop either */
+    }
+}
+
+/*
+ * Explosion machine: State::SpawnFlame (bboard.cpp:198-263) with SpawnFlameItem (:24-57) and the
+ * nested State::ExplodeBombAt (:111-118) it triggers, depth-first in the reference's order
+ * (rays +x, -x, +y, -y).  A stacked frame is 16 bits: flame slot (5) | ray (2) | step (4) |
+ * bomb index (5); the spawn's x, y and strength are read back from its flame-queue entry.
+ *   j0 = logical index of the bomb being exploded by ExplodeBombAt (its epilogue, which re-reads
+ *        bombs[j] AFTER the nested explosions — SURVEY Q6 — runs when the frame completes);
+ *        31 = a bare SpawnFlame (ExplodeTopBomb and fixtures: the caller does the epilogue).
+ */
+POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint32_t j0, int& flags)
+{
+    enum { PH_START, PH_RAY, PH_POST };
+    uint16_t stack[24];
+    int sp = 0;
+    int phase = PH_START;
+    uint32_t slot = 0, d = 0, i = 1, j = j0;
+    uint32_t p = p0, strength = strength0;
+    for(int guard = 0; guard < 8192; guard++)
+    {
+        if(phase == PH_START)
+        {
+            /* SpawnFlame prologue :200-218 */
+            const uint32_t fc = r[R_FCOUNT];
+            if(fc >= 20u) flags |= F_FLAME_OVF;
+            slot = ring20(r[R_FINDEX] + fc);
+            r[R_FPOS + slot] = uint8_t(p);
+            r[R_FSTR + slot] = uint8_t(strength);
+            r[R_FTIME + slot] = uint8_t(POM_FLAME_LIFETIME);
+            r[R_FCOUNT] = uint8_t(fc + 1u);
+            uint8_t* cell = r + R_BOARD + cell_of(p);
+            if(c_is_agent(*cell)) ag_kill(A, int(*cell) - C_AGENT0);
+            *cell = uint8_t(C_FLAME | (slot << 2));
+            d = 0; i = 1;
+            phase = PH_RAY;
+            continue;
+        }
+        if(phase == PH_RAY && d == 4u)
+        {
+            /* SpawnFlame returned */
+            if(j != 31u)
+            {
+                /* ExplodeBombAt epilogue :116-117 — bombs[j] re-read after the recursion */
+                const uint32_t b = bomb_at(r, j);
+                const int id = int((b >> 8) & 3u);
+                A.bcnt = with_byte(A.bcnt, id, byte_of(A.bcnt, id) - 1u);
+                bombs_remove_at(r, int(j));
+            }
+            if(sp == 0) return;
+            const uint32_t f = stack[--sp];
+            slot = f & 31u; d = (f >> 5) & 3u; i = (f >> 7) & 15u; j = (f >> 11) & 31u;
+            p = r[R_FPOS + slot]; strength = r[R_FSTR + slot];
+            phase = PH_POST;          /* resume the parent's SpawnFlameItem after ExplodeBombAt */
+            continue;
+        }
+        if(phase == PH_RAY && i > strength) { d++; i = 1; continue; }
+
+        /* cell (d, i) of the current spawn */
+        int cx = int(p & 15u), cy = int(p >> 4);
+        if(d == 0u) cx += int(i); else if(d == 1u) cx -= int(i); else if(d == 2u) cy += int(i); else cy -= int(i);
+        if(cx < 0 || cx > 10 || cy < 0 || cy > 10) { d++; i = 1; continue; }      /* ray bounds :223,234,245,256 */
+        uint8_t* cell = r + R_BOARD + cx + 11 * cy;
+
+        if(phase == PH_RAY)
+        {
+            /* SpawnFlameItem :26-40 */
+            const uint32_t c = *cell;
+            const bool isAgent = c_is_agent(c);
+            if(isAgent) ag_kill(A, int(c) - C_AGENT0);
+            if(c == uint32_t(C_BOMB) || isAgent)
+            {
+                const uint32_t cp = uint32_t(cx) | (uint32_t(cy) << 4);
+                const int jj = bomb_index(r, cp);
+                if(jj >= 0)
+                {
+                    if(sp >= 24) { flags |= F_LOOP_GUARD; return; }
+                    stack[sp++] = uint16_t(slot | (d << 5) | (i << 7) | (j << 11));
+                    const uint32_t b = bomb_at(r, jj);
+                    p = cp;
+                    strength = byte_of(A.astr, int((b >> 8) & 3u));    /* owner's CURRENT strength (Q5) */
+                    j = uint32_t(jj);
+                    phase = PH_START;
+                    continue;
+                }
+            }
+        }
+        /* SpawnFlameItem :42-56 */
+        {
+            const uint32_t c = *cell;
+            phase = PH_RAY;
+            if(c != uint32_t(C_RIGID))
+            {
+                const bool wasWood = c_is_wood(c);
+                *cell = uint8_t(C_FLAME | (slot << 2) | (wasWood ? ((c - 2u) & 3u) : 0u));
+                if(wasWood) { d++; i = 1; } else { i++; }
+            }
+            else { d++; i = 1; }
+        }
+    }
+    flags |= F_LOOP_GUARD;
+}
+
+/* util::AgentBombChainReversion, step_utility.cpp:62-128 (tail recursion -> loop).
+ * bd[k] = biased destination of bomb k snapshotted before the pre-pass (step.cpp:191-192). */
+POM_HD void revert_chain(uint8_t* r, Agents& A, uint32_t moves, const uint8_t* bd, int agentID, int& flags)
+{
+    for(int guard = 0; guard < 64; guard++)
+    {
+        const uint32_t ap = byte_of(A.pos, agentID);
+        const uint32_t oq = uint32_t(int(ap + 0x11u) - move_delta(byte_of(moves, agentID)));   /* OriginPosition :33-55 */
+        if(oob_biased(oq)) return;
+        const uint32_t origin = oq - 0x11u;
+        const int indexOriginAgent = get_agent(A, origin);
+        int bombDestIndex = -1;
+        int n = r[R_BCOUNT];
+        if(n > 20) n = 20;
+        for(int k = 0; k < n; k++)
+        {
+            if(bd[k] == oq) { bombDestIndex = k; break; }
+        }
+        A.pos = with_byte(A.pos, agentID, origin);
+        r[R_BOARD + cell_of(origin)] = uint8_t(C_AGENT0 + agentID);
+        if(indexOriginAgent != -1)
+        {
+            agentID = indexOriginAgent;
+            continue;
+        }
+        if(bombDestIndex != -1)
+        {
+            uint32_t& b = bomb_at(r, bombDestIndex);
+            const uint32_t bq = bd[bombDestIndex];
+            const uint32_t obq = uint32_t(int(bq) - move_delta((b >> 20) & 15u));
+            if(obq == bq)
+            {
+                /* bounced back onto a bomb he laid himself (:102-106) */
+                r[R_BOARD + cell_of(obq - 0x11u)] = uint8_t(C_AGENT0 + agentID);
+                return;
+            }
+            const uint32_t ob = obq - 0x11u;
+            const int hasAgent = get_agent(A, ob);
+            b = (b & ~0xF00000u);                                     /* SetBombDirection(IDLE) */
+            b = (b & ~0xFFu) + ob;                                    /* SetBombPosition        */
+            r[R_BOARD + cell_of(ob)] = uint8_t(C_BOMB);
+            if(hasAgent != -1)
+            {
+                agentID = hasAgent;
+                continue;
+            }
+        }
+        return;
+    }
+    flags |= F_LOOP_GUARD;
+}
+
+POM_HD uint32_t bomb_dest_biased(uint32_t b)                         /* util::DesiredPosition(Bomb), step_utility.cpp:57-60 */
+{
+    return uint32_t(int((b & 0xFFu) + 0x11u) + move_delta((b >> 20) & 15u));
+}
+
+POM_HD bool has_bomb_collision(uint8_t* r, uint32_t b, int index)    /* step_utility.cpp:279-293 */
+{
+    const uint32_t t = bomb_dest_biased(b);
+    const int n = r[R_BCOUNT];
+    for(int i = index; i < n; i++)
+    {
+        const uint32_t o = bomb_at(r, i);
+        if(o != b && bomb_dest_biased(o) == t) return true;
+    }
+    return false;
+}
+
+POM_HD void resolve_bomb_collision(uint8_t* r, Agents& A, uint32_t moves, const uint8_t* bd, int index, int& flags) /* step_utility.cpp:295-329 */
+{
+    uint32_t& b = bomb_at(r, index);
+    const uint32_t t = bomb_dest_biased(b);
+    bool collided = false;
+    const int n = r[R_BCOUNT];
+    for(int i = index; i < n; i++)
+    {
+        uint32_t& o = bomb_at(r, i);
+        if(o != b && bomb_dest_biased(o) == t)
+        {
+            o = o & ~0xF00000u;
+            collided = true;
+        }
+    }
+    if(collided && ((b >> 20) & 15u) != 0u)
+    {
+        b = b & ~0xF00000u;
+        const int a = get_agent(A, b & 0xFFu);
+        const uint32_t m = a >= 0 ? byte_of(moves, a) : 0u;
+        if(a >= 0 && m != uint32_t(POM_MOVE_IDLE) && m != uint32_t(POM_MOVE_BOMB))
+        {
+            revert_chain(r, A, moves, bd, a, flags);
+            r[R_BOARD + cell_of(b & 0xFFu)] = uint8_t(C_BOMB);       /* b re-read: the chain may have moved it */
+        }
+    }
+}
+
+/* leave the cell an agent stood on: BOMB if a queue entry sits there, else PASSAGE (step.cpp:89-96,127-134) */
+POM_HD void vacate(uint8_t* r, uint32_t p)
+{
+    r[R_BOARD + cell_of(p)] = uint8_t(bomb_index(r, p) >= 0 ? C_BOMB : C_PASSAGE);
+}
+
+/* body of the movement loop for agent i, step.cpp:46-184 */
+POM_HD void move_agent(uint8_t* r, Agents& A, uint32_t moves, const uint32_t* dq, bool ouroboros, int i, int& flags)
+{
+    const uint32_t m = byte_of(moves, i);
+    if(ag_dead(A, i) || m == uint32_t(POM_MOVE_IDLE)) return;
+    const uint32_t p = byte_of(A.pos, i);
+    if(m == uint32_t(POM_MOVE_BOMB))
+    {
+        /* PlantBombModifiedLife(x, y, i, BOMB_LIFETIME + 1), bboard.cpp:125-146; the slot's stale
+         * direction / moved bits survive (Q4); ticked to 10 at the end of this Step (Q3) */
+        if(int(int8_t(byte_of(A.bcnt, i))) >= int(byte_of(A.amax, i))) return;
+        const uint32_t cnt = r[R_BCOUNT];
+        if(cnt >= 20u) flags |= F_D4_BOMB_OVF;
+        uint32_t& b = bomb_slot(r, ring20(r[R_BINDEX] + cnt));
+        b = (b & ~0xF00u) + (uint32_t(i) << 8);
+        b = (b & ~0xFFu) + p;
+        b = (b & ~0xF000u) + (byte_of(A.astr, i) << 12);
+        b = (b & ~0xF0000u) + (uint32_t(POM_BOMB_LIFETIME + 1) << 16);
+        A.bcnt = with_byte(A.bcnt, i, byte_of(A.bcnt, i) + 1u);
+        r[R_BCOUNT] = uint8_t(cnt + 1u);
+        return;
+    }
+    const uint32_t d = dq[i];
+    if(oob_biased(d)) return;                                        /* :63 */
+    const uint32_t dp = d - 0x11u;
+    uint8_t* dcell = r + R_BOARD + cell_of(dp);
+    uint8_t* ocell = r + R_BOARD + cell_of(p);
+    uint32_t item = *dcell;
+    if(ouroboros && bomb_index(r, dp) >= 0) item = C_BOMB;           /* :71-82 */
+    if(c_is_flame(item))                                             /* :84-99 */
+    {
+        ag_kill(A, i);
+        if(*ocell == uint32_t(C_AGENT0 + i)) vacate(r, p);
+        return;
+    }
+    for(int k = 0; k < 4; k++)                                       /* HasDPCollision, step_utility.cpp:264-277 */
+    {
+        if(k != i && !ag_dead(A, k) && dq[k] == d) return;
+    }
+    if(c_is_powerup(item))                                           /* ConsumePowerup, step_utility.cpp:247-262 */
+    {
+        if(item == uint32_t(C_EXTRABOMB)) A.amax = with_byte(A.amax, i, byte_of(A.amax, i) + 1u);
+        else if(item == uint32_t(C_INCRRANGE)) A.astr = with_byte(A.astr, i, byte_of(A.astr, i) + 1u);
+        else A.flg |= uint32_t(AF_CANKICK) << (8 * i);
+        item = C_PASSAGE;
+    }
+    if(item == uint32_t(C_PASSAGE) || (ouroboros && c_is_agent(item)))   /* :120-140 */
+    {
+        if(*ocell == uint32_t(C_AGENT0 + i)) vacate(r, p);
+        *dcell = uint8_t(C_AGENT0 + i);
+        A.pos = with_byte(A.pos, i, dp);
+    }
+    else if(item == uint32_t(C_BOMB))                                /* :147-184: kick, or step onto the bomb (Q2) */
+    {
+        vacate(r, p);
+        *dcell = uint8_t(C_AGENT0 + i);
+        A.pos = with_byte(A.pos, i, dp);
+        if(byte_of(A.flg, i) & AF_CANKICK)
+        {
+            const int bi = bomb_index(r, dp);
+            if(bi < 0) flags |= F_D3_NULL_BOMB;                      /* the reference dereferences nullptr here (D3) */
+            else
+            {
+                uint32_t& b = bomb_at(r, bi);
+                b = (b & ~0xF00000u) + (m << 20);
+            }
+        }
+    }
+}
+
+POM_HD void load_agents(const uint8_t* r, Agents& A)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(r + R_APOS);
+    A.pos = w[0]; A.bcnt = w[1]; A.amax = w[2]; A.astr = w[3]; A.flg = w[4];
+    A.alive = int(int8_t(r[R_ALIVE]));
+}
+
+POM_HD void store_agents(uint8_t* r, const Agents& A)
+{
+    uint32_t* w = reinterpret_cast<uint32_t*>(r + R_APOS);
+    w[0] = A.pos; w[1] = A.bcnt; w[2] = A.amax; w[3] = A.astr; w[4] = A.flg;
+    r[R_ALIVE] = uint8_t(A.alive);
+}
+
+/* bboard::Step, step.cpp:9-284.  `moves`: byte a = Move of agent a.  Returns F_* flags. */
+POM_HD int step(uint8_t* r, uint32_t moves)
+{
+    int flags = 0;
+    for(int a = 0; a < 4; a++)
+    {
+        if(byte_of(moves, a) > 5u) { moves = with_byte(moves, a, 0u); flags |= F_BAD_MOVE; }
+    }
+
+    tick_flames(r);                                                  /* :15 */
+
+    Agents A;
+    load_agents(r, A);
+    const uint32_t oldPos = A.pos;                                   /* FillPositions :24 */
+    const uint32_t posq = A.pos + 0x11111111u;
+
+    uint32_t dq[4];
+    for(int a = 0; a < 4; a++)                                       /* FillDestPos :25 */
+        dq[a] = uint32_t(int(byte_of(posq, a)) + move_delta(byte_of(moves, a)));
+    for(int a = 0; a < 4; a++)                                       /* FixSwitchMove :26 (dead agents not skipped, Q1) */
+    {
+        for(int b = a + 1; b < 4; b++)
+        {
+            if(dq[a] == byte_of(posq, b) && dq[b] == byte_of(posq, a))
+            {
+                dq[a] = byte_of(posq, a);
+                dq[b] = byte_of(posq, b);
+            }
+        }
+    }
+
+    uint32_t dep = 0xFFFFFFFFu, roots = 0xFFFFFFFFu;                 /* ResolveDependencies :32, step_utility.cpp:172-205 */
+    int rootNumber = 0;
+    for(int a = 0; a < 4; a++)
+    {
+        bool isRoot = true;
+        if(!ag_dead(A, a))
+        {
+            for(int b = 0; b < 4; b++)
+            {
+                if(b == a || ag_dead(A, b)) continue;
+                if(dq[a] == byte_of(posq, b))
+                {
+                    dep = with_byte(dep, b, uint32_t(a));
+                    isRoot = false;
+                    break;
+                }
+            }
+        }
+        if(isRoot) roots = with_byte(roots, rootNumber++, uint32_t(a));
+    }
+    const bool ouroboros = rootNumber == 0;
+
+    {
+        int rootIdx = 0;
+        uint32_t i = rootNumber == 0 ? 0u : byte_of(roots, 0);
+        for(int k = 0; k < 4; k++)                                   /* :39-185 */
+        {
+            if(i == 0xFFu)
+            {
+                rootIdx++;
+                /* D1: the reference indexes roots/moves/agents with -1 here; canonical = stop */
+                if(rootIdx > 3 || byte_of(roots, rootIdx) == 0xFFu) { flags |= F_D1_UNREACHABLE; break; }
+                i = byte_of(roots, rootIdx);
+            }
+            move_agent(r, A, moves, dq, ouroboros, int(i), flags);
+            i = byte_of(dep, int(i));
+        }
+    }
+
+    int bc = r[R_BCOUNT];
+    if(bc > 0)
+    {
+        if(bc > 20) flags |= F_D4_BOMB_OVF;
+        uint8_t bd[20];
+        for(int k = 0; k < bc; k++)
+        {
+            uint32_t& b = bomb_at(r, k);
+            b = b & ~0xF000000u;                                     /* ResetBombFlags :188 */
+            if(k < 20) bd[k] = uint8_t(bomb_dest_biased(b));         /* FillBombDestPos :191-192 */
+        }
+
+        for(int k = 0; k < bc; k++)                                  /* :195-227 */
+        {
+            uint32_t& b = bomb_at(r, k);
+            const uint32_t bp = b & 0xFFu;
+            const uint32_t t = bomb_dest_biased(b);
+            bool blocked = oob_biased(t);
+            if(!blocked)
+            {
+                const uint32_t c = r[R_BOARD + cell_of(t - 0x11u)];
+                blocked = c_is_static(c) || c_is_agent(c);
+            }
+            if(blocked)
+            {
+                b = b & ~0xF00000u;
+                const int a = get_agent(A, bp);
+                if(a >= 0)
+                {
+                    const uint32_t m = byte_of(moves, a);
+                    if(m != uint32_t(POM_MOVE_IDLE) && m != uint32_t(POM_MOVE_BOMB) &&
+                            byte_of(A.pos, a) != byte_of(oldPos, a))
+                    {
+                        revert_chain(r, A, moves, bd, a, flags);
+                        if(get_agent(A, bp) == -1) r[R_BOARD + cell_of(bp)] = uint8_t(C_BOMB);
+                    }
+                }
+            }
+        }
+
+        for(int k = 0; k < int(r[R_BCOUNT]); k++)                    /* :230-278; the ring may shrink inside (Q7) */
+        {
+            uint32_t& b = bomb_at(r, k);
+            if(((b >> 20) & 15u) == 0u && has_bomb_collision(r, b, k))
+            {
+                resolve_bomb_collision(r, A, moves, bd, k, flags);
+                continue;
+            }
+            const uint32_t bp = b & 0xFFu;
+            const uint32_t t = bomb_dest_biased(b);
+            bool free_target = !oob_biased(t);
+            uint8_t* tcell = r;
+            if(free_target)
+            {
+                tcell = r + R_BOARD + cell_of(t - 0x11u);
+                free_target = !c_is_static(*tcell);
+            }
+            if(free_target)
+            {
+                if(has_bomb_collision(r, b, k))
+                {
+                    resolve_bomb_collision(r, A, moves, bd, k, flags);
+                    continue;
+                }
+                const uint32_t tp = t - 0x11u;
+                b = (b & ~0xFFu) + tp;                               /* SetBombPosition */
+                uint8_t* ocell = r + R_BOARD + cell_of(bp);
+                if(*ocell == uint32_t(C_BOMB) && bomb_index(r, bp) < 0) *ocell = uint8_t(C_PASSAGE);
+                const uint32_t ti = *tcell;
+                if(c_is_walkable(ti)) *tcell = uint8_t(C_BOMB);
+                else if(c_is_flame(ti))
+                {
+                    const int idx = bomb_index(r, tp);               /* ExplodeBombAt(GetBombIndex(target)) :271 */
+                    const uint32_t eb = bomb_at(r, idx);
+                    explode(r, A, tp, byte_of(A.astr, int((eb >> 8) & 3u)), uint32_t(idx), flags);
+                }
+            }
+            else
+            {
+                b = b & ~0xF00000u;
+            }
+        }
+
+        /* util::TickBombs :283, step_utility.cpp:224-245 */
+        bc = r[R_BCOUNT];
+        for(int k = 0; k < bc; k++) bomb_at(r, k) -= (1u << 16);     /* ReduceBombTimer, bboard.hpp:308-311 */
+        for(int k = 0; k < bc && r[R_BCOUNT] > 0; k++)
+        {
+            const uint32_t c = bomb_at(r, 0);
+            if(((c >> 16) & 15u) != 0u) break;
+            /* ExplodeTopBomb bboard.cpp:191-196 (strength stored in the bomb), then PopBomb :93-97 */
+            explode(r, A, c & 0xFFu, (c >> 12) & 15u, 31u, flags);
+            const int id = int((bomb_at(r, 0) >> 8) & 3u);
+            A.bcnt = with_byte(A.bcnt, id, byte_of(A.bcnt, id) - 1u);
+            r[R_BINDEX] = uint8_t(ring20(r[R_BINDEX] + 1u));
+            r[R_BCOUNT] = uint8_t(r[R_BCOUNT] - 1);
+        }
+    }
+
+    store_agents(r, A);
+    return flags;
+}
+
+/* Environment::Step on the record (environment.cpp:125-128,149-168): skip finished envs, Step,
+ * timeStep++, winner / draw.  Returns F_* flags (0 for a skipped env). */
+POM_HD int env_step(uint8_t* r, uint32_t moves)
+{
+    uint32_t st = r[R_STATUS];
+    if(st & POM_STATUS_DONE) return 0;
+    const int flags = step(r, moves);
+    uint16_t* ts = reinterpret_cast<uint16_t*>(r + R_TIME);
+    *ts = uint16_t(*ts + 1);
+    const int alive = int(int8_t(r[R_ALIVE]));
+    if(alive == 1)
+    {
+        uint32_t w = 0;
+        for(uint32_t a = 0; a < 4; a++)
+        {
+            if(!(r[R_AFLAGS + a] & AF_DEAD)) w = a;
+        }
+        st = (st & POM_STATUS_INVALID) | POM_STATUS_DONE | (w << POM_STATUS_WINNER_SHIFT);
+    }
+    if(alive == 0) st = (st & POM_STATUS_INVALID) | POM_STATUS_DONE | POM_STATUS_DRAW;
+    if(flags & F_INVALID_MASK) st |= POM_STATUS_INVALID;
+    r[R_STATUS] = uint8_t(st);
+    return flags;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * AoS <-> record converters (K5).  pack() returns 0, or a non-zero reason when the AoS state holds
+ * a value the record cannot carry (the env is then marked POM_STATUS_INVALID).
+ * ------------------------------------------------------------------------------------------- */
+POM_HD int pack(const pom_state* s, uint8_t status, uint8_t* r)
+{
+    int bad = 0;
+    /* rings first: flame cells need the flame queue */
+    r[R_BCOUNT] = uint8_t(s->bombs_count);
+    r[R_BINDEX] = uint8_t(s->bombs_index);
+    if(uint32_t(s->bombs_count) > 20u || uint32_t(s->bombs_index) >= 20u) bad = 1;
+    for(int k = 0; k < 20; k++) bomb_slot(r, k) = uint32_t(s->bombs[k]);
+    r[R_FCOUNT] = uint8_t(s->flames_count);
+    r[R_FINDEX] = uint8_t(s->flames_index);
+    if(uint32_t(s->flames_count) > 20u || uint32_t(s->flames_index) >= 20u) bad = 2;
+    for(int k = 0; k < 20; k++)
+    {
+        const pom_flame& f = s->flames[k];
+        if(uint32_t(f.x) > 10u || uint32_t(f.y) > 10u || f.timeLeft < -128 || f.timeLeft > 127 || uint32_t(f.strength) > 255u) bad = 3;
+        r[R_FPOS + k] = uint8_t((f.x & 15) | ((f.y & 15) << 4));
+        r[R_FTIME + k] = uint8_t(f.timeLeft);
+        r[R_FSTR + k] = uint8_t(f.strength);
+    }
+    for(int a = 0; a < 4; a++)
+    {
+        const pom_agent& g = s->agents[a];
+        if(uint32_t(g.x) > 10u || uint32_t(g.y) > 10u || g.bombCount < -128 || g.bombCount > 127 ||
+                uint32_t(g.maxBombCount) > 255u || uint32_t(g.bombStrength) > 255u) bad = 4;
+        r[R_APOS + a] = uint8_t((g.x & 15) | ((g.y & 15) << 4));
+        r[R_ABCNT + a] = uint8_t(g.bombCount);
+        r[R_AMAX + a] = uint8_t(g.maxBombCount);
+        r[R_ASTR + a] = uint8_t(g.bombStrength);
+        r[R_AFLAGS + a] = uint8_t((g.canKick ? AF_CANKICK : 0) | (g.dead ? AF_DEAD : 0));
+    }
+    if(uint32_t(s->timeStep) > 65535u) bad = 5;
+    *reinterpret_cast<uint16_t*>(r + R_TIME) = uint16_t(s->timeStep);
+    if(s->aliveAgents < -128 || s->aliveAgents > 127) bad = 6;
+    r[R_ALIVE] = uint8_t(s->aliveAgents);
+    const int fcount = s->flames_count, findex = s->flames_index;
+    for(int c = 0; c < POM_BOARD_CELLS; c++)
+    {
+        const int v = (&s->board[0][0])[c];
+        uint32_t code = 0;
+        if(v >= 0 && v <= 9)
+        {
+            /* PASSAGE RIGID - BOMB - FOG EXTRABOMB INCRRANGE KICK AGENTDUMMY */
+            const uint8_t map[10] = { C_PASSAGE, C_RIGID, 0xFF, C_BOMB, 0xFF, C_FOG, C_EXTRABOMB, C_INCRRANGE, C_KICK, C_AGENTDUMMY };
+            code = map[v];
+            if(code == 0xFFu) { bad = 7; code = 0; }
+        }
+        else if(v >= POM_ITEM_WOOD && v <= POM_ITEM_WOOD + 4) code = uint32_t(C_WOOD + (v - POM_ITEM_WOOD));
+        else if(v >= POM_ITEM_AGENT0 && v <= POM_ITEM_AGENT0 + 3) code = uint32_t(C_AGENT0 + (v - POM_ITEM_AGENT0));
+        else if((v >> 16) == 4 && (v & 4) == 0 && ((v & 0xFFFF) >> 3) < POM_BOARD_CELLS)
+        {
+            const int id = (v & 0xFFFF) >> 3;
+            const uint32_t op = uint32_t(id % 11) | (uint32_t(id / 11) << 4);
+            int slot = -1;
+            for(int k = 0; k < fcount && k < 20; k++)
+            {
+                const int sl = (findex + k) % 20;
+                if(r[R_FPOS + sl] == op) { slot = sl; break; }
+            }
+            if(slot < 0)
+            {
+                if(id == 0) slot = C_FLAME_ORPHAN_SLOT;
+                else { bad = 8; slot = C_FLAME_ORPHAN_SLOT; }
+            }
+            code = uint32_t(C_FLAME) | (uint32_t(slot) << 2) | uint32_t(v & 3);
+        }
+        else bad = 9;
+        r[R_BOARD + c] = uint8_t(code);
+    }
+    r[R_STATUS] = uint8_t(status | (bad ? POM_STATUS_INVALID : 0));
+    r[289] = r[290] = r[291] = 0;
+    return bad;
+}
+
+POM_HD uint8_t unpack(const uint8_t* r, pom_state* s)
+{
+    for(int c = 0; c < POM_BOARD_CELLS; c++)
+    {
+        const uint32_t code = r[R_BOARD + c];
+        int v;
+        if(code & 0x80u)
+        {
+            const uint32_t op = flame_origin(r, code);
+            v = POM_ITEM_FLAMES + ((int(op & 15u) + 11 * int(op >> 4)) << 3) + int(code & 3u);
+        }
+        else if(code <= 1u) v = int(code);
+        else if(code <= 6u) v = POM_ITEM_WOOD + int(code) - C_WOOD;
+        else if(code == uint32_t(C_BOMB)) v = POM_ITEM_BOMB;
+        else if(code == uint32_t(C_FOG)) v = POM_ITEM_FOG;
+        else if(code <= 11u) v = POM_ITEM_EXTRABOMB + int(code) - C_EXTRABOMB;
+        else if(code == uint32_t(C_AGENTDUMMY)) v = POM_ITEM_AGENTDUMMY;
+        else v = POM_ITEM_AGENT0 + int(code) - C_AGENT0;
+        (&s->board[0][0])[c] = v;
+    }
+    s->timeStep = *reinterpret_cast<const uint16_t*>(r + R_TIME);
+    s->aliveAgents = int(int8_t(r[R_ALIVE]));
+    for(int a = 0; a < 4; a++)
+    {
+        pom_agent& g = s->agents[a];
+        g.x = r[R_APOS + a] & 15;
+        g.y = r[R_APOS + a] >> 4;
+        g.bombCount = int(int8_t(r[R_ABCNT + a]));
+        g.maxBombCount = r[R_AMAX + a];
+        g.bombStrength = r[R_ASTR + a];
+        g.canKick = (r[R_AFLAGS + a] & AF_CANKICK) ? 1 : 0;
+        g.dead = (r[R_AFLAGS + a] & AF_DEAD) ? 1 : 0;
+        g._pad[0] = g._pad[1] = 0;
+    }
+    for(int k = 0; k < 20; k++) s->bombs[k] = int32_t(reinterpret_cast<const uint32_t*>(r + R_BOMBS)[k]);
+    s->bombs_index = r[R_BINDEX];
+    s->bombs_count = r[R_BCOUNT];
+    for(int k = 0; k < 20; k++)
+    {
+        pom_flame& f = s->flames[k];
+        f.x = r[R_FPOS + k] & 15;
+        f.y = r[R_FPOS + k] >> 4;
+        f.timeLeft = int(int8_t(r[R_FTIME + k]));
+        f.strength = r[R_FSTR + k];
+    }
+    s->flames_index = r[R_FINDEX];
+    s->flames_count = r[R_FCOUNT];
+    return r[R_STATUS];
+}
+
+/* the shared stateless action source (same arithmetic as oracle/pom_oracle.c pom_oracle_rng_moves) */
+POM_HD uint64_t splitmix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+POM_HD uint32_t rng_moves(uint64_t seed, uint64_t env, uint32_t tick, uint32_t n_actions)
+{
+    const uint64_t h = splitmix64(splitmix64(seed ^ (env * 0xD6E8FEB86659FD93ull)) + uint64_t(tick));
+    uint32_t out = 0;
+    for(int a = 0; a < 4; a++)
+    {
+        const uint32_t lane = uint32_t(h >> (16 * a)) & 0xFFFFu;
+        out |= ((lane * n_actions) >> 16) << (8 * a);
+    }
+    return out;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Board generation (K3): InitBoardItems (bboard.cpp:346-382) + PutAgentsInCorners (:322-333) on a
+ * zero-initialised State, written straight into a packed record.  std::mt19937_64 is the standard
+ * MT19937-64; uniform_int_distribution<int> is libstdc++ 13's Lemire multiply-high with rejection
+ * (bits/uniform_int_dist.h:252-281), which is what the reference binary uses.
+ * Returns 1 when the seed draws the inclusive upper bound q.count (reference defect D2: it then
+ * reads an uninitialised stack slot) — such seeds are skipped by the template builder.
+ * ------------------------------------------------------------------------------------------- */
+struct Mt64 { uint64_t mt[312]; int idx; };
+
+POM_HD void mt64_seed(Mt64& g, uint64_t seed)
+{
+    g.mt[0] = seed;
+    for(int i = 1; i < 312; i++) g.mt[i] = 6364136223846793005ull * (g.mt[i - 1] ^ (g.mt[i - 1] >> 62)) + uint64_t(i);
+    g.idx = 312;
+}
+
+POM_HD uint64_t mt64_next(Mt64& g)
+{
+    if(g.idx >= 312)
+    {
+        for(int i = 0; i < 312; i++)
+        {
+            const uint64_t x = (g.mt[i] & 0xFFFFFFFF80000000ull) | (g.mt[i == 311 ? 0 : i + 1] & 0x7FFFFFFFull);
+            const uint64_t xa = (x >> 1) ^ ((x & 1ull) ? 0xB5026F5AA96619E9ull : 0ull);
+            g.mt[i] = g.mt[i < 156 ? i + 156 : i - 156] ^ xa;
+        }
+        g.idx = 0;
+    }
+    uint64_t y = g.mt[g.idx++];
+    y ^= (y >> 29) & 0x5555555555555555ull;
+    y ^= (y << 17) & 0x71D67FFFEDA60000ull;
+    y ^= (y << 37) & 0xFFF7EEE000000000ull;
+    y ^= (y >> 43);
+    return y;
+}
+
+POM_HD void mul64wide(uint64_t a, uint64_t b, uint64_t& hi, uint64_t& lo)
+{
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umul64hi(a, b);
+#else
+    const unsigned __int128 p = (unsigned __int128)a * b;
+    lo = uint64_t(p);
+    hi = uint64_t(p >> 64);
+#endif
+}
+
+POM_HD int uniform_int(Mt64& g, int a, int b)
+{
+    const uint64_t range = uint64_t(b) - uint64_t(a) + 1ull;
+    uint64_t hi, lo;
+    mul64wide(mt64_next(g), range, hi, lo);
+    if(lo < range)
+    {
+        const uint64_t threshold = (0ull - range) % range;
+        while(lo < threshold) mul64wide(mt64_next(g), range, hi, lo);
+    }
+    return a + int(hi);
+}
+
+POM_HD int init_record(uint8_t* r, Mt64& g, int seed, int a0, int a1, int a2, int a3)
+{
+    for(int k = 0; k < POM_REC_BYTES; k++) r[k] = 0;
+    for(int k = 0; k < 20; k++) r[R_FTIME + k] = uint8_t(POM_FLAME_LIFETIME);   /* Flame::timeLeft default, bboard.hpp:345 */
+    for(int a = 0; a < 4; a++) { r[R_AMAX + a] = 1; r[R_ASTR + a] = POM_BOMB_DEFAULT_STRENGTH; }
+    r[R_ALIVE] = 4;
+
+    mt64_seed(g, uint64_t(int64_t(seed)));
+    uint8_t q[POM_BOARD_CELLS];
+    int count = 0;
+    for(int c = 0; c < POM_BOARD_CELLS; c++)
+    {
+        const int tmp = uniform_int(g, 0, 6);                        /* ChooseItemOuter, bboard.cpp:59-74 */
+        const uint8_t item = tmp == 2 ? uint8_t(C_WOOD) : (tmp == 1 ? uint8_t(C_RIGID) : uint8_t(C_PASSAGE));
+        r[R_BOARD + c] = item;
+        if(item == C_WOOD) q[count++] = uint8_t(c);
+    }
+    int dirty = 0, total = 0;
+    for(;;)
+    {
+        const int k = uniform_int(g, 0, count);                      /* inclusive bound: D2 when k == count */
+        if(k == count) { dirty = 1; break; }
+        const int idx = q[k];
+        if(r[R_BOARD + idx] == C_WOOD)                               /* (board & 0xFF) == 0: wood without flag */
+        {
+            r[R_BOARD + idx] = uint8_t(C_WOOD + uniform_int(g, 1, 4));
+            total++;
+        }
+        if(float(total) >= float(count) / 2) break;
+    }
+    r[R_BOARD + 0] = uint8_t(C_AGENT0 + a0);
+    r[R_BOARD + 10] = uint8_t(C_AGENT0 + a1);
+    r[R_BOARD + 120] = uint8_t(C_AGENT0 + a2);
+    r[R_BOARD + 110] = uint8_t(C_AGENT0 + a3);
+    r[R_APOS + a1] = uint8_t((r[R_APOS + a1] & 0xF0) | 10);
+    r[R_APOS + a2] = uint8_t(10 | (10 << 4));
+    r[R_APOS + a3] = uint8_t((r[R_APOS + a3] & 0x0F) | (10 << 4));
+    return dirty;
+}
+
+}
+
+#endif

@@ -1,0 +1,366 @@
+/*
+ * pom_kernels.cuh — sm_100a kernels of the batched step path.
+ *
+ *  K1 k_step        per-tick mode: one CTA stages a tile of TPB consecutive 292-byte records in shared
+ *                   memory with ONE 1-D TMA bulk copy (cp.async.bulk + mbarrier), every thread runs the
+ *                   tick (pom_core.cuh) on its own record in place, and the tile goes back with one bulk
+ *                   store.  HBM traffic per env-step = 292 B in + 292 B out + 4 B of moves; no thread
+ *                   issues a global load/store for state.  The record stride of 73 words is odd, so
+ *                   same-field accesses of the 32 lanes are bank-conflict free.
+ *  K2 k_rollout     fused K-tick mode: same staging, then K ticks on the resident record with actions
+ *                   from the stateless counter RNG, truncation, episode statistics and auto-reset from the
+ *                   template pool inside the kernel.
+ *  K3 k_make_templates / k_fill_from_templates   board generation on the device and env (re)initialisation.
+ *  K4 k_clone / k_expand_step                    state copy and tree-search fan-out (+ one Step, fused).
+ *  K5 k_pack / k_unpack                          AoS bboard::State <-> packed record.
+ *  K6 stats                                      warp-reduced counters -> one atomicAdd per warp and counter.
+ */
+#ifndef POM_KERNELS_CUH_
+#define POM_KERNELS_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pom_core.cuh"
+#include "pom_batch.h"
+
+namespace pomk
+{
+
+enum { ST_STEPS = 0, ST_EPISODES = 1, ST_WIN0 = 2, ST_DRAWS = 6, ST_TRUNC = 7, ST_SUMLEN = 8, ST_INVALID = 9 };
+
+struct BatchParams {
+    uint8_t*            recs;         /* n_tiles * TPB records                                  */
+    uint64_t            n_envs;
+    uint64_t            env_offset;   /* global index of env 0                                   */
+    const uint8_t*      templates;    /* n_templates packed records                              */
+    uint32_t            n_templates;
+    uint32_t            max_ticks;
+    uint32_t*           episodes;     /* per-env number of finished episodes                     */
+    unsigned long long* stats;        /* POM_STATS_WORDS counters                                */
+};
+
+/* ---------------------------------------------------------------- TMA 1-D bulk copy + mbarrier (PTX) */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* global -> shared, completion signalled on the mbarrier (SASS: UBLKCP) */
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+/* shared -> global, tracked by a bulk async-group */
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+/* ---------------------------------------------------------------- K6: episode statistics */
+__device__ __forceinline__ void warp_add(unsigned long long* dst, uint32_t v)
+{
+    const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, v);
+    if((threadIdx.x & 31u) == 0u && s) atomicAdd(dst, (unsigned long long)s);
+}
+
+/* called by ALL threads of a warp-converged region; `fin` = this thread's env finished an episode */
+__device__ __forceinline__ void account_episodes(unsigned long long* stats, bool fin, uint32_t status, uint32_t len)
+{
+    if(!__any_sync(0xFFFFFFFFu, fin)) return;
+    const bool draw = fin && (status & POM_STATUS_DRAW);
+    const bool trunc = fin && (status & POM_STATUS_TRUNCATED) && !(status & POM_STATUS_DONE);
+    const bool won = fin && (status & POM_STATUS_DONE) && !draw;
+    const uint32_t w = (status & POM_STATUS_WINNER_MASK) >> POM_STATUS_WINNER_SHIFT;
+    warp_add(stats + ST_EPISODES, fin ? 1u : 0u);
+    warp_add(stats + ST_DRAWS, draw ? 1u : 0u);
+    warp_add(stats + ST_TRUNC, trunc ? 1u : 0u);
+    warp_add(stats + ST_SUMLEN, fin ? len : 0u);
+    warp_add(stats + ST_INVALID, (fin && (status & POM_STATUS_INVALID)) ? 1u : 0u);
+#pragma unroll
+    for(uint32_t a = 0; a < 4; a++) warp_add(stats + ST_WIN0 + a, (won && w == a) ? 1u : 0u);
+}
+
+/* end-of-tick episode handling shared by K1 (auto-reset flag) and K2: truncate, count, reset */
+__device__ __forceinline__ void finish_and_reset(uint8_t* rec, const BatchParams& P, uint64_t env, bool active, bool do_reset)
+{
+    uint32_t st = active ? rec[R_STATUS] : 0u;
+    const uint32_t len = active ? *reinterpret_cast<const uint16_t*>(rec + R_TIME) : 0u;
+    if(active && !(st & POM_STATUS_DONE) && P.max_ticks && len >= P.max_ticks) st |= POM_STATUS_TRUNCATED;
+    const bool fin = active && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED)) != 0u;
+    account_episodes(P.stats, fin, st, len);
+    if(fin && do_reset)
+    {
+        const uint32_t ep = ++P.episodes[env];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(
+            P.templates + size_t((P.env_offset + env + ep) % P.n_templates) * POM_REC_BYTES);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(rec);
+#pragma unroll 1
+        for(int w = 0; w < POM_REC_WORDS; w++) dst[w] = __ldg(src + w);
+    }
+    else if(fin)
+    {
+        rec[R_STATUS] = uint8_t(st);
+    }
+}
+
+/* ---------------------------------------------------------------- K1: per-tick kernel */
+template<int TPB>
+__global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __restrict__ moves, uint32_t flags)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TPB * POM_REC_BYTES);
+    constexpr uint32_t TILE_BYTES = TPB * POM_REC_BYTES;
+    uint8_t* gtile = P.recs + size_t(blockIdx.x) * TILE_BYTES;
+
+    if(threadIdx.x == 0)
+    {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, TILE_BYTES);
+        bulk_g2s(smem, gtile, TILE_BYTES, bar);
+    }
+    const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
+    const bool active = env < P.n_envs;
+    const uint32_t m = active ? __ldg(moves + env) : 0u;     /* overlaps the bulk load */
+    __syncthreads();                                          /* barrier init visible to all waiters */
+    mbar_wait(bar, 0);
+
+    uint8_t* rec = smem + threadIdx.x * POM_REC_BYTES;
+    bool stepped = false;
+    if(active)
+    {
+        if(flags & POM_STEP_RAW)
+        {
+            const int f = pomcore::step(rec, m);
+            if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+            stepped = true;
+        }
+        else
+        {
+            stepped = !(rec[R_STATUS] & POM_STATUS_DONE);
+            pomcore::env_step(rec, m);
+        }
+    }
+    if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
+    if(flags & POM_STEP_AUTORESET) finish_and_reset(rec, P, env, active && stepped, true);
+
+    fence_proxy_async();                                      /* generic-proxy writes -> visible to the bulk store */
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        bulk_s2g(gtile, smem, TILE_BYTES);
+        bulk_wait_read_all();                                 /* smem must stay valid until it has been read */
+    }
+}
+
+/* ---------------------------------------------------------------- K2: fused K-tick rollout */
+template<int TPB>
+__global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, uint64_t seed, uint32_t tick0,
+                                                uint32_t n_actions, uint32_t no_reset)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TPB * POM_REC_BYTES);
+    constexpr uint32_t TILE_BYTES = TPB * POM_REC_BYTES;
+    uint8_t* gtile = P.recs + size_t(blockIdx.x) * TILE_BYTES;
+
+    if(threadIdx.x == 0)
+    {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, TILE_BYTES);
+        bulk_g2s(smem, gtile, TILE_BYTES, bar);
+    }
+    const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
+    const bool active = env < P.n_envs;
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    uint8_t* rec = smem + threadIdx.x * POM_REC_BYTES;
+    /* per-env RNG key hoisted out of the tick loop (first splitmix64 of pom_rng_moves) */
+    const uint64_t key = pomcore::splitmix64(seed ^ ((P.env_offset + env) * 0xD6E8FEB86659FD93ull));
+    uint32_t steps = 0;
+    for(uint32_t k = 0; k < ticks; k++)
+    {
+        bool stepped = false;
+        if(active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_TRUNCATED)))
+        {
+            const uint64_t h = pomcore::splitmix64(key + uint64_t(tick0 + k));
+            uint32_t m = 0;
+#pragma unroll
+            for(int a = 0; a < 4; a++)
+                m |= (((uint32_t(h >> (16 * a)) & 0xFFFFu) * n_actions) >> 16) << (8 * a);
+            pomcore::env_step(rec, m);
+            stepped = true;
+            steps++;
+        }
+        finish_and_reset(rec, P, env, active && stepped, !no_reset);
+    }
+    warp_add(P.stats + ST_STEPS, steps);
+
+    fence_proxy_async();
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        bulk_s2g(gtile, smem, TILE_BYTES);
+        bulk_wait_read_all();
+    }
+}
+
+/* ---------------------------------------------------------------- K3: templates and (re)initialisation */
+/* one thread per candidate seed; the 2.5 KB Mersenne state lives in local memory (init is off the hot path) */
+__global__ void k_make_templates(uint8_t* out_recs, uint8_t* dirty, int first_seed, uint32_t n_candidates)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n_candidates) return;
+    pomcore::Mt64 g;
+    uint8_t rec[POM_REC_BYTES];
+    const int d = pomcore::init_record(rec, g, first_seed + int(i), 0, 1, 2, 3);
+    dirty[i] = uint8_t(d);
+    uint8_t* o = out_recs + size_t(i) * POM_REC_BYTES;
+    for(int k = 0; k < POM_REC_BYTES; k++) o[k] = rec[k];
+}
+
+/* compaction of the clean candidates into the pool: pool[k] <- cand[pick[k]] (word copy) */
+__global__ void k_gather_records(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src,
+                                 const uint32_t* __restrict__ idx, uint64_t n_dst, uint64_t dst_first)
+{
+    const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(t >= n_dst * POM_REC_WORDS) return;
+    const uint64_t e = t / POM_REC_WORDS;
+    const uint32_t w = uint32_t(t - e * POM_REC_WORDS);
+    dst[(dst_first + e) * POM_REC_WORDS + w] = __ldg(src + uint64_t(idx[e]) * POM_REC_WORDS + w);
+}
+
+/* env e <- template[(env_offset + e + episode[e]) % n_templates]; episode numbers as given */
+__global__ void k_fill_from_templates(BatchParams P)
+{
+    const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(t >= P.n_envs * POM_REC_WORDS) return;
+    const uint64_t e = t / POM_REC_WORDS;
+    const uint32_t w = uint32_t(t - e * POM_REC_WORDS);
+    const uint64_t k = (P.env_offset + e + P.episodes[e]) % P.n_templates;
+    reinterpret_cast<uint32_t*>(P.recs)[t] = __ldg(reinterpret_cast<const uint32_t*>(P.templates) + k * POM_REC_WORDS + w);
+}
+
+/* ---------------------------------------------------------------- K4: tree-search expansion */
+/* child c = root_i * fanout + j: copy the root's record into the tile, apply joint action j
+ * (a_k = (j / 6^k) % 6), Step once, bulk-store the tile. */
+template<int TPB>
+__global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
+                                                    const uint32_t* __restrict__ src_idx, uint64_t n_children,
+                                                    uint32_t fanout, uint32_t flags)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t TILE_BYTES = TPB * POM_REC_BYTES;
+    const uint64_t c = uint64_t(blockIdx.x) * TPB + threadIdx.x;
+    uint8_t* rec = smem + threadIdx.x * POM_REC_BYTES;
+    uint32_t* rw = reinterpret_cast<uint32_t*>(rec);
+    if(c < n_children)
+    {
+        const uint64_t root = c / fanout;
+        const uint32_t j = uint32_t(c - root * fanout);
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(src + size_t(src_idx[root]) * POM_REC_BYTES);
+#pragma unroll 1
+        for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = __ldg(s + w);
+        const uint32_t m = (j % 6u) | (((j / 6u) % 6u) << 8) | (((j / 36u) % 6u) << 16) | (((j / 216u) % 6u) << 24);
+        if(flags & POM_STEP_RAW)
+        {
+            const int f = pomcore::step(rec, m);
+            if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+        }
+        else pomcore::env_step(rec, m);
+    }
+    else
+    {
+        for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = 0u;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        bulk_s2g(dst + size_t(blockIdx.x) * TILE_BYTES, smem, TILE_BYTES);
+        bulk_wait_read_all();
+    }
+}
+
+/* ---------------------------------------------------------------- K5: AoS <-> packed */
+__global__ void k_pack(const pom_state* __restrict__ aos, const uint8_t* __restrict__ status, uint8_t* recs,
+                       uint64_t first, uint64_t count, uint32_t* bad_count)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(i >= count) return;
+    const int bad = pomcore::pack(aos + i, status ? status[i] : uint8_t(0), recs + (first + i) * POM_REC_BYTES);
+    if(bad) atomicAdd(bad_count, 1u);
+}
+
+__global__ void k_unpack(const uint8_t* __restrict__ recs, pom_state* aos, uint8_t* status, uint64_t first, uint64_t count)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(i >= count) return;
+    if(aos)
+    {
+        const uint8_t st = pomcore::unpack(recs + (first + i) * POM_REC_BYTES, aos + i);
+        if(status) status[i] = st;
+    }
+    else if(status) status[i] = recs[(first + i) * POM_REC_BYTES + R_STATUS];
+}
+
+/* ---------------------------------------------------------------- misc */
+__global__ void k_generate_moves(uint32_t* moves, uint64_t n, uint64_t env_offset, uint64_t seed, uint32_t tick, uint32_t n_actions)
+{
+    const uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(e < n) moves[e] = pomcore::rng_moves(seed, env_offset + e, tick, n_actions);
+}
+
+__global__ void k_spawn_flame(uint8_t* recs, uint64_t env, uint32_t p, uint32_t strength)
+{
+    uint8_t* rec = recs + env * POM_REC_BYTES;
+    pomcore::Agents A;
+    pomcore::load_agents(rec, A);
+    int flags = 0;
+    pomcore::explode(rec, A, p, strength, 31u, flags);
+    pomcore::store_agents(rec, A);
+    if(flags & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+}
+
+__global__ void k_fill_zero(uint4* p, uint64_t n16)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(i < n16) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+}
+
+#endif

@@ -1,0 +1,63 @@
+/*
+ * hostsim.cpp — TEST-ONLY host build of the kernel body (pomcpp_b200/csrc/pom_core.cuh).
+ *
+ * The tick logic that the CUDA kernels run is a header of `__host__ __device__` functions; this
+ * file compiles the very same header with g++ so that the logic can be differential-tested against
+ * the oracle on the CPU-only build container (millions of steps in seconds) before any GPU time is
+ * spent.  It is NOT part of the product: libpom_b200.so contains no host stepping path and nothing
+ * in pomcpp_b200/ loads this library.
+ */
+#include <cstdint>
+#include <cstring>
+#include "pom_core.cuh"
+
+extern "C" {
+
+int hostsim_record_bytes() { return POM_REC_BYTES; }
+
+void hostsim_pack_batch(const pom_state* S, const uint8_t* status, long n, uint8_t* recs, uint8_t* bad)
+{
+    for(long e = 0; e < n; e++)
+    {
+        int b = pomcore::pack(&S[e], status ? status[e] : 0, recs + e * POM_REC_BYTES);
+        if(bad) bad[e] = uint8_t(b);
+    }
+}
+
+void hostsim_unpack_batch(const uint8_t* recs, long n, pom_state* S, uint8_t* status)
+{
+    for(long e = 0; e < n; e++)
+    {
+        uint8_t st = pomcore::unpack(recs + e * POM_REC_BYTES, &S[e]);
+        if(status) status[e] = st;
+    }
+}
+
+/* raw != 0: bboard::Step only; raw == 0: Environment::Step semantics */
+void hostsim_step_records(uint8_t* recs, long n, const uint8_t* moves, int raw, uint8_t* flags_out)
+{
+    for(long e = 0; e < n; e++)
+    {
+        uint32_t m;
+        std::memcpy(&m, moves + 4 * e, 4);
+        uint8_t* r = recs + e * POM_REC_BYTES;
+        int f = raw ? pomcore::step(r, m) : pomcore::env_step(r, m);
+        if(flags_out) flags_out[e] = uint8_t(f);
+    }
+}
+
+void hostsim_spawn_flame(uint8_t* rec, int x, int y, int strength)
+{
+    pomcore::Agents A;
+    pomcore::load_agents(rec, A);
+    int flags = 0;
+    pomcore::explode(rec, A, uint32_t(x) | (uint32_t(y) << 4), uint32_t(strength), 31u, flags);
+    pomcore::store_agents(rec, A);
+}
+
+uint32_t hostsim_rng_moves(uint64_t seed, uint64_t env, uint32_t tick, uint32_t n_actions)
+{
+    return pomcore::rng_moves(seed, env, tick, n_actions);
+}
+
+}

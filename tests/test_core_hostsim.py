@@ -1,0 +1,108 @@
+"""CPU tests (-m "not gpu") of the HOST LOGIC of the kernel body.
+
+pomcpp_b200/csrc/pom_core.cuh (packed record, explicit-stack explosion machine, loop-form chain
+reversion, AoS<->record converters) is compiled for the host by tests/hostsim (test-only) and
+compared with the oracle: the reference's known-answer scenarios, the golden transitions and long
+random traces where the records stay PACKED across ticks (so slot indirection, stale ring slots
+and signed counters have to survive many ticks), every field compared after every tick.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import scenarios
+from hostsim import HostSim, HostSimBackend
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    return HostSim()
+
+
+@pytest.mark.parametrize("fn", scenarios.STEP_SCENARIOS, ids=lambda f: f.__name__)
+def test_scenarios_core(orc, fn):
+    fn(HostSimBackend(orc))
+
+
+def test_golden_scenarios_core(orc, hs):
+    g = np.load(os.path.join(GOLD, "scenarios.npz"))
+    before = g["before"].copy().view(oracle.STATE_DT).reshape(-1)
+    after = g["after"].copy().view(oracle.STATE_DT).reshape(-1)
+    recs, bad = hs.pack(before)
+    assert not bad.any()
+    rt, _ = hs.unpack(recs)
+    assert orc.diff_batch(rt, before)[0] == -1, "pack/unpack round trip"
+    hs.step_records(recs, np.ascontiguousarray(g["moves"]), raw=True)
+    out, _ = hs.unpack(recs)
+    e, why = orc.diff_batch(out, after)
+    assert e == -1, "transition %d (%s) differs in field group %d" % (e, g["names"][e], why)
+
+
+def test_pack_rejects_unrepresentable(orc, hs):
+    s = orc.zero_state(4)
+    s["board"][0, 3, 3] = 4 << 16 | (17 << 3)       # flame id 17 without a queue entry
+    s["board"][1, 0, 0] = (2 << 8) + 9               # wood with an impossible flag
+    s["agents"][2, 1]["x"] = 11                      # agent out of bounds
+    recs, bad = hs.pack(s)
+    assert bad[0] and bad[1] and bad[2] and not bad[3]
+    _, status = hs.unpack(recs)
+    assert (status[:3] & 0x10).all() and status[3] == 0
+
+
+def _trace(orc, hs, n, ticks, nact, stress, seed, restart=True):
+    seeds = oracle.clean_seeds(128)
+    B = orc.zero_state(n)
+    for e in range(n):
+        assert orc.init_state(B[e:e + 1], seeds[e % len(seeds)]) == 0
+    if stress:
+        B["agents"]["canKick"] = 1
+        B["agents"]["maxBombCount"] = 5
+        B["agents"]["bombStrength"] = 4
+    B0 = B.copy()
+    recs, bad = hs.pack(B)
+    assert not bad.any()
+    recs0 = recs.copy()
+    sb = np.zeros(n, np.uint8)
+    fo = np.zeros(n, np.uint8)
+    fc = np.zeros(n, np.uint8)
+    steps = 0
+    for t in range(ticks):
+        mv = orc.rng_moves(seed, 0, n, t, nact)
+        orc.env_step_batch(B, sb, mv, fo)
+        hs.step_records(recs, mv, raw=False, flags=fc)
+        out, sc = hs.unpack(recs)
+        e, why = orc.diff_batch(out, B)
+        assert e == -1, "tick %d env %d field group %d" % (t, e, why)
+        assert (sc == sb).all(), "status differs at tick %d" % t
+        assert ((fo & 0x1F) == (fc & 0x1F)).all(), "flags differ at tick %d" % t
+        fin = (sb & 0x11) != 0
+        steps += int((~fin).sum())
+        if restart:
+            idx = np.nonzero(fin)[0]
+            B[idx] = B0[idx]
+            recs[idx] = recs0[idx]
+            sb[idx] = 0
+    return steps
+
+
+def test_core_random(orc, hs):
+    assert _trace(orc, hs, 2048, 100, 6, 0, 2001) > 150000
+
+
+def test_core_harmless(orc, hs):
+    assert _trace(orc, hs, 1024, 200, 5, 0, 2002) > 150000
+
+
+def test_core_stress(orc, hs):
+    assert _trace(orc, hs, 2048, 250, 6, 1, 2003) > 300000
+
+
+def test_core_rng_matches_oracle(orc, hs):
+    for env in (0, 1, 77, 2 ** 33 + 5):
+        for tick in (0, 1, 799):
+            for na in (5, 6):
+                assert hs.lib.hostsim_rng_moves(99, env, tick, na) == orc.lib.pom_oracle_rng_moves(99, env, tick, na)

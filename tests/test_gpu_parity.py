@@ -1,0 +1,317 @@
+"""GPU tests (-m gpu): the parity tests proper.  Everything goes through the C ABI
+(include/pom_batch.h) and is compared bit-exactly with the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import scenarios
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import pomcpp_b200 as pb
+    assert os.path.exists(pb.LIB_PATH), "libpom_b200.so missing on the GPU box"
+    assert pb.device_count() > 0, "no CUDA device"
+    return pb
+
+
+@pytest.fixture(scope="module")
+def gpu_be(pb, orc):
+    from gpu_backend import GpuBackend
+    return GpuBackend(orc)
+
+
+@pytest.mark.parametrize("fn", scenarios.STEP_SCENARIOS, ids=lambda f: f.__name__)
+def test_reference_scenarios_on_gpu(gpu_be, fn):
+    fn(gpu_be)
+
+
+def test_golden_scenarios(pb, orc):
+    g = np.load(os.path.join(GOLD, "scenarios.npz"))
+    before = g["before"].copy().view(oracle.STATE_DT).reshape(-1)
+    after = g["after"].copy().view(oracle.STATE_DT).reshape(-1)
+    n = before.shape[0]
+    b = pb.Batch(n, n_templates=1, empty=True)
+    b.upload(before)
+    rt, _ = b.download()
+    assert orc.diff_batch(rt, before)[0] == -1, "upload/download round trip"
+    b.step_host(np.ascontiguousarray(g["moves"]), None, pb.STEP_RAW)
+    out, st = b.download()
+    e, why = orc.diff_batch(out, after)
+    assert e == -1, "transition %d (%s) differs in field group %d" % (e, g["names"][e], why)
+    b.close()
+
+
+@pytest.mark.parametrize("name", ["random6", "harmless5", "stress6"])
+def test_golden_traces(pb, orc, name):
+    g = np.load(os.path.join(GOLD, "traces.npz"))
+    n, ticks, nact, stress, rs = [int(v) for v in g[name + "_cfg"]]
+    init = g[name + "_init"].copy().view(oracle.STATE_DT).reshape(-1)
+    excluded = g[name + "_excluded"]
+    b = pb.Batch(n, n_templates=1, empty=True)
+    b.upload(init)
+    moves_dev = b.alloc(4 * n)
+    for t in range(ticks):
+        b.generate_moves(moves_dev, rs, t, nact)
+        b.step(moves_dev, 0)
+        S, st = b.download()
+        live = (excluded < 0) | (excluded > t)
+        bad = (orc.hash_batch(S) != g[name + "_hash"][t]) & live
+        assert not bad.any(), "tick %d env %d" % (t, int(np.nonzero(bad)[0][0]))
+        assert (((st ^ g[name + "_status"][t]) & 0x0F)[live] == 0).all()
+    final = g[name + "_final"].copy().view(oracle.STATE_DT).reshape(-1)
+    assert orc.diff_batch(S, final, (excluded >= 0).astype(np.uint8))[0] == -1
+    b.free(moves_dev)
+    b.close()
+
+
+def test_device_init_matches_reference_init(pb, orc):
+    """K3: InitState on the device (mt19937_64 + libstdc++ Lemire) vs the oracle, incl. the golden boards."""
+    b = pb.Batch(8, n_templates=512, first_seed=0x1337)
+    T, seeds = b.templates()
+    g = np.load(os.path.join(GOLD, "init.npz"))
+    assert (seeds[:64] == g["seeds"]).all(), "clean-seed filter differs"
+    for k in range(64):
+        brd = g["boards"][k].copy()
+        brd[0, 0], brd[0, 10], brd[10, 10], brd[10, 0] = [(1 << 24) + i for i in range(4)]
+        assert (T["board"][k] == brd).all()
+    for k in range(0, 512, 7):
+        s = orc.zero_state()
+        assert orc.init_state(s, int(seeds[k])) == 0
+        assert orc.diff_batch(T[k:k + 1], s)[0] == -1, "template %d seed %d" % (k, seeds[k])
+    # env e starts as template[(offset + e) % n]
+    S, st = b.download()
+    assert orc.diff_batch(S, T[:8])[0] == -1 and not st.any()
+    b.close()
+
+
+def _run_vs_oracle(pb, orc, n, ticks, nact, stress, seed, every_tick=True, n_templates=256):
+    b = pb.Batch(n, n_templates=n_templates)
+    S, st = b.download()
+    if stress:
+        S["agents"]["canKick"] = 1
+        S["agents"]["maxBombCount"] = 5
+        S["agents"]["bombStrength"] = 4
+        b.upload(S)
+    status = np.zeros(n, np.uint8)
+    moves_dev = b.alloc(4 * n)
+    steps = 0
+    for t in range(ticks):
+        b.generate_moves(moves_dev, seed, t, nact)
+        b.step(moves_dev, 0)
+        mv = orc.rng_moves(seed, 0, n, t, nact)
+        steps += int(((status & 1) == 0).sum())
+        orc.env_step_batch(S, status, mv)
+        if every_tick or t == ticks - 1:
+            G, gst = b.download()
+            e, why = orc.diff_batch(G, S)
+            assert e == -1, "tick %d env %d field group %d" % (t, e, why)
+            assert (gst == status).all(), "status differs at tick %d" % t
+    b.free(moves_dev)
+    b.close()
+    return steps
+
+
+def test_config2_65536_harmless_800_ticks_every_field_every_tick(pb, orc):
+    """BASELINE config 2 at full size."""
+    steps = _run_vs_oracle(pb, orc, 65536, 800, 5, 0, 42)
+    assert steps == 65536 * 800
+
+
+def test_random_with_bombs_every_tick(pb, orc):
+    _run_vs_oracle(pb, orc, 16384, 96, 6, 0, 43)
+
+
+def test_stress_kicks_and_chains_every_tick(pb, orc):
+    _run_vs_oracle(pb, orc, 16384, 200, 6, 1, 44)
+
+
+def test_ragged_sizes(pb, orc):
+    for n in (1, 31, 129, 257, 1000):
+        _run_vs_oracle(pb, orc, n, 40, 6, 1, 45 + n, n_templates=7)
+
+
+def _oracle_rollout(orc, S, T, env0, ticks, seed, nact, max_ticks, tick0=0, no_reset=False):
+    """Host replay of pom_batch_rollout's rule: step, truncate, count, reset to template[(env+episode)%nT]."""
+    n = S.shape[0]
+    status = np.zeros(n, np.uint8)
+    episode = np.zeros(n, np.int64)
+    stats = np.zeros(10, np.int64)
+    nT = T.shape[0]
+    for k in range(ticks):
+        mv = orc.rng_moves(seed, env0, n, tick0 + k, nact)
+        live = (status & 0x21) == 0
+        stats[0] += int(live.sum())
+        frozen = ~live
+        before = S[frozen].copy()
+        sb = status[frozen].copy()
+        orc.env_step_batch(S, status, mv)
+        S[frozen] = before
+        status[frozen] = sb
+        if max_ticks:
+            tr = live & ((status & 1) == 0) & (S["timeStep"] >= max_ticks)
+            status[tr] |= 0x20
+        fin = live & ((status & 0x21) != 0)
+        for e in np.nonzero(fin)[0]:
+            stats[1] += 1
+            if status[e] & 1:
+                if status[e] & 2:
+                    stats[6] += 1
+                else:
+                    stats[2 + ((status[e] >> 2) & 3)] += 1
+            else:
+                stats[7] += 1
+            stats[8] += int(S["timeStep"][e])
+            if status[e] & 0x10:
+                stats[9] += 1
+            if not no_reset:
+                episode[e] += 1
+                S[e] = T[(env0 + e + episode[e]) % nT]
+                status[e] = 0
+    return status, stats
+
+
+@pytest.mark.parametrize("harmless,max_ticks", [(0, 800), (1, 60)])
+def test_rollout_fused_matches_oracle_replay(pb, orc, harmless, max_ticks):
+    n, ticks, seed, env0 = 2048, 150, 77, 1000
+    b = pb.Batch(n, env_offset=env0, n_templates=64, max_ticks=max_ticks)
+    T, _ = b.templates()
+    S, _ = b.download()
+    # two launches: the tick counter continues across launches
+    b.rollout(100, seed, 0, pb.ROLL_HARMLESS if harmless else 0)
+    b.rollout(ticks - 100, seed, 100, pb.ROLL_HARMLESS if harmless else 0)
+    G, gst = b.download()
+    status, stats = _oracle_rollout(orc, S, T, env0, ticks, seed, 5 if harmless else 6, max_ticks)
+    e, why = orc.diff_batch(G, S)
+    assert e == -1, "env %d field group %d" % (e, why)
+    assert (gst == status).all()
+    assert (b.stats().as_array() == stats).all(), (b.stats().as_dict(), stats)
+    assert stats[1] > 0
+    b.close()
+
+
+def test_rollout_no_reset_freezes(pb, orc):
+    n, ticks, seed = 1024, 120, 5
+    b = pb.Batch(n, n_templates=32, max_ticks=100)
+    T, _ = b.templates()
+    S, _ = b.download()
+    b.rollout(ticks, seed, 0, pb.ROLL_NO_RESET)
+    G, gst = b.download()
+    status, stats = _oracle_rollout(orc, S, T, 0, ticks, seed, 6, 100, no_reset=True)
+    assert orc.diff_batch(G, S)[0] == -1
+    assert (gst == status).all()
+    assert (b.stats().as_array() == stats).all()
+    b.close()
+
+
+def test_per_tick_autoreset_matches_rollout_rule(pb, orc):
+    n, ticks, seed = 2048, 90, 9
+    b = pb.Batch(n, n_templates=16, max_ticks=0)
+    T, _ = b.templates()
+    S, _ = b.download()
+    moves_dev = b.alloc(4 * n)
+    for t in range(ticks):
+        b.generate_moves(moves_dev, seed, t, 6)
+        b.step(moves_dev, pb.STEP_AUTORESET | pb.STEP_COUNT)
+    G, gst = b.download()
+    status, stats = _oracle_rollout(orc, S, T, 0, ticks, seed, 6, 0)
+    assert orc.diff_batch(G, S)[0] == -1
+    assert (gst == status).all()
+    assert (b.stats().as_array() == stats).all(), (b.stats().as_dict(), stats)
+    b.free(moves_dev)
+    b.close()
+
+
+def test_step_host_e2e_path(pb, orc):
+    n = 3000
+    b = pb.Batch(n, n_templates=50)
+    S, _ = b.download()
+    status = np.zeros(n, np.uint8)
+    out = np.zeros(n, np.uint8)
+    for t in range(40):
+        mv = orc.rng_moves(3, 0, n, t, 6)
+        b.step_host(mv, out, 0)
+        orc.env_step_batch(S, status, mv)
+        assert (out == status).all()
+    G, _ = b.download()
+    assert orc.diff_batch(G, S)[0] == -1
+    b.close()
+
+
+def test_clone_and_tree_search_expansion(pb, orc):
+    """BASELINE config 5 shape: roots x 6^4 joint actions, one Step each."""
+    n_roots_pool = 512
+    src = pb.Batch(n_roots_pool, n_templates=64)
+    moves_dev = src.alloc(4 * n_roots_pool)
+    for t in range(16):
+        src.generate_moves(moves_dev, 21, t, 6)
+        src.step(moves_dev, 0)
+    R, rst = src.download()
+    roots = np.nonzero((rst & 1) == 0)[0][:24].astype(np.uint32)
+    assert roots.shape[0] == 24
+    # plain clone (gather)
+    dst = pb.Batch(24 * 1296, n_templates=1, empty=True)
+    dst.clone_from(src, roots[::-1].copy(), first_dst=5)
+    C_, cst = dst.download(5, 24)
+    assert orc.diff_batch(C_, R[roots[::-1]])[0] == -1 and (cst == rst[roots[::-1]]).all()
+    # fused fan-out + Step
+    dst.expand_step_from(src, roots, 1296, 0)
+    G, gst = dst.download()
+    E = np.repeat(R[roots], 1296)
+    est = np.repeat(rst[roots], 1296)
+    j = np.tile(np.arange(1296), 24)
+    mv = np.stack([j % 6, (j // 6) % 6, (j // 36) % 6, (j // 216) % 6], axis=1).astype(np.uint8)
+    orc.env_step_batch(E, est, np.ascontiguousarray(mv))
+    e, why = orc.diff_batch(G, E)
+    assert e == -1, "child %d field group %d" % (e, why)
+    assert (gst == est).all()
+    src.free(moves_dev)
+    src.close()
+    dst.close()
+
+
+def test_upload_rejects_unrepresentable_states(pb, orc):
+    s = orc.zero_state(3)
+    s["board"][0, 3, 3] = (4 << 16) | (17 << 3)
+    b = pb.Batch(3, n_templates=1, empty=True)
+    with pytest.raises(pb.PomError) as e:
+        b.upload(s)
+    assert e.value.code == -5
+    st = b.status()
+    assert st[0] & pb.STATUS_INVALID and not st[1] & pb.STATUS_INVALID
+    with pytest.raises(pb.PomError):
+        b.download(2, 5)
+    b.close()
+
+
+def test_config3_1M_envs_properties(pb, orc):
+    """BASELINE config 3 at full size: 1,048,576 envs, random actions incl. bombs; size-independent
+    properties + a strided sample of envs compared with the oracle on every field."""
+    n, ticks, seed = 1 << 20, 64, 1234
+    b = pb.Batch(n, n_templates=4096, max_ticks=800)
+    T, _ = b.templates()
+    sample = np.arange(0, n, 509)
+    S0 = T[sample % 4096].copy()
+    moves_dev = b.alloc(4 * n)
+    for t in range(ticks):
+        b.generate_moves(moves_dev, seed, t, 6)
+        b.step(moves_dev, pb.STEP_AUTORESET | pb.STEP_COUNT)
+    s = b.stats()
+    assert s.env_steps == n * ticks
+    assert s.episodes == sum(s.wins) + s.draws + s.truncated
+    assert s.episodes > n and s.invalid == 0
+    assert 15 < s.sum_episode_len / s.episodes < 40        # mean episode length ~26 ticks
+    # sampled envs: replay each on the oracle with the same reset rule
+    for e in sample[:400]:
+        S = T[e % 4096: e % 4096 + 1].copy()
+        _oracle_rollout(orc, S, T, int(e), ticks, seed, 6, 800)
+        G, _ = b.download(int(e), 1)
+        assert orc.diff_batch(G, S)[0] == -1, "env %d" % e
+    b.free(moves_dev)
+    b.close()
