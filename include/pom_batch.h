@@ -73,12 +73,13 @@ enum {
 /* episode counters accumulated on the device (Environment::IsDone/IsDraw/GetWinner, bboard.hpp:617-631) */
 typedef struct pom_stats {
     uint64_t env_steps;        /* Steps executed (finished/frozen envs not counted) */
-    uint64_t episodes;         /* episodes finished (won + draw + truncated)        */
+    uint64_t episodes;         /* episodes finished (won + draw + truncated + invalid) */
     uint64_t wins[4];          /* episodes won by agent 0..3                         */
     uint64_t draws;            /* aliveAgents == 0                                   */
     uint64_t truncated;        /* timeStep reached max_ticks                         */
     uint64_t sum_episode_len;  /* sum of timeStep over finished episodes             */
-    uint64_t invalid;          /* envs that left the reference's defined domain      */
+    uint64_t invalid;          /* episodes aborted because the env left the reference's defined domain
+                                  (the reference itself would crash or hang there)  */
 } pom_stats;
 #define POM_STATS_WORDS 10
 
@@ -136,6 +137,8 @@ void*    pom_batch_stats_device_ptr(const pom_batch* b);/* POM_STATS_WORDS x uin
 void*    pom_batch_records_device_ptr(const pom_batch* b);
 int      pom_device_alloc(int device, uint64_t bytes, void** out);
 int      pom_device_free(int device, void* p);
+int      pom_host_alloc(uint64_t bytes, void** out);    /* pinned host memory for pom_batch_step_host */
+int      pom_host_free(void* p);
 /* timing helper: runs fn-less CUDA-event brackets on the handle's stream */
 int      pom_batch_event_record(pom_batch* b, int which /* 0 = start, 1 = stop */);
 int      pom_batch_event_elapsed_ms(pom_batch* b, float* ms);   /* synchronises on the stop event */

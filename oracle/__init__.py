@@ -155,7 +155,7 @@ class Reference:
             raise FileNotFoundError(path)
         L = self.lib = C.CDLL(path)
         assert L.ref_sizeof_state() == 1004
-        L.ref_env_step_batch.argtypes = [_vp, _vp, C.c_long, _vp, _vp]
+        L.ref_env_step_batch.argtypes = [_vp, _vp, C.c_long, _vp, _vp, _vp]
         L.ref_step_batch.argtypes = [_vp, C.c_long, _vp]
         L.ref_bench_steps.restype = C.c_double
         L.ref_bench_steps.argtypes = [_vp, _vp, C.c_long, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]
@@ -212,8 +212,11 @@ class Reference:
         n = self.lib.ref_resolve_dependencies(_ptr(s), _ptr(p), _ptr(dep), _ptr(roots))
         return n, dep, roots
 
-    def env_step_batch(self, S, status, moves, pre=None):
-        self.lib.ref_env_step_batch(_ptr(S), _ptr(status), S.shape[0], _ptr(moves), None if pre is None else _ptr(pre))
+    def env_step_batch(self, S, status, moves, pre=None, exclude=None):
+        """exclude: uint8 mask of envs NOT to step this tick (marked invalid instead) — the harness sets it
+        where the restatement detected defect D5 (the reference would hang there)."""
+        self.lib.ref_env_step_batch(_ptr(S), _ptr(status), S.shape[0], _ptr(moves), None if pre is None else _ptr(pre),
+                                    None if exclude is None else _ptr(exclude))
 
     def step_batch(self, S, moves):
         self.lib.ref_step_batch(_ptr(S), S.shape[0], _ptr(moves))

@@ -12,6 +12,9 @@
  *   D1: the dependency walk stops when the roots are exhausted (flag D1_UNREACHABLE).
  *   D3: a kicker on a BOMB cell without queue entry moves but sets no direction (flag).
  *   D4 / flame overflow: flagged; the ring wraps exactly as FixedQueue would.
+ *   D5: unbounded AgentBombChainReversion recursion (found by this project's differential runs: the
+ *       compiled reference hangs at -O3 and overflows the stack at -O0): flagged, chain stopped.
+ * An env whose tick raised D3/D4/D5/overflow/bad-move is marked POM_STATUS_INVALID and frozen.
  */
 #include "pom_oracle.h"
 
@@ -352,9 +355,20 @@ static int has_bomb_collision(pom_state* s, int b, int index)        /* step_uti
     return 0;
 }
 
-static pos_t chain_reversion(pom_state* s, const uint8_t moves[4], const pos_t destBombs[NB], int agentID) /* step_utility.cpp:62-128 */
+/* D5: the reference recurses without bound when the chain reaches an agent whose move is IDLE/BOMB
+ * (its "origin" is its own cell, where GetAgent finds the agent itself): stack overflow at -O0, endless
+ * tail-call loop at -O2/-O3.  Canonical: flag the env and stop the chain there. */
+static pos_t chain_reversion_d(pom_state* s, const uint8_t moves[4], const pos_t destBombs[NB], int agentID, int depth, int* flags);
+
+static pos_t chain_reversion(pom_state* s, const uint8_t moves[4], const pos_t destBombs[NB], int agentID, int* flags)
+{
+    return chain_reversion_d(s, moves, destBombs, agentID, 0, flags);
+}
+
+static pos_t chain_reversion_d(pom_state* s, const uint8_t moves[4], const pos_t destBombs[NB], int agentID, int depth, int* flags) /* step_utility.cpp:62-128 */
 {
     pom_agent* agent = &s->agents[agentID];
+    if (depth >= 64) { *flags |= POM_ORC_D5_REVERT_LOOP; pos_t r0 = { agent->x, agent->y }; return r0; }
     pos_t origin = origin_pos(agent->x, agent->y, moves[agentID]);
     if (!oob(origin.x, origin.y)) {
         int indexOriginAgent = get_agent(s, origin.x, origin.y);
@@ -365,8 +379,9 @@ static pos_t chain_reversion(pom_state* s, const uint8_t moves[4], const pos_t d
         agent->x = origin.x;
         agent->y = origin.y;
         s->board[origin.y][origin.x] = POM_ITEM_AGENT0 + agentID;
+        if (indexOriginAgent == agentID) { *flags |= POM_ORC_D5_REVERT_LOOP; return origin; }
         if (indexOriginAgent != -1) {
-            return chain_reversion(s, moves, destBombs, indexOriginAgent);
+            return chain_reversion_d(s, moves, destBombs, indexOriginAgent, depth + 1, flags);
         } else if (bombDestIndex != -1) {
             int* b = bomb_at(s, bombDestIndex);
             pos_t bombDest = destBombs[bombDestIndex];
@@ -379,7 +394,7 @@ static pos_t chain_reversion(pom_state* s, const uint8_t moves[4], const pos_t d
             b_set_dir(b, 0);
             b_set_pos(b, originBomb.x, originBomb.y);
             s->board[originBomb.y][originBomb.x] = POM_ITEM_BOMB;
-            if (hasAgent != -1) return chain_reversion(s, moves, destBombs, hasAgent);
+            if (hasAgent != -1) return chain_reversion_d(s, moves, destBombs, hasAgent, depth + 1, flags);
             return originBomb;
         }
         return origin;
@@ -388,7 +403,7 @@ static pos_t chain_reversion(pom_state* s, const uint8_t moves[4], const pos_t d
     return r;
 }
 
-static void resolve_bomb_collision(pom_state* s, const uint8_t moves[4], const pos_t destBombs[NB], int index) /* step_utility.cpp:295-329 */
+static void resolve_bomb_collision(pom_state* s, const uint8_t moves[4], const pos_t destBombs[NB], int index, int* flags) /* step_utility.cpp:295-329 */
 {
     int* b = bomb_at(s, index);
     pos_t t = bomb_desired(*b);
@@ -406,7 +421,7 @@ static void resolve_bomb_collision(pom_state* s, const uint8_t moves[4], const p
             b_set_dir(b, 0);
             int a = get_agent(s, b_x(*b), b_y(*b));
             if (a > -1 && moves[a] != POM_MOVE_IDLE && moves[a] != POM_MOVE_BOMB) {
-                chain_reversion(s, moves, destBombs, a);
+                chain_reversion(s, moves, destBombs, a, flags);
                 s->board[b_y(*b)][b_x(*b)] = POM_ITEM_BOMB;
             }
         }
@@ -504,7 +519,7 @@ int pom_oracle_step(pom_state* s, const uint8_t moves_in[4])
             int a = get_agent(s, bx, by);
             if (a > -1 && moves[a] != POM_MOVE_IDLE && moves[a] != POM_MOVE_BOMB &&
                 !(s->agents[a].x == oldPos[a].x && s->agents[a].y == oldPos[a].y)) {
-                chain_reversion(s, moves, bombDest, a);
+                chain_reversion(s, moves, bombDest, a, &flags);
                 if (get_agent(s, bx, by) == -1) s->board[by][bx] = POM_ITEM_BOMB;
             }
         }
@@ -514,7 +529,7 @@ int pom_oracle_step(pom_state* s, const uint8_t moves_in[4])
         int* b = bomb_at(s, k);
         if (b_dir(*b) == 0) {
             if (has_bomb_collision(s, *b, k)) {
-                resolve_bomb_collision(s, moves, bombDest, k);
+                resolve_bomb_collision(s, moves, bombDest, k, &flags);
                 continue;
             }
         }
@@ -523,7 +538,7 @@ int pom_oracle_step(pom_state* s, const uint8_t moves_in[4])
         /* the reference forms &board[t] before the bounds test but only reads it when in bounds */
         if (!oob(t.x, t.y) && !is_static_block(s->board[t.y][t.x])) {
             if (has_bomb_collision(s, *b, k)) {
-                resolve_bomb_collision(s, moves, bombDest, k);
+                resolve_bomb_collision(s, moves, bombDest, k, &flags);
                 continue;
             }
             b_set_pos(b, t.x, t.y);
@@ -542,7 +557,7 @@ int pom_oracle_step(pom_state* s, const uint8_t moves_in[4])
 
 int pom_oracle_env_step(pom_state* s, uint8_t* status, const uint8_t moves[4])   /* environment.cpp:125-128,149-168 */
 {
-    if (*status & POM_STATUS_DONE) return 0;
+    if (*status & (POM_STATUS_DONE | POM_STATUS_INVALID)) return 0;   /* invalid envs freeze: the reference would have crashed */
     int flags = pom_oracle_step(s, moves);
     s->timeStep++;
     if (s->aliveAgents == 1) {
@@ -551,7 +566,7 @@ int pom_oracle_env_step(pom_state* s, uint8_t* status, const uint8_t moves[4])  
         *status = (uint8_t)((*status & POM_STATUS_INVALID) | POM_STATUS_DONE | (w << POM_STATUS_WINNER_SHIFT));
     }
     if (s->aliveAgents == 0) *status = (uint8_t)((*status & POM_STATUS_INVALID) | POM_STATUS_DONE | POM_STATUS_DRAW);
-    if (flags & (POM_ORC_D3_NULL_BOMB | POM_ORC_D4_BOMB_OVF | POM_ORC_FLAME_OVF | POM_ORC_BAD_MOVE)) *status |= POM_STATUS_INVALID;
+    if (flags & POM_ORC_INVALID_MASK) *status |= POM_STATUS_INVALID;
     return flags;
 }
 
@@ -714,10 +729,10 @@ static void* bench_worker(void* arg)
     for (int k = 0; k < j->ticks; k++) {
         const uint8_t* mv = j->moves + ((size_t)k * (size_t)j->n) * 4;
         for (long e = j->lo; e < j->hi; e++) {
-            if (j->status[e] & POM_STATUS_DONE) continue;
+            if (j->status[e] & (POM_STATUS_DONE | POM_STATUS_INVALID)) continue;
             pom_oracle_env_step(&j->S[e], &j->status[e], mv + 4 * e);
             c++;
-            if (j->T && (j->status[e] & POM_STATUS_DONE)) {
+            if (j->T && (j->status[e] & (POM_STATUS_DONE | POM_STATUS_INVALID))) {
                 uint32_t ep = ++episode[e - j->lo];
                 j->S[e] = j->T[((uint64_t)e + ep) % (uint64_t)j->nT];
                 j->status[e] = 0;

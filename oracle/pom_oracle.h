@@ -29,7 +29,9 @@ enum {
     POM_ORC_D3_NULL_BOMB   = 0x02, /* kicker on a BOMB cell without queue entry (ref: crash) */
     POM_ORC_D4_BOMB_OVF    = 0x04, /* bomb queue would exceed 20 entries                    */
     POM_ORC_FLAME_OVF      = 0x08, /* flame queue would exceed 20 entries                   */
-    POM_ORC_BAD_MOVE       = 0x10  /* move byte outside 0..5 (treated as IDLE)              */
+    POM_ORC_BAD_MOVE       = 0x10, /* move byte outside 0..5 (treated as IDLE)              */
+    POM_ORC_D5_REVERT_LOOP = 0x20, /* AgentBombChainReversion would recurse forever (ref: hang/stack overflow) */
+    POM_ORC_INVALID_MASK   = 0x3E  /* everything but D1 takes the env out of the reference's defined domain */
 };
 
 /* std::make_unique<State>() : zero bytes + default member initialisers (bboard.hpp:225-240,372-373) */

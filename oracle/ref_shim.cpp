@@ -19,6 +19,11 @@
  *   D3  step.cpp:167 dereferences GetBomb()==nullptr when a kicker walks onto a BOMB cell
  *       that has no queue entry -> ref_precheck() flags the tick, the caller skips the env.
  *   D4  step.cpp:191 Position bombDestinations[20] overflows when bombs.count > 20.
+ *   D5  step_utility.cpp:89-92 AgentBombChainReversion recurses forever when the chain reaches an agent
+ *       whose move is IDLE/BOMB (it finds itself at its own "origin"); found by this project's
+ *       differential runs: the -O3 build hangs, the -O0 build overflows the stack.  It cannot be
+ *       pre-checked cheaply, so ref_env_step_batch takes an `exclude` mask from the caller (computed by
+ *       the restatement, which detects it exactly).
  */
 #include <cstdint>
 #include <cstring>
@@ -233,6 +238,49 @@ REF_API int ref_precheck(const void* st, const uint8_t* mv)
 }
 
 /*
+ * Cheap per-tick fence for the timed CPU baseline (no State copy): non-zero when the reference could
+ * crash or hang on this tick.  D3 exactly as ref_precheck; D4 by count; D5 conservatively: a live agent
+ * with move IDLE/BOMB stands on (or is about to plant into a stale ring slot holding) a bomb whose
+ * direction bits are non-zero — the only way AgentBombChainReversion can reach a non-moving agent.
+ */
+static inline int FenceTick(State& s, const uint8_t* mv)
+{
+    int planters = 0;
+    for(int a = 0; a < 4; a++)
+    {
+        const bboard::AgentInfo& ag = s.agents[a];
+        if(ag.dead) continue;
+        const int m = mv[a];
+        if(m == 0 || m == 5)
+        {
+            for(int k = 0; k < s.bombs.count; k++)
+            {
+                const bboard::Bomb b = s.bombs[k];
+                if(bboard::BMB_POS_X(b) == ag.x && bboard::BMB_POS_Y(b) == ag.y && bboard::BMB_DIR(b) != 0) return 5;
+            }
+            if(m == 5 && ag.bombCount < ag.maxBombCount) planters++;
+            continue;
+        }
+        if(m > 5) return 7;
+        if(ag.canKick)
+        {
+            bboard::Position d = bboard::util::DesiredPosition(ag.x, ag.y, Move(m));
+            if(!bboard::util::IsOutOfBounds(d) && s.board[d.y][d.x] == bboard::Item::BOMB && !s.HasBomb(d.x, d.y)) return 3;
+        }
+    }
+    if(planters)
+    {
+        if(s.bombs.count + planters > bboard::MAX_BOMBS) return 4;
+        for(int j = 0; j < planters; j++)
+        {
+            if(bboard::BMB_DIR(s.bombs[s.bombs.count + j]) != 0) return 5;
+        }
+    }
+    if(s.flames.count + s.bombs.count + planters > bboard::MAX_BOMBS) return 6;
+    return 0;
+}
+
+/*
  * CPU baseline: the reference's Step over a host AoS State[] partitioned
  * contiguously over `nthreads` threads; `moves` is [ticks][n][4].  Environment semantics
  * (skip finished envs, timeStep++, done/winner).  When `reset_templates` is non-null a
@@ -262,10 +310,10 @@ REF_API double ref_bench_steps(void* states, uint8_t* status, long n, const uint
                 const uint8_t* mv = moves + (size_t(k) * size_t(n)) * 4;
                 for(long e = lo; e < hi; e++)
                 {
-                    if(status[e] & 0x01) continue;
-                    EnvStep(&S[e], &status[e], mv + 4 * e);
-                    c++;
-                    if(T && (status[e] & 0x01))
+                    if(status[e] & 0x11) continue;
+                    if(FenceTick(S[e], mv + 4 * e)) status[e] |= 0x10;   /* the reference would crash/hang: abort the episode */
+                    else { EnvStep(&S[e], &status[e], mv + 4 * e); c++; }
+                    if(T && (status[e] & 0x11))
                     {
                         uint32_t ep = ++episode[size_t(e - lo)];
                         S[e] = T[(uint64_t(e) + ep) % uint64_t(n_templates)];
@@ -287,7 +335,8 @@ REF_API double ref_bench_steps(void* states, uint8_t* status, long n, const uint
 /* Batch Environment::Step for the harness: pre[e] receives ref_precheck(); envs whose pre-check
  * shows D3/D4/flame-overflow/bad-move risk are NOT stepped and get status |= 0x10 (excluded from
  * comparison from then on). */
-REF_API void ref_env_step_batch(void* states, uint8_t* status, long n, const uint8_t* moves, uint8_t* pre)
+REF_API void ref_env_step_batch(void* states, uint8_t* status, long n, const uint8_t* moves, uint8_t* pre,
+                                const uint8_t* exclude)
 {
     State* S = static_cast<State*>(states);
     for(long e = 0; e < n; e++)
@@ -295,7 +344,9 @@ REF_API void ref_env_step_batch(void* states, uint8_t* status, long n, const uin
         if(status[e] & 0x11) { if(pre) pre[e] = 0; continue; }
         int f = ref_precheck(&S[e], moves + 4 * e);
         if(pre) pre[e] = uint8_t(f);
-        if(f & 0xF0) { status[e] |= 0x10; continue; }
+        /* D5 (unbounded AgentBombChainReversion) cannot be predicted without running the tick: the
+         * harness passes exclude[e] != 0 for envs on which the restatement detected it this tick */
+        if((f & 0xF0) || (exclude && exclude[e])) { status[e] |= 0x10; continue; }
         EnvStep(&S[e], &status[e], moves + 4 * e);
     }
 }

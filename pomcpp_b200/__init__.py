@@ -97,6 +97,8 @@ def lib():
             getattr(L, f).argtypes = [vp]
         L.pom_device_alloc.argtypes = [i32, u64, C.POINTER(vp)]
         L.pom_device_free.argtypes = [i32, vp]
+        L.pom_host_alloc.argtypes = [u64, C.POINTER(vp)]
+        L.pom_host_free.argtypes = [vp]
         L.pom_batch_event_record.argtypes = [vp, i32]
         L.pom_batch_event_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.pom_batch_flush_l2.argtypes = [vp]
@@ -227,6 +229,21 @@ class Batch:
     def launch_count(self): return int(lib().pom_batch_launch_count(self.h))
     def stats_device_ptr(self): return lib().pom_batch_stats_device_ptr(self.h)
     def stream(self): return lib().pom_batch_stream(self.h)
+
+
+def pinned_array(shape, dtype):
+    """numpy array backed by pinned host memory (pom_host_alloc); keep the returned owner alive."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    _ck(lib().pom_host_alloc(n, C.byref(p)))
+    buf = (C.c_uint8 * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr, p
+
+
+def pinned_free(p):
+    _ck(lib().pom_host_free(p))
 
 
 def rng_moves(seed, env0, n, tick, n_actions=6):

@@ -527,6 +527,19 @@ int pom_device_free(int device, void* p)
     return POM_OK;
 }
 
+int pom_host_alloc(uint64_t bytes, void** out)
+{
+    if(!out) return fail(POM_E_ARG, "pom_host_alloc: null output");
+    if(cudaHostAlloc(out, bytes, cudaHostAllocDefault) != cudaSuccess) return fail(POM_E_NOMEM, "pom_host_alloc", cudaGetLastError());
+    return POM_OK;
+}
+
+int pom_host_free(void* p)
+{
+    CK(cudaFreeHost(p));
+    return POM_OK;
+}
+
 int pom_batch_event_record(pom_batch* b, int which)
 {
     int rc = use(b); if(rc) return rc;

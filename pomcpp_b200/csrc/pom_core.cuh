@@ -40,7 +40,7 @@ enum {
     F_D4_BOMB_OVF    = 0x04,
     F_FLAME_OVF      = 0x08,
     F_BAD_MOVE       = 0x10,
-    F_LOOP_GUARD     = 0x20,
+    F_LOOP_GUARD     = 0x20,   /* D5: AgentBombChainReversion would recurse forever (also: internal loop guards) */
     F_INVALID_MASK   = 0x3E
 };
 
@@ -308,6 +308,9 @@ POM_HD void revert_chain(uint8_t* r, Agents& A, uint32_t moves, const uint8_t* b
         }
         A.pos = with_byte(A.pos, agentID, origin);
         r[R_BOARD + cell_of(origin)] = uint8_t(C_AGENT0 + agentID);
+        /* D5: an agent whose move is IDLE/BOMB finds itself at its "origin": the reference recurses
+         * forever here (hang at -O3, stack overflow at -O0); canonical = flag the env and stop */
+        if(indexOriginAgent == agentID) { flags |= F_LOOP_GUARD; return; }
         if(indexOriginAgent != -1)
         {
             agentID = indexOriginAgent;
@@ -653,7 +656,7 @@ POM_HD int step(uint8_t* r, uint32_t moves)
 POM_HD int env_step(uint8_t* r, uint32_t moves)
 {
     uint32_t st = r[R_STATUS];
-    if(st & POM_STATUS_DONE) return 0;
+    if(st & (POM_STATUS_DONE | POM_STATUS_INVALID)) return 0;        /* invalid envs freeze: the reference would have crashed */
     const int flags = step(r, moves);
     uint16_t* ts = reinterpret_cast<uint16_t*>(r + R_TIME);
     *ts = uint16_t(*ts + 1);

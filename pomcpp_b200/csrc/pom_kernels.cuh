@@ -99,15 +99,18 @@ __device__ __forceinline__ void warp_add(unsigned long long* dst, uint32_t v)
 __device__ __forceinline__ void account_episodes(unsigned long long* stats, bool fin, uint32_t status, uint32_t len)
 {
     if(!__any_sync(0xFFFFFFFFu, fin)) return;
-    const bool draw = fin && (status & POM_STATUS_DRAW);
-    const bool trunc = fin && (status & POM_STATUS_TRUNCATED) && !(status & POM_STATUS_DONE);
-    const bool won = fin && (status & POM_STATUS_DONE) && !draw;
+    /* exactly one outcome per episode: DONE (won | draw) > TRUNCATED > aborted (left the reference's domain) */
+    const bool done = fin && (status & POM_STATUS_DONE);
+    const bool draw = done && (status & POM_STATUS_DRAW);
+    const bool trunc = fin && !done && (status & POM_STATUS_TRUNCATED);
+    const bool won = done && !draw;
+    const bool aborted = fin && !done && !trunc;
     const uint32_t w = (status & POM_STATUS_WINNER_MASK) >> POM_STATUS_WINNER_SHIFT;
     warp_add(stats + ST_EPISODES, fin ? 1u : 0u);
     warp_add(stats + ST_DRAWS, draw ? 1u : 0u);
     warp_add(stats + ST_TRUNC, trunc ? 1u : 0u);
     warp_add(stats + ST_SUMLEN, fin ? len : 0u);
-    warp_add(stats + ST_INVALID, (fin && (status & POM_STATUS_INVALID)) ? 1u : 0u);
+    warp_add(stats + ST_INVALID, aborted ? 1u : 0u);
 #pragma unroll
     for(uint32_t a = 0; a < 4; a++) warp_add(stats + ST_WIN0 + a, (won && w == a) ? 1u : 0u);
 }
@@ -118,7 +121,7 @@ __device__ __forceinline__ void finish_and_reset(uint8_t* rec, const BatchParams
     uint32_t st = active ? rec[R_STATUS] : 0u;
     const uint32_t len = active ? *reinterpret_cast<const uint16_t*>(rec + R_TIME) : 0u;
     if(active && !(st & POM_STATUS_DONE) && P.max_ticks && len >= P.max_ticks) st |= POM_STATUS_TRUNCATED;
-    const bool fin = active && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED)) != 0u;
+    const bool fin = active && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID)) != 0u;
     account_episodes(P.stats, fin, st, len);
     if(fin && do_reset)
     {
@@ -163,13 +166,16 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
     {
         if(flags & POM_STEP_RAW)
         {
-            const int f = pomcore::step(rec, m);
-            if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
-            stepped = true;
+            if(!(rec[R_STATUS] & POM_STATUS_INVALID))
+            {
+                const int f = pomcore::step(rec, m);
+                if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+                stepped = true;
+            }
         }
         else
         {
-            stepped = !(rec[R_STATUS] & POM_STATUS_DONE);
+            stepped = !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_INVALID));
             pomcore::env_step(rec, m);
         }
     }
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
     for(uint32_t k = 0; k < ticks; k++)
     {
         bool stepped = false;
-        if(active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_TRUNCATED)))
+        if(active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID)))
         {
             const uint64_t h = pomcore::splitmix64(key + uint64_t(tick0 + k));
             uint32_t m = 0;
@@ -297,8 +303,11 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
         const uint32_t m = (j % 6u) | (((j / 6u) % 6u) << 8) | (((j / 36u) % 6u) << 16) | (((j / 216u) % 6u) << 24);
         if(flags & POM_STEP_RAW)
         {
-            const int f = pomcore::step(rec, m);
-            if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+            if(!(rec[R_STATUS] & POM_STATUS_INVALID))
+            {
+                const int f = pomcore::step(rec, m);
+                if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+            }
         }
         else pomcore::env_step(rec, m);
     }

@@ -49,13 +49,18 @@ def run_trace(R, O, S, ticks, n_actions, rng_seed):
     n = S.shape[0]
     status = np.zeros(n, np.uint8)
     pre = np.zeros(n, np.uint8)
+    fo = np.zeros(n, np.uint8)
+    shadow = S.copy()
+    shadow_status = np.zeros(n, np.uint8)
     hashes = np.zeros((ticks, n), np.uint64)
     stat = np.zeros((ticks, n), np.uint8)
     excluded = np.full(n, -1, np.int32)
     d1 = 0
     for t in range(ticks):
         mv = O.rng_moves(rng_seed, 0, n, t, n_actions)
-        R.env_step_batch(S, status, mv, pre)
+        # the restatement runs the same tick first: it detects defect D5 (the reference would hang)
+        O.env_step_batch(shadow, shadow_status, mv, fo)
+        R.env_step_batch(S, status, mv, pre, ((fo & 0x20) != 0).astype(np.uint8))
         d1 += int(((pre & 7) > 0).sum())
         newly = ((status & 0x10) != 0) & (excluded < 0)
         excluded[newly] = t

@@ -71,6 +71,37 @@ def test_golden_traces(orc, name):
     assert orc.diff_batch(S, final, (excluded >= 0).astype(np.uint8))[0] == -1
 
 
+def test_defect_d5_unbounded_chain_reversion_is_fenced(orc):
+    """Found by this project's differential runs: AgentBombChainReversion (step_utility.cpp:89-92) recurses
+    forever when the chain reaches an agent whose move is BOMB/IDLE.  Agent 2 plants into a ring slot whose
+    stale direction bits say UP, agent 1 kicks a stacked bomb and is bounced back onto the cell
+    that stale bomb "moves" to.  The compiled reference hangs (-O3) / overflows its stack (-O0) on this state
+    (verified in a forked child in the build container); the restatement flags it and freezes the env."""
+    s = np.load(os.path.join(GOLD, "d5_state.npy")).view(oracle.STATE_DT).copy()
+    mv = np.array([0, 1, 5, 3], np.uint8)
+    st = np.zeros(1, np.uint8)
+    fl = np.zeros(1, np.uint8)
+    orc.env_step_batch(s, st, mv.reshape(1, 4), fl)
+    assert fl[0] & 0x20 and st[0] & 0x10
+    before = s.copy()
+    orc.env_step_batch(s, st, mv.reshape(1, 4), fl)      # frozen from now on
+    assert orc.diff_batch(s, before)[0] == -1 and fl[0] == 0
+
+
+def test_defect_d5_hangs_the_compiled_reference(ref):
+    import signal
+    s = np.load(os.path.join(GOLD, "d5_state.npy")).view(oracle.STATE_DT).copy()
+    mv = np.array([0, 1, 5, 3], np.uint8)
+    assert ref.precheck(s, mv) == 0                      # not predictable by the cheap pre-check
+    pid = os.fork()
+    if pid == 0:
+        signal.alarm(2)
+        ref.step(s, mv)
+        os._exit(0)
+    _, rc = os.waitpid(pid, 0)
+    assert rc != 0, "the reference returned from a tick this project believes to be unbounded"
+
+
 def test_rng_moves_range(orc):
     m6 = orc.rng_moves(7, 0, 4096, 3, 6)
     m5 = orc.rng_moves(7, 0, 4096, 3, 5)
@@ -98,11 +129,13 @@ def _differential(orc, ref, n, ticks, nact, stress, seed):
     sa = np.zeros(n, np.uint8)
     sb = np.zeros(n, np.uint8)
     pre = np.zeros(n, np.uint8)
+    fo = np.zeros(n, np.uint8)
     steps = 0
     for t in range(ticks):
         mv = orc.rng_moves(seed, 0, n, t, nact)
-        ref.env_step_batch(A, sa, mv, pre)
-        orc.env_step_batch(B, sb, mv)
+        orc.env_step_batch(B, sb, mv, fo)
+        # D5 (the reference hangs) can only be detected by running the tick: exclude those envs for the reference
+        ref.env_step_batch(A, sa, mv, pre, ((fo & 0x20) != 0).astype(np.uint8))
         skip = ((sa & 0x10) != 0).astype(np.uint8)
         e, why = orc.diff_batch(A, B, skip)
         assert e == -1, "tick %d env %d field group %d" % (t, e, why)
