@@ -15,7 +15,10 @@
  *   D1  step.cpp:39-46 walks roots[]/moves[]/agents[]/dependency[] at index -1 when an
  *       agent is unreachable in the dependency walk -> moves are passed inside a padded
  *       buffer holding Move::IDLE at [-1]; ref_precheck() reports how many agents are
- *       unreachable (>=2 makes the reference read a stack word: oracle output advisory).
+ *       unreachable.  One unreachable agent: every build gives the canonical result ("it does
+ *       not move").  Two (three agents converge on one occupied cell): the walk continues with
+ *       i = dependency[-1], a stack word -> undefined (observed: -O0 segfaults, -O3 returns a
+ *       non-canonical board); such ticks are excluded from the parity domain.
  *   D3  step.cpp:167 dereferences GetBomb()==nullptr when a kicker walks onto a BOMB cell
  *       that has no queue entry -> ref_precheck() flags the tick, the caller skips the env.
  *   D4  step.cpp:191 Position bombDestinations[20] overflows when bombs.count > 20.
@@ -246,6 +249,19 @@ REF_API int ref_precheck(const void* st, const uint8_t* mv)
 static inline int FenceTick(State& s, const uint8_t* mv)
 {
     int planters = 0;
+    for(int j = 0; j < 4; j++)
+    {
+        /* three live agents heading for one occupied cell => two unreachable agents in the walk (D1, UB) */
+        if(s.agents[j].dead) continue;
+        int incoming = 0;
+        for(int i = 0; i < 4; i++)
+        {
+            if(i == j || s.agents[i].dead) continue;
+            bboard::Position d = bboard::util::DesiredPosition(s.agents[i].x, s.agents[i].y, Move(int(mv[i])));
+            if(d.x == s.agents[j].x && d.y == s.agents[j].y) incoming++;
+        }
+        if(incoming >= 3) return 1;
+    }
     for(int a = 0; a < 4; a++)
     {
         const bboard::AgentInfo& ag = s.agents[a];
@@ -346,7 +362,9 @@ REF_API void ref_env_step_batch(void* states, uint8_t* status, long n, const uin
         if(pre) pre[e] = uint8_t(f);
         /* D5 (unbounded AgentBombChainReversion) cannot be predicted without running the tick: the
          * harness passes exclude[e] != 0 for envs on which the restatement detected it this tick */
-        if((f & 0xF0) || (exclude && exclude[e])) { status[e] |= 0x10; continue; }
+        /* two or more unreachable agents (D1): the reference then INDEXES moves[]/agents[] with a stack word
+         * (observed: -O0 segfaults, -O3 returns a non-canonical result) — outside the parity domain */
+        if((f & 0xF0) || (f & 7) >= 2 || (exclude && exclude[e])) { status[e] |= 0x10; continue; }
         EnvStep(&S[e], &status[e], moves + 4 * e);
     }
 }

@@ -160,3 +160,18 @@ def test_differential_harmless(orc, ref):
 
 def test_differential_stress(orc, ref):
     assert _differential(orc, ref, 2048, 200, 6, 1, 1003) > 300000
+
+
+def test_defect_d1_three_on_one_is_canonical_and_fenced(orc, ref):
+    """Three agents converge on one occupied cell: two agents are unreachable in the dependency walk and the
+    reference continues with i = dependency[-1] (a stack word; -O0 segfaults, -O3 returns a non-canonical board).
+    The restatement's canonical result: unreachable agents do not move.  ref_precheck reports 2."""
+    s = orc.zero_state()
+    for i, (x, y) in enumerate([(1, 1), (0, 1), (3, 1), (2, 1)]):
+        orc.put_agent(s, x, y, i)
+    mv = [4, 4, 3, 0]                       # a0 -> a3's cell, a1 -> a0's cell, a2 -> a3's cell, a3 idle
+    assert ref.precheck(s, mv) & 7 == 2
+    f = orc.step(s, mv)
+    assert f & 1
+    for i, (x, y) in enumerate([(1, 1), (0, 1), (3, 1), (2, 1)]):
+        scenarios.require_agent(s, i, x, y)
