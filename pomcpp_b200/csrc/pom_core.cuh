@@ -60,7 +60,15 @@ POM_HD uint32_t with_byte(uint32_t w, int i, uint32_t v)
     const int s = 8 * i;
     return (w & ~(0xFFu << s)) | ((v & 0xFFu) << s);
 }
-POM_HD uint32_t ring20(uint32_t a) { return a % 20u; }
+/* (index + i) % 20 for the FixedQueue rings; the common operands are < 40 */
+POM_HD uint32_t ring20(uint32_t a) { return a < 20u ? a : (a < 40u ? a - 20u : a % 20u); }
+POM_HD uint32_t ring_next(uint32_t slot) { return slot == 19u ? 0u : slot + 1u; }
+/* byte-wise equality of the four bytes of w with the byte v: 0x80 in every byte that matches */
+POM_HD uint32_t bytes_equal(uint32_t w, uint32_t v)
+{
+    const uint32_t x = w ^ (v * 0x01010101u);
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
 
 POM_HD uint32_t& bomb_slot(uint8_t* r, uint32_t slot) { return reinterpret_cast<uint32_t*>(r + R_BOMBS)[slot]; }
 POM_HD uint32_t& bomb_at(uint8_t* r, uint32_t logical) { return bomb_slot(r, ring20(r[R_BINDEX] + logical)); }
@@ -388,14 +396,20 @@ POM_HD void resolve_bomb_collision(uint8_t* r, Agents& A, uint32_t moves, const 
     }
 }
 
+/* Per-tick scratch shared by the movement phase. */
+struct TickCtx {
+    uint32_t onBomb;        /* 0x80 in byte a: a bomb queue entry sits on agent a's cell (State::HasBomb of the
+                               agent's start-of-tick cell; kept exact when bombs are planted this tick)            */
+};
+
 /* leave the cell an agent stood on: BOMB if a queue entry sits there, else PASSAGE (step.cpp:89-96,127-134) */
-POM_HD void vacate(uint8_t* r, uint32_t p)
+POM_HD void vacate(uint8_t* r, uint32_t p, const TickCtx& T, int i)
 {
-    r[R_BOARD + cell_of(p)] = uint8_t(bomb_index(r, p) >= 0 ? C_BOMB : C_PASSAGE);
+    r[R_BOARD + cell_of(p)] = uint8_t(((T.onBomb >> (8 * i + 7)) & 1u) ? C_BOMB : C_PASSAGE);
 }
 
 /* body of the movement loop for agent i, step.cpp:46-184 */
-POM_HD void move_agent(uint8_t* r, Agents& A, uint32_t moves, const uint32_t* dq, bool ouroboros, int i, int& flags)
+POM_HD void move_agent(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, const uint32_t* dq, bool ouroboros, int i, int& flags)
 {
     const uint32_t m = byte_of(moves, i);
     if(ag_dead(A, i) || m == uint32_t(POM_MOVE_IDLE)) return;
@@ -414,6 +428,7 @@ POM_HD void move_agent(uint8_t* r, Agents& A, uint32_t moves, const uint32_t* dq
         b = (b & ~0xF0000u) + (uint32_t(POM_BOMB_LIFETIME + 1) << 16);
         A.bcnt = with_byte(A.bcnt, i, byte_of(A.bcnt, i) + 1u);
         r[R_BCOUNT] = uint8_t(cnt + 1u);
+        T.onBomb |= bytes_equal(A.pos, p);
         return;
     }
     const uint32_t d = dq[i];
@@ -426,7 +441,7 @@ POM_HD void move_agent(uint8_t* r, Agents& A, uint32_t moves, const uint32_t* dq
     if(c_is_flame(item))                                             /* :84-99 */
     {
         ag_kill(A, i);
-        if(*ocell == uint32_t(C_AGENT0 + i)) vacate(r, p);
+        if(*ocell == uint32_t(C_AGENT0 + i)) vacate(r, p, T, i);
         return;
     }
     for(int k = 0; k < 4; k++)                                       /* HasDPCollision, step_utility.cpp:264-277 */
@@ -442,13 +457,13 @@ POM_HD void move_agent(uint8_t* r, Agents& A, uint32_t moves, const uint32_t* dq
     }
     if(item == uint32_t(C_PASSAGE) || (ouroboros && c_is_agent(item)))   /* :120-140 */
     {
-        if(*ocell == uint32_t(C_AGENT0 + i)) vacate(r, p);
+        if(*ocell == uint32_t(C_AGENT0 + i)) vacate(r, p, T, i);
         *dcell = uint8_t(C_AGENT0 + i);
         A.pos = with_byte(A.pos, i, dp);
     }
     else if(item == uint32_t(C_BOMB))                                /* :147-184: kick, or step onto the bomb (Q2) */
     {
-        vacate(r, p);
+        vacate(r, p, T, i);
         *dcell = uint8_t(C_AGENT0 + i);
         A.pos = with_byte(A.pos, i, dp);
         if(byte_of(A.flg, i) & AF_CANKICK)
@@ -478,6 +493,163 @@ POM_HD void store_agents(uint8_t* r, const Agents& A)
     r[R_ALIVE] = uint8_t(A.alive);
 }
 
+/* util::AgentBombChainReversion when EVERY bomb is idle (direction 0): destBombs[k] is then bomb k's own
+ * cell, the bomb branch (step_utility.cpp:94-106) only re-writes the agent's cell, and the chain reduces to
+ * walking agents back along their moves. */
+POM_HD void revert_chain_idle(uint8_t* r, Agents& A, uint32_t moves, int agentID, int& flags)
+{
+    for(int guard = 0; guard < 64; guard++)
+    {
+        const uint32_t ap = byte_of(A.pos, agentID);
+        const uint32_t oq = uint32_t(int(ap + 0x11u) - move_delta(byte_of(moves, agentID)));
+        if(oob_biased(oq)) return;
+        const uint32_t origin = oq - 0x11u;
+        const int indexOriginAgent = get_agent(A, origin);
+        A.pos = with_byte(A.pos, agentID, origin);
+        r[R_BOARD + cell_of(origin)] = uint8_t(C_AGENT0 + agentID);
+        if(indexOriginAgent == agentID) { flags |= F_LOOP_GUARD; return; }    /* D5 */
+        if(indexOriginAgent == -1) return;
+        agentID = indexOriginAgent;
+    }
+    flags |= F_LOOP_GUARD;
+}
+
+/* The bomb phase of Step (step.cpp:187-278) in its general form: some bomb has a direction. */
+POM_HD void bomb_phase_general(uint8_t* r, Agents& A, uint32_t moves, uint32_t oldPos, int bc, int& flags)
+{
+    if(bc > 20) flags |= F_D4_BOMB_OVF;
+    uint8_t bd[20];
+    for(int k = 0; k < bc && k < 20; k++) bd[k] = uint8_t(bomb_dest_biased(bomb_at(r, k)));   /* FillBombDestPos :191-192 */
+
+    for(int k = 0; k < bc; k++)                                      /* :195-227 */
+    {
+        uint32_t& b = bomb_at(r, k);
+        const uint32_t bp = b & 0xFFu;
+        const uint32_t t = bomb_dest_biased(b);
+        bool blocked = oob_biased(t);
+        if(!blocked)
+        {
+            const uint32_t c = r[R_BOARD + cell_of(t - 0x11u)];
+            blocked = c_is_static(c) || c_is_agent(c);
+        }
+        if(blocked)
+        {
+            b = b & ~0xF00000u;
+            const int a = get_agent(A, bp);
+            if(a >= 0)
+            {
+                const uint32_t m = byte_of(moves, a);
+                if(m != uint32_t(POM_MOVE_IDLE) && m != uint32_t(POM_MOVE_BOMB) &&
+                        byte_of(A.pos, a) != byte_of(oldPos, a))
+                {
+                    revert_chain(r, A, moves, bd, a, flags);
+                    if(get_agent(A, bp) == -1) r[R_BOARD + cell_of(bp)] = uint8_t(C_BOMB);
+                }
+            }
+        }
+    }
+
+    for(int k = 0; k < int(r[R_BCOUNT]); k++)                        /* :230-278; the ring may shrink inside (Q7) */
+    {
+        uint32_t& b = bomb_at(r, k);
+        if(((b >> 20) & 15u) == 0u && has_bomb_collision(r, b, k))
+        {
+            resolve_bomb_collision(r, A, moves, bd, k, flags);
+            continue;
+        }
+        const uint32_t bp = b & 0xFFu;
+        const uint32_t t = bomb_dest_biased(b);
+        bool free_target = !oob_biased(t);
+        uint8_t* tcell = r;
+        if(free_target)
+        {
+            tcell = r + R_BOARD + cell_of(t - 0x11u);
+            free_target = !c_is_static(*tcell);
+        }
+        if(free_target)
+        {
+            if(has_bomb_collision(r, b, k))
+            {
+                resolve_bomb_collision(r, A, moves, bd, k, flags);
+                continue;
+            }
+            const uint32_t tp = t - 0x11u;
+            b = (b & ~0xFFu) + tp;                                   /* SetBombPosition */
+            uint8_t* ocell = r + R_BOARD + cell_of(bp);
+            if(*ocell == uint32_t(C_BOMB) && bomb_index(r, bp) < 0) *ocell = uint8_t(C_PASSAGE);
+            const uint32_t ti = *tcell;
+            if(c_is_walkable(ti)) *tcell = uint8_t(C_BOMB);
+            else if(c_is_flame(ti))
+            {
+                const int idx = bomb_index(r, tp);                   /* ExplodeBombAt(GetBombIndex(target)) :271 */
+                const uint32_t eb = bomb_at(r, idx);
+                explode(r, A, tp, byte_of(A.astr, int((eb >> 8) & 3u)), uint32_t(idx), flags);
+            }
+        }
+        else
+        {
+            b = b & ~0xF00000u;
+        }
+    }
+}
+
+/* The same phase when every bomb is idle (the common tick).  With all directions 0 the reference's loops
+ * reduce to: (pre-pass, :195-227) bounce back agents that walked onto a bomb this tick; (move loop, :230-278)
+ * a bomb whose cell reads PASSAGE is re-stamped BOMB, a bomb whose cell reads FLAMES explodes — unless a
+ * later ring entry with a different value sits on the same cell (HasBombCollision -> `continue`, Q13). */
+POM_HD void bomb_phase_idle(uint8_t* r, Agents& A, uint32_t moves, uint32_t oldPos, int bc, bool anyAgentMoved, int& flags)
+{
+    const uint32_t bi = r[R_BINDEX];
+    if(anyAgentMoved)   /* only an agent that moved this tick can be bounced back (step.cpp:209-214) */
+    {
+        uint32_t slot = bi;
+        for(int k = 0; k < bc; k++, slot = ring_next(slot))
+        {
+            const uint32_t bp = bomb_slot(r, slot) & 0xFFu;
+            const uint32_t c = r[R_BOARD + cell_of(bp)];
+            if(c_is_agent(c) || c_is_static(c))
+            {
+                const int a = get_agent(A, bp);
+                if(a >= 0)
+                {
+                    const uint32_t m = byte_of(moves, a);
+                    if(m != uint32_t(POM_MOVE_IDLE) && m != uint32_t(POM_MOVE_BOMB) &&
+                            byte_of(A.pos, a) != byte_of(oldPos, a))
+                    {
+                        revert_chain_idle(r, A, moves, a, flags);
+                        if(get_agent(A, bp) == -1) r[R_BOARD + cell_of(bp)] = uint8_t(C_BOMB);
+                    }
+                }
+            }
+        }
+    }
+    for(int k = 0; k < int(r[R_BCOUNT]); k++)
+    {
+        const uint32_t b = bomb_at(r, k);
+        const uint32_t bp = b & 0xFFu;
+        uint8_t* cell = r + R_BOARD + cell_of(bp);
+        const uint32_t c = *cell;
+        if(c == uint32_t(C_PASSAGE) || c_is_flame(c))
+        {
+            bool collides = false;
+            const int n = r[R_BCOUNT];
+            for(int i = k + 1; i < n; i++)
+            {
+                const uint32_t o = bomb_at(r, i);
+                if(o != b && (o & 0xFFu) == bp) { collides = true; break; }
+            }
+            if(collides) continue;
+            if(c == uint32_t(C_PASSAGE)) *cell = uint8_t(C_BOMB);
+            else
+            {
+                const int idx = bomb_index(r, bp);
+                const uint32_t eb = bomb_at(r, idx);
+                explode(r, A, bp, byte_of(A.astr, int((eb >> 8) & 3u)), uint32_t(idx), flags);
+            }
+        }
+    }
+}
+
 /* bboard::Step, step.cpp:9-284.  `moves`: byte a = Move of agent a.  Returns F_* flags. */
 POM_HD int step(uint8_t* r, uint32_t moves)
 {
@@ -493,6 +665,15 @@ POM_HD int step(uint8_t* r, uint32_t moves)
     load_agents(r, A);
     const uint32_t oldPos = A.pos;                                   /* FillPositions :24 */
     const uint32_t posq = A.pos + 0x11111111u;
+
+    /* which agents stand on a bomb queue entry (State::HasBomb of their cell, used when they leave it) */
+    TickCtx T;
+    T.onBomb = 0u;
+    {
+        const int bc0 = r[R_BCOUNT];
+        uint32_t slot = r[R_BINDEX];
+        for(int k = 0; k < bc0; k++, slot = ring_next(slot)) T.onBomb |= bytes_equal(A.pos, bomb_slot(r, slot) & 0xFFu);
+    }
 
     uint32_t dq[4];
     for(int a = 0; a < 4; a++)                                       /* FillDestPos :25 */
@@ -543,7 +724,7 @@ POM_HD int step(uint8_t* r, uint32_t moves)
                 if(rootIdx > 3 || byte_of(roots, rootIdx) == 0xFFu) { flags |= F_D1_UNREACHABLE; break; }
                 i = byte_of(roots, rootIdx);
             }
-            move_agent(r, A, moves, dq, ouroboros, int(i), flags);
+            move_agent(r, A, T, moves, dq, ouroboros, int(i), flags);
             i = byte_of(dep, int(i));
         }
     }
@@ -551,98 +732,35 @@ POM_HD int step(uint8_t* r, uint32_t moves)
     int bc = r[R_BCOUNT];
     if(bc > 0)
     {
-        if(bc > 20) flags |= F_D4_BOMB_OVF;
-        uint8_t bd[20];
-        for(int k = 0; k < bc; k++)
+        /* ResetBombFlags :188 + does any bomb have a direction? */
+        uint32_t anyDir = 0u;
         {
-            uint32_t& b = bomb_at(r, k);
-            b = b & ~0xF000000u;                                     /* ResetBombFlags :188 */
-            if(k < 20) bd[k] = uint8_t(bomb_dest_biased(b));         /* FillBombDestPos :191-192 */
-        }
-
-        for(int k = 0; k < bc; k++)                                  /* :195-227 */
-        {
-            uint32_t& b = bomb_at(r, k);
-            const uint32_t bp = b & 0xFFu;
-            const uint32_t t = bomb_dest_biased(b);
-            bool blocked = oob_biased(t);
-            if(!blocked)
+            uint32_t slot = r[R_BINDEX];
+            for(int k = 0; k < bc; k++, slot = ring_next(slot))
             {
-                const uint32_t c = r[R_BOARD + cell_of(t - 0x11u)];
-                blocked = c_is_static(c) || c_is_agent(c);
-            }
-            if(blocked)
-            {
-                b = b & ~0xF00000u;
-                const int a = get_agent(A, bp);
-                if(a >= 0)
-                {
-                    const uint32_t m = byte_of(moves, a);
-                    if(m != uint32_t(POM_MOVE_IDLE) && m != uint32_t(POM_MOVE_BOMB) &&
-                            byte_of(A.pos, a) != byte_of(oldPos, a))
-                    {
-                        revert_chain(r, A, moves, bd, a, flags);
-                        if(get_agent(A, bp) == -1) r[R_BOARD + cell_of(bp)] = uint8_t(C_BOMB);
-                    }
-                }
+                const uint32_t b = bomb_slot(r, slot);
+                if(b & 0xF000000u) bomb_slot(r, slot) = b & ~0xF000000u;
+                anyDir |= b & 0xF00000u;
             }
         }
-
-        for(int k = 0; k < int(r[R_BCOUNT]); k++)                    /* :230-278; the ring may shrink inside (Q7) */
-        {
-            uint32_t& b = bomb_at(r, k);
-            if(((b >> 20) & 15u) == 0u && has_bomb_collision(r, b, k))
-            {
-                resolve_bomb_collision(r, A, moves, bd, k, flags);
-                continue;
-            }
-            const uint32_t bp = b & 0xFFu;
-            const uint32_t t = bomb_dest_biased(b);
-            bool free_target = !oob_biased(t);
-            uint8_t* tcell = r;
-            if(free_target)
-            {
-                tcell = r + R_BOARD + cell_of(t - 0x11u);
-                free_target = !c_is_static(*tcell);
-            }
-            if(free_target)
-            {
-                if(has_bomb_collision(r, b, k))
-                {
-                    resolve_bomb_collision(r, A, moves, bd, k, flags);
-                    continue;
-                }
-                const uint32_t tp = t - 0x11u;
-                b = (b & ~0xFFu) + tp;                               /* SetBombPosition */
-                uint8_t* ocell = r + R_BOARD + cell_of(bp);
-                if(*ocell == uint32_t(C_BOMB) && bomb_index(r, bp) < 0) *ocell = uint8_t(C_PASSAGE);
-                const uint32_t ti = *tcell;
-                if(c_is_walkable(ti)) *tcell = uint8_t(C_BOMB);
-                else if(c_is_flame(ti))
-                {
-                    const int idx = bomb_index(r, tp);               /* ExplodeBombAt(GetBombIndex(target)) :271 */
-                    const uint32_t eb = bomb_at(r, idx);
-                    explode(r, A, tp, byte_of(A.astr, int((eb >> 8) & 3u)), uint32_t(idx), flags);
-                }
-            }
-            else
-            {
-                b = b & ~0xF00000u;
-            }
-        }
+        if(anyDir) bomb_phase_general(r, A, moves, oldPos, bc, flags);
+        else bomb_phase_idle(r, A, moves, oldPos, bc, A.pos != oldPos, flags);
 
         /* util::TickBombs :283, step_utility.cpp:224-245 */
         bc = r[R_BCOUNT];
-        for(int k = 0; k < bc; k++) bomb_at(r, k) -= (1u << 16);     /* ReduceBombTimer, bboard.hpp:308-311 */
+        {
+            uint32_t slot = r[R_BINDEX];
+            for(int k = 0; k < bc; k++, slot = ring_next(slot)) bomb_slot(r, slot) -= (1u << 16);   /* ReduceBombTimer, bboard.hpp:308-311 */
+        }
         for(int k = 0; k < bc && r[R_BCOUNT] > 0; k++)
         {
-            const uint32_t c = bomb_at(r, 0);
+            const uint32_t c = bomb_slot(r, r[R_BINDEX]);
             if(((c >> 16) & 15u) != 0u) break;
             /* ExplodeTopBomb bboard.cpp:191-196 (strength stored in the bomb), then PopBomb :93-97 */
             explode(r, A, c & 0xFFu, (c >> 12) & 15u, 31u, flags);
-            const int id = int((bomb_at(r, 0) >> 8) & 3u);
+            const int id = int((bomb_slot(r, r[R_BINDEX]) >> 8) & 3u);
             A.bcnt = with_byte(A.bcnt, id, byte_of(A.bcnt, id) - 1u);
-            r[R_BINDEX] = uint8_t(ring20(r[R_BINDEX] + 1u));
+            r[R_BINDEX] = uint8_t(ring_next(r[R_BINDEX]));
             r[R_BCOUNT] = uint8_t(r[R_BCOUNT] - 1);
         }
     }

@@ -115,27 +115,44 @@ __device__ __forceinline__ void account_episodes(unsigned long long* stats, bool
     for(uint32_t a = 0; a < 4; a++) warp_add(stats + ST_WIN0 + a, (won && w == a) ? 1u : 0u);
 }
 
-/* end-of-tick episode handling shared by K1 (auto-reset flag) and K2: truncate, count, reset */
-__device__ __forceinline__ void finish_and_reset(uint8_t* rec, const BatchParams& P, uint64_t env, bool active, bool do_reset)
+/* end-of-tick episode handling shared by K1 (auto-reset flag) and K2: truncate, count, reset.
+ * Must be called by all 32 lanes of a warp.  The reset is warp-cooperative: for every lane whose env
+ * finished, all 32 lanes copy that env's template record (73 words) into shared memory, instead of one
+ * lane running a 73-iteration loop while 31 lanes wait.  `tile` is the CTA's record tile. */
+__device__ __forceinline__ void finish_and_reset(uint8_t* tile, uint8_t* rec, const BatchParams& P, uint64_t env, bool active, bool do_reset)
 {
     uint32_t st = active ? rec[R_STATUS] : 0u;
     const uint32_t len = active ? *reinterpret_cast<const uint16_t*>(rec + R_TIME) : 0u;
     if(active && !(st & POM_STATUS_DONE) && P.max_ticks && len >= P.max_ticks) st |= POM_STATUS_TRUNCATED;
     const bool fin = active && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID)) != 0u;
+    uint32_t pending = __ballot_sync(0xFFFFFFFFu, fin);
+    if(pending == 0u) return;
     account_episodes(P.stats, fin, st, len);
-    if(fin && do_reset)
+    if(!do_reset)
+    {
+        if(fin) rec[R_STATUS] = uint8_t(st);
+        return;
+    }
+    uint32_t tmpl = 0u;
+    if(fin)
     {
         const uint32_t ep = ++P.episodes[env];
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(
-            P.templates + size_t((P.env_offset + env + ep) % P.n_templates) * POM_REC_BYTES);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(rec);
-#pragma unroll 1
-        for(int w = 0; w < POM_REC_WORDS; w++) dst[w] = __ldg(src + w);
+        tmpl = uint32_t((P.env_offset + env + ep) % P.n_templates);
     }
-    else if(fin)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp_first = threadIdx.x & ~31u;
+    while(pending)
     {
-        rec[R_STATUS] = uint8_t(st);
+        const uint32_t src_lane = uint32_t(__ffs(int(pending))) - 1u;
+        pending &= pending - 1u;
+        const uint32_t t = __shfl_sync(0xFFFFFFFFu, tmpl, int(src_lane));
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.templates) + size_t(t) * POM_REC_WORDS;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tile + size_t(warp_first + src_lane) * POM_REC_BYTES);
+        dst[lane] = __ldg(src + lane);
+        dst[lane + 32u] = __ldg(src + lane + 32u);
+        if(lane < uint32_t(POM_REC_WORDS - 64)) dst[lane + 64u] = __ldg(src + lane + 64u);
     }
+    __syncwarp();
 }
 
 /* ---------------------------------------------------------------- K1: per-tick kernel */
@@ -180,7 +197,7 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
         }
     }
     if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
-    if(flags & POM_STEP_AUTORESET) finish_and_reset(rec, P, env, active && stepped, true);
+    if(flags & POM_STEP_AUTORESET) finish_and_reset(smem, rec, P, env, active && stepped, true);
 
     fence_proxy_async();                                      /* generic-proxy writes -> visible to the bulk store */
     __syncthreads();
@@ -231,7 +248,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
             stepped = true;
             steps++;
         }
-        finish_and_reset(rec, P, env, active && stepped, !no_reset);
+        finish_and_reset(smem, rec, P, env, active && stepped, !no_reset);
     }
     warp_add(P.stats + ST_STEPS, steps);
 
