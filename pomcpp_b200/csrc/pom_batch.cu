@@ -47,7 +47,7 @@ struct pom_batch {
     uint64_t  env_offset = 0;
     uint32_t  n_templates = 0;
     uint32_t  max_ticks = 0;
-    int       tpb = 128;
+    int       tpb = 256;
     uint8_t*  recs = nullptr;
     uint8_t*  templates = nullptr;
     uint32_t* episodes = nullptr;
@@ -85,7 +85,7 @@ int use(const pom_batch* b)
 template<int TPB, typename K>
 int set_smem(K kernel)
 {
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TPB * POM_REC_BYTES + 16));
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pomk::TileScratch<TPB>::BYTES)));
     return POM_OK;
 }
 
@@ -173,7 +173,7 @@ int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
     static bool once = false;
     if(!once) { int rc = set_smem<TPB>(pomk::k_step<TPB>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
-    pomk::k_step<TPB><<<grid, TPB, TPB * POM_REC_BYTES + 16, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags);
+    pomk::k_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -185,7 +185,7 @@ int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, 
     static bool once = false;
     if(!once) { int rc = set_smem<TPB>(pomk::k_rollout<TPB>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
-    pomk::k_rollout<TPB><<<grid, TPB, TPB * POM_REC_BYTES + 16, b->stream>>>(
+    pomk::k_rollout<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(
         b->params(), ticks, seed, tick0, (flags & POM_ROLL_HARMLESS) ? 5u : 6u, (flags & POM_ROLL_NO_RESET) ? 1u : 0u);
     b->launches++;
     CK(cudaGetLastError());
@@ -198,7 +198,7 @@ int launch_expand(pom_batch* dst, const pom_batch* src, const uint32_t* idx_dev,
     static bool once = false;
     if(!once) { int rc = set_smem<TPB>(pomk::k_expand_step<TPB>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((n_children + TPB - 1) / TPB);
-    pomk::k_expand_step<TPB><<<grid, TPB, TPB * POM_REC_BYTES + 16, dst->stream>>>(dst->recs, src->recs, idx_dev, n_children, fanout, flags);
+    pomk::k_expand_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, dst->stream>>>(dst->recs, src->recs, idx_dev, n_children, fanout, flags);
     dst->launches++;
     CK(cudaGetLastError());
     return POM_OK;

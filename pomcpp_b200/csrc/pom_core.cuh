@@ -105,13 +105,20 @@ POM_HD void ag_kill(Agents& A, int i)                                 /* State::
     }
 }
 
+POM_HD int first_set_byte(uint32_t m)   /* index of the lowest byte of m that has a bit set, m != 0 */
+{
+#if defined(__CUDA_ARCH__)
+    return (__ffs(int(m)) - 1) >> 3;
+#else
+    return (__builtin_ffs(int(m)) - 1) >> 3;
+#endif
+}
+
 POM_HD int get_agent(const Agents& A, uint32_t p)                    /* State::GetAgent, bboard.cpp:289-299 */
 {
-    for(int i = 0; i < 4; i++)
-    {
-        if(!ag_dead(A, i) && byte_of(A.pos, i) == p) return i;
-    }
-    return -1;
+    /* first LIVE agent standing on p: byte-parallel compare, dead agents masked out (AF_DEAD = bit 1) */
+    const uint32_t eq = bytes_equal(A.pos, p) & ~(A.flg << 6);
+    return eq ? first_set_byte(eq) : -1;
 }
 
 POM_HD int bomb_index(uint8_t* r, uint32_t p)                        /* GetBombIndex / GetBomb / HasBomb, bboard.cpp:265-311 */
@@ -178,21 +185,35 @@ POM_HD void pop_flame(uint8_t* r)                                    /* State::P
     r[R_FCOUNT] = uint8_t(r[R_FCOUNT] - 1);
 }
 
-POM_HD void tick_flames(uint8_t* r)                                  /* util::TickFlames, step_utility.cpp:208-222 */
+/* util::TickFlames, step_utility.cpp:208-222, in two halves so that kernels can run the (rare, long) pops
+ * of a whole CTA tile with dense warps: flames_age() decrements every timer and says whether the front flame
+ * expired; flames_pop_due() is the loop `for i < flameCount: if flames[0].timeLeft == 0 PopFlame()`. */
+POM_HD bool flames_age(uint8_t* r)
 {
     const int n = r[R_FCOUNT];
-    if(n == 0) return;
-    const uint32_t fi = r[R_FINDEX];
-    for(int i = 0; i < n; i++)
+    if(n == 0) return false;
+    uint32_t slot = r[R_FINDEX];
+    for(int i = 0; i < n; i++, slot = ring_next(slot))
     {
-        uint8_t* t = r + R_FTIME + ring20(fi + i);
+        uint8_t* t = r + R_FTIME + slot;
         *t = uint8_t(*t - 1);
     }
+    return r[R_FTIME + r[R_FINDEX]] == 0;
+}
+
+POM_HD void flames_pop_due(uint8_t* r)
+{
+    const int n = r[R_FCOUNT];
     for(int i = 0; i < n; i++)
     {
         if(r[R_FTIME + r[R_FINDEX]] == 0) pop_flame(r);
         else break;   /* flames[0] unchanged => no later iteration can pop either */
     }
+}
+
+POM_HD void tick_flames(uint8_t* r)
+{
+    if(flames_age(r)) flames_pop_due(r);
 }
 
 /*
@@ -650,16 +671,19 @@ POM_HD void bomb_phase_idle(uint8_t* r, Agents& A, uint32_t moves, uint32_t oldP
     }
 }
 
-/* bboard::Step, step.cpp:9-284.  `moves`: byte a = Move of agent a.  Returns F_* flags. */
-POM_HD int step(uint8_t* r, uint32_t moves)
+/* bboard::Step, step.cpp:9-284, is split in four pieces so that the kernels can run the two rare, long,
+ * divergent pieces (flame pops at the start, timed-out bomb explosions at the end) for a whole CTA tile
+ * with dense warps:   flames_age -> [flames_pop_due] -> step_body -> [step_explode_due]
+ * step_body is everything between TickFlames and the explosion loop of TickBombs; it returns the F_* flags
+ * and sets `explode_due` when bombs[0] has timed out.  `moves`: byte a = Move of agent a. */
+POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due)
 {
     int flags = 0;
+    explode_due = false;
     for(int a = 0; a < 4; a++)
     {
         if(byte_of(moves, a) > 5u) { moves = with_byte(moves, a, 0u); flags |= F_BAD_MOVE; }
     }
-
-    tick_flames(r);                                                  /* :15 */
 
     Agents A;
     load_agents(r, A);
@@ -732,8 +756,12 @@ POM_HD int step(uint8_t* r, uint32_t moves)
     int bc = r[R_BCOUNT];
     if(bc > 0)
     {
-        /* ResetBombFlags :188 + does any bomb have a direction? */
+        /* ResetBombFlags :188, fused with two questions that decide how much of :195-278 has to run:
+         * does any bomb have a direction, and (if none has) is there any bomb the idle-form loops would
+         * touch — one whose cell reads PASSAGE/FLAMES, or, when an agent moved this tick, AGENT/static. */
         uint32_t anyDir = 0u;
+        bool idleWork = false;
+        const bool anyAgentMoved = A.pos != oldPos;
         {
             uint32_t slot = r[R_BINDEX];
             for(int k = 0; k < bc; k++, slot = ring_next(slot))
@@ -741,10 +769,13 @@ POM_HD int step(uint8_t* r, uint32_t moves)
                 const uint32_t b = bomb_slot(r, slot);
                 if(b & 0xF000000u) bomb_slot(r, slot) = b & ~0xF000000u;
                 anyDir |= b & 0xF00000u;
+                const uint32_t c = r[R_BOARD + cell_of(b & 0xFFu)];
+                idleWork = idleWork || c == uint32_t(C_PASSAGE) || c_is_flame(c) ||
+                           (anyAgentMoved && (c_is_agent(c) || c_is_static(c)));
             }
         }
         if(anyDir) bomb_phase_general(r, A, moves, oldPos, bc, flags);
-        else bomb_phase_idle(r, A, moves, oldPos, bc, A.pos != oldPos, flags);
+        else if(idleWork) bomb_phase_idle(r, A, moves, oldPos, bc, anyAgentMoved, flags);
 
         /* util::TickBombs :283, step_utility.cpp:224-245 */
         bc = r[R_BCOUNT];
@@ -752,30 +783,49 @@ POM_HD int step(uint8_t* r, uint32_t moves)
             uint32_t slot = r[R_BINDEX];
             for(int k = 0; k < bc; k++, slot = ring_next(slot)) bomb_slot(r, slot) -= (1u << 16);   /* ReduceBombTimer, bboard.hpp:308-311 */
         }
-        for(int k = 0; k < bc && r[R_BCOUNT] > 0; k++)
-        {
-            const uint32_t c = bomb_slot(r, r[R_BINDEX]);
-            if(((c >> 16) & 15u) != 0u) break;
-            /* ExplodeTopBomb bboard.cpp:191-196 (strength stored in the bomb), then PopBomb :93-97 */
-            explode(r, A, c & 0xFFu, (c >> 12) & 15u, 31u, flags);
-            const int id = int((bomb_slot(r, r[R_BINDEX]) >> 8) & 3u);
-            A.bcnt = with_byte(A.bcnt, id, byte_of(A.bcnt, id) - 1u);
-            r[R_BINDEX] = uint8_t(ring_next(r[R_BINDEX]));
-            r[R_BCOUNT] = uint8_t(r[R_BCOUNT] - 1);
-        }
+        explode_due = bc > 0 && ((bomb_slot(r, r[R_BINDEX]) >> 16) & 15u) == 0u;
     }
 
     store_agents(r, A);
     return flags;
 }
 
-/* Environment::Step on the record (environment.cpp:125-128,149-168): skip finished envs, Step,
- * timeStep++, winner / draw.  Returns F_* flags (0 for a skipped env). */
-POM_HD int env_step(uint8_t* r, uint32_t moves)
+/* the explosion loop of util::TickBombs (step_utility.cpp:231-244): while bombs[0] has timed out,
+ * ExplodeTopBomb (bboard.cpp:191-196, strength stored in the bomb) and PopBomb (:93-97). */
+POM_HD int step_explode_due(uint8_t* r)
+{
+    int flags = 0;
+    Agents A;
+    load_agents(r, A);
+    const int bc = r[R_BCOUNT];
+    for(int k = 0; k < bc && r[R_BCOUNT] > 0; k++)
+    {
+        const uint32_t c = bomb_slot(r, r[R_BINDEX]);
+        if(((c >> 16) & 15u) != 0u) break;
+        explode(r, A, c & 0xFFu, (c >> 12) & 15u, 31u, flags);
+        const int id = int((bomb_slot(r, r[R_BINDEX]) >> 8) & 3u);
+        A.bcnt = with_byte(A.bcnt, id, byte_of(A.bcnt, id) - 1u);
+        r[R_BINDEX] = uint8_t(ring_next(r[R_BINDEX]));
+        r[R_BCOUNT] = uint8_t(r[R_BCOUNT] - 1);
+    }
+    store_agents(r, A);
+    return flags;
+}
+
+/* bboard::Step, step.cpp:9-284 */
+POM_HD int step(uint8_t* r, uint32_t moves)
+{
+    tick_flames(r);                                                  /* :15 */
+    bool due;
+    int flags = step_body(r, moves, due);
+    if(due) flags |= step_explode_due(r);
+    return flags;
+}
+
+/* Environment::Step's bookkeeping after bboard::Step (environment.cpp:150-168) */
+POM_HD void env_post(uint8_t* r)
 {
     uint32_t st = r[R_STATUS];
-    if(st & (POM_STATUS_DONE | POM_STATUS_INVALID)) return 0;        /* invalid envs freeze: the reference would have crashed */
-    const int flags = step(r, moves);
     uint16_t* ts = reinterpret_cast<uint16_t*>(r + R_TIME);
     *ts = uint16_t(*ts + 1);
     const int alive = int(int8_t(r[R_ALIVE]));
@@ -789,8 +839,17 @@ POM_HD int env_step(uint8_t* r, uint32_t moves)
         st = (st & POM_STATUS_INVALID) | POM_STATUS_DONE | (w << POM_STATUS_WINNER_SHIFT);
     }
     if(alive == 0) st = (st & POM_STATUS_INVALID) | POM_STATUS_DONE | POM_STATUS_DRAW;
-    if(flags & F_INVALID_MASK) st |= POM_STATUS_INVALID;
     r[R_STATUS] = uint8_t(st);
+}
+
+/* Environment::Step on the record (environment.cpp:125-128,149-168): skip finished envs, Step,
+ * timeStep++, winner / draw.  Returns F_* flags (0 for a skipped env). */
+POM_HD int env_step(uint8_t* r, uint32_t moves)
+{
+    if(r[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_INVALID)) return 0;   /* invalid envs freeze: the reference would have crashed */
+    const int flags = step(r, moves);
+    if(flags & F_INVALID_MASK) r[R_STATUS] |= POM_STATUS_INVALID;
+    env_post(r);
     return flags;
 }
 

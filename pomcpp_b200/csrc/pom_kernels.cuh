@@ -155,12 +155,88 @@ __device__ __forceinline__ void finish_and_reset(uint8_t* tile, uint8_t* rec, co
     __syncwarp();
 }
 
+/* ---------------------------------------------------------------- one tick of a CTA tile
+ * Per-CTA scratch behind the record tile: mbarrier, two counters and two index lists (one byte per env).
+ * SMEM_EXTRA bytes are added to the dynamic shared memory of every tile kernel. */
+template<int TPB> struct TileScratch {
+    static constexpr uint32_t OFF_BAR = TPB * POM_REC_BYTES;          /* 8-byte mbarrier           */
+    static constexpr uint32_t OFF_CNT = OFF_BAR + 16;                 /* uint32 cnt[2]             */
+    static constexpr uint32_t OFF_LIST0 = OFF_CNT + 16;               /* uint8 list[TPB]: flame pops */
+    static constexpr uint32_t OFF_LIST1 = OFF_LIST0 + TPB;            /* uint8 list[TPB]: explosions */
+    static constexpr uint32_t BYTES = OFF_LIST1 + TPB;
+};
+
+/* append this thread's env to a CTA-level list (warp-aggregated: one shared-memory atomic per warp) */
+__device__ __forceinline__ void list_push(bool want, uint32_t* cnt, uint8_t* list)
+{
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+    if(m == 0u) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0u;
+    if(lane == 0u) base = atomicAdd(cnt, uint32_t(__popc(m)));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if(want) list[base + uint32_t(__popc(m & ((1u << lane) - 1u)))] = uint8_t(threadIdx.x);
+}
+
+/*
+ * One tick for the whole tile; must be called by all TPB threads (it synchronises the CTA).
+ * Thread t owns env t for the always-executed part of the tick (pom_core.cuh step_body).  The two rare,
+ * long and divergent pieces — PopFlame at the start and the timed-out-bomb explosions of TickBombs at the
+ * end — are collected into CTA-level lists and executed by the first threads of the CTA on ANY env of the
+ * tile (records are in shared memory, so every thread reaches every record): a warp that would have run
+ * `explode` with 2-3 active lanes runs it with up to 32.
+ *   step   : this thread's env takes part in the tick
+ *   raw    : bare bboard::Step (no Environment bookkeeping)
+ */
+template<int TPB>
+__device__ __forceinline__ void tile_tick(uint8_t* smem, uint8_t* rec, uint32_t m, bool step, bool raw)
+{
+    typedef TileScratch<TPB> TS;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + TS::OFF_CNT);
+    uint8_t* list_pop = smem + TS::OFF_LIST0;
+    uint8_t* list_exp = smem + TS::OFF_LIST1;
+    if(threadIdx.x < 2) cnt[threadIdx.x] = 0u;
+    __syncthreads();
+
+    /* TickFlames: age every flame, defer the pops */
+    const bool pop_due = step && pomcore::flames_age(rec);
+    list_push(pop_due, cnt + 0, list_pop);
+    __syncthreads();
+    {
+        const uint32_t n = cnt[0];
+        for(uint32_t e = threadIdx.x; e < n; e += TPB) pomcore::flames_pop_due(smem + uint32_t(list_pop[e]) * POM_REC_BYTES);
+        if(n) __syncthreads();      /* n is CTA-uniform */
+    }
+
+    /* movement, bomb movement, timers; defer the timed-out explosions */
+    bool exp_due = false;
+    if(step)
+    {
+        const int f = pomcore::step_body(rec, m, exp_due);
+        if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+    }
+    list_push(exp_due, cnt + 1, list_exp);
+    __syncthreads();
+    {
+        const uint32_t n = cnt[1];
+        for(uint32_t e = threadIdx.x; e < n; e += TPB)
+        {
+            uint8_t* r2 = smem + uint32_t(list_exp[e]) * POM_REC_BYTES;
+            const int f = pomcore::step_explode_due(r2);
+            if(f & pomcore::F_INVALID_MASK) r2[R_STATUS] |= POM_STATUS_INVALID;
+        }
+        if(n) __syncthreads();
+    }
+
+    if(step && !raw) pomcore::env_post(rec);
+}
+
 /* ---------------------------------------------------------------- K1: per-tick kernel */
 template<int TPB>
 __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __restrict__ moves, uint32_t flags)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TPB * POM_REC_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR);
     constexpr uint32_t TILE_BYTES = TPB * POM_REC_BYTES;
     uint8_t* gtile = P.recs + size_t(blockIdx.x) * TILE_BYTES;
 
@@ -178,24 +254,10 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
     mbar_wait(bar, 0);
 
     uint8_t* rec = smem + threadIdx.x * POM_REC_BYTES;
-    bool stepped = false;
-    if(active)
-    {
-        if(flags & POM_STEP_RAW)
-        {
-            if(!(rec[R_STATUS] & POM_STATUS_INVALID))
-            {
-                const int f = pomcore::step(rec, m);
-                if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
-                stepped = true;
-            }
-        }
-        else
-        {
-            stepped = !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_INVALID));
-            pomcore::env_step(rec, m);
-        }
-    }
+    const bool raw = (flags & POM_STEP_RAW) != 0u;
+    /* finished envs are skipped (environment.cpp:125) unless raw; invalid envs always freeze */
+    const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
+    tile_tick<TPB>(smem, rec, m, stepped, raw);
     if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
     if(flags & POM_STEP_AUTORESET) finish_and_reset(smem, rec, P, env, active && stepped, true);
 
@@ -214,7 +276,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
                                                 uint32_t n_actions, uint32_t no_reset)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TPB * POM_REC_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR);
     constexpr uint32_t TILE_BYTES = TPB * POM_REC_BYTES;
     uint8_t* gtile = P.recs + size_t(blockIdx.x) * TILE_BYTES;
 
@@ -236,18 +298,17 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
     uint32_t steps = 0;
     for(uint32_t k = 0; k < ticks; k++)
     {
-        bool stepped = false;
-        if(active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID)))
+        const bool stepped = active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID));
+        uint32_t m = 0;
+        if(stepped)
         {
             const uint64_t h = pomcore::splitmix64(key + uint64_t(tick0 + k));
-            uint32_t m = 0;
 #pragma unroll
             for(int a = 0; a < 4; a++)
                 m |= (((uint32_t(h >> (16 * a)) & 0xFFFFu) * n_actions) >> 16) << (8 * a);
-            pomcore::env_step(rec, m);
-            stepped = true;
             steps++;
         }
+        tile_tick<TPB>(smem, rec, m, stepped, false);
         finish_and_reset(smem, rec, P, env, active && stepped, !no_reset);
     }
     warp_add(P.stats + ST_STEPS, steps);
@@ -310,6 +371,8 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
     const uint64_t c = uint64_t(blockIdx.x) * TPB + threadIdx.x;
     uint8_t* rec = smem + threadIdx.x * POM_REC_BYTES;
     uint32_t* rw = reinterpret_cast<uint32_t*>(rec);
+    uint32_t m = 0u;
+    bool stepped = false;
     if(c < n_children)
     {
         const uint64_t root = c / fanout;
@@ -317,21 +380,15 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
         const uint32_t* s = reinterpret_cast<const uint32_t*>(src + size_t(src_idx[root]) * POM_REC_BYTES);
 #pragma unroll 1
         for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = __ldg(s + w);
-        const uint32_t m = (j % 6u) | (((j / 6u) % 6u) << 8) | (((j / 36u) % 6u) << 16) | (((j / 216u) % 6u) << 24);
-        if(flags & POM_STEP_RAW)
-        {
-            if(!(rec[R_STATUS] & POM_STATUS_INVALID))
-            {
-                const int f = pomcore::step(rec, m);
-                if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
-            }
-        }
-        else pomcore::env_step(rec, m);
+        m = (j % 6u) | (((j / 6u) % 6u) << 8) | (((j / 36u) % 6u) << 16) | (((j / 216u) % 6u) << 24);
+        const bool raw = (flags & POM_STEP_RAW) != 0u;
+        stepped = !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
     }
     else
     {
         for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = 0u;
     }
+    tile_tick<TPB>(smem, rec, m, stepped, (flags & POM_STEP_RAW) != 0u);
     fence_proxy_async();
     __syncthreads();
     if(threadIdx.x == 0)
