@@ -48,6 +48,7 @@ struct pom_batch {
     uint32_t  n_templates = 0;
     uint32_t  max_ticks = 0;
     int       tpb = 256;
+    bool      defer = false;
     uint8_t*  recs = nullptr;
     uint8_t*  templates = nullptr;
     uint32_t* episodes = nullptr;
@@ -167,44 +168,59 @@ int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, c
     return POM_OK;
 }
 
-template<int TPB>
+template<int TPB, bool DEFER>
 int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
 {
     static bool once = false;
-    if(!once) { int rc = set_smem<TPB>(pomk::k_step<TPB>); if(rc) return rc; once = true; }
+    if(!once) { int rc = set_smem<TPB>(pomk::k_step<TPB, DEFER>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
-    pomk::k_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags);
+    pomk::k_step<TPB, DEFER><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
 }
 
-template<int TPB>
+template<int TPB, bool DEFER>
 int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, uint32_t flags)
 {
     static bool once = false;
-    if(!once) { int rc = set_smem<TPB>(pomk::k_rollout<TPB>); if(rc) return rc; once = true; }
+    if(!once) { int rc = set_smem<TPB>(pomk::k_rollout<TPB, DEFER>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
-    pomk::k_rollout<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(
+    pomk::k_rollout<TPB, DEFER><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(
         b->params(), ticks, seed, tick0, (flags & POM_ROLL_HARMLESS) ? 5u : 6u, (flags & POM_ROLL_NO_RESET) ? 1u : 0u);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
 }
 
-template<int TPB>
+template<int TPB, bool DEFER>
 int launch_expand(pom_batch* dst, const pom_batch* src, const uint32_t* idx_dev, uint64_t n_children, uint32_t fanout, uint32_t flags)
 {
     static bool once = false;
-    if(!once) { int rc = set_smem<TPB>(pomk::k_expand_step<TPB>); if(rc) return rc; once = true; }
+    if(!once) { int rc = set_smem<TPB>(pomk::k_expand_step<TPB, DEFER>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((n_children + TPB - 1) / TPB);
-    pomk::k_expand_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, dst->stream>>>(dst->recs, src->recs, idx_dev, n_children, fanout, flags);
+    pomk::k_expand_step<TPB, DEFER><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, dst->stream>>>(dst->recs, src->recs, idx_dev, n_children, fanout, flags);
     dst->launches++;
     CK(cudaGetLastError());
     return POM_OK;
 }
 
 }
+
+/* tile geometry: threads (= envs) per CTA and whether explosions are deferred to dense warps.
+ * Tunable through POM_TPB / POM_DEFER for experiments; the defaults are the measured best. */
+#define POM_DISPATCH(h, fn, ...) \
+    do { \
+        if((h)->defer) { \
+            if((h)->tpb == 64) return fn<64, true>(__VA_ARGS__); \
+            if((h)->tpb == 256) return fn<256, true>(__VA_ARGS__); \
+            return fn<128, true>(__VA_ARGS__); \
+        } \
+        if((h)->tpb == 32) return fn<32, false>(__VA_ARGS__); \
+        if((h)->tpb == 64) return fn<64, false>(__VA_ARGS__); \
+        if((h)->tpb == 256) return fn<256, false>(__VA_ARGS__); \
+        return fn<128, false>(__VA_ARGS__); \
+    } while(0)
 
 extern "C" {
 
@@ -237,8 +253,9 @@ int pom_batch_init(pom_batch** out, int device, uint64_t n_envs, const pom_init_
     if(const char* e = std::getenv("POM_TPB"))
     {
         const int t = std::atoi(e);
-        if(t == 64 || t == 128 || t == 256) b->tpb = t;
+        if(t == 32 || t == 64 || t == 128 || t == 256) b->tpb = t;
     }
+    if(const char* e = std::getenv("POM_DEFER")) b->defer = std::atoi(e) != 0 && b->tpb >= 64;
     int rc = POM_OK;
     do {
         if(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -364,9 +381,7 @@ int pom_batch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
 {
     int rc = use(b); if(rc) return rc;
     if(!moves_dev) return fail(POM_E_ARG, "pom_batch_step: null moves");
-    if(b->tpb == 64) return launch_step<64>(b, moves_dev, flags);
-    if(b->tpb == 256) return launch_step<256>(b, moves_dev, flags);
-    return launch_step<128>(b, moves_dev, flags);
+    POM_DISPATCH(b, launch_step, b, moves_dev, flags);
 }
 
 int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags)
@@ -390,9 +405,7 @@ int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status
 int pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t tick0, uint32_t flags)
 {
     int rc = use(b); if(rc) return rc;
-    if(b->tpb == 64) return launch_rollout<64>(b, ticks, rng_seed, tick0, flags);
-    if(b->tpb == 256) return launch_rollout<256>(b, ticks, rng_seed, tick0, flags);
-    return launch_rollout<128>(b, ticks, rng_seed, tick0, flags);
+    POM_DISPATCH(b, launch_rollout, b, ticks, rng_seed, tick0, flags);
 }
 
 int pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_dst)
@@ -441,9 +454,7 @@ int pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* 
     CK(cudaMalloc(&idx_dev, n_roots * sizeof(uint32_t)));
     CK(cudaMemcpyAsync(idx_dev, src_idx, n_roots * sizeof(uint32_t), cudaMemcpyHostToDevice, dst->stream));
     cudaStreamSynchronize(src->stream);
-    if(dst->tpb == 64) rc = launch_expand<64>(dst, src, idx_dev, n_children, fanout, flags);
-    else if(dst->tpb == 256) rc = launch_expand<256>(dst, src, idx_dev, n_children, fanout, flags);
-    else rc = launch_expand<128>(dst, src, idx_dev, n_children, fanout, flags);
+    rc = [&]() -> int { POM_DISPATCH(dst, launch_expand, dst, src, idx_dev, n_children, fanout, flags); }();
     cudaError_t ce = cudaStreamSynchronize(dst->stream);
     cudaFree(idx_dev);
     if(rc) return rc;

@@ -159,10 +159,9 @@ __device__ __forceinline__ void finish_and_reset(uint8_t* tile, uint8_t* rec, co
  * Per-CTA scratch behind the record tile: mbarrier, two counters and two index lists (one byte per env).
  * SMEM_EXTRA bytes are added to the dynamic shared memory of every tile kernel. */
 template<int TPB> struct TileScratch {
-    static constexpr uint32_t OFF_BAR = TPB * POM_REC_BYTES;          /* 8-byte mbarrier           */
-    static constexpr uint32_t OFF_CNT = OFF_BAR + 16;                 /* uint32 cnt[2]             */
-    static constexpr uint32_t OFF_LIST0 = OFF_CNT + 16;               /* uint8 list[TPB]: flame pops */
-    static constexpr uint32_t OFF_LIST1 = OFF_LIST0 + TPB;            /* uint8 list[TPB]: explosions */
+    static constexpr uint32_t OFF_BAR = TPB * POM_REC_BYTES;          /* one 8-byte mbarrier per warp */
+    static constexpr uint32_t OFF_CNT = OFF_BAR + 64;                 /* uint32 cnt[4] (3 used)    */
+    static constexpr uint32_t OFF_LIST1 = OFF_CNT + 16;               /* uint8 list[TPB]: explosions */
     static constexpr uint32_t BYTES = OFF_LIST1 + TPB;
 };
 
@@ -179,67 +178,107 @@ __device__ __forceinline__ void list_push(bool want, uint32_t* cnt, uint8_t* lis
 }
 
 /*
- * One tick for the whole tile; must be called by all TPB threads (it synchronises the CTA).
- * Thread t owns env t for the always-executed part of the tick (pom_core.cuh step_body).  The two rare,
- * long and divergent pieces — PopFlame at the start and the timed-out-bomb explosions of TickBombs at the
- * end — are collected into CTA-level lists and executed by the first threads of the CTA on ANY env of the
- * tile (records are in shared memory, so every thread reaches every record): a warp that would have run
- * `explode` with 2-3 active lanes runs it with up to 32.
+ * One tick for the whole tile; must be called by all TPB threads (it synchronises the CTA twice).
+ * Thread t owns env t for everything up to the bomb timers (pom_core.cuh step_body).  The rare, long and
+ * divergent tail of the tick — the timed-out-bomb explosions of TickBombs — is collected into a CTA-level
+ * list and executed by the first threads of the CTA on ANY env of the tile (records are in shared memory, so
+ * every thread reaches every record): a warp that would have run `explode` with 2-3 active lanes runs it with
+ * up to 32.  Environment::Step's bookkeeping follows on whichever thread finished the env's Step.
  *   step   : this thread's env takes part in the tick
  *   raw    : bare bboard::Step (no Environment bookkeeping)
+ *   phase  : tick number mod 3, selects the list counter.  cnt[] must be all zero before the first tick;
+ *            after the barrier of tick k thread 0 clears the counter of tick k+2, whose previous readers
+ *            (tick k-1) have all passed this barrier and whose next writers (tick k+2) are ordered behind
+ *            the barrier of tick k+1
  */
-template<int TPB>
-__device__ __forceinline__ void tile_tick(uint8_t* smem, uint8_t* rec, uint32_t m, bool step, bool raw)
+template<int TPB, bool DEFER>
+__device__ __forceinline__ void tile_tick(uint8_t* smem, uint8_t* rec, uint32_t m, bool step, bool raw, uint32_t phase)
 {
+    if(!DEFER)
+    {
+        /* every thread runs the whole tick of its own env; no CTA synchronisation */
+        if(step)
+        {
+            const int f = pomcore::step(rec, m);
+            if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+            if(!raw) pomcore::env_post(rec);
+        }
+        return;
+    }
     typedef TileScratch<TPB> TS;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + TS::OFF_CNT);
-    uint8_t* list_pop = smem + TS::OFF_LIST0;
     uint8_t* list_exp = smem + TS::OFF_LIST1;
-    if(threadIdx.x < 2) cnt[threadIdx.x] = 0u;
-    __syncthreads();
 
-    /* TickFlames: age every flame, defer the pops */
-    const bool pop_due = step && pomcore::flames_age(rec);
-    list_push(pop_due, cnt + 0, list_pop);
-    __syncthreads();
-    {
-        const uint32_t n = cnt[0];
-        for(uint32_t e = threadIdx.x; e < n; e += TPB) pomcore::flames_pop_due(smem + uint32_t(list_pop[e]) * POM_REC_BYTES);
-        if(n) __syncthreads();      /* n is CTA-uniform */
-    }
-
-    /* movement, bomb movement, timers; defer the timed-out explosions */
     bool exp_due = false;
     if(step)
     {
+        pomcore::tick_flames(rec);
         const int f = pomcore::step_body(rec, m, exp_due);
         if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+        if(!exp_due && !raw) pomcore::env_post(rec);
     }
-    list_push(exp_due, cnt + 1, list_exp);
+    list_push(exp_due, cnt + phase, list_exp);
     __syncthreads();
+    const uint32_t n = cnt[phase];
+    if(threadIdx.x == 0) cnt[phase >= 1u ? phase - 1u : 2u] = 0u;      /* (phase + 2) % 3 */
+    if(n == 0u) return;                      /* CTA-uniform */
+    for(uint32_t e = threadIdx.x; e < n; e += TPB)
     {
-        const uint32_t n = cnt[1];
-        for(uint32_t e = threadIdx.x; e < n; e += TPB)
-        {
-            uint8_t* r2 = smem + uint32_t(list_exp[e]) * POM_REC_BYTES;
-            const int f = pomcore::step_explode_due(r2);
-            if(f & pomcore::F_INVALID_MASK) r2[R_STATUS] |= POM_STATUS_INVALID;
-        }
-        if(n) __syncthreads();
+        uint8_t* r2 = smem + uint32_t(list_exp[e]) * POM_REC_BYTES;
+        const int f = pomcore::step_explode_due(r2);
+        if(f & pomcore::F_INVALID_MASK) r2[R_STATUS] |= POM_STATUS_INVALID;
+        if(!raw) pomcore::env_post(r2);
     }
-
-    if(step && !raw) pomcore::env_post(rec);
+    __syncthreads();
 }
 
 /* ---------------------------------------------------------------- K1: per-tick kernel */
-template<int TPB>
+template<int TPB, bool DEFER>
 __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __restrict__ moves, uint32_t flags)
 {
     extern __shared__ __align__(128) uint8_t smem[];
+    const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
+    const bool active = env < P.n_envs;
+    uint8_t* rec = smem + threadIdx.x * POM_REC_BYTES;
+    const bool raw = (flags & POM_STEP_RAW) != 0u;
+
+    if(!DEFER)
+    {
+        /* Warp-independent staging: every warp bulk-loads, steps and bulk-stores its own 32-record slice
+         * (9344 bytes) behind its own mbarrier.  No CTA-wide barrier: a warp whose 32 envs had a quiet tick
+         * does not wait for a warp that had to run a chain explosion. */
+        constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR) + warp;
+        uint8_t* sslice = smem + warp * SLICE_BYTES;
+        uint8_t* gslice = P.recs + (size_t(blockIdx.x) * TPB + warp * 32u) * POM_REC_BYTES;
+        if(lane == 0)
+        {
+            mbar_init(bar, 1);
+            fence_barrier_init();
+            mbar_expect_tx(bar, SLICE_BYTES);
+            bulk_g2s(sslice, gslice, SLICE_BYTES, bar);
+        }
+        const uint32_t m = active ? __ldg(moves + env) : 0u;     /* overlaps the bulk load */
+        __syncwarp();
+        mbar_wait(bar, 0);
+        const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
+        tile_tick<TPB, false>(smem, rec, m, stepped, raw, 0u);
+        if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
+        if(flags & POM_STEP_AUTORESET) finish_and_reset(smem, rec, P, env, active && stepped, true);
+        fence_proxy_async();                                      /* generic-proxy writes -> visible to the bulk store */
+        __syncwarp();
+        if(lane == 0)
+        {
+            bulk_s2g(gslice, sslice, SLICE_BYTES);
+            bulk_wait_read_all();                                 /* smem must stay valid until it has been read */
+        }
+        return;
+    }
+
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR);
     constexpr uint32_t TILE_BYTES = TPB * POM_REC_BYTES;
     uint8_t* gtile = P.recs + size_t(blockIdx.x) * TILE_BYTES;
-
     if(threadIdx.x == 0)
     {
         mbar_init(bar, 1);
@@ -247,17 +286,14 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
         mbar_expect_tx(bar, TILE_BYTES);
         bulk_g2s(smem, gtile, TILE_BYTES, bar);
     }
-    const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
-    const bool active = env < P.n_envs;
     const uint32_t m = active ? __ldg(moves + env) : 0u;     /* overlaps the bulk load */
-    __syncthreads();                                          /* barrier init visible to all waiters */
+    if(threadIdx.x < 4) reinterpret_cast<uint32_t*>(smem + TileScratch<TPB>::OFF_CNT)[threadIdx.x] = 0u;
+    __syncthreads();                                          /* barrier init + list counters visible to all */
     mbar_wait(bar, 0);
 
-    uint8_t* rec = smem + threadIdx.x * POM_REC_BYTES;
-    const bool raw = (flags & POM_STEP_RAW) != 0u;
     /* finished envs are skipped (environment.cpp:125) unless raw; invalid envs always freeze */
     const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
-    tile_tick<TPB>(smem, rec, m, stepped, raw);
+    tile_tick<TPB, true>(smem, rec, m, stepped, raw, 0u);
     if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
     if(flags & POM_STEP_AUTORESET) finish_and_reset(smem, rec, P, env, active && stepped, true);
 
@@ -271,7 +307,7 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
 }
 
 /* ---------------------------------------------------------------- K2: fused K-tick rollout */
-template<int TPB>
+template<int TPB, bool DEFER>
 __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, uint64_t seed, uint32_t tick0,
                                                 uint32_t n_actions, uint32_t no_reset)
 {
@@ -289,6 +325,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
     }
     const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
     const bool active = env < P.n_envs;
+    if(threadIdx.x < 4) reinterpret_cast<uint32_t*>(smem + TileScratch<TPB>::OFF_CNT)[threadIdx.x] = 0u;
     __syncthreads();
     mbar_wait(bar, 0);
 
@@ -308,7 +345,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
                 m |= (((uint32_t(h >> (16 * a)) & 0xFFFFu) * n_actions) >> 16) << (8 * a);
             steps++;
         }
-        tile_tick<TPB>(smem, rec, m, stepped, false);
+        tile_tick<TPB, DEFER>(smem, rec, m, stepped, false, k % 3u);
         finish_and_reset(smem, rec, P, env, active && stepped, !no_reset);
     }
     warp_add(P.stats + ST_STEPS, steps);
@@ -361,7 +398,7 @@ __global__ void k_fill_from_templates(BatchParams P)
 /* ---------------------------------------------------------------- K4: tree-search expansion */
 /* child c = root_i * fanout + j: copy the root's record into the tile, apply joint action j
  * (a_k = (j / 6^k) % 6), Step once, bulk-store the tile. */
-template<int TPB>
+template<int TPB, bool DEFER>
 __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
                                                     const uint32_t* __restrict__ src_idx, uint64_t n_children,
                                                     uint32_t fanout, uint32_t flags)
@@ -373,6 +410,8 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
     uint32_t* rw = reinterpret_cast<uint32_t*>(rec);
     uint32_t m = 0u;
     bool stepped = false;
+    if(threadIdx.x < 4) reinterpret_cast<uint32_t*>(smem + TileScratch<TPB>::OFF_CNT)[threadIdx.x] = 0u;
+    __syncthreads();
     if(c < n_children)
     {
         const uint64_t root = c / fanout;
@@ -388,7 +427,7 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
     {
         for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = 0u;
     }
-    tile_tick<TPB>(smem, rec, m, stepped, (flags & POM_STEP_RAW) != 0u);
+    tile_tick<TPB, DEFER>(smem, rec, m, stepped, (flags & POM_STEP_RAW) != 0u, 0u);
     fence_proxy_async();
     __syncthreads();
     if(threadIdx.x == 0)
