@@ -26,8 +26,10 @@
 
 #if defined(__CUDACC__)
 #define POM_HD __host__ __device__ inline
+#define POM_HD_COLD __host__ __device__ __noinline__   /* rare paths: one out-of-line copy keeps the hot code small */
 #else
 #define POM_HD inline
+#define POM_HD_COLD inline
 #endif
 
 namespace pomcore
@@ -430,7 +432,7 @@ POM_HD void vacate(uint8_t* r, uint32_t p, const TickCtx& T, int i)
 }
 
 /* body of the movement loop for agent i, step.cpp:46-184 */
-POM_HD void move_agent(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, const uint32_t* dq, bool ouroboros, int i, int& flags)
+POM_HD void move_agent(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, uint32_t dq, bool ouroboros, int i, int& flags)
 {
     const uint32_t m = byte_of(moves, i);
     if(ag_dead(A, i) || m == uint32_t(POM_MOVE_IDLE)) return;
@@ -452,7 +454,7 @@ POM_HD void move_agent(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, const 
         T.onBomb |= bytes_equal(A.pos, p);
         return;
     }
-    const uint32_t d = dq[i];
+    const uint32_t d = byte_of(dq, i);
     if(oob_biased(d)) return;                                        /* :63 */
     const uint32_t dp = d - 0x11u;
     uint8_t* dcell = r + R_BOARD + cell_of(dp);
@@ -467,7 +469,7 @@ POM_HD void move_agent(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, const 
     }
     for(int k = 0; k < 4; k++)                                       /* HasDPCollision, step_utility.cpp:264-277 */
     {
-        if(k != i && !ag_dead(A, k) && dq[k] == d) return;
+        if(k != i && !ag_dead(A, k) && byte_of(dq, k) == d) return;
     }
     if(c_is_powerup(item))                                           /* ConsumePowerup, step_utility.cpp:247-262 */
     {
@@ -535,9 +537,14 @@ POM_HD void revert_chain_idle(uint8_t* r, Agents& A, uint32_t moves, int agentID
     flags |= F_LOOP_GUARD;
 }
 
-/* The bomb phase of Step (step.cpp:187-278) in its general form: some bomb has a direction. */
-POM_HD void bomb_phase_general(uint8_t* r, Agents& A, uint32_t moves, uint32_t oldPos, int bc, int& flags)
+/* The bomb phase of Step (step.cpp:187-278) in its general form: some bomb has a direction.  Rare
+ * (needs a kick or a stale-direction plant), so it is kept out of line; the agents travel through the
+ * record instead of registers. */
+POM_HD_COLD int bomb_phase_general(uint8_t* r, uint32_t moves, uint32_t oldPos, int bc)
 {
+    int flags = 0;
+    Agents A;
+    load_agents(r, A);
     if(bc > 20) flags |= F_D4_BOMB_OVF;
     uint8_t bd[20];
     for(int k = 0; k < bc && k < 20; k++) bd[k] = uint8_t(bomb_dest_biased(bomb_at(r, k)));   /* FillBombDestPos :191-192 */
@@ -612,6 +619,20 @@ POM_HD void bomb_phase_general(uint8_t* r, Agents& A, uint32_t moves, uint32_t o
             b = b & ~0xF00000u;
         }
     }
+    store_agents(r, A);
+    return flags;
+}
+
+/* State::ExplodeBombAt(idx) (bboard.cpp:111-118) out of line, agents through the record */
+POM_HD_COLD int explode_bomb_at_cold(uint8_t* r, uint32_t p, int idx)
+{
+    int flags = 0;
+    Agents A;
+    load_agents(r, A);
+    const uint32_t eb = bomb_at(r, idx);
+    explode(r, A, p, byte_of(A.astr, int((eb >> 8) & 3u)), uint32_t(idx), flags);
+    store_agents(r, A);
+    return flags;
 }
 
 /* The same phase when every bomb is idle (the common tick).  With all directions 0 the reference's loops
@@ -663,9 +684,9 @@ POM_HD void bomb_phase_idle(uint8_t* r, Agents& A, uint32_t moves, uint32_t oldP
             if(c == uint32_t(C_PASSAGE)) *cell = uint8_t(C_BOMB);
             else
             {
-                const int idx = bomb_index(r, bp);
-                const uint32_t eb = bomb_at(r, idx);
-                explode(r, A, bp, byte_of(A.astr, int((eb >> 8) & 3u)), uint32_t(idx), flags);
+                store_agents(r, A);
+                flags |= explode_bomb_at_cold(r, bp, bomb_index(r, bp));
+                load_agents(r, A);
             }
         }
     }
@@ -699,17 +720,19 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due)
         for(int k = 0; k < bc0; k++, slot = ring_next(slot)) T.onBomb |= bytes_equal(A.pos, bomb_slot(r, slot) & 0xFFu);
     }
 
-    uint32_t dq[4];
+    /* destinations, one biased byte per agent (kept in a register: a dynamically indexed array would
+     * live in local memory) */
+    uint32_t dq = 0u;
     for(int a = 0; a < 4; a++)                                       /* FillDestPos :25 */
-        dq[a] = uint32_t(int(byte_of(posq, a)) + move_delta(byte_of(moves, a)));
+        dq |= (uint32_t(int(byte_of(posq, a)) + move_delta(byte_of(moves, a))) & 0xFFu) << (8 * a);
     for(int a = 0; a < 4; a++)                                       /* FixSwitchMove :26 (dead agents not skipped, Q1) */
     {
         for(int b = a + 1; b < 4; b++)
         {
-            if(dq[a] == byte_of(posq, b) && dq[b] == byte_of(posq, a))
+            if(byte_of(dq, a) == byte_of(posq, b) && byte_of(dq, b) == byte_of(posq, a))
             {
-                dq[a] = byte_of(posq, a);
-                dq[b] = byte_of(posq, b);
+                dq = with_byte(dq, a, byte_of(posq, a));
+                dq = with_byte(dq, b, byte_of(posq, b));
             }
         }
     }
@@ -724,7 +747,7 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due)
             for(int b = 0; b < 4; b++)
             {
                 if(b == a || ag_dead(A, b)) continue;
-                if(dq[a] == byte_of(posq, b))
+                if(byte_of(dq, a) == byte_of(posq, b))
                 {
                     dep = with_byte(dep, b, uint32_t(a));
                     isRoot = false;
@@ -774,7 +797,12 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due)
                            (anyAgentMoved && (c_is_agent(c) || c_is_static(c)));
             }
         }
-        if(anyDir) bomb_phase_general(r, A, moves, oldPos, bc, flags);
+        if(anyDir)
+        {
+            store_agents(r, A);
+            flags |= bomb_phase_general(r, moves, oldPos, bc);
+            load_agents(r, A);
+        }
         else if(idleWork) bomb_phase_idle(r, A, moves, oldPos, bc, anyAgentMoved, flags);
 
         /* util::TickBombs :283, step_utility.cpp:224-245 */
