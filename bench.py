@@ -185,9 +185,11 @@ def run_own(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import pomcpp_b200 as pb
+    from pomcpp_b200 import shard
     n = ENVS_PER_GPU
     K, W = args.steps, args.warmup
-    b = pb.Batch(n, device=local_rank, env_offset=rank * n, n_templates=N_TEMPLATES, max_ticks=800)
+    plan = shard.shard_plan(rank, world, n)
+    b = pb.Batch(n, device=local_rank, env_offset=plan["first"], n_templates=N_TEMPLATES, max_ticks=800)
     ring = min(MOVE_RING, K + W)
     moves_dev = b.alloc(4 * n * ring)
     for t in range(ring):
@@ -238,15 +240,10 @@ def run_own(args):
     barrier()
 
     # ---- aggregate over ranks
-    ms_max, e2e_max = ms, e2e_s
-    counters = b.stats().as_array()
-    if dist is not None:
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max, e2e_max = float(t[0]), float(t[1])
-        c = torch.from_numpy(counters).cuda()
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)          # the one collective: final NCCL reduce of episode counters
-        counters = c.cpu().numpy()
+    dev = "cuda" if dist is not None else "cpu"
+    ms_max, e2e_max = [float(v) for v in shard.max_over_ranks([ms, e2e_s], dist, dev)]
+    # the one collective of the run: final NCCL reduce of the episode counters
+    counters = shard.reduce_counters(b.stats().as_array(), dist, dev)
 
     if rank == 0:
         peak, peak_src = measured_peak()

@@ -115,8 +115,20 @@ int  pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, c
  * fanout <= 1296; dst needs n_roots * fanout envs.                                                  */
 int  pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_roots, uint32_t fanout, uint32_t flags);
 
-/* ---- State::SpawnFlame (bboard.cpp:198-263) on one env, used by fixtures ---- */
+/* ---- State primitives on ONE env, executed by the device code of the step path (fixtures, the
+ *      bboard::State host mirror).  a0..a2 depend on op:
+ *      POM_OP_SPAWN_FLAME  x, y, strength   State::SpawnFlame     (bboard.cpp:198-263)
+ *      POM_OP_EXPLODE_TOP  -                State::ExplodeTopBomb (bboard.cpp:191-196)
+ *      POM_OP_EXPLODE_AT   index            State::ExplodeBombAt  (bboard.cpp:111-118)
+ *      POM_OP_POP_FLAME    -                State::PopFlame       (bboard.cpp:148-180)          ---- */
+enum { POM_OP_SPAWN_FLAME = 0, POM_OP_EXPLODE_TOP = 1, POM_OP_EXPLODE_AT = 2, POM_OP_POP_FLAME = 3 };
+int  pom_batch_apply(pom_batch* b, uint64_t env, int op, int a0, int a1, int a2);
 int  pom_batch_spawn_flame(pom_batch* b, uint64_t env, int x, int y, int strength);
+
+/* InitBoardItems(state, seed) (bboard.cpp:346-382) for one seed, generated on `device`: fills board of a
+ * zero-initialised State (agents are NOT placed).  *dirty = 1 when the seed hits the reference's
+ * uninitialised read (the board is then whatever the draw sequence produced up to that point).          */
+int  pom_make_board(int device, int32_t seed, pom_state* out, int* dirty);
 
 /* ---- results ---- */
 int  pom_batch_status(pom_batch* b, uint64_t first, uint64_t count, uint8_t* status_host);

@@ -83,6 +83,8 @@ def lib():
         L.pom_batch_clone.argtypes = [vp, u64, vp, vp, u64]
         L.pom_batch_expand_step.argtypes = [vp, vp, vp, u64, u32, u32]
         L.pom_batch_spawn_flame.argtypes = [vp, u64, i32, i32, i32]
+        L.pom_batch_apply.argtypes = [vp, u64, i32, i32, i32, i32]
+        L.pom_make_board.argtypes = [i32, C.c_int32, vp, C.POINTER(C.c_int)]
         L.pom_batch_status.argtypes = [vp, u64, u64, vp]
         L.pom_batch_stats.argtypes = [vp, C.POINTER(Stats)]
         L.pom_batch_clear_stats.argtypes = [vp]
@@ -198,6 +200,9 @@ class Batch:
     def spawn_flame(self, env, x, y, strength):
         _ck(lib().pom_batch_spawn_flame(self.h, env, x, y, strength))
 
+    def apply(self, env, op, a0=0, a1=0, a2=0):
+        _ck(lib().pom_batch_apply(self.h, env, op, a0, a1, a2))
+
     def status(self, first=0, count=None):
         return self.download(first, count, with_states=False)[1]
 
@@ -229,6 +234,14 @@ class Batch:
     def launch_count(self): return int(lib().pom_batch_launch_count(self.h))
     def stats_device_ptr(self): return lib().pom_batch_stats_device_ptr(self.h)
     def stream(self): return lib().pom_batch_stream(self.h)
+
+
+def make_board(seed, device=0):
+    """InitBoardItems(state, seed) generated on the device; returns (state, dirty)."""
+    s = np.zeros(1, STATE_DT)
+    d = C.c_int(0)
+    _ck(lib().pom_make_board(device, seed, _p(s), C.byref(d)))
+    return s, d.value
 
 
 def pinned_array(shape, dtype):

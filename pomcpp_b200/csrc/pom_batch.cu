@@ -47,7 +47,7 @@ struct pom_batch {
     uint64_t  env_offset = 0;
     uint32_t  n_templates = 0;
     uint32_t  max_ticks = 0;
-    int       tpb = 256;
+    int       tpb = 128;
     bool      defer = false;
     uint8_t*  recs = nullptr;
     uint8_t*  templates = nullptr;
@@ -462,15 +462,46 @@ int pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* 
     return POM_OK;
 }
 
-int pom_batch_spawn_flame(pom_batch* b, uint64_t env, int x, int y, int strength)
+int pom_batch_apply(pom_batch* b, uint64_t env, int op, int a0, int a1, int a2)
 {
     int rc = use(b); if(rc) return rc;
-    if(env >= b->n_envs) return fail(POM_E_RANGE, "pom_batch_spawn_flame: env outside the batch");
-    if(x < 0 || x > 10 || y < 0 || y > 10 || strength < 0 || strength > 255) return fail(POM_E_ARG, "pom_batch_spawn_flame: bad argument");
-    pomk::k_spawn_flame<<<1, 1, 0, b->stream>>>(b->recs, env, uint32_t(x) | (uint32_t(y) << 4), uint32_t(strength));
+    if(env >= b->n_envs) return fail(POM_E_RANGE, "pom_batch_apply: env outside the batch");
+    if(op < POM_OP_SPAWN_FLAME || op > POM_OP_POP_FLAME) return fail(POM_E_ARG, "pom_batch_apply: unknown op");
+    if(op == POM_OP_SPAWN_FLAME && (a0 < 0 || a0 > 10 || a1 < 0 || a1 > 10 || a2 < 0 || a2 > 255))
+        return fail(POM_E_ARG, "pom_batch_apply: SpawnFlame needs 0 <= x,y <= 10 and 0 <= strength <= 255");
+    pomk::k_apply<<<1, 1, 0, b->stream>>>(b->recs, env, op, a0, a1, a2);
     b->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(b->stream));
+    return POM_OK;
+}
+
+int pom_batch_spawn_flame(pom_batch* b, uint64_t env, int x, int y, int strength)
+{
+    return pom_batch_apply(b, env, POM_OP_SPAWN_FLAME, x, y, strength);
+}
+
+int pom_make_board(int device, int32_t seed, pom_state* out, int* dirty)
+{
+    if(!out) return fail(POM_E_ARG, "pom_make_board: null output");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if(ce != cudaSuccess || ndev == 0) return fail(POM_E_CUDA, "no CUDA device: the step path has no CPU fallback", ce);
+    if(device < 0 || device >= ndev) return fail(POM_E_ARG, "pom_make_board: no such device");
+    CK(cudaSetDevice(device));
+    uint8_t* rec = nullptr; uint8_t* d = nullptr; pom_state* aos = nullptr; uint8_t* st = nullptr;
+    CK(cudaMalloc(&rec, POM_REC_BYTES));
+    CK(cudaMalloc(&d, 1));
+    CK(cudaMalloc(&aos, sizeof(pom_state)));
+    CK(cudaMalloc(&st, 1));
+    pomk::k_make_board<<<1, 1>>>(rec, d, seed);
+    pomk::k_unpack<<<1, 1>>>(rec, aos, st, 0, 1);
+    uint8_t hd = 0;
+    ce = cudaMemcpy(out, aos, sizeof(pom_state), cudaMemcpyDeviceToHost);
+    if(ce == cudaSuccess) ce = cudaMemcpy(&hd, d, 1, cudaMemcpyDeviceToHost);
+    cudaFree(rec); cudaFree(d); cudaFree(aos); cudaFree(st);
+    if(ce != cudaSuccess) return fail(POM_E_CUDA, "pom_make_board", ce);
+    if(dirty) *dirty = hd;
     return POM_OK;
 }
 

@@ -1091,7 +1091,8 @@ POM_HD int uniform_int(Mt64& g, int a, int b)
     return a + int(hi);
 }
 
-POM_HD int init_record(uint8_t* r, Mt64& g, int seed, int a0, int a1, int a2, int a3)
+/* zero-initialised State + InitBoardItems(seed); returns the D2 flag */
+POM_HD int init_board(uint8_t* r, Mt64& g, int seed)
 {
     for(int k = 0; k < POM_REC_BYTES; k++) r[k] = 0;
     for(int k = 0; k < 20; k++) r[R_FTIME + k] = uint8_t(POM_FLAME_LIFETIME);   /* Flame::timeLeft default, bboard.hpp:345 */
@@ -1121,6 +1122,12 @@ POM_HD int init_record(uint8_t* r, Mt64& g, int seed, int a0, int a1, int a2, in
         }
         if(float(total) >= float(count) / 2) break;
     }
+    return dirty;
+}
+
+/* State::PutAgentsInCorners, bboard.cpp:322-333 (relies on zeroed agent coordinates, as the reference does) */
+POM_HD void put_agents_in_corners(uint8_t* r, int a0, int a1, int a2, int a3)
+{
     r[R_BOARD + 0] = uint8_t(C_AGENT0 + a0);
     r[R_BOARD + 10] = uint8_t(C_AGENT0 + a1);
     r[R_BOARD + 120] = uint8_t(C_AGENT0 + a2);
@@ -1128,6 +1135,13 @@ POM_HD int init_record(uint8_t* r, Mt64& g, int seed, int a0, int a1, int a2, in
     r[R_APOS + a1] = uint8_t((r[R_APOS + a1] & 0xF0) | 10);
     r[R_APOS + a2] = uint8_t(10 | (10 << 4));
     r[R_APOS + a3] = uint8_t((r[R_APOS + a3] & 0x0F) | (10 << 4));
+}
+
+/* InitState (bboard.cpp:339-344) on a zero-initialised State */
+POM_HD int init_record(uint8_t* r, Mt64& g, int seed, int a0, int a1, int a2, int a3)
+{
+    const int dirty = init_board(r, g, seed);
+    put_agents_in_corners(r, a0, a1, a2, a3);
     return dirty;
 }
 

@@ -466,15 +466,39 @@ __global__ void k_generate_moves(uint32_t* moves, uint64_t n, uint64_t env_offse
     if(e < n) moves[e] = pomcore::rng_moves(seed, env_offset + e, tick, n_actions);
 }
 
-__global__ void k_spawn_flame(uint8_t* recs, uint64_t env, uint32_t p, uint32_t strength)
+__global__ void k_apply(uint8_t* recs, uint64_t env, int op, int a0, int a1, int a2)
 {
     uint8_t* rec = recs + env * POM_REC_BYTES;
     pomcore::Agents A;
     pomcore::load_agents(rec, A);
     int flags = 0;
-    pomcore::explode(rec, A, p, strength, 31u, flags);
+    if(op == POM_OP_SPAWN_FLAME) pomcore::explode(rec, A, uint32_t(a0) | (uint32_t(a1) << 4), uint32_t(a2), 31u, flags);
+    else if(op == POM_OP_EXPLODE_TOP && rec[R_BCOUNT] > 0)
+    {
+        const uint32_t c = pomcore::bomb_at(rec, 0);
+        pomcore::explode(rec, A, c & 0xFFu, (c >> 12) & 15u, 31u, flags);
+        const int id = int((pomcore::bomb_at(rec, 0) >> 8) & 3u);
+        A.bcnt = pomcore::with_byte(A.bcnt, id, pomcore::byte_of(A.bcnt, id) - 1u);
+        rec[R_BINDEX] = uint8_t(pomcore::ring_next(rec[R_BINDEX]));
+        rec[R_BCOUNT] = uint8_t(rec[R_BCOUNT] - 1);
+    }
+    else if(op == POM_OP_EXPLODE_AT && a0 >= 0 && a0 < int(rec[R_BCOUNT]))
+    {
+        const uint32_t eb = pomcore::bomb_at(rec, a0);
+        pomcore::explode(rec, A, eb & 0xFFu, pomcore::byte_of(A.astr, int((eb >> 8) & 3u)), uint32_t(a0), flags);
+    }
+    else if(op == POM_OP_POP_FLAME && rec[R_FCOUNT] > 0) pomcore::pop_flame(rec);
     pomcore::store_agents(rec, A);
     if(flags & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+}
+
+/* one seed -> zero-initialised State + InitBoardItems (no agents placed) */
+__global__ void k_make_board(uint8_t* out_rec, uint8_t* dirty, int seed)
+{
+    pomcore::Mt64 g;
+    uint8_t rec[POM_REC_BYTES];
+    dirty[0] = uint8_t(pomcore::init_board(rec, g, seed));
+    for(int k = 0; k < POM_REC_BYTES; k++) out_rec[k] = rec[k];
 }
 
 __global__ void k_fill_zero(uint4* p, uint64_t n16)

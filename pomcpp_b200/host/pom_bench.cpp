@@ -1,0 +1,159 @@
+/*
+ * pom_bench.cpp — the repo's own C++ host driver of the hot path (north star: "called from the repo's own
+ * C++ host code").  Single process, one host thread + one pom_batch handle + one stream per GPU; envs are
+ * sharded contiguously over the GPUs with no collective on the data path; the only collective is one
+ * ncclAllReduce of the episode counters after the run.
+ *
+ *   pom_bench [--gpus N] [--envs-per-gpu E] [--steps K] [--warmup W] [--mode step|rollout] [--ticks T]
+ *
+ * mode step    : K launches of the per-tick kernel (pom_batch_step, auto-reset), moves pre-generated on device
+ * mode rollout : K launches of the fused kernel (pom_batch_rollout), T ticks each, in-kernel RNG + auto-reset
+ * Prints one JSON line.  (The CPU reference baseline is reported by bench.py, which alone may load oracle/.)
+ */
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+#ifdef POM_WITH_NCCL
+#include <nccl.h>
+#endif
+
+#include "pom_batch.h"
+
+namespace
+{
+
+struct Args { int gpus = 1; uint64_t envs = 1u << 20; int steps = 200; int warmup = 10; std::string mode = "step"; uint32_t ticks = 800; };
+
+struct Shard { pom_batch* h = nullptr; void* moves = nullptr; float ms = 0.f; pom_stats stats; int rc = 0; std::string err; };
+
+void die(const char* what) { std::fprintf(stderr, "pom_bench: %s: %s\n", what, pom_last_error()); std::exit(2); }
+
+}
+
+int main(int argc, char** argv)
+{
+    Args a;
+    for(int i = 1; i < argc; i++)
+    {
+        std::string k = argv[i];
+        auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : "0"; };
+        if(k == "--gpus") a.gpus = std::atoi(next());
+        else if(k == "--envs-per-gpu") a.envs = std::strtoull(next(), nullptr, 10);
+        else if(k == "--steps") a.steps = std::atoi(next());
+        else if(k == "--warmup") a.warmup = std::atoi(next());
+        else if(k == "--mode") a.mode = next();
+        else if(k == "--ticks") a.ticks = uint32_t(std::atoi(next()));
+    }
+    if(a.gpus < 1 || a.gpus > pom_device_count()) { std::fprintf(stderr, "pom_bench: %d GPUs requested, %d present\n", a.gpus, pom_device_count()); return 2; }
+    const bool rollout = a.mode == "rollout";
+    const int ring = 64;
+    const uint64_t seed = 20240229;
+    std::vector<Shard> sh(size_t(a.gpus));
+
+    /* set-up: one handle per GPU, shard g owns global envs [g*E, (g+1)*E) */
+    for(int g = 0; g < a.gpus; g++)
+    {
+        pom_init_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.env_offset = uint64_t(g) * a.envs;
+        d.n_templates = 4096;
+        d.first_seed = 0x1337;
+        d.max_ticks = 800;
+        if(pom_batch_init(&sh[size_t(g)].h, g, a.envs, &d)) die("pom_batch_init");
+        if(!rollout)
+        {
+            if(pom_device_alloc(g, 4 * a.envs * ring, &sh[size_t(g)].moves)) die("pom_device_alloc");
+            for(int t = 0; t < ring; t++)
+                if(pom_batch_generate_moves(sh[size_t(g)].h, static_cast<uint8_t*>(sh[size_t(g)].moves) + 4 * a.envs * size_t(t), seed, 100000u + uint32_t(t), 6)) die("generate_moves");
+            if(pom_batch_rollout(sh[size_t(g)].h, 96, seed, 0, 0)) die("preroll");
+        }
+        if(pom_batch_sync(sh[size_t(g)].h)) die("sync");
+        pom_batch_clear_stats(sh[size_t(g)].h);
+    }
+
+    /* timed region: one host thread per GPU, CUDA events on each handle's stream */
+    auto work = [&](int g)
+    {
+        Shard& s = sh[size_t(g)];
+        auto one = [&](int k) -> int
+        {
+            if(rollout) return pom_batch_rollout(s.h, a.ticks, seed, uint32_t(k) * a.ticks, 0);
+            return pom_batch_step(s.h, static_cast<uint8_t*>(s.moves) + 4 * a.envs * size_t(k % ring), POM_STEP_AUTORESET | POM_STEP_COUNT);
+        };
+        for(int w = 0; w < a.warmup && !s.rc; w++) s.rc = one(w);
+        if(!s.rc) s.rc = pom_batch_sync(s.h);
+        if(!s.rc) s.rc = pom_batch_event_record(s.h, 0);
+        for(int k = 0; k < a.steps && !s.rc; k++) s.rc = one(a.warmup + k);
+        if(!s.rc) s.rc = pom_batch_event_record(s.h, 1);
+        if(!s.rc) s.rc = pom_batch_event_elapsed_ms(s.h, &s.ms);
+        if(s.rc) s.err = pom_last_error();
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for(int g = 0; g < a.gpus; g++) th.emplace_back(work, g);
+    for(auto& t : th) t.join();
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for(int g = 0; g < a.gpus; g++) if(sh[size_t(g)].rc) { std::fprintf(stderr, "pom_bench: GPU %d: %s\n", g, sh[size_t(g)].err.c_str()); return 2; }
+
+    /* the one collective: sum the episode counters over the GPUs */
+    unsigned long long total[POM_STATS_WORDS] = {0};
+    const char* reduced = "host sum";
+#ifdef POM_WITH_NCCL
+    if(a.gpus > 1)
+    {
+        std::vector<ncclComm_t> comms(size_t(a.gpus));
+        std::vector<int> devs(size_t(a.gpus));
+        for(int g = 0; g < a.gpus; g++) devs[size_t(g)] = g;
+        if(ncclCommInitAll(comms.data(), a.gpus, devs.data()) == ncclSuccess)
+        {
+            ncclGroupStart();
+            for(int g = 0; g < a.gpus; g++)
+            {
+                void* p = pom_batch_stats_device_ptr(sh[size_t(g)].h);
+                ncclAllReduce(p, p, POM_STATS_WORDS, ncclUint64, ncclSum, comms[size_t(g)], static_cast<cudaStream_t>(pom_batch_stream(sh[size_t(g)].h)));
+            }
+            ncclGroupEnd();
+            for(int g = 0; g < a.gpus; g++) pom_batch_sync(sh[size_t(g)].h);
+            pom_stats s;
+            pom_batch_stats(sh[0].h, &s);
+            std::memcpy(total, &s, sizeof(total));
+            for(auto c : comms) ncclCommDestroy(c);
+            reduced = "ncclAllReduce";
+        }
+    }
+#endif
+    if(std::strcmp(reduced, "host sum") == 0)
+    {
+        for(int g = 0; g < a.gpus; g++)
+        {
+            pom_stats s;
+            pom_batch_stats(sh[size_t(g)].h, &s);
+            const unsigned long long* w = reinterpret_cast<const unsigned long long*>(&s);
+            for(int i = 0; i < POM_STATS_WORDS; i++) total[i] += w[i];
+        }
+    }
+
+    float ms_max = 0.f;
+    for(int g = 0; g < a.gpus; g++) ms_max = sh[size_t(g)].ms > ms_max ? sh[size_t(g)].ms : ms_max;
+    const double env_steps_timed = double(a.gpus) * double(a.envs) * double(a.steps) * (rollout ? double(a.ticks) : 1.0);
+    const double value = env_steps_timed / (double(ms_max) * 1e-3);
+    std::printf("{\"metric\": \"env-steps/sec\", \"value\": %.6g, \"unit\": \"env-steps/s\", \"n_gpus\": %d, \"mode\": \"%s\", "
+                "\"envs_per_gpu\": %llu, \"steps\": %d, \"warmup\": %d, \"ticks_per_step\": %u, \"ms_per_step\": %.6g, \"wall_s\": %.4g, "
+                "\"hbm_gbs_algorithmic_per_gpu\": %.6g, \"episode_stats\": {\"env_steps\": %llu, \"episodes\": %llu, \"wins\": [%llu, %llu, %llu, %llu], "
+                "\"draws\": %llu, \"truncated\": %llu, \"sum_episode_len\": %llu, \"invalid\": %llu, \"reduced_with\": \"%s\"}}\n",
+                value, a.gpus, a.mode.c_str(), (unsigned long long)a.envs, a.steps, a.warmup, rollout ? a.ticks : 1u, double(ms_max) / a.steps, wall,
+                rollout ? 0.0 : 582.0 * double(a.envs) / (double(ms_max) / a.steps * 1e-3) / 1e9,
+                total[0], total[1], total[2], total[3], total[4], total[5], total[6], total[7], total[8], total[9], reduced);
+    for(int g = 0; g < a.gpus; g++)
+    {
+        if(sh[size_t(g)].moves) pom_device_free(g, sh[size_t(g)].moves);
+        pom_batch_destroy(sh[size_t(g)].h);
+    }
+    return 0;
+}

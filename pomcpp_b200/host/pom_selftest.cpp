@@ -1,0 +1,146 @@
+/*
+ * pom_selftest.cpp — known-answer checks written against the bboard mirror (include/pom_bboard.hpp) in the
+ * style of the reference's Catch2 suite (unit_test/bboard/board_logic.cpp, general_test.cpp): the fixtures
+ * and REQUIREs of a representative subset, with bboard::Step running on the GPU.  The complete scenario list
+ * runs from Python (tests/scenarios.py); this binary proves that code written against the reference header
+ * compiles and behaves the same when pointed at this library.  Exit code 0 = all passed.
+ */
+#include <cstdio>
+#include <memory>
+
+#include "bboard.hpp"
+#include "pom_agents.hpp"
+
+using namespace bboard;
+
+static int failures = 0;
+#define REQUIRE(cond) do { if(!(cond)) { std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond); failures++; } } while(0)
+
+static void REQUIRE_AGENT(State* s, int agent, int x, int y)          /* board_logic.cpp:11-17 */
+{
+    REQUIRE(s->agents[agent].x == x);
+    REQUIRE(s->agents[agent].y == y);
+    REQUIRE(s->board[y][x] == Item::AGENT0 + agent);
+}
+
+static void SeveralSteps(int times, State* s, Move* m) { for(int i = 0; i < times; i++) bboard::Step(s, m); }
+
+static void TestQueue(FixedQueue<Bomb, 10>& q)                        /* general_test.cpp:8-40 */
+{
+    for(int i = 0; i < 10; i++) { q.NextPos() = i; q.count++; }
+    REQUIRE(q.count == 10);
+    q.PopElem(); q.PopElem(); q.PopElem();
+    REQUIRE(q.count == 7); REQUIRE(q[0] == 3);
+    q.RemoveAt(5);
+    REQUIRE(q.count == 6); REQUIRE(q[4] == 7); REQUIRE(q[5] == 9);
+    q.RemoveAt(0);
+    REQUIRE(q[0] == 4);
+    q.RemoveAt(4);
+    REQUIRE(q.count == 4); REQUIRE(q[3] == 7);
+}
+
+int main()
+{
+    const Move id = Move::IDLE;
+    {   /* "Fixed Size Queue", general_test.cpp:41-61 */
+        for(int start : {0, 5, 2})
+        {
+            auto q = std::make_unique<FixedQueue<Bomb, 10>>();
+            q->index = start;
+            TestQueue(*q);
+        }
+    }
+    {   /* "Basic Non-Obstacle Movement", board_logic.cpp:55-83 */
+        auto s = std::make_unique<State>();
+        s->PutAgentsInCorners(0, 1, 2, 3);
+        Move m[4] = {id, id, id, id};
+        m[0] = Move::RIGHT; Step(s.get(), m); REQUIRE_AGENT(s.get(), 0, 1, 0);
+        m[0] = Move::DOWN;  Step(s.get(), m); REQUIRE_AGENT(s.get(), 0, 1, 1);
+        m[0] = Move::LEFT;  Step(s.get(), m); REQUIRE_AGENT(s.get(), 0, 0, 1);
+        m[0] = Move::UP;    Step(s.get(), m); REQUIRE_AGENT(s.get(), 0, 0, 0);
+        m[3] = Move::UP;    Step(s.get(), m); REQUIRE_AGENT(s.get(), 3, 0, 9);
+    }
+    {   /* "Movement Against Flames", :104-119 */
+        auto s = std::make_unique<State>();
+        Move m[4] = {id, id, id, id};
+        s->PutAgentsInCorners(0, 1, 2, 3);
+        s->SpawnFlame(1, 1, 2);
+        m[0] = Move::RIGHT;
+        Step(s.get(), m);
+        REQUIRE(s->agents[0].dead);
+        REQUIRE(s->board[0][0] == Item::PASSAGE);
+    }
+    {   /* "Movement Dependency Handling" / "Move Ouroboros", :221-238 */
+        auto s = std::make_unique<State>();
+        s->PutAgent(0, 0, 0); s->PutAgent(1, 0, 1); s->PutAgent(1, 1, 2); s->PutAgent(0, 1, 3);
+        Move m[4] = {Move::RIGHT, Move::DOWN, Move::LEFT, Move::UP};
+        Step(s.get(), m);
+        REQUIRE_AGENT(s.get(), 3, 0, 0); REQUIRE_AGENT(s.get(), 0, 1, 0);
+        REQUIRE_AGENT(s.get(), 1, 1, 1); REQUIRE_AGENT(s.get(), 2, 0, 1);
+    }
+    {   /* "Bomb Explosion" / "Destroy Objects and Agents", :331-345 */
+        auto s = std::make_unique<State>();
+        Move m[4] = {id, id, id, id};
+        s->Kill(2, 3);
+        s->PutAgent(5, 5, 0);
+        s->PutItem(6, 5, Item::WOOD);
+        s->PutAgent(4, 5, 1);
+        m[0] = Move::BOMB; Step(s.get(), m);
+        m[0] = Move::UP; SeveralSteps(BOMB_LIFETIME, s.get(), m);
+        REQUIRE(s->agents[1].dead);
+        REQUIRE(IS_FLAME(s->board[5][4]));
+        REQUIRE(IS_FLAME(s->board[5][6]));
+    }
+    {   /* "Chained Explosions" / "Two Bombs Covered By Agent", :450-469 */
+        auto s = std::make_unique<State>();
+        Move m[4] = {id, id, id, id};
+        s->PutAgent(5, 5, 0); s->PutAgent(4, 5, 1);
+        s->Kill(2, 3);
+        m[0] = Move::BOMB; Step(s.get(), m);
+        m[1] = Move::BOMB; Step(s.get(), m);
+        m[0] = m[1] = Move::DOWN;
+        SeveralSteps(BOMB_LIFETIME - 2, s.get(), m);
+        REQUIRE(s->bombs.count == 2);
+        Step(s.get(), m);
+        REQUIRE(s->bombs.count == 0);
+        REQUIRE(s->flames.count == 2);
+    }
+    {   /* "Bomb Kick Mechanics" / "Bounce Back Agent", :474-484, 549-562 */
+        auto s = std::make_unique<State>();
+        Move m[4] = {id, id, id, id};
+        s->PutAgent(0, 1, 0);
+        s->agents[0].canKick = true;
+        s->PlantBomb(1, 1, 0, true);
+        s->agents[0].maxBombCount = MAX_BOMBS_PER_AGENT;
+        m[0] = Move::RIGHT;
+        s->Kill(2, 3);
+        s->PutAgent(0, 2, 1);
+        m[1] = Move::UP;
+        s->PlantBomb(2, 2, 0, true);
+        SetBombDirection(s->bombs[1], Direction::UP);
+        Step(s.get(), m);
+        REQUIRE_AGENT(s.get(), 0, 0, 1); REQUIRE_AGENT(s.get(), 1, 0, 2);
+        REQUIRE(BMB_POS_X(s->bombs[0]) == 1); REQUIRE(BMB_POS_X(s->bombs[1]) == 2);
+    }
+    {   /* Environment + trivial agents: a game runs to its end on the GPU (environment.cpp:68-88) */
+        agents::RandomAgent r[4] = {agents::RandomAgent(1), agents::RandomAgent(2), agents::RandomAgent(3), agents::RandomAgent(4)};
+        Environment env;
+        env.MakeGame({&r[0], &r[1], &r[2], &r[3]});
+        env.StartGame(800, false);
+        REQUIRE(env.IsDone() || env.GetState().timeStep == 800);
+        REQUIRE(env.GetState().aliveAgents <= 1 || !env.IsDone());
+    }
+    {   /* BatchEnvironment: host agents on 512 games, then a fused rollout */
+        agents::HarmlessAgent h(7);
+        BatchEnvironment be(512, 0, 0, 64);
+        size_t running = 0;
+        for(int t = 0; t < 20; t++) running = be.Step({&h, &h, &h, &h});
+        REQUIRE(running == 512);                       /* harmless agents cannot end a game */
+        REQUIRE(be.States()[0].timeStep == 20);
+        pom_stats st = be.Rollout(200, 5);
+        REQUIRE(st.env_steps == 512ull * 200ull);
+        REQUIRE(st.episodes == st.wins[0] + st.wins[1] + st.wins[2] + st.wins[3] + st.draws + st.truncated + st.invalid);
+    }
+    std::printf(failures ? "pom_selftest: %d FAILED\n" : "pom_selftest: all passed\n", failures);
+    return failures ? 1 : 0;
+}

@@ -315,3 +315,46 @@ def test_config3_1M_envs_properties(pb, orc):
         assert orc.diff_batch(G, S)[0] == -1, "env %d" % e
     b.free(moves_dev)
     b.close()
+
+
+def test_cpp_host_layer_selftest(pb):
+    """The reference-style known-answer checks compiled against include/bboard.hpp (the drop-in mirror)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pb.LIB_PATH), "host", "pom_selftest")
+    assert os.path.exists(exe), "pomcpp_b200/host/pom_selftest not built"
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "all passed" in out.stdout
+
+
+def test_cpp_bench_driver_runs(pb):
+    import json
+    import subprocess
+    exe = os.path.join(os.path.dirname(pb.LIB_PATH), "host", "pom_bench")
+    out = subprocess.run([exe, "--gpus", "1", "--envs-per-gpu", "65536", "--steps", "20", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["episode_stats"]["env_steps"] == 65536 * 23 and d["value"] > 1e8
+
+
+def test_state_primitives_on_device(pb, orc):
+    """pom_batch_apply: ExplodeTopBomb / ExplodeBombAt / PopFlame vs the restatement's Step-internal behaviour."""
+    s = orc.zero_state()
+    orc.put_agents_in_corners(s)
+    orc.plant_bomb(s, 5, 5, 0, True)
+    orc.plant_bomb(s, 6, 5, 1, True)
+    b = pb.Batch(1, n_templates=1, empty=True)
+    b.upload(s)
+    b.apply(0, 2, 1)                       # ExplodeBombAt(1): chain-explodes bomb 0 as well
+    G, _ = b.download()
+    assert int(G["bombs_count"][0]) == 0 and int(G["flames_count"][0]) == 2
+    b.apply(0, 3)                          # PopFlame
+    G, _ = b.download()
+    assert int(G["flames_count"][0]) == 1
+    brd, dirty = pb.make_board(0x1337)
+    ref = orc.zero_state()
+    assert orc.init_board_items(ref, 0x1337) == 0 and dirty == 0
+    assert (brd["board"] == ref["board"]).all()
+    assert pb.make_board(0x13327)[1] == 1
+    b.close()
