@@ -174,7 +174,9 @@ int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
     static bool once = false;
     if(!once) { int rc = set_smem<TPB>(pomk::k_step<TPB, DEFER>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
-    pomk::k_step<TPB, DEFER><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags);
+    static int pad = -1;
+    if(pad < 0) { const char* e = std::getenv("POM_SMEM_PAD"); pad = e ? std::atoi(e) : 0; if(pad) cudaFuncSetAttribute(pomk::k_step<TPB, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pomk::TileScratch<TPB>::BYTES) + pad); }
+    pomk::k_step<TPB, DEFER><<<grid, TPB, pomk::TileScratch<TPB>::BYTES + pad, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;

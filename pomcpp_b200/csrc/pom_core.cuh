@@ -154,32 +154,31 @@ POM_HD uint32_t flame_origin(const uint8_t* r, uint32_t c)
 
 POM_HD void pop_flame(uint8_t* r)                                    /* State::PopFlame, bboard.cpp:148-180 */
 {
+    /* The reference walks i = -s..s on both axes with bounds checks and clears every flame cell whose id is
+     * the popped flame's origin.  Same cell set here: the origin plus four clipped arms (no ray blocking).
+     * A cell written by this very flame carries its slot, so the origin look-up is only needed for cells of
+     * another flame (which may share the origin). */
     const uint32_t fi = r[R_FINDEX];
     const uint32_t p = r[R_FPOS + fi];
-    int s = r[R_FSTR + fi];
-    if(s > 10) s = 10;
-    const int x = int(p & 15u), y = int(p >> 4);
-    for(int i = -s; i <= s; i++)
+    const uint32_t s = r[R_FSTR + fi];
+    const uint32_t x = p & 15u, y = p >> 4;
+    const uint32_t own = uint32_t(C_FLAME) | (fi << 2);
+    const uint32_t c0 = x + 11u * y;
+    for(uint32_t d = 0; d < 4u; d++)
     {
-        const int cx = x + i, cy = y + i;
-        if(cx >= 0 && cx < 11)
+        const uint32_t room = d == 0u ? 10u - x : (d == 1u ? x : (d == 2u ? 10u - y : y));
+        const int stride = d == 0u ? 1 : (d == 1u ? -1 : (d == 2u ? 11 : -11));
+        uint32_t n = s < room ? s : room;
+        if(d == 0u) n++;                       /* arm 0 also covers the origin cell */
+        uint32_t ci = d == 0u ? uint32_t(int(c0) - stride) : c0;
+        for(; n > 0u; n--)
         {
-            uint8_t* cell = r + R_BOARD + cx + 11 * y;
-            const uint32_t c = *cell;
-            if(c_is_flame(c) && flame_origin(r, c) == p)
+            ci = uint32_t(int(ci) + stride);
+            const uint32_t c = r[R_BOARD + ci];
+            if(c_is_flame(c) && ((c & 0xFCu) == own || flame_origin(r, c) == p))
             {
                 const uint32_t pw = c & 3u;                          /* FlagItem, bboard.cpp:182-189 */
-                *cell = uint8_t(pw ? 8u + pw : 0u);
-            }
-        }
-        if(cy >= 0 && cy < 11)
-        {
-            uint8_t* cell = r + R_BOARD + x + 11 * cy;
-            const uint32_t c = *cell;
-            if(c_is_flame(c) && flame_origin(r, c) == p)
-            {
-                const uint32_t pw = c & 3u;
-                *cell = uint8_t(pw ? 8u + pw : 0u);
+                r[R_BOARD + ci] = uint8_t(pw ? 8u + pw : 0u);
             }
         }
     }
@@ -219,25 +218,26 @@ POM_HD void tick_flames(uint8_t* r)
 }
 
 /*
- * Explosion machine: State::SpawnFlame (bboard.cpp:198-263) with SpawnFlameItem (:24-57) and the
- * nested State::ExplodeBombAt (:111-118) it triggers, depth-first in the reference's order
- * (rays +x, -x, +y, -y).  A stacked frame is 16 bits: flame slot (5) | ray (2) | step (4) |
- * bomb index (5); the spawn's x, y and strength are read back from its flame-queue entry.
- *   j0 = logical index of the bomb being exploded by ExplodeBombAt (its epilogue, which re-reads
- *        bombs[j] AFTER the nested explosions — SURVEY Q6 — runs when the frame completes);
- *        31 = a bare SpawnFlame (ExplodeTopBomb and fixtures: the caller does the epilogue).
+ * Explosion machine: State::SpawnFlame (bboard.cpp:198-263) with SpawnFlameItem (:24-57) and the nested
+ * State::ExplodeBombAt (:111-118) it triggers, depth-first in the reference's order (rays +x, -x, +y, -y).
+ * One loop iteration handles one cell of one ray, so lanes that are in different rays, cells or nesting
+ * depths still execute the same instructions.  Per spawn ("frame") the live state is: flame slot, ray d,
+ * cells left in the ray, current cell index, and the logical index j of the bomb whose ExplodeBombAt opened
+ * the frame (31 = a bare SpawnFlame: ExplodeTopBomb and fixtures, the caller does the epilogue).  A parent
+ * frame is 32 bits on an explicit stack; the spawn's strength is read back from its flame-queue entry.
+ * ExplodeBombAt's epilogue re-reads bombs[j] AFTER the nested explosions.
  */
 POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint32_t j0, int& flags)
 {
-    enum { PH_START, PH_RAY, PH_POST };
-    uint16_t stack[24];
+    uint32_t stack[24];
     int sp = 0;
-    int phase = PH_START;
-    uint32_t slot = 0, d = 0, i = 1, j = j0;
+    uint32_t slot = 0, d = 0, rem = 0, ci = 0, j = j0;
+    int stride = 0;
     uint32_t p = p0, strength = strength0;
+    bool start = true;
     for(int guard = 0; guard < 8192; guard++)
     {
-        if(phase == PH_START)
+        if(start)
         {
             /* SpawnFlame prologue :200-218 */
             const uint32_t fc = r[R_FCOUNT];
@@ -247,74 +247,77 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
             r[R_FSTR + slot] = uint8_t(strength);
             r[R_FTIME + slot] = uint8_t(POM_FLAME_LIFETIME);
             r[R_FCOUNT] = uint8_t(fc + 1u);
-            uint8_t* cell = r + R_BOARD + cell_of(p);
-            if(c_is_agent(*cell)) ag_kill(A, int(*cell) - C_AGENT0);
-            *cell = uint8_t(C_FLAME | (slot << 2));
-            d = 0; i = 1;
-            phase = PH_RAY;
-            continue;
+            ci = uint32_t(cell_of(p));
+            const uint32_t c = r[R_BOARD + ci];
+            if(c_is_agent(c)) ag_kill(A, int(c) - C_AGENT0);
+            r[R_BOARD + ci] = uint8_t(C_FLAME | (slot << 2));
+            d = 0xFFFFFFFFu;            /* the ray set-up below advances to ray 0 */
+            rem = 0;
+            start = false;
         }
-        if(phase == PH_RAY && d == 4u)
+        if(rem == 0u)
         {
-            /* SpawnFlame returned */
-            if(j != 31u)
+            /* next ray of this spawn, or the spawn is complete */
+            d++;
+            if(d >= 4u)
             {
-                /* ExplodeBombAt epilogue :116-117 — bombs[j] re-read after the recursion */
-                const uint32_t b = bomb_at(r, j);
-                const int id = int((b >> 8) & 3u);
-                A.bcnt = with_byte(A.bcnt, id, byte_of(A.bcnt, id) - 1u);
-                bombs_remove_at(r, int(j));
-            }
-            if(sp == 0) return;
-            const uint32_t f = stack[--sp];
-            slot = f & 31u; d = (f >> 5) & 3u; i = (f >> 7) & 15u; j = (f >> 11) & 31u;
-            p = r[R_FPOS + slot]; strength = r[R_FSTR + slot];
-            phase = PH_POST;          /* resume the parent's SpawnFlameItem after ExplodeBombAt */
-            continue;
-        }
-        if(phase == PH_RAY && i > strength) { d++; i = 1; continue; }
-
-        /* cell (d, i) of the current spawn */
-        int cx = int(p & 15u), cy = int(p >> 4);
-        if(d == 0u) cx += int(i); else if(d == 1u) cx -= int(i); else if(d == 2u) cy += int(i); else cy -= int(i);
-        if(cx < 0 || cx > 10 || cy < 0 || cy > 10) { d++; i = 1; continue; }      /* ray bounds :223,234,245,256 */
-        uint8_t* cell = r + R_BOARD + cx + 11 * cy;
-
-        if(phase == PH_RAY)
-        {
-            /* SpawnFlameItem :26-40 */
-            const uint32_t c = *cell;
-            const bool isAgent = c_is_agent(c);
-            if(isAgent) ag_kill(A, int(c) - C_AGENT0);
-            if(c == uint32_t(C_BOMB) || isAgent)
-            {
-                const uint32_t cp = uint32_t(cx) | (uint32_t(cy) << 4);
-                const int jj = bomb_index(r, cp);
-                if(jj >= 0)
+                if(j != 31u)
                 {
-                    if(sp >= 24) { flags |= F_LOOP_GUARD; return; }
-                    stack[sp++] = uint16_t(slot | (d << 5) | (i << 7) | (j << 11));
-                    const uint32_t b = bomb_at(r, jj);
-                    p = cp;
-                    strength = byte_of(A.astr, int((b >> 8) & 3u));    /* owner's CURRENT strength (Q5) */
-                    j = uint32_t(jj);
-                    phase = PH_START;
-                    continue;
+                    /* ExplodeBombAt epilogue :116-117 */
+                    const uint32_t b = bomb_at(r, j);
+                    const int id = int((b >> 8) & 3u);
+                    A.bcnt = with_byte(A.bcnt, id, byte_of(A.bcnt, id) - 1u);
+                    bombs_remove_at(r, int(j));
                 }
+                if(sp == 0) return;
+                /* back in the parent's SpawnFlameItem, after its ExplodeBombAt call (:42-52): the cell now holds
+                 * the child's flame (not RIGID, not wood), so it takes the parent's signature and the ray goes on */
+                const uint32_t f = stack[--sp];
+                slot = f & 31u; d = (f >> 5) & 3u; rem = (f >> 7) & 15u; ci = (f >> 11) & 127u; j = (f >> 18) & 31u;
+                stride = d == 0u ? 1 : (d == 1u ? -1 : (d == 2u ? 11 : -11));
+                r[R_BOARD + ci] = uint8_t(C_FLAME | (slot << 2));
+                continue;
             }
+            const uint32_t po = r[R_FPOS + slot];
+            const uint32_t x = po & 15u, y = po >> 4;
+            const uint32_t room = d == 0u ? 10u - x : (d == 1u ? x : (d == 2u ? 10u - y : y));   /* ray bounds :223,234,245,256 */
+            const uint32_t s = r[R_FSTR + slot];
+            rem = s < room ? s : room;
+            stride = d == 0u ? 1 : (d == 1u ? -1 : (d == 2u ? 11 : -11));
+            ci = x + 11u * y;
+            continue;
         }
-        /* SpawnFlameItem :42-56 */
+        /* SpawnFlameItem on the next cell of the ray */
+        ci = uint32_t(int(ci) + stride);
+        rem--;
+        uint8_t* cell = r + R_BOARD + ci;
+        const uint32_t c = *cell;
+        if(c == uint32_t(C_RIGID)) { rem = 0; continue; }                 /* :53-56 */
+        if(c_is_wood(c))                                                  /* :45-51: only one wood per ray */
         {
-            const uint32_t c = *cell;
-            phase = PH_RAY;
-            if(c != uint32_t(C_RIGID))
-            {
-                const bool wasWood = c_is_wood(c);
-                *cell = uint8_t(C_FLAME | (slot << 2) | (wasWood ? ((c - 2u) & 3u) : 0u));
-                if(wasWood) { d++; i = 1; } else { i++; }
-            }
-            else { d++; i = 1; }
+            *cell = uint8_t(C_FLAME | (slot << 2) | ((c - 2u) & 3u));
+            rem = 0;
+            continue;
         }
+        const bool isAgent = c_is_agent(c);
+        if(isAgent || c == uint32_t(C_BOMB))                              /* :26-40 */
+        {
+            if(isAgent) ag_kill(A, int(c) - C_AGENT0);
+            const uint32_t cp = (ci % 11u) | ((ci / 11u) << 4);
+            const int jj = bomb_index(r, cp);
+            if(jj >= 0)
+            {
+                if(sp >= 24) { flags |= F_LOOP_GUARD; return; }
+                stack[sp++] = slot | (d << 5) | (rem << 7) | (ci << 11) | (j << 18);
+                const uint32_t b = bomb_at(r, jj);
+                p = cp;
+                strength = byte_of(A.astr, int((b >> 8) & 3u));           /* owner's CURRENT strength (Q5) */
+                j = uint32_t(jj);
+                start = true;
+                continue;
+            }
+        }
+        *cell = uint8_t(C_FLAME | (slot << 2));
     }
     flags |= F_LOOP_GUARD;
 }
