@@ -154,31 +154,33 @@ POM_HD uint32_t flame_origin(const uint8_t* r, uint32_t c)
 
 POM_HD void pop_flame(uint8_t* r)                                    /* State::PopFlame, bboard.cpp:148-180 */
 {
-    /* The reference walks i = -s..s on both axes with bounds checks and clears every flame cell whose id is
-     * the popped flame's origin.  Same cell set here: the origin plus four clipped arms (no ray blocking).
-     * A cell written by this very flame carries its slot, so the origin look-up is only needed for cells of
-     * another flame (which may share the origin). */
     const uint32_t fi = r[R_FINDEX];
     const uint32_t p = r[R_FPOS + fi];
-    const uint32_t s = r[R_FSTR + fi];
-    const uint32_t x = p & 15u, y = p >> 4;
-    const uint32_t own = uint32_t(C_FLAME) | (fi << 2);
-    const uint32_t c0 = x + 11u * y;
-    for(uint32_t d = 0; d < 4u; d++)
+    int s = r[R_FSTR + fi];
+    if(s > 10) s = 10;
+    const int x = int(p & 15u), y = int(p >> 4);
+    const uint32_t own = uint32_t(C_FLAME) | (fi << 2);   /* cells written by this very flame carry its slot */
+    for(int i = -s; i <= s; i++)
     {
-        const uint32_t room = d == 0u ? 10u - x : (d == 1u ? x : (d == 2u ? 10u - y : y));
-        const int stride = d == 0u ? 1 : (d == 1u ? -1 : (d == 2u ? 11 : -11));
-        uint32_t n = s < room ? s : room;
-        if(d == 0u) n++;                       /* arm 0 also covers the origin cell */
-        uint32_t ci = d == 0u ? uint32_t(int(c0) - stride) : c0;
-        for(; n > 0u; n--)
+        const int cx = x + i, cy = y + i;
+        if(cx >= 0 && cx < 11)
         {
-            ci = uint32_t(int(ci) + stride);
-            const uint32_t c = r[R_BOARD + ci];
+            uint8_t* cell = r + R_BOARD + cx + 11 * y;
+            const uint32_t c = *cell;
             if(c_is_flame(c) && ((c & 0xFCu) == own || flame_origin(r, c) == p))
             {
                 const uint32_t pw = c & 3u;                          /* FlagItem, bboard.cpp:182-189 */
-                r[R_BOARD + ci] = uint8_t(pw ? 8u + pw : 0u);
+                *cell = uint8_t(pw ? 8u + pw : 0u);
+            }
+        }
+        if(cy >= 0 && cy < 11)
+        {
+            uint8_t* cell = r + R_BOARD + x + 11 * cy;
+            const uint32_t c = *cell;
+            if(c_is_flame(c) && ((c & 0xFCu) == own || flame_origin(r, c) == p))
+            {
+                const uint32_t pw = c & 3u;
+                *cell = uint8_t(pw ? 8u + pw : 0u);
             }
         }
     }

@@ -95,10 +95,10 @@ __device__ __forceinline__ void warp_add(unsigned long long* dst, uint32_t v)
     if((threadIdx.x & 31u) == 0u && s) atomicAdd(dst, (unsigned long long)s);
 }
 
-/* called by ALL threads of a warp-converged region; `fin` = this thread's env finished an episode */
+/* called by ALL 32 lanes; `fin` = this lane's env finished an episode.  Counters of at most 32 per warp
+ * are packed four to a word so that three warp reductions serve all nine counters. */
 __device__ __forceinline__ void account_episodes(unsigned long long* stats, bool fin, uint32_t status, uint32_t len)
 {
-    if(!__any_sync(0xFFFFFFFFu, fin)) return;
     /* exactly one outcome per episode: DONE (won | draw) > TRUNCATED > aborted (left the reference's domain) */
     const bool done = fin && (status & POM_STATUS_DONE);
     const bool draw = done && (status & POM_STATUS_DRAW);
@@ -106,13 +106,22 @@ __device__ __forceinline__ void account_episodes(unsigned long long* stats, bool
     const bool won = done && !draw;
     const bool aborted = fin && !done && !trunc;
     const uint32_t w = (status & POM_STATUS_WINNER_MASK) >> POM_STATUS_WINNER_SHIFT;
-    warp_add(stats + ST_EPISODES, fin ? 1u : 0u);
-    warp_add(stats + ST_DRAWS, draw ? 1u : 0u);
-    warp_add(stats + ST_TRUNC, trunc ? 1u : 0u);
-    warp_add(stats + ST_SUMLEN, fin ? len : 0u);
-    warp_add(stats + ST_INVALID, aborted ? 1u : 0u);
+    const uint32_t a = (fin ? 1u : 0u) | (draw ? 1u << 8 : 0u) | (trunc ? 1u << 16 : 0u) | (aborted ? 1u << 24 : 0u);
+    const uint32_t b = won ? 1u << (8u * w) : 0u;
+    const uint32_t sa = __reduce_add_sync(0xFFFFFFFFu, a);
+    const uint32_t sb = __reduce_add_sync(0xFFFFFFFFu, b);
+    const uint32_t sl = __reduce_add_sync(0xFFFFFFFFu, fin ? len : 0u);
+    if((threadIdx.x & 31u) == 0u)
+    {
+        atomicAdd(stats + ST_EPISODES, (unsigned long long)(sa & 0xFFu));
+        if((sa >> 8) & 0xFFu) atomicAdd(stats + ST_DRAWS, (unsigned long long)((sa >> 8) & 0xFFu));
+        if((sa >> 16) & 0xFFu) atomicAdd(stats + ST_TRUNC, (unsigned long long)((sa >> 16) & 0xFFu));
+        if(sa >> 24) atomicAdd(stats + ST_INVALID, (unsigned long long)(sa >> 24));
+        atomicAdd(stats + ST_SUMLEN, (unsigned long long)sl);
 #pragma unroll
-    for(uint32_t a = 0; a < 4; a++) warp_add(stats + ST_WIN0 + a, (won && w == a) ? 1u : 0u);
+        for(uint32_t k = 0; k < 4; k++)
+            if((sb >> (8u * k)) & 0xFFu) atomicAdd(stats + ST_WIN0 + k, (unsigned long long)((sb >> (8u * k)) & 0xFFu));
+    }
 }
 
 /* end-of-tick episode handling shared by K1 (auto-reset flag) and K2: truncate, count, reset.
