@@ -276,16 +276,17 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
                  * the child's flame (not RIGID, not wood), so it takes the parent's signature and the ray goes on */
                 const uint32_t f = stack[--sp];
                 slot = f & 31u; d = (f >> 5) & 3u; rem = (f >> 7) & 15u; ci = (f >> 11) & 127u; j = (f >> 18) & 31u;
-                stride = d == 0u ? 1 : (d == 1u ? -1 : (d == 2u ? 11 : -11));
+                stride = int(int8_t(0xF50BFF01u >> (8u * d)));            /* +1, -1, +11, -11 */
                 r[R_BOARD + ci] = uint8_t(C_FLAME | (slot << 2));
                 continue;
             }
             const uint32_t po = r[R_FPOS + slot];
             const uint32_t x = po & 15u, y = po >> 4;
-            const uint32_t room = d == 0u ? 10u - x : (d == 1u ? x : (d == 2u ? 10u - y : y));   /* ray bounds :223,234,245,256 */
+            const uint32_t rooms = (10u - x) | (x << 8) | ((10u - y) << 16) | (y << 24);          /* ray bounds :223,234,245,256 */
+            const uint32_t room = (rooms >> (8u * d)) & 0xFFu;
             const uint32_t s = r[R_FSTR + slot];
             rem = s < room ? s : room;
-            stride = d == 0u ? 1 : (d == 1u ? -1 : (d == 2u ? 11 : -11));
+            stride = int(int8_t(0xF50BFF01u >> (8u * d)));                /* +1, -1, +11, -11 */
             ci = x + 11u * y;
             continue;
         }
@@ -472,10 +473,8 @@ POM_HD void move_agent(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, uint32
         if(*ocell == uint32_t(C_AGENT0 + i)) vacate(r, p, T, i);
         return;
     }
-    for(int k = 0; k < 4; k++)                                       /* HasDPCollision, step_utility.cpp:264-277 */
-    {
-        if(k != i && !ag_dead(A, k) && byte_of(dq, k) == d) return;
-    }
+    /* HasDPCollision, step_utility.cpp:264-277: another LIVE agent with the same destination */
+    if(bytes_equal(dq, d) & ~(A.flg << 6) & ~(0x80u << (8 * i))) return;
     if(c_is_powerup(item))                                           /* ConsumePowerup, step_utility.cpp:247-262 */
     {
         if(item == uint32_t(C_EXTRABOMB)) A.amax = with_byte(A.amax, i, byte_of(A.amax, i) + 1u);
@@ -749,15 +748,12 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due)
         bool isRoot = true;
         if(!ag_dead(A, a))
         {
-            for(int b = 0; b < 4; b++)
+            /* first other LIVE agent standing on a's destination */
+            const uint32_t hit = bytes_equal(posq, byte_of(dq, a)) & ~(A.flg << 6) & ~(0x80u << (8 * a));
+            if(hit)
             {
-                if(b == a || ag_dead(A, b)) continue;
-                if(byte_of(dq, a) == byte_of(posq, b))
-                {
-                    dep = with_byte(dep, b, uint32_t(a));
-                    isRoot = false;
-                    break;
-                }
+                dep = with_byte(dep, first_set_byte(hit), uint32_t(a));
+                isRoot = false;
             }
         }
         if(isRoot) roots = with_byte(roots, rootNumber++, uint32_t(a));
