@@ -234,6 +234,7 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
     uint32_t stack[24];
     int sp = 0;
     uint32_t slot = 0, d = 0, rem = 0, ci = 0, j = j0;
+    uint32_t rooms = 0, ci0 = 0;                /* per spawn: cells to the border on the four rays, origin cell */
     int stride = 0;
     uint32_t p = p0, strength = strength0;
     bool start = true;
@@ -249,10 +250,12 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
             r[R_FSTR + slot] = uint8_t(strength);
             r[R_FTIME + slot] = uint8_t(POM_FLAME_LIFETIME);
             r[R_FCOUNT] = uint8_t(fc + 1u);
-            ci = uint32_t(cell_of(p));
-            const uint32_t c = r[R_BOARD + ci];
+            const uint32_t x = p & 15u, y = p >> 4;
+            rooms = (10u - x) | (x << 8) | ((10u - y) << 16) | (y << 24);         /* ray bounds :223,234,245,256 */
+            ci0 = x + 11u * y;
+            const uint32_t c = r[R_BOARD + ci0];
             if(c_is_agent(c)) ag_kill(A, int(c) - C_AGENT0);
-            r[R_BOARD + ci] = uint8_t(C_FLAME | (slot << 2));
+            r[R_BOARD + ci0] = uint8_t(C_FLAME | (slot << 2));
             d = 0xFFFFFFFFu;            /* the ray set-up below advances to ray 0 */
             rem = 0;
             start = false;
@@ -261,33 +264,34 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
         {
             /* next ray of this spawn, or the spawn is complete */
             d++;
-            if(d >= 4u)
+            if(d < 4u)
             {
-                if(j != 31u)
-                {
-                    /* ExplodeBombAt epilogue :116-117 */
-                    const uint32_t b = bomb_at(r, j);
-                    const int id = int((b >> 8) & 3u);
-                    A.bcnt = with_byte(A.bcnt, id, byte_of(A.bcnt, id) - 1u);
-                    bombs_remove_at(r, int(j));
-                }
-                if(sp == 0) return;
-                /* back in the parent's SpawnFlameItem, after its ExplodeBombAt call (:42-52): the cell now holds
-                 * the child's flame (not RIGID, not wood), so it takes the parent's signature and the ray goes on */
-                const uint32_t f = stack[--sp];
-                slot = f & 31u; d = (f >> 5) & 3u; rem = (f >> 7) & 15u; ci = (f >> 11) & 127u; j = (f >> 18) & 31u;
+                const uint32_t room = (rooms >> (8u * d)) & 0xFFu;
+                rem = strength < room ? strength : room;
                 stride = int(int8_t(0xF50BFF01u >> (8u * d)));            /* +1, -1, +11, -11 */
-                r[R_BOARD + ci] = uint8_t(C_FLAME | (slot << 2));
+                ci = ci0;
                 continue;
             }
+            if(j != 31u)
+            {
+                /* ExplodeBombAt epilogue :116-117 */
+                const uint32_t b = bomb_at(r, j);
+                const int id = int((b >> 8) & 3u);
+                A.bcnt = with_byte(A.bcnt, id, byte_of(A.bcnt, id) - 1u);
+                bombs_remove_at(r, int(j));
+            }
+            if(sp == 0) return;
+            /* back in the parent's SpawnFlameItem, after its ExplodeBombAt call (:42-52): the cell now holds
+             * the child's flame (not RIGID, not wood), so it takes the parent's signature and the ray goes on */
+            const uint32_t f = stack[--sp];
+            slot = f & 31u; d = (f >> 5) & 3u; rem = (f >> 7) & 15u; ci = (f >> 11) & 127u; j = (f >> 18) & 31u;
+            stride = int(int8_t(0xF50BFF01u >> (8u * d)));
             const uint32_t po = r[R_FPOS + slot];
             const uint32_t x = po & 15u, y = po >> 4;
-            const uint32_t rooms = (10u - x) | (x << 8) | ((10u - y) << 16) | (y << 24);          /* ray bounds :223,234,245,256 */
-            const uint32_t room = (rooms >> (8u * d)) & 0xFFu;
-            const uint32_t s = r[R_FSTR + slot];
-            rem = s < room ? s : room;
-            stride = int(int8_t(0xF50BFF01u >> (8u * d)));                /* +1, -1, +11, -11 */
-            ci = x + 11u * y;
+            rooms = (10u - x) | (x << 8) | ((10u - y) << 16) | (y << 24);
+            ci0 = x + 11u * y;
+            strength = r[R_FSTR + slot];
+            r[R_BOARD + ci] = uint8_t(C_FLAME | (slot << 2));
             continue;
         }
         /* SpawnFlameItem on the next cell of the ray */

@@ -128,7 +128,19 @@ __device__ __forceinline__ void account_episodes(unsigned long long* stats, bool
  * Must be called by all 32 lanes of a warp.  The reset is warp-cooperative: for every lane whose env
  * finished, all 32 lanes copy that env's template record (73 words) into shared memory, instead of one
  * lane running a 73-iteration loop while 31 lanes wait.  `tile` is the CTA's record tile. */
-__device__ __forceinline__ void finish_and_reset(uint8_t* tile, uint8_t* rec, const BatchParams& P, uint64_t env, bool active, bool do_reset)
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+/* `ep_now` = this env's episode number, loaded by the caller at kernel start (one coalesced load) so that
+ * the reset path does not expose a dependent global load */
+__device__ __forceinline__ void finish_and_reset(uint8_t* tile, uint8_t* rec, const BatchParams& P, uint64_t env, bool active, bool do_reset,
+                                                 uint32_t& ep_now)
 {
     uint32_t st = active ? rec[R_STATUS] : 0u;
     const uint32_t len = active ? *reinterpret_cast<const uint16_t*>(rec + R_TIME) : 0u;
@@ -145,8 +157,11 @@ __device__ __forceinline__ void finish_and_reset(uint8_t* tile, uint8_t* rec, co
     uint32_t tmpl = 0u;
     if(fin)
     {
-        const uint32_t ep = ++P.episodes[env];
-        tmpl = uint32_t((P.env_offset + env + ep) % P.n_templates);
+        const uint32_t ep = ++ep_now;
+        P.episodes[env] = ep;
+        /* (env_offset + env + ep) % n_templates without 64-bit division on the common path */
+        const uint64_t g = P.env_offset + env + ep;
+        tmpl = g < 0xFFFFFFFFull ? uint32_t(g) % P.n_templates : uint32_t(g % P.n_templates);
     }
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp_first = threadIdx.x & ~31u;
@@ -157,10 +172,12 @@ __device__ __forceinline__ void finish_and_reset(uint8_t* tile, uint8_t* rec, co
         const uint32_t t = __shfl_sync(0xFFFFFFFFu, tmpl, int(src_lane));
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P.templates) + size_t(t) * POM_REC_WORDS;
         uint32_t* dst = reinterpret_cast<uint32_t*>(tile + size_t(warp_first + src_lane) * POM_REC_BYTES);
-        dst[lane] = __ldg(src + lane);
-        dst[lane + 32u] = __ldg(src + lane + 32u);
-        if(lane < uint32_t(POM_REC_WORDS - 64)) dst[lane + 64u] = __ldg(src + lane + 64u);
+        /* asynchronous global->shared copies: the templates of all finished lanes are in flight together */
+        cp_async_4(dst + lane, src + lane);
+        cp_async_4(dst + lane + 32u, src + lane + 32u);
+        if(lane < uint32_t(POM_REC_WORDS - 64)) cp_async_4(dst + lane + 64u, src + lane + 64u);
     }
+    cp_async_wait_all();
     __syncwarp();
 }
 
@@ -269,12 +286,13 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
             bulk_g2s(sslice, gslice, SLICE_BYTES, bar);
         }
         const uint32_t m = active ? __ldg(moves + env) : 0u;     /* overlaps the bulk load */
+        uint32_t ep_now = (active && (flags & POM_STEP_AUTORESET)) ? P.episodes[env] : 0u;
         __syncwarp();
         mbar_wait(bar, 0);
         const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
         tile_tick<TPB, false>(smem, rec, m, stepped, raw, 0u);
         if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
-        if(flags & POM_STEP_AUTORESET) finish_and_reset(smem, rec, P, env, active && stepped, true);
+        if(flags & POM_STEP_AUTORESET) finish_and_reset(smem, rec, P, env, active && stepped, true, ep_now);
         fence_proxy_async();                                      /* generic-proxy writes -> visible to the bulk store */
         __syncwarp();
         if(lane == 0)
@@ -304,7 +322,8 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
     const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
     tile_tick<TPB, true>(smem, rec, m, stepped, raw, 0u);
     if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
-    if(flags & POM_STEP_AUTORESET) finish_and_reset(smem, rec, P, env, active && stepped, true);
+    uint32_t ep_now2 = (active && (flags & POM_STEP_AUTORESET)) ? P.episodes[env] : 0u;
+    if(flags & POM_STEP_AUTORESET) finish_and_reset(smem, rec, P, env, active && stepped, true, ep_now2);
 
     fence_proxy_async();                                      /* generic-proxy writes -> visible to the bulk store */
     __syncthreads();
@@ -342,6 +361,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
     /* per-env RNG key hoisted out of the tick loop (first splitmix64 of pom_rng_moves) */
     const uint64_t key = pomcore::splitmix64(seed ^ ((P.env_offset + env) * 0xD6E8FEB86659FD93ull));
     uint32_t steps = 0;
+    uint32_t ep_now = active ? P.episodes[env] : 0u;
     for(uint32_t k = 0; k < ticks; k++)
     {
         const bool stepped = active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID));
@@ -355,7 +375,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
             steps++;
         }
         tile_tick<TPB, DEFER>(smem, rec, m, stepped, false, k % 3u);
-        finish_and_reset(smem, rec, P, env, active && stepped, !no_reset);
+        finish_and_reset(smem, rec, P, env, active && stepped, !no_reset, ep_now);
     }
     warp_add(P.stats + ST_STEPS, steps);
 
