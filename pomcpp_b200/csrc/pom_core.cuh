@@ -705,13 +705,17 @@ POM_HD void bomb_phase_idle(uint8_t* r, Agents& A, uint32_t moves, uint32_t oldP
  * with dense warps:   flames_age -> [flames_pop_due] -> step_body -> [step_explode_due]
  * step_body is everything between TickFlames and the explosion loop of TickBombs; it returns the F_* flags
  * and sets `explode_due` when bombs[0] has timed out.  `moves`: byte a = Move of agent a. */
-POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due)
+POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode_inline = false)
 {
     int flags = 0;
     explode_due = false;
-    for(int a = 0; a < 4; a++)
+    /* a move byte outside 0..5 is treated as IDLE and flagged (all four bytes tested at once) */
+    if((((moves & 0x7F7F7F7Fu) + 0x7A7A7A7Au) | moves) & 0x80808080u)
     {
-        if(byte_of(moves, a) > 5u) { moves = with_byte(moves, a, 0u); flags |= F_BAD_MOVE; }
+        for(int a = 0; a < 4; a++)
+        {
+            if(byte_of(moves, a) > 5u) { moves = with_byte(moves, a, 0u); flags |= F_BAD_MOVE; }
+        }
     }
 
     Agents A;
@@ -817,6 +821,21 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due)
             for(int k = 0; k < bc; k++, slot = ring_next(slot)) bomb_slot(r, slot) -= (1u << 16);   /* ReduceBombTimer, bboard.hpp:308-311 */
         }
         explode_due = bc > 0 && ((bomb_slot(r, r[R_BINDEX]) >> 16) & 15u) == 0u;
+        if(explode_due && explode_inline)
+        {
+            /* the explosion loop of util::TickBombs with the agents still in registers (see step_explode_due) */
+            for(int k = 0; k < bc && r[R_BCOUNT] > 0; k++)
+            {
+                const uint32_t c = bomb_slot(r, r[R_BINDEX]);
+                if(((c >> 16) & 15u) != 0u) break;
+                explode(r, A, c & 0xFFu, (c >> 12) & 15u, 31u, flags);
+                const int id = int((bomb_slot(r, r[R_BINDEX]) >> 8) & 3u);
+                A.bcnt = with_byte(A.bcnt, id, byte_of(A.bcnt, id) - 1u);
+                r[R_BINDEX] = uint8_t(ring_next(r[R_BINDEX]));
+                r[R_BCOUNT] = uint8_t(r[R_BCOUNT] - 1);
+            }
+            explode_due = false;
+        }
     }
 
     store_agents(r, A);
@@ -850,9 +869,7 @@ POM_HD int step(uint8_t* r, uint32_t moves)
 {
     tick_flames(r);                                                  /* :15 */
     bool due;
-    int flags = step_body(r, moves, due);
-    if(due) flags |= step_explode_due(r);
-    return flags;
+    return step_body(r, moves, due, true);
 }
 
 /* Environment::Step's bookkeeping after bboard::Step (environment.cpp:150-168) */
