@@ -53,7 +53,7 @@ def test_pack_rejects_unrepresentable(orc, hs):
     assert (status[:3] & 0x10).all() and status[3] == 0
 
 
-def _trace(orc, hs, n, ticks, nact, stress, seed, restart=True):
+def _trace(orc, hs, n, ticks, nact, stress, seed, restart=True, ring_start=None):
     seeds = oracle.clean_seeds(128)
     B = orc.zero_state(n)
     for e in range(n):
@@ -62,6 +62,11 @@ def _trace(orc, hs, n, ticks, nact, stress, seed, restart=True):
         B["agents"]["canKick"] = 1
         B["agents"]["maxBombCount"] = 5
         B["agents"]["bombStrength"] = 4
+    if ring_start is not None:
+        # empty rings that start near the end of the physical array: every queue operation wraps
+        # (FixedQueue index arithmetic, reference general_test.cpp:41-61 "Index 5 / Index 2")
+        B["bombs_index"] = (np.arange(n) + ring_start) % 20
+        B["flames_index"] = (np.arange(n) * 7 + ring_start) % 20
     B0 = B.copy()
     recs, bad = hs.pack(B)
     assert not bad.any()
@@ -99,6 +104,10 @@ def test_core_harmless(orc, hs):
 
 def test_core_stress(orc, hs):
     assert _trace(orc, hs, 2048, 250, 6, 1, 2003) > 300000
+
+
+def test_core_ring_wraparound(orc, hs):
+    assert _trace(orc, hs, 2048, 150, 6, 1, 2004, ring_start=15) > 200000
 
 
 def test_core_rng_matches_oracle(orc, hs):

@@ -91,13 +91,17 @@ def test_device_init_matches_reference_init(pb, orc):
     b.close()
 
 
-def _run_vs_oracle(pb, orc, n, ticks, nact, stress, seed, every_tick=True, n_templates=256):
+def _run_vs_oracle(pb, orc, n, ticks, nact, stress, seed, every_tick=True, n_templates=256, ring_start=None):
     b = pb.Batch(n, n_templates=n_templates)
     S, st = b.download()
     if stress:
         S["agents"]["canKick"] = 1
         S["agents"]["maxBombCount"] = 5
         S["agents"]["bombStrength"] = 4
+    if ring_start is not None:
+        S["bombs_index"] = (np.arange(n) + ring_start) % 20
+        S["flames_index"] = (np.arange(n) * 7 + ring_start) % 20
+    if stress or ring_start is not None:
         b.upload(S)
     status = np.zeros(n, np.uint8)
     moves_dev = b.alloc(4 * n)
@@ -130,6 +134,11 @@ def test_random_with_bombs_every_tick(pb, orc):
 
 def test_stress_kicks_and_chains_every_tick(pb, orc):
     _run_vs_oracle(pb, orc, 16384, 200, 6, 1, 44)
+
+
+def test_ring_wraparound(pb, orc):
+    """FixedQueue index arithmetic (reference general_test.cpp:41-61): rings that start near the end of the array."""
+    _run_vs_oracle(pb, orc, 8192, 150, 6, 1, 46, ring_start=15)
 
 
 def test_ragged_sizes(pb, orc):
