@@ -8,6 +8,8 @@
  *
  * mode step    : K launches of the per-tick kernel (pom_batch_step, auto-reset), moves pre-generated on device
  * mode rollout : K launches of the fused kernel (pom_batch_rollout), T ticks each, in-kernel RNG + auto-reset
+ * mode expand  : tree-search expansion (BASELINE config 5): --roots R root states (taken from a 16-tick pre-roll)
+ *                x 6^4 joint actions, one Step each, K repetitions of pom_batch_expand_step (GPU 0 only)
  * Prints one JSON line.  (The CPU reference baseline is reported by bench.py, which alone may load oracle/.)
  */
 #include <chrono>
@@ -28,7 +30,7 @@
 namespace
 {
 
-struct Args { int gpus = 1; uint64_t envs = 1u << 20; int steps = 200; int warmup = 10; std::string mode = "step"; uint32_t ticks = 800; };
+struct Args { int gpus = 1; uint64_t envs = 1u << 20; int steps = 200; int warmup = 10; std::string mode = "step"; uint32_t ticks = 800; uint64_t roots = 4096; };
 
 struct Shard { pom_batch* h = nullptr; void* moves = nullptr; float ms = 0.f; pom_stats stats; int rc = 0; std::string err; };
 
@@ -49,6 +51,31 @@ int main(int argc, char** argv)
         else if(k == "--warmup") a.warmup = std::atoi(next());
         else if(k == "--mode") a.mode = next();
         else if(k == "--ticks") a.ticks = uint32_t(std::atoi(next()));
+        else if(k == "--roots") a.roots = std::strtoull(next(), nullptr, 10);
+    }
+    if(a.mode == "expand")
+    {
+        /* config 5: R roots x 1296 joint actions, clone + one Step fused */
+        pom_batch* src = nullptr; pom_batch* dst = nullptr;
+        pom_init_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.n_templates = 1024; d.first_seed = 0x1337;
+        if(pom_batch_init(&src, 0, a.roots, &d)) die("pom_batch_init(src)");
+        if(pom_batch_rollout(src, 16, 7, 0, POM_ROLL_NO_RESET)) die("preroll");
+        d.flags = POM_INIT_EMPTY; d.n_templates = 1;
+        if(pom_batch_init(&dst, 0, a.roots * 1296, &d)) die("pom_batch_init(dst)");
+        std::vector<uint32_t> idx(a.roots);
+        for(uint64_t i = 0; i < a.roots; i++) idx[i] = uint32_t(i);
+        for(int w = 0; w < a.warmup; w++) if(pom_batch_expand_step(dst, src, idx.data(), a.roots, 1296, 0)) die("expand");
+        auto t0 = std::chrono::steady_clock::now();
+        for(int k = 0; k < a.steps; k++) if(pom_batch_expand_step(dst, src, idx.data(), a.roots, 1296, 0)) die("expand");
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double children = double(a.roots) * 1296.0 * a.steps;
+        std::printf("{\"metric\": \"env-steps/sec\", \"mode\": \"expand\", \"value\": %.6g, \"unit\": \"children (clone+Step)/s\", \"roots\": %llu, "
+                    "\"fanout\": 1296, \"steps\": %d, \"ms_per_step\": %.6g, \"hbm_write_gbs\": %.6g}\n",
+                    children / s, (unsigned long long)a.roots, a.steps, 1e3 * s / a.steps, children * 292.0 / s / 1e9);
+        pom_batch_destroy(src); pom_batch_destroy(dst);
+        return 0;
     }
     if(a.gpus < 1 || a.gpus > pom_device_count()) { std::fprintf(stderr, "pom_bench: %d GPUs requested, %d present\n", a.gpus, pom_device_count()); return 2; }
     const bool rollout = a.mode == "rollout";
