@@ -48,7 +48,6 @@ struct pom_batch {
     uint32_t  n_templates = 0;
     uint32_t  max_ticks = 0;
     int       tpb = 128;
-    bool      defer = false;
     uint8_t*  recs = nullptr;
     uint8_t*  templates = nullptr;
     uint32_t* episodes = nullptr;
@@ -168,40 +167,40 @@ int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, c
     return POM_OK;
 }
 
-template<int TPB, bool DEFER>
+template<int TPB>
 int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
 {
     static bool once = false;
-    if(!once) { int rc = set_smem<TPB>(pomk::k_step<TPB, DEFER>); if(rc) return rc; once = true; }
+    if(!once) { int rc = set_smem<TPB>(pomk::k_step<TPB>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
     static int pad = -1;
-    if(pad < 0) { const char* e = std::getenv("POM_SMEM_PAD"); pad = e ? std::atoi(e) : 0; if(pad) cudaFuncSetAttribute(pomk::k_step<TPB, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pomk::TileScratch<TPB>::BYTES) + pad); }
-    pomk::k_step<TPB, DEFER><<<grid, TPB, pomk::TileScratch<TPB>::BYTES + pad, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags);
+    if(pad < 0) { const char* e = std::getenv("POM_SMEM_PAD"); pad = e ? std::atoi(e) : 0; if(pad) cudaFuncSetAttribute(pomk::k_step<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pomk::TileScratch<TPB>::BYTES) + pad); }
+    pomk::k_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES + pad, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
 }
 
-template<int TPB, bool DEFER>
+template<int TPB>
 int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, uint32_t flags)
 {
     static bool once = false;
-    if(!once) { int rc = set_smem<TPB>(pomk::k_rollout<TPB, DEFER>); if(rc) return rc; once = true; }
+    if(!once) { int rc = set_smem<TPB>(pomk::k_rollout<TPB>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
-    pomk::k_rollout<TPB, DEFER><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(
+    pomk::k_rollout<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(
         b->params(), ticks, seed, tick0, (flags & POM_ROLL_HARMLESS) ? 5u : 6u, (flags & POM_ROLL_NO_RESET) ? 1u : 0u);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
 }
 
-template<int TPB, bool DEFER>
+template<int TPB>
 int launch_expand(pom_batch* dst, const pom_batch* src, const uint32_t* idx_dev, uint64_t n_children, uint32_t fanout, uint32_t flags)
 {
     static bool once = false;
-    if(!once) { int rc = set_smem<TPB>(pomk::k_expand_step<TPB, DEFER>); if(rc) return rc; once = true; }
+    if(!once) { int rc = set_smem<TPB>(pomk::k_expand_step<TPB>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((n_children + TPB - 1) / TPB);
-    pomk::k_expand_step<TPB, DEFER><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, dst->stream>>>(dst->recs, src->recs, idx_dev, n_children, fanout, flags);
+    pomk::k_expand_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, dst->stream>>>(dst->recs, src->recs, idx_dev, n_children, fanout, flags);
     dst->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -209,19 +208,13 @@ int launch_expand(pom_batch* dst, const pom_batch* src, const uint32_t* idx_dev,
 
 }
 
-/* tile geometry: threads (= envs) per CTA and whether explosions are deferred to dense warps.
- * Tunable through POM_TPB / POM_DEFER for experiments; the defaults are the measured best. */
+/* tile geometry: threads (= envs) per CTA; tunable through POM_TPB for experiments, default = measured best */
 #define POM_DISPATCH(h, fn, ...) \
     do { \
-        if((h)->defer) { \
-            if((h)->tpb == 64) return fn<64, true>(__VA_ARGS__); \
-            if((h)->tpb == 256) return fn<256, true>(__VA_ARGS__); \
-            return fn<128, true>(__VA_ARGS__); \
-        } \
-        if((h)->tpb == 32) return fn<32, false>(__VA_ARGS__); \
-        if((h)->tpb == 64) return fn<64, false>(__VA_ARGS__); \
-        if((h)->tpb == 256) return fn<256, false>(__VA_ARGS__); \
-        return fn<128, false>(__VA_ARGS__); \
+        if((h)->tpb == 32) return fn<32>(__VA_ARGS__); \
+        if((h)->tpb == 64) return fn<64>(__VA_ARGS__); \
+        if((h)->tpb == 256) return fn<256>(__VA_ARGS__); \
+        return fn<128>(__VA_ARGS__); \
     } while(0)
 
 extern "C" {
@@ -257,7 +250,6 @@ int pom_batch_init(pom_batch** out, int device, uint64_t n_envs, const pom_init_
         const int t = std::atoi(e);
         if(t == 32 || t == 64 || t == 128 || t == 256) b->tpb = t;
     }
-    if(const char* e = std::getenv("POM_DEFER")) b->defer = std::atoi(e) != 0 && b->tpb >= 64;
     int rc = POM_OK;
     do {
         if(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -127,7 +127,7 @@ __device__ __forceinline__ void account_episodes(unsigned long long* stats, bool
 /* end-of-tick episode handling shared by K1 (auto-reset flag) and K2: truncate, count, reset.
  * Must be called by all 32 lanes of a warp.  The reset is warp-cooperative: for every lane whose env
  * finished, all 32 lanes copy that env's template record (73 words) into shared memory, instead of one
- * lane running a 73-iteration loop while 31 lanes wait.  `tile` is the CTA's record tile. */
+ * lane running a 73-iteration loop while 31 lanes wait.  `warp_recs` = the warp's 32 consecutive records. */
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -139,7 +139,7 @@ __device__ __forceinline__ void cp_async_wait_all()
 
 /* `ep_now` = this env's episode number, loaded by the caller at kernel start (one coalesced load) so that
  * the reset path does not expose a dependent global load */
-__device__ __forceinline__ void finish_and_reset(uint8_t* tile, uint8_t* rec, const BatchParams& P, uint64_t env, bool active, bool do_reset,
+__device__ __forceinline__ void finish_and_reset(uint8_t* warp_recs, uint8_t* rec, const BatchParams& P, uint64_t env, bool active, bool do_reset,
                                                  uint32_t& ep_now)
 {
     uint32_t st = active ? rec[R_STATUS] : 0u;
@@ -164,14 +164,13 @@ __device__ __forceinline__ void finish_and_reset(uint8_t* tile, uint8_t* rec, co
         tmpl = g < 0xFFFFFFFFull ? uint32_t(g) % P.n_templates : uint32_t(g % P.n_templates);
     }
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp_first = threadIdx.x & ~31u;
     while(pending)
     {
         const uint32_t src_lane = uint32_t(__ffs(int(pending))) - 1u;
         pending &= pending - 1u;
         const uint32_t t = __shfl_sync(0xFFFFFFFFu, tmpl, int(src_lane));
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P.templates) + size_t(t) * POM_REC_WORDS;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(tile + size_t(warp_first + src_lane) * POM_REC_BYTES);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(warp_recs + size_t(src_lane) * POM_REC_BYTES);
         /* asynchronous global->shared copies: the templates of all finished lanes are in flight together */
         cp_async_4(dst + lane, src + lane);
         cp_async_4(dst + lane + 32u, src + lane + 32u);
@@ -181,187 +180,95 @@ __device__ __forceinline__ void finish_and_reset(uint8_t* tile, uint8_t* rec, co
     __syncwarp();
 }
 
-/* ---------------------------------------------------------------- one tick of a CTA tile
- * Per-CTA scratch behind the record tile: mbarrier, two counters and two index lists (one byte per env).
- * SMEM_EXTRA bytes are added to the dynamic shared memory of every tile kernel. */
-template<int TPB> struct TileScratch {
-    static constexpr uint32_t OFF_BAR = TPB * POM_REC_BYTES;          /* one 8-byte mbarrier per warp */
-    static constexpr uint32_t OFF_CNT = OFF_BAR + 64;                 /* uint32 cnt[4] (3 used)    */
-    static constexpr uint32_t OFF_LIST1 = OFF_CNT + 16;               /* uint8 list[TPB]: explosions */
-    static constexpr uint32_t BYTES = OFF_LIST1 + TPB;
-};
-
-/* append this thread's env to a CTA-level list (warp-aggregated: one shared-memory atomic per warp) */
-__device__ __forceinline__ void list_push(bool want, uint32_t* cnt, uint8_t* list)
+/* ---------------------------------------------------------------- one tick of one env */
+__device__ __forceinline__ void env_tick(uint8_t* rec, uint32_t m, bool step, bool raw)
 {
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
-    if(m == 0u) return;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t base = 0u;
-    if(lane == 0u) base = atomicAdd(cnt, uint32_t(__popc(m)));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if(want) list[base + uint32_t(__popc(m & ((1u << lane) - 1u)))] = uint8_t(threadIdx.x);
-}
-
-/*
- * One tick for the whole tile; must be called by all TPB threads (it synchronises the CTA twice).
- * Thread t owns env t for everything up to the bomb timers (pom_core.cuh step_body).  The rare, long and
- * divergent tail of the tick — the timed-out-bomb explosions of TickBombs — is collected into a CTA-level
- * list and executed by the first threads of the CTA on ANY env of the tile (records are in shared memory, so
- * every thread reaches every record): a warp that would have run `explode` with 2-3 active lanes runs it with
- * up to 32.  Environment::Step's bookkeeping follows on whichever thread finished the env's Step.
- *   step   : this thread's env takes part in the tick
- *   raw    : bare bboard::Step (no Environment bookkeeping)
- *   phase  : tick number mod 3, selects the list counter.  cnt[] must be all zero before the first tick;
- *            after the barrier of tick k thread 0 clears the counter of tick k+2, whose previous readers
- *            (tick k-1) have all passed this barrier and whose next writers (tick k+2) are ordered behind
- *            the barrier of tick k+1
- */
-template<int TPB, bool DEFER>
-__device__ __forceinline__ void tile_tick(uint8_t* smem, uint8_t* rec, uint32_t m, bool step, bool raw, uint32_t phase)
-{
-    if(!DEFER)
-    {
-        /* every thread runs the whole tick of its own env; no CTA synchronisation */
-        if(step)
-        {
-            const int f = pomcore::step(rec, m);
-            if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
-            if(!raw) pomcore::env_post(rec);
-        }
-        return;
-    }
-    typedef TileScratch<TPB> TS;
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + TS::OFF_CNT);
-    uint8_t* list_exp = smem + TS::OFF_LIST1;
-
-    bool exp_due = false;
     if(step)
     {
-        pomcore::tick_flames(rec);
-        const int f = pomcore::step_body(rec, m, exp_due);
+        const int f = pomcore::step(rec, m);
         if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
-        if(!exp_due && !raw) pomcore::env_post(rec);
+        if(!raw) pomcore::env_post(rec);
     }
-    list_push(exp_due, cnt + phase, list_exp);
-    __syncthreads();
-    const uint32_t n = cnt[phase];
-    if(threadIdx.x == 0) cnt[phase >= 1u ? phase - 1u : 2u] = 0u;      /* (phase + 2) % 3 */
-    if(n == 0u) return;                      /* CTA-uniform */
-    for(uint32_t e = threadIdx.x; e < n; e += TPB)
-    {
-        uint8_t* r2 = smem + uint32_t(list_exp[e]) * POM_REC_BYTES;
-        const int f = pomcore::step_explode_due(r2);
-        if(f & pomcore::F_INVALID_MASK) r2[R_STATUS] |= POM_STATUS_INVALID;
-        if(!raw) pomcore::env_post(r2);
-    }
-    __syncthreads();
 }
 
+/* dynamic shared memory of the tile kernels: TPB records + one mbarrier per warp */
+template<int TPB> struct TileScratch {
+    static constexpr uint32_t OFF_BAR = TPB * POM_REC_BYTES;
+    static constexpr uint32_t BYTES = OFF_BAR + 64;
+};
+
 /* ---------------------------------------------------------------- K1: per-tick kernel */
-template<int TPB, bool DEFER>
+template<int TPB>
 __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __restrict__ moves, uint32_t flags)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
     const bool active = env < P.n_envs;
-    uint8_t* rec = smem + threadIdx.x * POM_REC_BYTES;
     const bool raw = (flags & POM_STEP_RAW) != 0u;
 
-    if(!DEFER)
-    {
-        /* Warp-independent staging: every warp bulk-loads, steps and bulk-stores its own 32-record slice
-         * (9344 bytes) behind its own mbarrier.  No CTA-wide barrier: a warp whose 32 envs had a quiet tick
-         * does not wait for a warp that had to run a chain explosion. */
-        constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
-        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-        uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR) + warp;
-        uint8_t* sslice = smem + warp * SLICE_BYTES;
-        uint8_t* gslice = P.recs + (size_t(blockIdx.x) * TPB + warp * 32u) * POM_REC_BYTES;
-        if(lane == 0)
-        {
-            mbar_init(bar, 1);
-            fence_barrier_init();
-            mbar_expect_tx(bar, SLICE_BYTES);
-            bulk_g2s(sslice, gslice, SLICE_BYTES, bar);
-        }
-        const uint32_t m = active ? __ldg(moves + env) : 0u;     /* overlaps the bulk load */
-        uint32_t ep_now = (active && (flags & POM_STEP_AUTORESET)) ? P.episodes[env] : 0u;
-        __syncwarp();
-        mbar_wait(bar, 0);
-        const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
-        tile_tick<TPB, false>(smem, rec, m, stepped, raw, 0u);
-        if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
-        if(flags & POM_STEP_AUTORESET) finish_and_reset(smem, rec, P, env, active && stepped, true, ep_now);
-        fence_proxy_async();                                      /* generic-proxy writes -> visible to the bulk store */
-        __syncwarp();
-        if(lane == 0)
-        {
-            bulk_s2g(gslice, sslice, SLICE_BYTES);
-            bulk_wait_read_all();                                 /* smem must stay valid until it has been read */
-        }
-        return;
-    }
-
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR);
-    constexpr uint32_t TILE_BYTES = TPB * POM_REC_BYTES;
-    uint8_t* gtile = P.recs + size_t(blockIdx.x) * TILE_BYTES;
-    if(threadIdx.x == 0)
+    /* Warp-independent staging: every warp bulk-loads, steps and bulk-stores its own 32-record slice
+     * (9344 bytes) behind its own mbarrier.  No CTA-wide barrier: a warp whose 32 envs had a quiet tick
+     * does not wait for a warp that had to run a chain explosion. */
+    constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR) + warp;
+    uint8_t* sslice = smem + warp * SLICE_BYTES;
+    uint8_t* gslice = P.recs + (size_t(blockIdx.x) * TPB + warp * 32u) * POM_REC_BYTES;
+    if(lane == 0)
     {
         mbar_init(bar, 1);
         fence_barrier_init();
-        mbar_expect_tx(bar, TILE_BYTES);
-        bulk_g2s(smem, gtile, TILE_BYTES, bar);
+        mbar_expect_tx(bar, SLICE_BYTES);
+        bulk_g2s(sslice, gslice, SLICE_BYTES, bar);
     }
-    const uint32_t m = active ? __ldg(moves + env) : 0u;     /* overlaps the bulk load */
-    if(threadIdx.x < 4) reinterpret_cast<uint32_t*>(smem + TileScratch<TPB>::OFF_CNT)[threadIdx.x] = 0u;
-    __syncthreads();                                          /* barrier init + list counters visible to all */
+    const uint32_t m = active ? __ldg(moves + env) : 0u;     /* both loads overlap the bulk load */
+    uint32_t ep_now = (active && (flags & POM_STEP_AUTORESET)) ? P.episodes[env] : 0u;
+    __syncwarp();
     mbar_wait(bar, 0);
 
+    uint8_t* rec = sslice + lane * POM_REC_BYTES;
     /* finished envs are skipped (environment.cpp:125) unless raw; invalid envs always freeze */
     const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
-    tile_tick<TPB, true>(smem, rec, m, stepped, raw, 0u);
+    env_tick(rec, m, stepped, raw);
     if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
-    uint32_t ep_now2 = (active && (flags & POM_STEP_AUTORESET)) ? P.episodes[env] : 0u;
-    if(flags & POM_STEP_AUTORESET) finish_and_reset(smem, rec, P, env, active && stepped, true, ep_now2);
-
+    if(flags & POM_STEP_AUTORESET) finish_and_reset(sslice, rec, P, env, active && stepped, true, ep_now);
     fence_proxy_async();                                      /* generic-proxy writes -> visible to the bulk store */
-    __syncthreads();
-    if(threadIdx.x == 0)
+    __syncwarp();
+    if(lane == 0)
     {
-        bulk_s2g(gtile, smem, TILE_BYTES);
+        bulk_s2g(gslice, sslice, SLICE_BYTES);
         bulk_wait_read_all();                                 /* smem must stay valid until it has been read */
     }
 }
 
 /* ---------------------------------------------------------------- K2: fused K-tick rollout */
-template<int TPB, bool DEFER>
+template<int TPB>
 __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, uint64_t seed, uint32_t tick0,
                                                 uint32_t n_actions, uint32_t no_reset)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR);
-    constexpr uint32_t TILE_BYTES = TPB * POM_REC_BYTES;
-    uint8_t* gtile = P.recs + size_t(blockIdx.x) * TILE_BYTES;
-
-    if(threadIdx.x == 0)
+    const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
+    const bool active = env < P.n_envs;
+    constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR) + warp;
+    uint8_t* sslice = smem + warp * SLICE_BYTES;
+    uint8_t* gslice = P.recs + (size_t(blockIdx.x) * TPB + warp * 32u) * POM_REC_BYTES;
+    if(lane == 0)
     {
         mbar_init(bar, 1);
         fence_barrier_init();
-        mbar_expect_tx(bar, TILE_BYTES);
-        bulk_g2s(smem, gtile, TILE_BYTES, bar);
+        mbar_expect_tx(bar, SLICE_BYTES);
+        bulk_g2s(sslice, gslice, SLICE_BYTES, bar);
     }
-    const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
-    const bool active = env < P.n_envs;
-    if(threadIdx.x < 4) reinterpret_cast<uint32_t*>(smem + TileScratch<TPB>::OFF_CNT)[threadIdx.x] = 0u;
-    __syncthreads();
+    uint32_t ep_now = active ? P.episodes[env] : 0u;
+    __syncwarp();
     mbar_wait(bar, 0);
 
-    uint8_t* rec = smem + threadIdx.x * POM_REC_BYTES;
+    uint8_t* rec = sslice + lane * POM_REC_BYTES;
     /* per-env RNG key hoisted out of the tick loop (first splitmix64 of pom_rng_moves) */
     const uint64_t key = pomcore::splitmix64(seed ^ ((P.env_offset + env) * 0xD6E8FEB86659FD93ull));
     uint32_t steps = 0;
-    uint32_t ep_now = active ? P.episodes[env] : 0u;
     for(uint32_t k = 0; k < ticks; k++)
     {
         const bool stepped = active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID));
@@ -374,16 +281,16 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
                 m |= (((uint32_t(h >> (16 * a)) & 0xFFFFu) * n_actions) >> 16) << (8 * a);
             steps++;
         }
-        tile_tick<TPB, DEFER>(smem, rec, m, stepped, false, k % 3u);
-        finish_and_reset(smem, rec, P, env, active && stepped, !no_reset, ep_now);
+        env_tick(rec, m, stepped, false);
+        finish_and_reset(sslice, rec, P, env, active && stepped, !no_reset, ep_now);
     }
     warp_add(P.stats + ST_STEPS, steps);
 
     fence_proxy_async();
-    __syncthreads();
-    if(threadIdx.x == 0)
+    __syncwarp();
+    if(lane == 0)
     {
-        bulk_s2g(gtile, smem, TILE_BYTES);
+        bulk_s2g(gslice, sslice, SLICE_BYTES);
         bulk_wait_read_all();
     }
 }
@@ -427,20 +334,21 @@ __global__ void k_fill_from_templates(BatchParams P)
 /* ---------------------------------------------------------------- K4: tree-search expansion */
 /* child c = root_i * fanout + j: copy the root's record into the tile, apply joint action j
  * (a_k = (j / 6^k) % 6), Step once, bulk-store the tile. */
-template<int TPB, bool DEFER>
+template<int TPB>
 __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
                                                     const uint32_t* __restrict__ src_idx, uint64_t n_children,
                                                     uint32_t fanout, uint32_t flags)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr uint32_t TILE_BYTES = TPB * POM_REC_BYTES;
+    constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint64_t c = uint64_t(blockIdx.x) * TPB + threadIdx.x;
-    uint8_t* rec = smem + threadIdx.x * POM_REC_BYTES;
+    uint8_t* sslice = smem + warp * SLICE_BYTES;
+    uint8_t* rec = sslice + lane * POM_REC_BYTES;
     uint32_t* rw = reinterpret_cast<uint32_t*>(rec);
+    const bool raw = (flags & POM_STEP_RAW) != 0u;
     uint32_t m = 0u;
     bool stepped = false;
-    if(threadIdx.x < 4) reinterpret_cast<uint32_t*>(smem + TileScratch<TPB>::OFF_CNT)[threadIdx.x] = 0u;
-    __syncthreads();
     if(c < n_children)
     {
         const uint64_t root = c / fanout;
@@ -449,19 +357,18 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
 #pragma unroll 1
         for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = __ldg(s + w);
         m = (j % 6u) | (((j / 6u) % 6u) << 8) | (((j / 36u) % 6u) << 16) | (((j / 216u) % 6u) << 24);
-        const bool raw = (flags & POM_STEP_RAW) != 0u;
         stepped = !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
     }
     else
     {
         for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = 0u;
     }
-    tile_tick<TPB, DEFER>(smem, rec, m, stepped, (flags & POM_STEP_RAW) != 0u, 0u);
+    env_tick(rec, m, stepped, raw);
     fence_proxy_async();
-    __syncthreads();
-    if(threadIdx.x == 0)
+    __syncwarp();
+    if(lane == 0)
     {
-        bulk_s2g(dst + size_t(blockIdx.x) * TILE_BYTES, smem, TILE_BYTES);
+        bulk_s2g(dst + (size_t(blockIdx.x) * TPB + warp * 32u) * POM_REC_BYTES, sslice, SLICE_BYTES);
         bulk_wait_read_all();
     }
 }
