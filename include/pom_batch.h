@@ -101,7 +101,10 @@ int  pom_batch_templates(pom_batch* b, pom_state* out /* n_templates */, int32_t
  * bookkeeping (environment.cpp:125-128,149-168) for every env.  moves_dev: DEVICE pointer to
  * n_envs x 4 bytes, byte a of env e = Move of agent a (bboard.hpp:35-43), values 0..5.         */
 int  pom_batch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags);
-/* same with HOST buffers: copies moves in, steps, copies the status bytes out (may be NULL), synchronises */
+/* same with HOST buffers: copies moves in, steps, copies the status bytes out (may be NULL), synchronises.
+ * status_host[e] is the env's status at the END of this tick; with POM_STEP_AUTORESET it is the status of the
+ * episode that just ended (done / winner / draw / truncated / invalid) even though the env itself has already
+ * been re-initialised — the "done" signal an RL loop needs.                                              */
 int  pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags);
 /* `ticks` fused ticks with the boards resident in shared memory; actions from pom_rng_moves(rng_seed,
  * global env index, tick0 + k); auto-reset unless POM_ROLL_NO_RESET.  Replaces the loop of

@@ -168,14 +168,14 @@ int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, c
 }
 
 template<int TPB>
-int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
+int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* status_dev)
 {
     static bool once = false;
     if(!once) { int rc = set_smem<TPB>(pomk::k_step<TPB>); if(rc) return rc; once = true; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
     static int pad = -1;
     if(pad < 0) { const char* e = std::getenv("POM_SMEM_PAD"); pad = e ? std::atoi(e) : 0; if(pad) cudaFuncSetAttribute(pomk::k_step<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pomk::TileScratch<TPB>::BYTES) + pad); }
-    pomk::k_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES + pad, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags);
+    pomk::k_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES + pad, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags, status_dev);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -375,7 +375,7 @@ int pom_batch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
 {
     int rc = use(b); if(rc) return rc;
     if(!moves_dev) return fail(POM_E_ARG, "pom_batch_step: null moves");
-    POM_DISPATCH(b, launch_step, b, moves_dev, flags);
+    POM_DISPATCH(b, launch_step, b, moves_dev, flags, nullptr);
 }
 
 int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags)
@@ -383,15 +383,10 @@ int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status
     int rc = use(b); if(rc) return rc;
     if(!moves_host) return fail(POM_E_ARG, "pom_batch_step_host: null moves");
     CK(cudaMemcpyAsync(b->moves_buf, moves_host, b->n_envs * 4, cudaMemcpyHostToDevice, b->stream));
-    rc = pom_batch_step(b, reinterpret_cast<const uint8_t*>(b->moves_buf), flags);
+    /* the kernel itself writes the end-of-tick status bytes (before any auto-reset) */
+    rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, reinterpret_cast<const uint8_t*>(b->moves_buf), flags, status_host ? b->status_buf : nullptr); }();
     if(rc) return rc;
-    if(status_host)
-    {
-        pomk::k_unpack<<<unsigned((b->n_envs + 255) / 256), 256, 0, b->stream>>>(b->recs, nullptr, b->status_buf, 0, b->n_envs);
-        b->launches++;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(status_host, b->status_buf, b->n_envs, cudaMemcpyDeviceToHost, b->stream));
-    }
+    if(status_host) CK(cudaMemcpyAsync(status_host, b->status_buf, b->n_envs, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     return POM_OK;
 }

@@ -138,8 +138,9 @@ __device__ __forceinline__ void cp_async_wait_all()
 }
 
 /* `ep_now` = this env's episode number, loaded by the caller at kernel start (one coalesced load) so that
- * the reset path does not expose a dependent global load */
-__device__ __forceinline__ void finish_and_reset(uint8_t* warp_recs, uint8_t* rec, const BatchParams& P, uint64_t env, bool active, bool do_reset,
+ * the reset path does not expose a dependent global load.  Returns the env's end-of-tick status byte as it was
+ * BEFORE a reset (what an RL loop needs to see: done / winner / truncated of the episode that just ended). */
+__device__ __forceinline__ uint32_t finish_and_reset(uint8_t* warp_recs, uint8_t* rec, const BatchParams& P, uint64_t env, bool active, bool do_reset,
                                                  uint32_t& ep_now)
 {
     uint32_t st = active ? rec[R_STATUS] : 0u;
@@ -147,12 +148,12 @@ __device__ __forceinline__ void finish_and_reset(uint8_t* warp_recs, uint8_t* re
     if(active && !(st & POM_STATUS_DONE) && P.max_ticks && len >= P.max_ticks) st |= POM_STATUS_TRUNCATED;
     const bool fin = active && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID)) != 0u;
     uint32_t pending = __ballot_sync(0xFFFFFFFFu, fin);
-    if(pending == 0u) return;
+    if(pending == 0u) return st;
     account_episodes(P.stats, fin, st, len);
     if(!do_reset)
     {
         if(fin) rec[R_STATUS] = uint8_t(st);
-        return;
+        return st;
     }
     uint32_t tmpl = 0u;
     if(fin)
@@ -178,6 +179,7 @@ __device__ __forceinline__ void finish_and_reset(uint8_t* warp_recs, uint8_t* re
     }
     cp_async_wait_all();
     __syncwarp();
+    return st;
 }
 
 /* ---------------------------------------------------------------- one tick of one env */
@@ -199,7 +201,7 @@ template<int TPB> struct TileScratch {
 
 /* ---------------------------------------------------------------- K1: per-tick kernel */
 template<int TPB>
-__global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __restrict__ moves, uint32_t flags)
+__global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __restrict__ moves, uint32_t flags, uint8_t* __restrict__ status_out)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
@@ -231,7 +233,13 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
     const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
     env_tick(rec, m, stepped, raw);
     if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
-    if(flags & POM_STEP_AUTORESET) finish_and_reset(sslice, rec, P, env, active && stepped, true, ep_now);
+    uint32_t st_end = active ? rec[R_STATUS] : 0u;
+    if(flags & POM_STEP_AUTORESET)
+    {
+        const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, true, ep_now);
+        if(active && stepped) st_end = st;
+    }
+    if(status_out && active) status_out[env] = uint8_t(st_end);   /* one coalesced byte per env */
     fence_proxy_async();                                      /* generic-proxy writes -> visible to the bulk store */
     __syncwarp();
     if(lane == 0)

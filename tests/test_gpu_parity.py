@@ -367,3 +367,30 @@ def test_state_primitives_on_device(pb, orc):
     assert (brd["board"] == ref["board"]).all()
     assert pb.make_board(0x13327)[1] == 1
     b.close()
+
+
+def test_step_host_reports_terminal_status_with_autoreset(pb, orc):
+    """With auto-reset the status bytes returned by pom_batch_step_host are those of the episode that just ended."""
+    n, ticks, seed = 4096, 60, 12
+    b = pb.Batch(n, n_templates=32, max_ticks=0)
+    T, _ = b.templates()
+    S, _ = b.download()
+    status = np.zeros(n, np.uint8)
+    episode = np.zeros(n, np.int64)
+    out = np.zeros(n, np.uint8)
+    seen_done = 0
+    for t in range(ticks):
+        mv = orc.rng_moves(seed, 0, n, t, 6)
+        b.step_host(mv, out, pb.STEP_AUTORESET)
+        orc.env_step_batch(S, status, mv)
+        assert (out == status).all(), "tick %d" % t
+        fin = np.nonzero(status & 0x11)[0]
+        seen_done += fin.shape[0]
+        for e in fin:
+            episode[e] += 1
+            S[e] = T[(e + episode[e]) % 32]
+            status[e] = 0
+    assert seen_done > n
+    G, gst = b.download()
+    assert orc.diff_batch(G, S)[0] == -1 and not gst.any()
+    b.close()
