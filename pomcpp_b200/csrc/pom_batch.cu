@@ -60,6 +60,11 @@ struct pom_batch {
     void*     flush_buf = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = { nullptr, nullptr };
+    /* pom_batch_step_host pipelines chunks of the batch: H2D of chunk c+1 and D2H of chunk c-1 overlap the
+     * kernel of chunk c (copy engines + SMs), ordered by events */
+    static constexpr int MAX_CHUNKS = 8;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {}, ev_out = nullptr, ev_begin = nullptr;
     std::vector<int32_t> seeds;
     uint64_t  launches = 0;
 
@@ -168,14 +173,22 @@ int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, c
 }
 
 template<int TPB>
-int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* status_dev)
+int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* status_dev, uint64_t first = 0, uint64_t count = 0)
 {
     static bool once = false;
     if(!once) { int rc = set_smem<TPB>(pomk::k_step<TPB>); if(rc) return rc; once = true; }
-    const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
+    /* envs [first, first + count) only (first is a multiple of TPB); count == 0 means the whole batch */
+    pomk::BatchParams P = b->params();
+    if(count)
+    {
+        P.recs += first * POM_REC_BYTES; P.episodes += first; P.env_offset += first; P.n_envs = count;
+        moves_dev += 4 * first;
+        if(status_dev) status_dev += first;
+    }
+    const unsigned grid = unsigned((P.n_envs + TPB - 1) / TPB);
     static int pad = -1;
     if(pad < 0) { const char* e = std::getenv("POM_SMEM_PAD"); pad = e ? std::atoi(e) : 0; if(pad) cudaFuncSetAttribute(pomk::k_step<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pomk::TileScratch<TPB>::BYTES) + pad); }
-    pomk::k_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES + pad, b->stream>>>(b->params(), reinterpret_cast<const uint32_t*>(moves_dev), flags, status_dev);
+    pomk::k_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES + pad, b->stream>>>(P, reinterpret_cast<const uint32_t*>(moves_dev), flags, status_dev);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -253,7 +266,11 @@ int pom_batch_init(pom_batch** out, int device, uint64_t n_envs, const pom_init_
     int rc = POM_OK;
     do {
         if(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
-           cudaEventCreate(&b->ev[0]) != cudaSuccess || cudaEventCreate(&b->ev[1]) != cudaSuccess)
+           cudaEventCreate(&b->ev[0]) != cudaSuccess || cudaEventCreate(&b->ev[1]) != cudaSuccess ||
+           cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+           cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+           cudaEventCreateWithFlags(&b->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+           cudaEventCreateWithFlags(&b->ev_begin, cudaEventDisableTiming) != cudaSuccess)
         { rc = fail(POM_E_CUDA, "stream/event creation failed", cudaGetLastError()); break; }
         if(cudaMalloc(&b->recs, b->n_alloc * POM_REC_BYTES) != cudaSuccess ||
            cudaMalloc(&b->templates, size_t(b->n_templates) * POM_REC_BYTES) != cudaSuccess ||
@@ -300,6 +317,11 @@ int pom_batch_destroy(pom_batch* b)
     cudaFree(b->bad_count); cudaFree(b->flush_buf);
     if(b->ev[0]) cudaEventDestroy(b->ev[0]);
     if(b->ev[1]) cudaEventDestroy(b->ev[1]);
+    for(int i = 0; i < pom_batch::MAX_CHUNKS; i++) { if(b->ev_in[i]) cudaEventDestroy(b->ev_in[i]); if(b->ev_done[i]) cudaEventDestroy(b->ev_done[i]); }
+    if(b->ev_out) cudaEventDestroy(b->ev_out);
+    if(b->ev_begin) cudaEventDestroy(b->ev_begin);
+    if(b->s_h2d) cudaStreamDestroy(b->s_h2d);
+    if(b->s_d2h) cudaStreamDestroy(b->s_d2h);
     if(b->stream) cudaStreamDestroy(b->stream);
     delete b;
     return POM_OK;
@@ -382,11 +404,44 @@ int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status
 {
     int rc = use(b); if(rc) return rc;
     if(!moves_host) return fail(POM_E_ARG, "pom_batch_step_host: null moves");
-    CK(cudaMemcpyAsync(b->moves_buf, moves_host, b->n_envs * 4, cudaMemcpyHostToDevice, b->stream));
-    /* the kernel itself writes the end-of-tick status bytes (before any auto-reset) */
-    rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, reinterpret_cast<const uint8_t*>(b->moves_buf), flags, status_host ? b->status_buf : nullptr); }();
-    if(rc) return rc;
-    if(status_host) CK(cudaMemcpyAsync(status_host, b->status_buf, b->n_envs, cudaMemcpyDeviceToHost, b->stream));
+    /* Chunked pipeline over three streams: copy-in, compute (the handle's stream), copy-out.  The kernel itself
+     * writes the end-of-tick status bytes (before any auto-reset), so no extra pass is needed for them. */
+    const uint64_t n = b->n_envs;
+    int chunks = n >= (uint64_t(1) << 18) ? 4 : 1;
+    const uint64_t per = ((n + chunks - 1) / chunks + 1023) / 1024 * 1024;      /* multiple of every TPB */
+    chunks = int((n + per - 1) / per);
+    for(int c = 0; c < chunks; c++)
+    {
+        if(!b->ev_in[c])
+        {
+            CK(cudaEventCreateWithFlags(&b->ev_in[c], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&b->ev_done[c], cudaEventDisableTiming));
+        }
+    }
+    /* everything already queued on the handle's stream happens before this step */
+    CK(cudaEventRecord(b->ev_begin, b->stream));
+    CK(cudaStreamWaitEvent(b->s_h2d, b->ev_begin, 0));
+    for(int c = 0; c < chunks; c++)
+    {
+        const uint64_t first = uint64_t(c) * per, count = (first + per <= n) ? per : n - first;
+        CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(b->moves_buf) + 4 * first, moves_host + 4 * first, 4 * count, cudaMemcpyHostToDevice, b->s_h2d));
+        CK(cudaEventRecord(b->ev_in[c], b->s_h2d));
+        CK(cudaStreamWaitEvent(b->stream, b->ev_in[c], 0));
+        rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, reinterpret_cast<const uint8_t*>(b->moves_buf), flags,
+                                         status_host ? b->status_buf : nullptr, first, count); }();
+        if(rc) return rc;
+        if(status_host)
+        {
+            CK(cudaEventRecord(b->ev_done[c], b->stream));
+            CK(cudaStreamWaitEvent(b->s_d2h, b->ev_done[c], 0));
+            CK(cudaMemcpyAsync(status_host + first, b->status_buf + first, count, cudaMemcpyDeviceToHost, b->s_d2h));
+        }
+    }
+    if(status_host)
+    {
+        CK(cudaEventRecord(b->ev_out, b->s_d2h));
+        CK(cudaStreamWaitEvent(b->stream, b->ev_out, 0));
+    }
     CK(cudaStreamSynchronize(b->stream));
     return POM_OK;
 }
