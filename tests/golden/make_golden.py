@@ -69,6 +69,29 @@ def run_trace(R, O, S, ticks, n_actions, rng_seed):
     return hashes, stat, excluded, d1
 
 
+def write_pomtrc(R, O, path, n, ticks, nact, stress, rs, seeds):
+    import struct
+    S = initial_states(R, n, stress, seeds)
+    init = S.copy()
+    status = np.zeros(n, np.uint8)
+    shadow, shadow_status, fo = S.copy(), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    moves = np.zeros((ticks, n, 4), np.uint8)
+    for t in range(ticks):
+        mv = O.rng_moves(rs, 0, n, t, nact)
+        moves[t] = mv
+        O.env_step_batch(shadow, shadow_status, mv, fo)
+        R.env_step_batch(S, status, mv, None, ((fo & 0x20) != 0).astype(np.uint8))
+    assert not (status & 0x10).any(), "pick another seed: an env left the parity domain"
+    with open(path, "wb") as f:
+        f.write(b"POMTRC1\0")
+        f.write(struct.pack("<4I", n, ticks, 0, 0))
+        f.write(init.tobytes())
+        f.write(moves.tobytes())
+        f.write(O.hash_batch(S).tobytes())
+        f.write(status.tobytes())
+    print("%s: %d envs x %d ticks, %d done, %d bytes" % (os.path.basename(path), n, ticks, int((status & 1).sum()), os.path.getsize(path)))
+
+
 def main():
     oracle.build()
     R = oracle.reference()
@@ -112,6 +135,10 @@ def main():
         print("%s: %d envs x %d ticks, D1 steps %d, excluded envs %d, done %d" %
               (name, n, ticks, d1, int((excluded >= 0).sum()), int((stat[-1] & 1).sum())))
     np.savez_compressed(os.path.join(HERE, "traces.npz"), **out)
+
+    # 4. an on-disk trace in the POMTRC1 format (pomcpp_b200/host/pom_trace.hpp) for pom_replay:
+    #    96 envs x 120 ticks, boosted kick/bomb regime, produced by the compiled reference
+    write_pomtrc(R, O, os.path.join(HERE, "stress96.pomtrc"), 96, 120, 6, 1, 45, seeds)
     for f in ("scenarios.npz", "init.npz", "traces.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 

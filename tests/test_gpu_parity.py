@@ -394,3 +394,12 @@ def test_step_host_reports_terminal_status_with_autoreset(pb, orc):
     G, gst = b.download()
     assert orc.diff_batch(G, S)[0] == -1 and not gst.any()
     b.close()
+
+
+def test_replay_tool_on_golden_trace_file(pb):
+    """pom_replay re-runs the reference-generated POMTRC1 trace on the GPU; exit code 0 = all hashes match."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pb.LIB_PATH), "host", "pom_replay")
+    out = subprocess.run([exe, os.path.join(GOLD, "stress96.pomtrc"), "--print", "3"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr
+    assert "0 mismatches" in out.stdout and "agent 0:" in out.stdout

@@ -175,3 +175,29 @@ def test_defect_d1_three_on_one_is_canonical_and_fenced(orc, ref):
     assert f & 1
     for i, (x, y) in enumerate([(1, 1), (0, 1), (3, 1), (2, 1)]):
         scenarios.require_agent(s, i, x, y)
+
+
+def read_pomtrc(path):
+    """POMTRC1 trace file (pomcpp_b200/host/pom_trace.hpp)."""
+    import struct
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"POMTRC1\0"
+    n, ticks, flags, _ = struct.unpack("<4I", raw[8:24])
+    o = 24
+    init = np.frombuffer(raw, oracle.STATE_DT, n, o).copy(); o += n * 1004
+    moves = np.frombuffer(raw, np.uint8, ticks * n * 4, o).reshape(ticks, n, 4).copy(); o += ticks * n * 4
+    hashes = np.frombuffer(raw, np.uint64, n, o).copy(); o += 8 * n
+    status = np.frombuffer(raw, np.uint8, n, o).copy(); o += n
+    assert o == len(raw)
+    return init, moves, hashes, status, flags
+
+
+def test_golden_trace_file(orc):
+    """The on-disk golden trace (written from the compiled reference) replays bit-exactly on the restatement."""
+    init, moves, hashes, status, flags = read_pomtrc(os.path.join(GOLD, "stress96.pomtrc"))
+    S = init.copy()
+    st = np.zeros(S.shape[0], np.uint8)
+    for t in range(moves.shape[0]):
+        orc.env_step_batch(S, st, np.ascontiguousarray(moves[t]))
+    assert (orc.hash_batch(S) == hashes).all()
+    assert (((st ^ status) & 0x1F) == 0).all()
