@@ -107,13 +107,11 @@ POM_HD void ag_kill(Agents& A, int i)                                 /* State::
     }
 }
 
-POM_HD int first_set_byte(uint32_t m)   /* index of the lowest byte of m that has a bit set, m != 0 */
+POM_HD int first_set_byte(uint32_t m)   /* m has bits only at positions 7/15/23/31; index of the lowest one, m != 0 */
 {
-#if defined(__CUDA_ARCH__)
-    return (__ffs(int(m)) - 1) >> 3;
-#else
-    return (__builtin_ffs(int(m)) - 1) >> 3;
-#endif
+    /* plain ALU ops: find-first-set (BREV + FLO) goes to the quarter-rate XU pipe, which this kernel keeps busy */
+    const uint32_t l = m & (0u - m);
+    return int(((l >> 15) & 1u) | ((l >> 22) & 2u) | ((l >> 31) * 3u));
 }
 
 POM_HD int get_agent(const Agents& A, uint32_t p)                    /* State::GetAgent, bboard.cpp:289-299 */
