@@ -403,3 +403,37 @@ def test_replay_tool_on_golden_trace_file(pb):
     out = subprocess.run([exe, os.path.join(GOLD, "stress96.pomtrc"), "--print", "3"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr
     assert "0 mismatches" in out.stdout and "agent 0:" in out.stdout
+
+
+def test_abi_error_codes(pb):
+    """Every entry point reports bad input with a negative code and a message instead of crashing."""
+    import ctypes as C
+    L = pb.lib()
+    h = C.c_void_p()
+    d = pb.InitDesc()
+    d.n_templates = 4
+    d.first_seed = 0x1337
+    assert L.pom_batch_init(C.byref(h), 0, 0, C.byref(d)) == -1                    # POM_E_ARG: no envs
+    assert L.pom_batch_init(C.byref(h), 99, 16, C.byref(d)) == -1                  # no such device
+    d.n_templates = 0
+    assert L.pom_batch_init(C.byref(h), 0, 16, C.byref(d)) == -1
+    assert b"bad argument" in L.pom_last_error()
+    b = pb.Batch(64, n_templates=4)
+    b2 = pb.Batch(64, n_templates=1, empty=True)
+    assert L.pom_batch_step(b.h, None, 0) == -1
+    assert L.pom_batch_step_host(b.h, None, None, 0) == -1
+    idx = np.array([1, 2, 64], np.uint32)
+    assert L.pom_batch_clone(b2.h, 0, b.h, idx.ctypes.data_as(C.c_void_p), 3) == -4          # POM_E_RANGE: source index
+    assert L.pom_batch_clone(b2.h, 63, b.h, idx.ctypes.data_as(C.c_void_p), 2) == -4         # destination range
+    assert L.pom_batch_expand_step(b2.h, b.h, idx.ctypes.data_as(C.c_void_p), 1, 0, 0) == -1  # fanout 0
+    assert L.pom_batch_expand_step(b2.h, b.h, idx.ctypes.data_as(C.c_void_p), 1, 1296, 0) == -4  # destination too small
+    assert L.pom_batch_apply(b.h, 64, 0, 1, 1, 1) == -4 and L.pom_batch_apply(b.h, 0, 9, 0, 0, 0) == -1
+    assert L.pom_batch_apply(b.h, 0, 0, 11, 0, 1) == -1
+    st = np.zeros(8, np.uint8)
+    assert L.pom_batch_download(b.h, 60, 8, None, st.ctypes.data_as(C.c_void_p)) == -4
+    assert L.pom_batch_generate_moves(b.h, None, 1, 0, 6) == -1
+    # the handle is still usable after all these errors
+    S, s0 = b.download()
+    assert S.shape[0] == 64 and not s0.any()
+    b.close()
+    b2.close()
