@@ -1,0 +1,73 @@
+/*
+ * sanitize_main.cpp — TEST-ONLY.  Runs the kernel body (pom_core.cuh, host build) and the plain-C restatement
+ * side by side under AddressSanitizer + UndefinedBehaviorSanitizer on seeded random traces (incl. the all-kick
+ * stress regime), comparing every field after every tick.  compute-sanitizer is not available on the GPU pool,
+ * so this is the memory-safety check of the exact code the CUDA kernels run: every record access of the tick
+ * happens inside a 292-byte heap block of its own, so an out-of-bounds ring / board / stack index trips ASan.
+ *
+ *   sanitize_main [n_envs] [ticks]        exit 0 = no sanitizer report, no mismatch
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "pom_core.cuh"
+extern "C" {
+#include "pom_oracle.h"
+}
+
+int main(int argc, char** argv)
+{
+    const int n = argc > 1 ? std::atoi(argv[1]) : 512;
+    const int ticks = argc > 2 ? std::atoi(argv[2]) : 200;
+    long steps = 0, invalid = 0;
+    for(int stress = 0; stress < 2; stress++)
+    {
+        std::vector<pom_state> S(static_cast<size_t>(n)), T(static_cast<size_t>(n));
+        std::vector<uint8_t*> recs(static_cast<size_t>(n));
+        std::vector<uint8_t> st(static_cast<size_t>(n), 0);
+        int seed = 0x1337;
+        for(int e = 0; e < n; e++)
+        {
+            do { pom_oracle_zero_state(&S[size_t(e)]); } while(pom_oracle_init_state(&S[size_t(e)], seed++, 0, 1, 2, 3));
+            if(stress)
+            {
+                for(int a = 0; a < 4; a++) { S[size_t(e)].agents[a].canKick = 1; S[size_t(e)].agents[a].maxBombCount = 5; S[size_t(e)].agents[a].bombStrength = 4; }
+                S[size_t(e)].bombs_index = (e * 3) % 20;       /* rings that wrap */
+                S[size_t(e)].flames_index = (e * 7) % 20;
+            }
+            recs[size_t(e)] = static_cast<uint8_t*>(std::malloc(POM_REC_BYTES));   /* exact-size heap block: ASan guards both ends */
+            if(pomcore::pack(&S[size_t(e)], 0, recs[size_t(e)])) { std::printf("pack failed\n"); return 1; }
+        }
+        const std::vector<pom_state> S0 = S;
+        for(int t = 0; t < ticks; t++)
+        {
+            for(int e = 0; e < n; e++)
+            {
+                const uint32_t m = pom_oracle_rng_moves(99 + uint64_t(stress), uint64_t(e), uint32_t(t), 6);
+                uint8_t mv[4];
+                std::memcpy(mv, &m, 4);
+                if(!(st[size_t(e)] & 0x11)) steps++;
+                pom_oracle_env_step(&S[size_t(e)], &st[size_t(e)], mv);
+                pomcore::env_step(recs[size_t(e)], m);
+                const uint8_t st2 = pomcore::unpack(recs[size_t(e)], &T[size_t(e)]);
+                if(pom_oracle_state_diff(&S[size_t(e)], &T[size_t(e)]) || st2 != st[size_t(e)])
+                {
+                    std::printf("MISMATCH stress %d tick %d env %d\n", stress, t, e);
+                    return 1;
+                }
+                if(st[size_t(e)] & 0x11)
+                {
+                    if(st[size_t(e)] & 0x10) invalid++;
+                    S[size_t(e)] = S0[size_t(e)];
+                    st[size_t(e)] = 0;
+                    pomcore::pack(&S[size_t(e)], 0, recs[size_t(e)]);
+                }
+            }
+        }
+        for(int e = 0; e < n; e++) std::free(recs[size_t(e)]);
+    }
+    std::printf("sanitize_main: %ld env-steps, %ld aborted episodes, clean\n", steps, invalid);
+    return 0;
+}
