@@ -27,9 +27,11 @@
 #if defined(__CUDACC__)
 #define POM_HD __host__ __device__ inline
 #define POM_HD_COLD __host__ __device__ __noinline__   /* rare paths: one out-of-line copy keeps the hot code small */
+#define POM_LOOP _Pragma("unroll 1")   /* data-dependent trip counts: unrolling only bloats the code (I-cache) */
 #else
 #define POM_HD inline
 #define POM_HD_COLD inline
+#define POM_LOOP
 #endif
 
 namespace pomcore
@@ -124,6 +126,7 @@ POM_HD int get_agent(const Agents& A, uint32_t p)                    /* State::G
 POM_HD int bomb_index(uint8_t* r, uint32_t p)                        /* GetBombIndex / GetBomb / HasBomb, bboard.cpp:265-311 */
 {
     const int n = r[R_BCOUNT];
+    POM_LOOP
     for(int i = 0; i < n; i++)
     {
         if((bomb_at(r, i) & 0xFFu) == p) return i;
@@ -135,6 +138,7 @@ POM_HD void bombs_remove_at(uint8_t* r, int at)                      /* FixedQue
 {
     const int n = r[R_BCOUNT];
     const uint32_t bi = r[R_BINDEX];
+    POM_LOOP
     for(int i = at + 1; i < n; i++)
     {
         const uint32_t t = ring20(bi + i);
@@ -158,6 +162,7 @@ POM_HD void pop_flame(uint8_t* r)                                    /* State::P
     if(s > 10) s = 10;
     const int x = int(p & 15u), y = int(p >> 4);
     const uint32_t own = uint32_t(C_FLAME) | (fi << 2);   /* cells written by this very flame carry its slot */
+    POM_LOOP
     for(int i = -s; i <= s; i++)
     {
         const int cx = x + i, cy = y + i;
@@ -194,6 +199,7 @@ POM_HD bool flames_age(uint8_t* r)
     const int n = r[R_FCOUNT];
     if(n == 0) return false;
     uint32_t slot = r[R_FINDEX];
+    POM_LOOP
     for(int i = 0; i < n; i++, slot = ring_next(slot))
     {
         uint8_t* t = r + R_FTIME + slot;
@@ -205,6 +211,7 @@ POM_HD bool flames_age(uint8_t* r)
 POM_HD void flames_pop_due(uint8_t* r)
 {
     const int n = r[R_FCOUNT];
+    POM_LOOP
     for(int i = 0; i < n; i++)
     {
         if(r[R_FTIME + r[R_FINDEX]] == 0) pop_flame(r);
@@ -236,6 +243,7 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
     int stride = 0;
     uint32_t p = p0, strength = strength0;
     bool start = true;
+    POM_LOOP
     for(int guard = 0; guard < 8192; guard++)
     {
         if(start)
@@ -331,6 +339,7 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
  * bd[k] = biased destination of bomb k snapshotted before the pre-pass (step.cpp:191-192). */
 POM_HD void revert_chain(uint8_t* r, Agents& A, uint32_t moves, const uint8_t* bd, int agentID, int& flags)
 {
+    POM_LOOP
     for(int guard = 0; guard < 64; guard++)
     {
         const uint32_t ap = byte_of(A.pos, agentID);
@@ -341,6 +350,7 @@ POM_HD void revert_chain(uint8_t* r, Agents& A, uint32_t moves, const uint8_t* b
         int bombDestIndex = -1;
         int n = r[R_BCOUNT];
         if(n > 20) n = 20;
+        POM_LOOP
         for(int k = 0; k < n; k++)
         {
             if(bd[k] == oq) { bombDestIndex = k; break; }
@@ -391,6 +401,7 @@ POM_HD bool has_bomb_collision(uint8_t* r, uint32_t b, int index)    /* step_uti
 {
     const uint32_t t = bomb_dest_biased(b);
     const int n = r[R_BCOUNT];
+    POM_LOOP
     for(int i = index; i < n; i++)
     {
         const uint32_t o = bomb_at(r, i);
@@ -405,6 +416,7 @@ POM_HD void resolve_bomb_collision(uint8_t* r, Agents& A, uint32_t moves, const 
     const uint32_t t = bomb_dest_biased(b);
     bool collided = false;
     const int n = r[R_BCOUNT];
+    POM_LOOP
     for(int i = index; i < n; i++)
     {
         uint32_t& o = bomb_at(r, i);
@@ -527,6 +539,7 @@ POM_HD void store_agents(uint8_t* r, const Agents& A)
  * walking agents back along their moves. */
 POM_HD void revert_chain_idle(uint8_t* r, Agents& A, uint32_t moves, int agentID, int& flags)
 {
+    POM_LOOP
     for(int guard = 0; guard < 64; guard++)
     {
         const uint32_t ap = byte_of(A.pos, agentID);
@@ -553,8 +566,10 @@ POM_HD_COLD int bomb_phase_general(uint8_t* r, uint32_t moves, uint32_t oldPos, 
     load_agents(r, A);
     if(bc > 20) flags |= F_D4_BOMB_OVF;
     uint8_t bd[20];
+    POM_LOOP
     for(int k = 0; k < bc && k < 20; k++) bd[k] = uint8_t(bomb_dest_biased(bomb_at(r, k)));   /* FillBombDestPos :191-192 */
 
+    POM_LOOP
     for(int k = 0; k < bc; k++)                                      /* :195-227 */
     {
         uint32_t& b = bomb_at(r, k);
@@ -651,6 +666,7 @@ POM_HD void bomb_phase_idle(uint8_t* r, Agents& A, uint32_t moves, uint32_t oldP
     if(anyAgentMoved)   /* only an agent that moved this tick can be bounced back (step.cpp:209-214) */
     {
         uint32_t slot = bi;
+        POM_LOOP
         for(int k = 0; k < bc; k++, slot = ring_next(slot))
         {
             const uint32_t bp = bomb_slot(r, slot) & 0xFFu;
@@ -681,6 +697,7 @@ POM_HD void bomb_phase_idle(uint8_t* r, Agents& A, uint32_t moves, uint32_t oldP
         {
             bool collides = false;
             const int n = r[R_BCOUNT];
+            POM_LOOP
             for(int i = k + 1; i < n; i++)
             {
                 const uint32_t o = bomb_at(r, i);
@@ -727,6 +744,7 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
     {
         const int bc0 = r[R_BCOUNT];
         uint32_t slot = r[R_BINDEX];
+        POM_LOOP
         for(int k = 0; k < bc0; k++, slot = ring_next(slot)) T.onBomb |= bytes_equal(A.pos, bomb_slot(r, slot) & 0xFFu);
     }
 
@@ -794,6 +812,7 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
         const bool anyAgentMoved = A.pos != oldPos;
         {
             uint32_t slot = r[R_BINDEX];
+            POM_LOOP
             for(int k = 0; k < bc; k++, slot = ring_next(slot))
             {
                 const uint32_t b = bomb_slot(r, slot);
@@ -816,12 +835,14 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
         bc = r[R_BCOUNT];
         {
             uint32_t slot = r[R_BINDEX];
+            POM_LOOP
             for(int k = 0; k < bc; k++, slot = ring_next(slot)) bomb_slot(r, slot) -= (1u << 16);   /* ReduceBombTimer, bboard.hpp:308-311 */
         }
         explode_due = bc > 0 && ((bomb_slot(r, r[R_BINDEX]) >> 16) & 15u) == 0u;
         if(explode_due && explode_inline)
         {
             /* the explosion loop of util::TickBombs with the agents still in registers (see step_explode_due) */
+            POM_LOOP
             for(int k = 0; k < bc && r[R_BCOUNT] > 0; k++)
             {
                 const uint32_t c = bomb_slot(r, r[R_BINDEX]);
@@ -848,6 +869,7 @@ POM_HD int step_explode_due(uint8_t* r)
     Agents A;
     load_agents(r, A);
     const int bc = r[R_BCOUNT];
+    POM_LOOP
     for(int k = 0; k < bc && r[R_BCOUNT] > 0; k++)
     {
         const uint32_t c = bomb_slot(r, r[R_BINDEX]);
