@@ -276,8 +276,12 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
                 rem = strength < room ? strength : room;
                 stride = int(int8_t(0xF50BFF01u >> (8u * d)));            /* +1, -1, +11, -11 */
                 ci = ci0;
-                continue;
+                /* no `continue`: fall through to the first cell of the new ray in this very iteration, so that
+                 * lanes which just finished a ray stay in step with lanes that are in the middle of one */
+                if(rem == 0u) continue;
             }
+            else
+            {
             if(j != 31u)
             {
                 /* ExplodeBombAt epilogue :116-117 */
@@ -299,6 +303,7 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
             strength = r[R_FSTR + slot];
             r[R_BOARD + ci] = uint8_t(C_FLAME | (slot << 2));
             continue;
+            }
         }
         /* SpawnFlameItem on the next cell of the ray */
         ci = uint32_t(int(ci) + stride);
