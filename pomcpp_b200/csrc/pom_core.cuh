@@ -448,6 +448,8 @@ POM_HD void resolve_bomb_collision(uint8_t* r, Agents& A, uint32_t moves, const 
 struct TickCtx {
     uint32_t onBomb;        /* 0x80 in byte a: a bomb queue entry sits on agent a's cell (State::HasBomb of the
                                agent's start-of-tick cell; kept exact when bombs are planted this tick)            */
+    uint32_t anyDir;        /* non-zero iff some bomb in the queue has a direction: start-of-tick directions, kicks
+                               and stale direction bits inherited by bombs planted this tick           */
 };
 
 /* leave the cell an agent stood on: BOMB if a queue entry sits there, else PASSAGE (step.cpp:89-96,127-134) */
@@ -477,6 +479,7 @@ POM_HD void move_agent(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, uint32
         A.bcnt = with_byte(A.bcnt, i, byte_of(A.bcnt, i) + 1u);
         r[R_BCOUNT] = uint8_t(cnt + 1u);
         T.onBomb |= bytes_equal(A.pos, p);
+        T.anyDir |= b & 0xF00000u;
         return;
     }
     const uint32_t d = byte_of(dq, i);
@@ -520,6 +523,7 @@ POM_HD void move_agent(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, uint32
             {
                 uint32_t& b = bomb_at(r, bi);
                 b = (b & ~0xF00000u) + (m << 20);
+                T.anyDir |= b & 0xF00000u;
             }
         }
     }
@@ -661,37 +665,12 @@ POM_HD_COLD int explode_bomb_at_cold(uint8_t* r, uint32_t p, int idx)
     return flags;
 }
 
-/* The same phase when every bomb is idle (the common tick).  With all directions 0 the reference's loops
- * reduce to: (pre-pass, :195-227) bounce back agents that walked onto a bomb this tick; (move loop, :230-278)
- * a bomb whose cell reads PASSAGE is re-stamped BOMB, a bomb whose cell reads FLAMES explodes — unless a
- * later ring entry with a different value sits on the same cell (HasBombCollision -> `continue`, Q13). */
-POM_HD void bomb_phase_idle(uint8_t* r, Agents& A, uint32_t moves, uint32_t oldPos, int bc, bool anyAgentMoved, int& flags)
+/* The move loop of Step (:230-278) when every bomb is idle: a bomb whose cell reads PASSAGE is re-stamped
+ * BOMB, a bomb whose cell reads FLAMES explodes — unless a later ring entry with a different value sits on
+ * the same cell (HasBombCollision -> `continue`, Q13). */
+POM_HD void bomb_move_idle(uint8_t* r, Agents& A, int& flags)
 {
-    const uint32_t bi = r[R_BINDEX];
-    if(anyAgentMoved)   /* only an agent that moved this tick can be bounced back (step.cpp:209-214) */
-    {
-        uint32_t slot = bi;
-        POM_LOOP
-        for(int k = 0; k < bc; k++, slot = ring_next(slot))
-        {
-            const uint32_t bp = bomb_slot(r, slot) & 0xFFu;
-            const uint32_t c = r[R_BOARD + cell_of(bp)];
-            if(c_is_agent(c) || c_is_static(c))
-            {
-                const int a = get_agent(A, bp);
-                if(a >= 0)
-                {
-                    const uint32_t m = byte_of(moves, a);
-                    if(m != uint32_t(POM_MOVE_IDLE) && m != uint32_t(POM_MOVE_BOMB) &&
-                            byte_of(A.pos, a) != byte_of(oldPos, a))
-                    {
-                        revert_chain_idle(r, A, moves, a, flags);
-                        if(get_agent(A, bp) == -1) r[R_BOARD + cell_of(bp)] = uint8_t(C_BOMB);
-                    }
-                }
-            }
-        }
-    }
+    POM_LOOP
     for(int k = 0; k < int(r[R_BCOUNT]); k++)
     {
         const uint32_t b = bomb_at(r, k);
@@ -746,11 +725,17 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
     /* which agents stand on a bomb queue entry (State::HasBomb of their cell, used when they leave it) */
     TickCtx T;
     T.onBomb = 0u;
+    T.anyDir = 0u;
     {
         const int bc0 = r[R_BCOUNT];
         uint32_t slot = r[R_BINDEX];
         POM_LOOP
-        for(int k = 0; k < bc0; k++, slot = ring_next(slot)) T.onBomb |= bytes_equal(A.pos, bomb_slot(r, slot) & 0xFFu);
+        for(int k = 0; k < bc0; k++, slot = ring_next(slot))
+        {
+            const uint32_t b = bomb_slot(r, slot);
+            T.onBomb |= bytes_equal(A.pos, b & 0xFFu);
+            T.anyDir |= b & 0xF00000u;
+        }
     }
 
     /* destinations, one biased byte per agent (kept in a register: a dynamically indexed array would
@@ -809,32 +794,50 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
     int bc = r[R_BCOUNT];
     if(bc > 0)
     {
-        /* ResetBombFlags :188, fused with two questions that decide how much of :195-278 has to run:
-         * does any bomb have a direction, and (if none has) is there any bomb the idle-form loops would
-         * touch — one whose cell reads PASSAGE/FLAMES, or, when an agent moved this tick, AGENT/static. */
-        uint32_t anyDir = 0u;
-        bool idleWork = false;
-        const bool anyAgentMoved = A.pos != oldPos;
+        if(T.anyDir)
         {
+            /* some bomb moves (a kick, or a stale-direction plant): the general form of :187-278, out of line */
+            uint32_t slot = r[R_BINDEX];
+            POM_LOOP
+            for(int k = 0; k < bc; k++, slot = ring_next(slot)) bomb_slot(r, slot) &= ~0xF000000u;   /* ResetBombFlags :188 */
+            store_agents(r, A);
+            flags |= bomb_phase_general(r, moves, oldPos, bc);
+            load_agents(r, A);
+        }
+        else
+        {
+            /* Every bomb is idle.  One pass does ResetBombFlags (:188) and the idle form of the pre-pass (:195-227:
+             * bounce back an agent that walked onto a bomb this tick), and notes whether the idle form of the move
+             * loop (:230-278) has anything to do: it only re-stamps / explodes bombs whose cell reads PASSAGE / FLAMES.
+             * Reversions write AGENT or BOMB codes only, so they cannot create such a cell behind the pass. */
+            bool needMove = false;
+            const bool anyAgentMoved = A.pos != oldPos;
             uint32_t slot = r[R_BINDEX];
             POM_LOOP
             for(int k = 0; k < bc; k++, slot = ring_next(slot))
             {
                 const uint32_t b = bomb_slot(r, slot);
                 if(b & 0xF000000u) bomb_slot(r, slot) = b & ~0xF000000u;
-                anyDir |= b & 0xF00000u;
-                const uint32_t c = r[R_BOARD + cell_of(b & 0xFFu)];
-                idleWork = idleWork || c == uint32_t(C_PASSAGE) || c_is_flame(c) ||
-                           (anyAgentMoved && (c_is_agent(c) || c_is_static(c)));
+                const uint32_t bp = b & 0xFFu;
+                const uint32_t c = r[R_BOARD + cell_of(bp)];
+                needMove = needMove || c == uint32_t(C_PASSAGE) || c_is_flame(c);
+                if(anyAgentMoved && (c_is_agent(c) || c_is_static(c)))
+                {
+                    const int a = get_agent(A, bp);
+                    if(a >= 0)
+                    {
+                        const uint32_t m = byte_of(moves, a);
+                        if(m != uint32_t(POM_MOVE_IDLE) && m != uint32_t(POM_MOVE_BOMB) &&
+                                byte_of(A.pos, a) != byte_of(oldPos, a))
+                        {
+                            revert_chain_idle(r, A, moves, a, flags);
+                            if(get_agent(A, bp) == -1) r[R_BOARD + cell_of(bp)] = uint8_t(C_BOMB);
+                        }
+                    }
+                }
             }
+            if(needMove) bomb_move_idle(r, A, flags);
         }
-        if(anyDir)
-        {
-            store_agents(r, A);
-            flags |= bomb_phase_general(r, moves, oldPos, bc);
-            load_agents(r, A);
-        }
-        else if(idleWork) bomb_phase_idle(r, A, moves, oldPos, bc, anyAgentMoved, flags);
 
         /* util::TickBombs :283, step_utility.cpp:224-245 */
         bc = r[R_BCOUNT];
