@@ -794,6 +794,7 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
     int bc = r[R_BCOUNT];
     if(bc > 0)
     {
+        bool timers_ticked = false;
         if(T.anyDir)
         {
             /* some bomb moves (a kick, or a stale-direction plant): the general form of :187-278, out of line */
@@ -817,7 +818,9 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
             for(int k = 0; k < bc; k++, slot = ring_next(slot))
             {
                 const uint32_t b = bomb_slot(r, slot);
-                if(b & 0xF000000u) bomb_slot(r, slot) = b & ~0xF000000u;
+                /* ResetBombFlags, and — speculatively — ReduceBombTimer of TickBombs (:283): in the common tick
+                 * nothing between here and TickBombs touches the ring, so the timers are ticked in this pass */
+                bomb_slot(r, slot) = (b & ~0xF000000u) - (1u << 16);
                 const uint32_t bp = b & 0xFFu;
                 const uint32_t c = r[R_BOARD + cell_of(bp)];
                 needMove = needMove || c == uint32_t(C_PASSAGE) || c_is_flame(c);
@@ -836,11 +839,22 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
                     }
                 }
             }
-            if(needMove) bomb_move_idle(r, A, flags);
+            timers_ticked = true;
+            if(needMove)
+            {
+                /* rare: the move loop may explode bombs (RemoveAt leaves un-ticked stale copies in the reference),
+                 * so take the speculative tick back, run the loop, and let TickBombs tick as usual */
+                slot = r[R_BINDEX];
+                POM_LOOP
+                for(int k = 0; k < bc; k++, slot = ring_next(slot)) bomb_slot(r, slot) += (1u << 16);
+                timers_ticked = false;
+                bomb_move_idle(r, A, flags);
+            }
         }
 
         /* util::TickBombs :283, step_utility.cpp:224-245 */
         bc = r[R_BCOUNT];
+        if(!timers_ticked)
         {
             uint32_t slot = r[R_BINDEX];
             POM_LOOP
