@@ -58,11 +58,23 @@ struct Agents {
     int      alive;  /* aliveAgents                  */
 };
 
-POM_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+/* byte i of w / w with byte i replaced by v: one PRMT on the device (the index is usually dynamic) */
+POM_HD uint32_t byte_of(uint32_t w, int i)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, 0x4440u + uint32_t(i));
+#else
+    return (w >> (8 * i)) & 0xFFu;
+#endif
+}
 POM_HD uint32_t with_byte(uint32_t w, int i, uint32_t v)
 {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, v, 0x3210u + (uint32_t(4 - i) << (4 * i)));
+#else
     const int s = 8 * i;
     return (w & ~(0xFFu << s)) | ((v & 0xFFu) << s);
+#endif
 }
 /* (index + i) % 20 for the FixedQueue rings; the common operands are < 40 */
 POM_HD uint32_t ring20(uint32_t a) { return a < 20u ? a : (a < 40u ? a - 20u : a % 20u); }
