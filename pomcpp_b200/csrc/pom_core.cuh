@@ -755,27 +755,40 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
     uint32_t dq = 0u;
     for(int a = 0; a < 4; a++)                                       /* FillDestPos :25 */
         dq |= (uint32_t(int(byte_of(posq, a)) + move_delta(byte_of(moves, a))) & 0xFFu) << (8 * a);
-    for(int a = 0; a < 4; a++)                                       /* FixSwitchMove :26 (dead agents not skipped, Q1) */
+    /* tgt[a]: 0x80 in byte b iff agent a's destination is agent b's cell.  The same four masks serve
+     * FixSwitchMove (:26, step_utility.cpp:154-170; dead agents NOT skipped, Q1) and ResolveDependencies
+     * (:32, step_utility.cpp:172-205). */
+    uint32_t tgt[4];
+#pragma unroll
+    for(int a = 0; a < 4; a++) tgt[a] = bytes_equal(posq, byte_of(dq, a));
+#pragma unroll
+    for(int a = 0; a < 4; a++)
     {
+#pragma unroll
         for(int b = a + 1; b < 4; b++)
         {
-            if(byte_of(dq, a) == byte_of(posq, b) && byte_of(dq, b) == byte_of(posq, a))
+            if((tgt[a] & (0x80u << (8 * b))) && (tgt[b] & (0x80u << (8 * a))))
             {
+                /* a and b would swap cells: both stay (rare, so the masks are simply recomputed) */
                 dq = with_byte(dq, a, byte_of(posq, a));
                 dq = with_byte(dq, b, byte_of(posq, b));
+                tgt[a] = bytes_equal(posq, byte_of(posq, a));
+                tgt[b] = bytes_equal(posq, byte_of(posq, b));
             }
         }
     }
 
-    uint32_t dep = 0xFFFFFFFFu, roots = 0xFFFFFFFFu;                 /* ResolveDependencies :32, step_utility.cpp:172-205 */
+    uint32_t dep = 0xFFFFFFFFu, roots = 0xFFFFFFFFu;
     int rootNumber = 0;
+    const uint32_t liveMask = ~(A.flg << 6);
+#pragma unroll
     for(int a = 0; a < 4; a++)
     {
         bool isRoot = true;
         if(!ag_dead(A, a))
         {
             /* first other LIVE agent standing on a's destination */
-            const uint32_t hit = bytes_equal(posq, byte_of(dq, a)) & ~(A.flg << 6) & ~(0x80u << (8 * a));
+            const uint32_t hit = tgt[a] & liveMask & ~(0x80u << (8 * a));
             if(hit)
             {
                 dep = with_byte(dep, first_set_byte(hit), uint32_t(a));
