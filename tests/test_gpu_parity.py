@@ -437,3 +437,68 @@ def test_abi_error_codes(pb):
     assert S.shape[0] == 64 and not s0.any()
     b.close()
     b2.close()
+
+
+def test_config1_single_game_fixed_trace(pb, orc):
+    """BASELINE config 1: one 11x11 FFA game on the default board (InitState, seed 0x1337), four RandomAgents
+    replaced by a fixed-seed joint-action trace, one Step per tick until the game ends or 800 ticks."""
+    for trace_seed in range(8):
+        b = pb.Batch(1, n_templates=1, first_seed=0x1337)
+        S, _ = b.download()
+        ref0 = orc.zero_state()
+        assert orc.init_state(ref0, 0x1337) == 0 and orc.diff_batch(S, ref0)[0] == -1
+        status = np.zeros(1, np.uint8)
+        out = np.zeros(1, np.uint8)
+        for t in range(800):
+            mv = orc.rng_moves(1000 + trace_seed, 0, 1, t, 6)
+            b.step_host(mv, out, 0)
+            orc.env_step_batch(S, status, mv)
+            G, gst = b.download()
+            assert orc.diff_batch(G, S)[0] == -1 and gst[0] == status[0] == out[0], (trace_seed, t)
+            if status[0] & 1:
+                break
+        assert status[0] & 1, "random agents always finish well before 800 ticks"
+        b.close()
+
+
+def test_config4_fused_800_tick_rollout(pb, orc):
+    """BASELINE config 4 (one GPU's shard at reduced width): fused 800-tick rollout with in-kernel RNG, truncation at
+    800 and auto-reset; counters are consistent and sampled envs replay bit-exactly on the oracle."""
+    n, ticks, seed, env0 = 131072, 800, 4242, 3 * 524288
+    b = pb.Batch(n, env_offset=env0, n_templates=4096, max_ticks=800)
+    T, _ = b.templates()
+    b.rollout(500, seed, 0, 0)
+    b.rollout(300, seed, 500, 0)
+    s = b.stats()
+    assert s.env_steps == n * ticks
+    assert s.episodes == sum(s.wins) + s.draws + s.truncated + s.invalid
+    assert 20 < s.sum_episode_len / s.episodes < 35 and s.invalid < 1e-4 * s.episodes
+    for e in (0, 1, 777, 65535, 131071):
+        S = T[(env0 + e) % 4096: (env0 + e) % 4096 + 1].copy()
+        status, _ = _oracle_rollout(orc, S, T, env0 + e, ticks, seed, 6, 800)
+        G, gst = b.download(e, 1)
+        assert orc.diff_batch(G, S)[0] == -1 and gst[0] == status[0], "env %d" % e
+    b.close()
+
+
+def test_config5_expansion_full_size(pb, orc):
+    """BASELINE config 5 at full size: 4096 root states x 6^4 joint actions (5,308,416 children), clone + one Step fused;
+    all children of sampled roots compared with the oracle."""
+    n_roots = 4096
+    src = pb.Batch(n_roots, n_templates=512)
+    src.rollout(16, 99, 0, pb.ROLL_NO_RESET)
+    R, rst = src.download()
+    dst = pb.Batch(n_roots * 1296, n_templates=1, empty=True)
+    dst.expand_step_from(src, np.arange(n_roots, dtype=np.uint32), 1296, 0)
+    j = np.arange(1296)
+    mv = np.ascontiguousarray(np.stack([j % 6, (j // 6) % 6, (j // 36) % 6, (j // 216) % 6], axis=1).astype(np.uint8))
+    for root in (0, 1, 2047, 4095):
+        G, gst = dst.download(root * 1296, 1296)
+        E = np.repeat(R[root:root + 1], 1296)
+        est = np.repeat(rst[root:root + 1], 1296)
+        orc.env_step_batch(E, est, mv)
+        e, why = orc.diff_batch(G, E)
+        assert e == -1, "root %d child %d field group %d" % (root, e, why)
+        assert (gst == est).all()
+    src.close()
+    dst.close()
