@@ -407,7 +407,9 @@ int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status
     /* Chunked pipeline over three streams: copy-in, compute (the handle's stream), copy-out.  The kernel itself
      * writes the end-of-tick status bytes (before any auto-reset), so no extra pass is needed for them. */
     const uint64_t n = b->n_envs;
-    int chunks = n >= (uint64_t(1) << 18) ? 4 : 1;
+    static int want = -1;
+    if(want < 0) { const char* e = std::getenv("POM_CHUNKS"); want = e ? std::atoi(e) : 3; if(want < 1 || want > pom_batch::MAX_CHUNKS) want = 3; }
+    int chunks = n >= (uint64_t(1) << 18) ? want : 1;
     const uint64_t per = ((n + chunks - 1) / chunks + 1023) / 1024 * 1024;      /* multiple of every TPB */
     chunks = int((n + per - 1) / per);
     for(int c = 0; c < chunks; c++)
