@@ -10,7 +10,7 @@
  * Semantics follow the reference tick exactly (src/bboard/step.cpp:9-284 and the helpers it
  * calls); each function cites the lines it re-states.  The reference's recursion
  * (SpawnFlame <-> SpawnFlameItem <-> ExplodeBombAt, bboard.cpp:24-57,111-118,198-263) is run
- * by an explicit stack of 16-bit frames (`explode`), its tail recursion
+ * by an explicit stack of 32-bit frames (`explode`), its tail recursion
  * (AgentBombChainReversion, step_utility.cpp:62-128) by a loop (`revert_chain`).
  *
  * The header also compiles as plain C++ (POM_HD expands to `inline`); tests/hostsim builds it

@@ -1,19 +1,21 @@
 /*
  * pom_kernels.cuh — sm_100a kernels of the batched step path.
  *
- *  K1 k_step        per-tick mode: one CTA stages a tile of TPB consecutive 292-byte records in shared
- *                   memory with ONE 1-D TMA bulk copy (cp.async.bulk + mbarrier), every thread runs the
- *                   tick (pom_core.cuh) on its own record in place, and the tile goes back with one bulk
- *                   store.  HBM traffic per env-step = 292 B in + 292 B out + 4 B of moves; no thread
- *                   issues a global load/store for state.  The record stride of 73 words is odd, so
- *                   same-field accesses of the 32 lanes are bank-conflict free.
+ *  K1 k_step        per-tick mode: every WARP stages its own 32 consecutive 292-byte records (9344 B) in
+ *                   shared memory with ONE 1-D TMA bulk copy (cp.async.bulk + its own mbarrier), every thread
+ *                   runs the tick (pom_core.cuh) on its own record in place, and the slice goes back with one
+ *                   bulk store.  No CTA-wide barrier.  HBM traffic per env-step = 292 B in + 292 B out + 4 B of
+ *                   moves (+ 1 status byte when asked for); no thread issues a global load/store for state.
+ *                   The record stride of 73 words is odd, so same-field accesses of the 32 lanes are
+ *                   bank-conflict free.
  *  K2 k_rollout     fused K-tick mode: same staging, then K ticks on the resident record with actions
  *                   from the stateless counter RNG, truncation, episode statistics and auto-reset from the
  *                   template pool inside the kernel.
  *  K3 k_make_templates / k_fill_from_templates   board generation on the device and env (re)initialisation.
  *  K4 k_clone / k_expand_step                    state copy and tree-search fan-out (+ one Step, fused).
  *  K5 k_pack / k_unpack                          AoS bboard::State <-> packed record.
- *  K6 stats                                      warp-reduced counters -> one atomicAdd per warp and counter.
+ *  K6 stats                                      nine counters packed into three warp reductions, then one atomicAdd
+ *                                                 per warp and non-zero counter; warp-cooperative reset (cp.async).
  */
 #ifndef POM_KERNELS_CUH_
 #define POM_KERNELS_CUH_
