@@ -89,6 +89,26 @@ typedef struct pom_state {
     int32_t   flames_count;
 } pom_state;
 
+/*
+ * Persistent members of the reference's heuristic agent, agents::SimpleAgent (reference
+ * include/agents.hpp:55-76), 8 bytes per agent, used by the device-side rollout policy
+ * (include/pom_batch.h pom_batch_policy_moves / POM_ROLL_SIMPLE).  Everything else the agent holds
+ * (`danger`, the reachability map `r`) is recomputed by every act(); its private mt19937_64 is replaced
+ * by the shared counter RNG (one uniform{0..4} draw per agent and tick).
+ *   recent[k]   recentPositions.queue[k] (PHYSICAL slot), x&15 | (y&15)<<4 with x,y in -1..11
+ *               (a random move can point off the board, simple_agent.cpp:86,124-125); zero = (0,0), which
+ *               is what a zero-initialised agent holds in its unwritten slots (read by _HasRPLoop, :24-35)
+ *   rp_index    recentPositions.index   rp_count  recentPositions.count (0..4)
+ *   move_queue  moveQueue.queue[4], 3 bits per slot; the slot beyond `count` is read when count == 1
+ *               and the draw is odd (simple_agent.cpp:48,116), so stale contents are state
+ */
+typedef struct pom_simple_agent {
+    uint8_t  recent[4];
+    uint8_t  rp_index;
+    uint8_t  rp_count;
+    uint16_t move_queue;
+} pom_simple_agent;
+
 /* Per-env status byte kept next to the state by the batch engine.  The reference
  * keeps these in `Environment` (include/bboard.hpp:551-556, src/bboard/environment.cpp:150-168). */
 enum {
@@ -105,6 +125,7 @@ enum {
 }
 static_assert(sizeof(pom_state) == 1004, "pom_state must mirror bboard::State (1004 bytes)");
 static_assert(sizeof(pom_agent) == 24, "pom_agent must mirror bboard::AgentInfo");
+static_assert(sizeof(pom_simple_agent) == 8, "pom_simple_agent is 8 bytes");
 #endif
 
 #endif /* POM_STATE_H_ */

@@ -23,6 +23,9 @@ STATE_DT = np.dtype([("board", "<i4", (11, 11)), ("timeStep", "<i4"), ("aliveAge
                      ("bombs_count", "<i4"), ("flames", FLAME_DT, (20,)), ("flames_index", "<i4"),
                      ("flames_count", "<i4")])
 assert STATE_DT.itemsize == 1004
+# include/pom_state.h pom_simple_agent (persistent members of agents::SimpleAgent), 8 bytes
+SIMPLE_DT = np.dtype([("recent", "u1", (4,)), ("rp_index", "u1"), ("rp_count", "u1"), ("move_queue", "<u2")])
+assert SIMPLE_DT.itemsize == 8
 
 _vp = C.c_void_p
 _u8p = C.c_void_p
@@ -136,6 +139,29 @@ class Restatement:
         self.lib.pom_oracle_rng_moves_batch(seed, env0, n, tick, n_actions, _ptr(out))
         return out
 
+    # --- agents::SimpleAgent / bboard::strategy (oracle/pom_oracle_agent.c) ---
+    def simple_agents(self, n_envs):
+        return np.zeros((n_envs, 4), dtype=SIMPLE_DT)
+
+    def simple_act(self, s, agent_id, st, draw):
+        """st: one SIMPLE_DT element (array of shape (1,))"""
+        return self.lib.pom_oracle_simple_act(_ptr(s), agent_id, _ptr(st), int(draw))
+
+    def simple_moves_batch(self, S, status, A, seed, env0, tick, agent_mask, moves):
+        self.lib.pom_oracle_simple_moves_batch(_ptr(S), None if status is None else _ptr(status), C.c_long(S.shape[0]),
+                                               _ptr(A), C.c_uint64(seed), C.c_uint64(env0), C.c_uint32(tick),
+                                               C.c_uint(agent_mask), _ptr(moves))
+
+    def is_adjacent_enemy(self, s, agent_id, dist): return bool(self.lib.pom_oracle_is_adjacent_enemy(_ptr(s), agent_id, dist))
+    def is_in_danger(self, s, x, y): return self.lib.pom_oracle_is_in_danger(_ptr(s), x, y)
+
+    def fill_rmap(self, s, agent_id):
+        out = np.zeros((11, 11), dtype=np.int32)
+        self.lib.pom_oracle_fill_rmap(_ptr(s), agent_id, _ptr(out))
+        return out
+
+    def move_towards(self, s, agent_id, kind, a, b=0): return self.lib.pom_oracle_move_towards(_ptr(s), agent_id, kind, a, b)
+
     def bench_steps(self, S, status, moves, nthreads, templates=None):
         steps = C.c_ulonglong(0)
         t = self.lib.pom_oracle_bench_steps(_ptr(S), _ptr(status), S.shape[0], _ptr(moves), moves.shape[0], nthreads,
@@ -230,6 +256,51 @@ class Reference:
 
     def hardware_concurrency(self):
         return self.lib.ref_hardware_concurrency()
+
+    # --- agents::SimpleAgent / bboard::strategy, unmodified reference code ---
+    class SimpleAgents:
+        """n_envs x 4 reference SimpleAgent objects (zero-initialised memory, engine re-seeded per act)."""
+
+        def __init__(self, lib, n_envs):
+            self.lib, self.n = lib, 4 * n_envs
+            lib.ref_simple_new.restype = C.c_void_p
+            lib.ref_simple_new.argtypes = [C.c_long]
+            lib.ref_simple_free.argtypes = [C.c_void_p, C.c_long]
+            lib.ref_simple_act.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_int]
+            lib.ref_simple_export.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+            lib.ref_simple_moves_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
+            self.mem = lib.ref_simple_new(self.n)
+
+        def __del__(self):
+            if getattr(self, "mem", None):
+                self.lib.ref_simple_free(self.mem, self.n)
+                self.mem = None
+
+        def act(self, env, agent_id, s, draw):
+            return self.lib.ref_simple_act(self.mem, 4 * env + agent_id, _ptr(s), agent_id, int(draw))
+
+        def moves_batch(self, S, status, draws, agent_mask, moves):
+            self.lib.ref_simple_moves_batch(_ptr(S), None if status is None else _ptr(status), S.shape[0], self.mem,
+                                            _ptr(draws), agent_mask, _ptr(moves))
+
+        def export(self):
+            out = np.zeros(self.n, dtype=SIMPLE_DT)
+            for i in range(self.n):
+                self.lib.ref_simple_export(self.mem, i, _ptr(out[i:i + 1]))
+            return out.reshape(-1, 4)
+
+    def simple_agents(self, n_envs):
+        return Reference.SimpleAgents(self.lib, n_envs)
+
+    def is_adjacent_enemy(self, s, agent_id, dist): return bool(self.lib.ref_is_adjacent_enemy(_ptr(s), agent_id, dist))
+    def is_in_danger(self, s, x, y): return self.lib.ref_is_in_danger(_ptr(s), x, y)
+
+    def fill_rmap(self, s, agent_id):
+        out = np.zeros((11, 11), dtype=np.int32)
+        self.lib.ref_fill_rmap(_ptr(s), agent_id, _ptr(out))
+        return out
+
+    def move_towards(self, s, agent_id, kind, a, b=0): return self.lib.ref_move_towards(_ptr(s), agent_id, kind, a, b)
 
 
 _cache = {}

@@ -85,6 +85,22 @@ long pom_oracle_diff_batch(const pom_state* A, const pom_state* B, long n, const
 void pom_oracle_hash_batch(const pom_state* S, long n, uint64_t* out);
 void pom_oracle_rng_moves_batch(uint64_t seed, uint64_t env0, long n, uint32_t tick, uint32_t n_actions, uint8_t* moves_out);
 
+/* ---- agents::SimpleAgent + bboard::strategy (pom_oracle_agent.c) ----
+ * act() of the reference's heuristic agent `id` on state s (simple_agent.cpp:128-141); `st` holds the
+ * agent's persistent members, `draw` (0..4) replaces its one intDist(rng) call.  Returns the Move. */
+int  pom_oracle_simple_act(const pom_state* s, int id, pom_simple_agent* st, int draw);
+/* moves of the agents in agent_mask for a batch (A: [n][4] agent records; draws from
+ * pom_oracle_rng_moves(seed, env0+e, tick, 5)); entries of other agents are kept, dead agents get IDLE */
+void pom_oracle_simple_moves_batch(const pom_state* S, const uint8_t* status, long n, pom_simple_agent* A,
+                                   uint64_t seed, uint64_t env0, uint32_t tick, unsigned agent_mask, uint8_t* moves);
+/* strategy helpers for the reference's [strategy] known-answer tests */
+int  pom_oracle_is_adjacent_enemy(const pom_state* s, int id, int distance);           /* strategy.cpp:296-312 */
+int  pom_oracle_is_in_danger(const pom_state* s, int x, int y);                        /* strategy.cpp:225-246 */
+void pom_oracle_fill_rmap(const pom_state* s, int id, int32_t map_out[POM_BOARD_CELLS]); /* strategy.cpp:58-95  */
+/* kind 0: MoveTowardsPosition(a,b)  1: MoveTowardsPowerup(radius a)  2: MoveTowardsEnemy(radius a)
+ * 3: MoveTowardsSafePlace(radius a)  (strategy.cpp:101-183) */
+int  pom_oracle_move_towards(const pom_state* s, int id, int kind, int a, int b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,7 +2,8 @@
  * ref_shim.cpp — TEST INFRASTRUCTURE ONLY.  C shim around the UNMODIFIED reference.
  *
  * Built by oracle/Makefile into oracle/_ref/libpomref.so from this file plus the
- * reference's own src/bboard/{bboard,step,step_utility}.cpp, compiled where they lie
+ * reference's own src/bboard/{bboard,step,step_utility,strategy}.cpp and src/agents/simple_agent.cpp,
+ * compiled where they lie
  * under /root/reference (never copied into this repo).  Everything except the
  * `ref_*` C functions below has hidden visibility, so the reference's bboard::*
  * symbols never meet the product's in one link scope (SURVEY §8b ODR warning).
@@ -38,6 +39,8 @@
 
 #include "bboard.hpp"
 #include "step_utility.hpp"
+#include "agents.hpp"
+#include "strategy.hpp"
 
 #define REF_API extern "C" __attribute__((visibility("default")))
 
@@ -378,4 +381,129 @@ REF_API void ref_step_batch(void* states, long n, const uint8_t* moves)
 REF_API int ref_hardware_concurrency()
 {
     return int(std::thread::hardware_concurrency());
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * agents::SimpleAgent (reference src/agents/simple_agent.cpp, src/bboard/strategy.cpp), unmodified.
+ *
+ * The agent owns a std::mt19937_64 seeded from std::random_device and draws intDist(0,4) at most once
+ * per act().  To make games reproducible the shim re-seeds that engine before every act() with a seed
+ * whose FIRST intDist draw is the value the caller asks for (found by search at start-up), so the
+ * reference code itself still performs the draw.  Agent objects are constructed by placement-new on
+ * zeroed memory: the reference leaves moveQueue.queue / recentPositions.queue indeterminate and reads
+ * unwritten slots (simple_agent.cpp:28,48,125); zero is the canonical content.
+ */
+namespace
+{
+unsigned long long g_seed_for_draw[5];
+bool g_seed_ready = false;
+
+void FindDrawSeeds()
+{
+    if(g_seed_ready) return;
+    int found = 0;
+    bool have[5] = {false, false, false, false, false};
+    for(unsigned long long sd = 1; found < 5; sd++)
+    {
+        std::mt19937_64 g(sd);
+        std::uniform_int_distribution<int> d(0, 4);
+        int v = d(g);
+        if(!have[v]) { have[v] = true; g_seed_for_draw[v] = sd; found++; }
+    }
+    g_seed_ready = true;
+}
+}
+
+REF_API int ref_sizeof_simple_agent()
+{
+    return int(sizeof(agents::SimpleAgent));
+}
+
+REF_API void* ref_simple_new(long n)
+{
+    FindDrawSeeds();
+    void* mem = ::operator new(sizeof(agents::SimpleAgent) * size_t(n));
+    std::memset(mem, 0, sizeof(agents::SimpleAgent) * size_t(n));
+    agents::SimpleAgent* a = static_cast<agents::SimpleAgent*>(mem);
+    for(long i = 0; i < n; i++) new(&a[i]) agents::SimpleAgent;      // default-init: keeps the zero bytes of the PODs
+    return mem;
+}
+
+REF_API void ref_simple_free(void* mem, long n)
+{
+    agents::SimpleAgent* a = static_cast<agents::SimpleAgent*>(mem);
+    for(long i = 0; i < n; i++) a[i].~SimpleAgent();
+    ::operator delete(mem);
+}
+
+REF_API int ref_simple_act(void* mem, long idx, const void* st, int id, int draw)
+{
+    agents::SimpleAgent& a = static_cast<agents::SimpleAgent*>(mem)[idx];
+    a.id = id;
+    a.rng.seed(g_seed_for_draw[draw]);
+    return int(a.act(static_cast<const State*>(st)));
+}
+
+/* the agent's persistent members in the layout of pom_simple_agent (include/pom_state.h) */
+REF_API void ref_simple_export(void* mem, long idx, uint8_t out[8])
+{
+    agents::SimpleAgent& a = static_cast<agents::SimpleAgent*>(mem)[idx];
+    unsigned mq = 0;
+    for(int k = 0; k < 4; k++)
+    {
+        out[k] = uint8_t((a.recentPositions.queue[k].x & 15) | ((a.recentPositions.queue[k].y & 15) << 4));
+        mq |= (unsigned(a.moveQueue.queue[k]) & 7u) << (3 * k);
+    }
+    out[4] = uint8_t(a.recentPositions.index);
+    out[5] = uint8_t(a.recentPositions.count);
+    out[6] = uint8_t(mq & 0xFF);
+    out[7] = uint8_t(mq >> 8);
+}
+
+/* Environment::Step's collection loop (environment.cpp:137-146) over a batch: agents of env e are
+ * mem[4*e .. 4*e+3]; draws is [n][4] bytes (0..4); entries of `moves` outside agent_mask are kept;
+ * a dead agent's entry becomes IDLE. */
+REF_API void ref_simple_moves_batch(const void* states, const uint8_t* status, long n, void* mem,
+                                    const uint8_t* draws, unsigned agent_mask, uint8_t* moves)
+{
+    const State* S = static_cast<const State*>(states);
+    for(long e = 0; e < n; e++)
+    {
+        if(status && (status[e] & 0x11)) continue;
+        for(int a = 0; a < 4; a++)
+        {
+            if(!((agent_mask >> a) & 1)) continue;
+            if(S[e].agents[a].dead) { moves[4 * e + a] = 0; continue; }
+            moves[4 * e + a] = uint8_t(ref_simple_act(mem, 4 * e + a, &S[e], a, draws[4 * e + a]));
+        }
+    }
+}
+
+/* strategy known-answer helpers (unit_test/bboard/strategy_test.cpp) */
+REF_API void ref_fill_rmap(const void* st, int id, int32_t* map_out)
+{
+    bboard::strategy::RMap r;
+    bboard::strategy::FillRMap(*static_cast<const State*>(st), r, id);
+    std::memcpy(map_out, r.map, sizeof(r.map));
+}
+
+REF_API int ref_move_towards(const void* st, int id, int kind, int a, int b)
+{
+    const State& s = *static_cast<const State*>(st);
+    bboard::strategy::RMap r;
+    bboard::strategy::FillRMap(s, r, id);
+    if(kind == 0) return int(bboard::strategy::MoveTowardsPosition(r, {a, b}));
+    if(kind == 1) return int(bboard::strategy::MoveTowardsPowerup(s, r, a));
+    if(kind == 2) return int(bboard::strategy::MoveTowardsEnemy(s, r, a));
+    return int(bboard::strategy::MoveTowardsSafePlace(s, r, a));
+}
+
+REF_API int ref_is_adjacent_enemy(const void* st, int id, int distance)
+{
+    return bboard::strategy::IsAdjacentEnemy(*static_cast<const State*>(st), id, distance) ? 1 : 0;
+}
+
+REF_API int ref_is_in_danger(const void* st, int x, int y)
+{
+    return bboard::strategy::IsInDanger(*static_cast<const State*>(st), x, y);
 }

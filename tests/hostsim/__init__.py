@@ -14,7 +14,7 @@ REC = 292
 def build():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     src = os.path.join(HERE, "hostsim.cpp")
-    deps = [src] + [os.path.join(ROOT, "pomcpp_b200", "csrc", f) for f in ("pom_core.cuh", "pom_record.h")]
+    deps = [src] + [os.path.join(ROOT, "pomcpp_b200", "csrc", f) for f in ("pom_core.cuh", "pom_policy.cuh", "pom_record.h")]
     if os.path.exists(SO) and all(os.path.getmtime(SO) > os.path.getmtime(d) for d in deps):
         return
     cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-x", "c++",
@@ -39,6 +39,7 @@ class HostSim:
         L.hostsim_spawn_flame.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         L.hostsim_rng_moves.restype = C.c_uint32
         L.hostsim_rng_moves.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.hostsim_simple_moves.argtypes = [vp, C.c_long, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp]
         assert L.hostsim_record_bytes() == REC
 
     def pack(self, S, status=None):
@@ -62,6 +63,9 @@ class HostSim:
 
     def spawn_flame(self, rec, x, y, s):
         self.lib.hostsim_spawn_flame(_p(rec), x, y, s)
+
+    def simple_moves(self, recs, A, seed, env0, tick, mask, moves):
+        self.lib.hostsim_simple_moves(_p(recs), recs.shape[0], _p(A), seed, env0, tick, mask, _p(moves))
 
 
 class HostSimBackend:

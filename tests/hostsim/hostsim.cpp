@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstring>
 #include "pom_core.cuh"
+#include "pom_policy.cuh"
 
 extern "C" {
 
@@ -53,6 +54,25 @@ void hostsim_spawn_flame(uint8_t* rec, int x, int y, int strength)
     int flags = 0;
     pomcore::explode(rec, A, uint32_t(x) | (uint32_t(y) << 4), uint32_t(strength), 31u, flags);
     pomcore::store_agents(rec, A);
+}
+
+/* the device rollout policy (pom_policy.cuh) on packed records: moves of the agents in `mask` are replaced;
+ * A = [n][4] pom_simple_agent; draws from rng_moves(seed, env0 + e, tick, 5) */
+void hostsim_simple_moves(const uint8_t* recs, long n, pom_simple_agent* A, uint64_t seed, uint64_t env0, uint32_t tick,
+                          uint32_t mask, uint8_t* moves)
+{
+    for(long e = 0; e < n; e++)
+    {
+        const uint8_t* r = recs + e * POM_REC_BYTES;
+        if(r[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_INVALID)) continue;
+        uint32_t m;
+        std::memcpy(&m, moves + 4 * e, 4);
+        pompolicy::SimpleSt st[4];
+        std::memcpy(st, A + 4 * e, sizeof st);
+        m = pompolicy::simple_moves(r, mask, m, pomcore::rng_moves(seed, env0 + uint64_t(e), tick, 5), st);
+        std::memcpy(A + 4 * e, st, sizeof st);
+        std::memcpy(moves + 4 * e, &m, 4);
+    }
 }
 
 uint32_t hostsim_rng_moves(uint64_t seed, uint64_t env, uint32_t tick, uint32_t n_actions)
