@@ -50,8 +50,12 @@ enum {
  * default is {0..5} (RandomAgent, basic_agents.cpp:12-22). */
 enum {
     POM_ROLL_HARMLESS  = 0x1,
-    POM_ROLL_NO_RESET  = 0x2  /* finished envs freeze (Environment::Step, environment.cpp:125-128) instead of auto-resetting */
+    POM_ROLL_NO_RESET  = 0x2, /* finished envs freeze (Environment::Step, environment.cpp:125-128) instead of auto-resetting */
+    /* bits 8..11: agent a plays the reference's heuristic SimpleAgent (simple_agent.cpp:12-141) instead of drawing
+     * uniformly; the reference's own benchmark runs four of them (performance_test.cpp:38,59-63) */
+    POM_ROLL_SIMPLE_SHIFT = 8
 };
+#define POM_ROLL_SIMPLE(agent_mask) (((uint32_t)(agent_mask) & 0xFu) << POM_ROLL_SIMPLE_SHIFT)
 
 /* How pom_batch_init fills the batch.  Replaces InitState / InitBoardItems / PutAgentsInCorners
  * (bboard.hpp:651,661; bboard.cpp:322-382) and Environment::MakeGame (environment.cpp:53-66). */
@@ -108,8 +112,26 @@ int  pom_batch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags);
 int  pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags);
 /* `ticks` fused ticks with the boards resident in shared memory; actions from pom_rng_moves(rng_seed,
  * global env index, tick0 + k); auto-reset unless POM_ROLL_NO_RESET.  Replaces the loop of
- * Environment::StartGame (environment.cpp:68-88) with RandomAgent/HarmlessAgent::act (bboard.hpp:517-533). */
+ * Environment::StartGame (environment.cpp:68-88) with RandomAgent/HarmlessAgent::act (bboard.hpp:517-533), or with
+ * SimpleAgent::act for the agents named by POM_ROLL_SIMPLE(mask) (their draw: byte a of pom_rng_moves(.., 5)). */
 int  pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t tick0, uint32_t flags);
+
+/* ---- the reference's heuristic agent as a device-side action source (agents::SimpleAgent, simple_agent.cpp:12-141;
+ *      bboard::strategy, strategy.cpp:37-338): the caller of the step path in Environment::Step
+ *      (environment.cpp:137-146) and in the reference's benchmark.
+ * For every running env and every agent a in agent_mask (bit a), byte a of moves_dev[env] <- SimpleAgent::act(state);
+ * IDLE for a dead agent; bytes of agents outside the mask are kept, so a caller can mix its own moves with device
+ * opponents.  The agent's one random draw per act is byte a of pom_rng_moves(seed, env_offset + env, tick, 5).
+ * The agents' memories (pom_simple_agent, 8 bytes per agent) live on the device; they start zeroed and are zeroed
+ * again when their env starts a new episode.  Follow with pom_batch_step(b, moves_dev, ...). */
+int  pom_batch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_t tick, uint32_t agent_mask);
+/* same with HOST moves (n_envs x 4 bytes, read and written): upload, act, download, synchronise */
+int  pom_batch_policy_moves_host(pom_batch* b, uint8_t* moves_host, uint64_t seed, uint32_t tick, uint32_t agent_mask);
+int  pom_batch_policy_reset(pom_batch* b);                          /* all agents forget (new SimpleAgent objects) */
+/* agent memories of envs [first, first+count) as count x 4 pom_simple_agent (HOST memory) */
+int  pom_batch_policy_download(pom_batch* b, uint64_t first, uint64_t count, pom_simple_agent* out);
+int  pom_batch_policy_upload(pom_batch* b, uint64_t first, uint64_t count, const pom_simple_agent* in);
+
 /* state copy for tree search (the reference copies the POD State by assignment, README.md:4):
  * dst env first_dst + i <- src env src_idx[i] (HOST array of n_dst indices).  dst may equal src.    */
 int  pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_dst);

@@ -507,3 +507,66 @@ REF_API int ref_is_in_danger(const void* st, int x, int y)
 {
     return bboard::strategy::IsInDanger(*static_cast<const State*>(st), x, y);
 }
+
+/* CPU baseline for the SimpleAgent setting of the reference's own benchmark (performance_test.cpp:38-50): every env is
+ * played by four SimpleAgent objects (their own random_device-seeded engines, as in the reference) through
+ * act() x alive agents + bboard::Step + Environment bookkeeping; a finished env restarts from
+ * template[(env + episode) % n_templates] with four new agents.  Envs are partitioned over `nthreads` threads.
+ * Returns the wall time of the loop; *steps_out = env-steps executed. */
+REF_API double ref_bench_simple(void* states, long n, int ticks, int nthreads, const void* reset_templates, int n_templates,
+                                uint64_t /*seed: unused, the agents seed themselves*/, unsigned long long* steps_out)
+{
+    State* S = static_cast<State*>(states);
+    const State* T = static_cast<const State*>(reset_templates);
+    if(nthreads < 1) nthreads = 1;
+    std::vector<std::thread> th;
+    std::vector<unsigned long long> counts(size_t(nthreads), 0ull);
+    auto t0 = std::chrono::steady_clock::now();
+    for(int t = 0; t < nthreads; t++)
+    {
+        long lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+        th.emplace_back([=, &counts]()
+        {
+            unsigned long long c = 0;
+            const long m = hi - lo;
+            void* mem = ::operator new(sizeof(agents::SimpleAgent) * size_t(4 * m + 1));
+            std::memset(mem, 0, sizeof(agents::SimpleAgent) * size_t(4 * m + 1));
+            agents::SimpleAgent* ag = static_cast<agents::SimpleAgent*>(mem);
+            for(long i = 0; i < 4 * m; i++) { new(&ag[i]) agents::SimpleAgent; ag[i].id = int(i & 3); }
+            std::vector<uint8_t> status(size_t(m), 0);
+            std::vector<uint32_t> episode(size_t(m), 0u);
+            for(int k = 0; k < ticks; k++)
+            {
+                for(long e = lo; e < hi; e++)
+                {
+                    const long j = e - lo;
+                    uint8_t mv[4] = {0, 0, 0, 0};
+                    for(int a = 0; a < 4; a++)
+                        if(!S[e].agents[a].dead) mv[a] = uint8_t(ag[4 * j + a].act(&S[e]));
+                    if(FenceTick(S[e], mv)) status[size_t(j)] |= 0x10;
+                    else { EnvStep(&S[e], &status[size_t(j)], mv); c++; }
+                    if((status[size_t(j)] & 0x11) || S[e].timeStep >= 800)
+                    {
+                        uint32_t ep = ++episode[size_t(j)];
+                        S[e] = T[(uint64_t(e) + ep) % uint64_t(n_templates)];
+                        status[size_t(j)] = 0;
+                        for(int a = 0; a < 4; a++)
+                        {
+                            agents::SimpleAgent& x = ag[4 * j + a];
+                            x.recentPositions.count = 0; x.recentPositions.index = 0; x.moveQueue.count = 0;
+                        }
+                    }
+                }
+            }
+            for(long i = 0; i < 4 * m; i++) ag[i].~SimpleAgent();
+            ::operator delete(mem);
+            counts[size_t(t)] = c;
+        });
+    }
+    for(auto& x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
+    unsigned long long tot = 0;
+    for(auto c : counts) tot += c;
+    if(steps_out) *steps_out = tot;
+    return std::chrono::duration<double>(t1 - t0).count();
+}

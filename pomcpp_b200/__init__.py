@@ -18,6 +18,13 @@ ALGO_BYTES_PER_ENV_STEP = 2 * 289 + 4      # packed state in + out 
 
 STEP_RAW, STEP_AUTORESET, STEP_COUNT = 1, 2, 4
 ROLL_HARMLESS, ROLL_NO_RESET = 1, 2
+
+
+def ROLL_SIMPLE(agent_mask):
+    """rollout flag: the agents in agent_mask (bit a) play the reference's SimpleAgent"""
+    return (agent_mask & 0xF) << 8
+
+
 INIT_EMPTY = 1
 
 STATUS_DONE, STATUS_DRAW, STATUS_INVALID, STATUS_TRUNCATED = 0x01, 0x02, 0x10, 0x20
@@ -30,6 +37,9 @@ STATE_DT = np.dtype([("board", "<i4", (11, 11)), ("timeStep", "<i4"), ("aliveAge
                      ("bombs_count", "<i4"), ("flames", FLAME_DT, (20,)), ("flames_index", "<i4"),
                      ("flames_count", "<i4")])
 assert STATE_DT.itemsize == 1004
+# include/pom_state.h pom_simple_agent
+SIMPLE_DT = np.dtype([("recent", "u1", (4,)), ("rp_index", "u1"), ("rp_count", "u1"), ("move_queue", "<u2")])
+assert SIMPLE_DT.itemsize == 8
 
 
 class InitDesc(C.Structure):
@@ -80,6 +90,11 @@ def lib():
         L.pom_batch_step.argtypes = [vp, vp, u32]
         L.pom_batch_step_host.argtypes = [vp, vp, vp, u32]
         L.pom_batch_rollout.argtypes = [vp, u32, u64, u32, u32]
+        L.pom_batch_policy_moves.argtypes = [vp, vp, u64, u32, u32]
+        L.pom_batch_policy_moves_host.argtypes = [vp, vp, u64, u32, u32]
+        L.pom_batch_policy_reset.argtypes = [vp]
+        L.pom_batch_policy_download.argtypes = [vp, u64, u64, vp]
+        L.pom_batch_policy_upload.argtypes = [vp, u64, u64, vp]
         L.pom_batch_clone.argtypes = [vp, u64, vp, vp, u64]
         L.pom_batch_expand_step.argtypes = [vp, vp, vp, u64, u32, u32]
         L.pom_batch_spawn_flame.argtypes = [vp, u64, i32, i32, i32]
@@ -188,6 +203,25 @@ class Batch:
 
     def rollout(self, ticks, seed, tick0=0, flags=0):
         _ck(lib().pom_batch_rollout(self.h, ticks, seed, tick0, flags))
+
+    def policy_moves(self, moves_dev, seed, tick, agent_mask=15):
+        _ck(lib().pom_batch_policy_moves(self.h, moves_dev, seed, tick, agent_mask))
+
+    def policy_moves_host(self, moves, seed, tick, agent_mask=15):
+        assert moves.dtype == np.uint8 and moves.size == 4 * self.n and moves.flags.c_contiguous
+        _ck(lib().pom_batch_policy_moves_host(self.h, _p(moves), seed, tick, agent_mask))
+
+    def policy_reset(self): _ck(lib().pom_batch_policy_reset(self.h))
+
+    def policy_download(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        A = np.zeros((count, 4), SIMPLE_DT)
+        _ck(lib().pom_batch_policy_download(self.h, first, count, _p(A)))
+        return A
+
+    def policy_upload(self, A, first=0):
+        assert A.dtype == SIMPLE_DT and A.flags.c_contiguous and A.shape[1] == 4
+        _ck(lib().pom_batch_policy_upload(self.h, first, A.shape[0], _p(A)))
 
     def clone_from(self, src, src_idx, first_dst=0):
         idx = np.ascontiguousarray(src_idx, dtype=np.uint32)

@@ -57,6 +57,7 @@ struct pom_batch {
     pom_state* aos_stage = nullptr;            /* XFER_CHUNK states                          */
     uint8_t*  st_stage = nullptr;
     uint32_t* bad_count = nullptr;
+    uint32_t* policy = nullptr;                /* 9 x n_alloc words: SimpleAgent memories (allocated on first use) */
     void*     flush_buf = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = { nullptr, nullptr };
@@ -73,6 +74,7 @@ struct pom_batch {
         pomk::BatchParams P;
         P.recs = recs; P.n_envs = n_envs; P.env_offset = env_offset; P.templates = templates;
         P.n_templates = n_templates; P.max_ticks = max_ticks; P.episodes = episodes; P.stats = stats;
+        P.policy = policy; P.policy_stride = n_alloc;
         return P;
     }
 };
@@ -101,6 +103,16 @@ int ensure_stage(pom_batch* b)
         CK(cudaMalloc(&b->aos_stage, XFER_CHUNK * sizeof(pom_state)));
         CK(cudaMalloc(&b->st_stage, XFER_CHUNK));
         CK(cudaMalloc(&b->bad_count, sizeof(uint32_t)));
+    }
+    return POM_OK;
+}
+
+int ensure_policy(pom_batch* b)
+{
+    if(!b->policy)
+    {
+        CK(cudaMalloc(&b->policy, 9 * b->n_alloc * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(b->policy, 0, 9 * b->n_alloc * sizeof(uint32_t), b->stream));
     }
     return POM_OK;
 }
@@ -197,11 +209,38 @@ int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t*
 template<int TPB>
 int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, uint32_t flags)
 {
-    static bool once = false;
-    if(!once) { int rc = set_smem<TPB>(pomk::k_rollout<TPB>); if(rc) return rc; once = true; }
+    const uint32_t n_actions = (flags & POM_ROLL_HARMLESS) ? 5u : 6u, no_reset = (flags & POM_ROLL_NO_RESET) ? 1u : 0u;
+    const uint32_t mask = (flags >> POM_ROLL_SIMPLE_SHIFT) & 0xFu;
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
-    pomk::k_rollout<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(
-        b->params(), ticks, seed, tick0, (flags & POM_ROLL_HARMLESS) ? 5u : 6u, (flags & POM_ROLL_NO_RESET) ? 1u : 0u);
+    if(mask)
+    {
+        static bool once = false;
+        if(!once)
+        {
+            CK(cudaFuncSetAttribute(pomk::k_rollout<TPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pomk::RolloutScratch<TPB, true>::BYTES)));
+            once = true;
+        }
+        int rc = ensure_policy(b); if(rc) return rc;
+        pomk::k_rollout<TPB, true><<<grid, TPB, pomk::RolloutScratch<TPB, true>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, mask);
+    }
+    else
+    {
+        static bool once = false;
+        if(!once) { int rc = set_smem<TPB>(pomk::k_rollout<TPB, false>); if(rc) return rc; once = true; }
+        pomk::k_rollout<TPB, false><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, 0u);
+    }
+    b->launches++;
+    CK(cudaGetLastError());
+    return POM_OK;
+}
+
+template<int TPB>
+int launch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_t tick, uint32_t mask)
+{
+    static bool once = false;
+    if(!once) { int rc = set_smem<TPB>(pomk::k_policy_moves<TPB>); if(rc) return rc; once = true; }
+    const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
+    pomk::k_policy_moves<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), reinterpret_cast<uint32_t*>(moves_dev), seed, tick, mask);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -314,7 +353,7 @@ int pom_batch_destroy(pom_batch* b)
     if(b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->recs); cudaFree(b->templates); cudaFree(b->episodes); cudaFree(b->stats);
     cudaFree(b->moves_buf); cudaFree(b->status_buf); cudaFree(b->aos_stage); cudaFree(b->st_stage);
-    cudaFree(b->bad_count); cudaFree(b->flush_buf);
+    cudaFree(b->bad_count); cudaFree(b->flush_buf); cudaFree(b->policy);
     if(b->ev[0]) cudaEventDestroy(b->ev[0]);
     if(b->ev[1]) cudaEventDestroy(b->ev[1]);
     for(int i = 0; i < pom_batch::MAX_CHUNKS; i++) { if(b->ev_in[i]) cudaEventDestroy(b->ev_in[i]); if(b->ev_done[i]) cudaEventDestroy(b->ev_done[i]); }
@@ -369,6 +408,7 @@ int pom_batch_reset(pom_batch* b)
     int rc = use(b); if(rc) return rc;
     CK(cudaMemsetAsync(b->episodes, 0, b->n_alloc * sizeof(uint32_t), b->stream));
     CK(cudaMemsetAsync(b->stats, 0, POM_STATS_WORDS * sizeof(unsigned long long), b->stream));
+    if(b->policy) CK(cudaMemsetAsync(b->policy, 0, 9 * b->n_alloc * sizeof(uint32_t), b->stream));
     return fill_from_templates(b);
 }
 
@@ -452,6 +492,76 @@ int pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t 
 {
     int rc = use(b); if(rc) return rc;
     POM_DISPATCH(b, launch_rollout, b, ticks, rng_seed, tick0, flags);
+}
+
+int pom_batch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_t tick, uint32_t agent_mask)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!moves_dev) return fail(POM_E_ARG, "pom_batch_policy_moves: null moves");
+    if(agent_mask == 0 || agent_mask > 0xFu) return fail(POM_E_ARG, "pom_batch_policy_moves: agent_mask must be 1..15");
+    rc = ensure_policy(b); if(rc) return rc;
+    POM_DISPATCH(b, launch_policy_moves, b, moves_dev, seed, tick, agent_mask);
+}
+
+int pom_batch_policy_moves_host(pom_batch* b, uint8_t* moves_host, uint64_t seed, uint32_t tick, uint32_t agent_mask)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!moves_host) return fail(POM_E_ARG, "pom_batch_policy_moves_host: null moves");
+    CK(cudaMemcpyAsync(b->moves_buf, moves_host, 4 * b->n_envs, cudaMemcpyHostToDevice, b->stream));
+    rc = pom_batch_policy_moves(b, reinterpret_cast<uint8_t*>(b->moves_buf), seed, tick, agent_mask);
+    if(rc) return rc;
+    CK(cudaMemcpyAsync(moves_host, b->moves_buf, 4 * b->n_envs, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return POM_OK;
+}
+
+int pom_batch_policy_reset(pom_batch* b)
+{
+    int rc = use(b); if(rc) return rc;
+    if(b->policy) CK(cudaMemsetAsync(b->policy, 0, 8 * b->n_alloc * sizeof(uint32_t), b->stream));
+    /* word 8 (the episode tag) is left alone: zeroed memories are valid for any episode */
+    return POM_OK;
+}
+
+int pom_batch_policy_download(pom_batch* b, uint64_t first, uint64_t count, pom_simple_agent* out)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!out) return fail(POM_E_ARG, "pom_batch_policy_download: null output");
+    if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_policy_download: range outside the batch");
+    if(count == 0) return POM_OK;
+    rc = ensure_policy(b); if(rc) return rc;
+    uint32_t* tmp = nullptr;
+    CK(cudaMalloc(&tmp, count * 32));
+    pomk::k_policy_export<<<unsigned((count + 127) / 128), 128, 0, b->stream>>>(b->params(), first, count, tmp);
+    b->launches++;
+    cudaError_t ce = cudaGetLastError();
+    if(ce == cudaSuccess) ce = cudaMemcpyAsync(out, tmp, count * 32, cudaMemcpyDeviceToHost, b->stream);
+    if(ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
+    cudaFree(tmp);
+    if(ce != cudaSuccess) return fail(POM_E_CUDA, "pom_batch_policy_download", ce);
+    return POM_OK;
+}
+
+int pom_batch_policy_upload(pom_batch* b, uint64_t first, uint64_t count, const pom_simple_agent* in)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!in) return fail(POM_E_ARG, "pom_batch_policy_upload: null input");
+    if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_policy_upload: range outside the batch");
+    if(count == 0) return POM_OK;
+    rc = ensure_policy(b); if(rc) return rc;
+    uint32_t* tmp = nullptr;
+    CK(cudaMalloc(&tmp, count * 32));
+    cudaError_t ce = cudaMemcpyAsync(tmp, in, count * 32, cudaMemcpyHostToDevice, b->stream);
+    if(ce == cudaSuccess)
+    {
+        pomk::k_policy_import<<<unsigned((count + 127) / 128), 128, 0, b->stream>>>(b->params(), first, count, tmp);
+        b->launches++;
+        ce = cudaGetLastError();
+    }
+    if(ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
+    cudaFree(tmp);
+    if(ce != cudaSuccess) return fail(POM_E_CUDA, "pom_batch_policy_upload", ce);
+    return POM_OK;
 }
 
 int pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_dst)

@@ -14,6 +14,9 @@
  *  K3 k_make_templates / k_fill_from_templates   board generation on the device and env (re)initialisation.
  *  K4 k_clone / k_expand_step                    state copy and tree-search fan-out (+ one Step, fused).
  *  K5 k_pack / k_unpack                          AoS bboard::State <-> packed record.
+ *  K7 k_policy_moves / k_rollout<TPB, true>   the reference's SimpleAgent (pom_policy.cuh) as the action source: per tick
+ *                                                 into a moves buffer, or inside the fused rollout with the agents'
+ *                                                 8-byte memories resident in shared memory.
  *  K6 stats                                      nine counters packed into three warp reductions, then one atomicAdd
  *                                                 per warp and non-zero counter; warp-cooperative reset (cp.async).
  */
@@ -23,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "pom_core.cuh"
+#include "pom_policy.cuh"
 #include "pom_batch.h"
 
 namespace pomk
@@ -31,7 +35,7 @@ namespace pomk
 enum { ST_STEPS = 0, ST_EPISODES = 1, ST_WIN0 = 2, ST_DRAWS = 6, ST_TRUNC = 7, ST_SUMLEN = 8, ST_INVALID = 9 };
 
 struct BatchParams {
-    uint8_t*            recs;         /* n_tiles * TPB records                                  */
+    uint8_t*            recs;         /* n_envs packed records, allocated in whole 256-env tiles */
     uint64_t            n_envs;
     uint64_t            env_offset;   /* global index of env 0                                   */
     const uint8_t*      templates;    /* n_templates packed records                              */
@@ -39,6 +43,10 @@ struct BatchParams {
     uint32_t            max_ticks;
     uint32_t*           episodes;     /* per-env number of finished episodes                     */
     unsigned long long* stats;        /* POM_STATS_WORDS counters                                */
+    uint32_t*           policy;       /* SimpleAgent memories, SoA: word k of env e at [k * policy_stride + e], k = 2*agent + {0,1}
+                                         (the two words of pom_simple_agent); k = 8: the episode number they belong to.
+                                         Null until a policy entry point is used. */
+    uint64_t            policy_stride;
 };
 
 /* ---------------------------------------------------------------- TMA 1-D bulk copy + mbarrier (PTX) */
@@ -251,10 +259,104 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
     }
 }
 
-/* ---------------------------------------------------------------- K2: fused K-tick rollout */
+/* ---------------------------------------------------------------- K7: agent memories of the SimpleAgent policy */
+/* An env's memories are valid for the episode they were written in: a reset by any path (k_step auto-reset, rollout,
+ * pom_batch_reset) bumps or clears episodes[env], and the next reader starts from zeroed agents, which is what four
+ * freshly constructed SimpleAgent objects hold (performance_test.cpp:59-61 builds new agents per game). */
+struct GlobalAgentStore {
+    uint32_t* base;           /* &policy[env] */
+    uint64_t  stride;
+    __device__ __forceinline__ pompolicy::SimpleSt load(int a) const
+    {
+        pompolicy::SimpleSt s;
+        s.w0 = base[uint64_t(2 * a) * stride];
+        s.w1 = base[uint64_t(2 * a + 1) * stride];
+        return s;
+    }
+    __device__ __forceinline__ void store(int a, const pompolicy::SimpleSt& v)
+    {
+        base[uint64_t(2 * a) * stride] = v.w0;
+        base[uint64_t(2 * a + 1) * stride] = v.w1;
+    }
+    __device__ __forceinline__ void claim(uint32_t episode)
+    {
+        if(base[8 * stride] != episode)
+        {
+#pragma unroll
+            for(int k = 0; k < 8; k++) base[uint64_t(k) * stride] = 0u;
+            base[8 * stride] = episode;
+        }
+    }
+};
+
+/* the same eight words in shared memory, [word][thread] so that the lanes of a warp never share a bank */
+template<int TPB> struct SharedAgentStore {
+    uint32_t* base;           /* &words[threadIdx.x] */
+    __device__ __forceinline__ pompolicy::SimpleSt load(int a) const
+    {
+        pompolicy::SimpleSt s;
+        s.w0 = base[(2 * a) * TPB];
+        s.w1 = base[(2 * a + 1) * TPB];
+        return s;
+    }
+    __device__ __forceinline__ void store(int a, const pompolicy::SimpleSt& v)
+    {
+        base[(2 * a) * TPB] = v.w0;
+        base[(2 * a + 1) * TPB] = v.w1;
+    }
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for(int k = 0; k < 8; k++) base[k * TPB] = 0u;
+    }
+};
+
+/* per-tick mode: moves[env] byte a <- SimpleAgent::act for every agent a in `mask` of every running env (IDLE for a dead
+ * agent); the other bytes are kept.  Records are staged read-only with the same per-warp bulk load as k_step. */
 template<int TPB>
+__global__ void __launch_bounds__(TPB) k_policy_moves(BatchParams P, uint32_t* __restrict__ moves, uint64_t seed, uint32_t tick, uint32_t mask)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
+    const bool active = env < P.n_envs;
+    constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR) + warp;
+    uint8_t* sslice = smem + warp * SLICE_BYTES;
+    const uint8_t* gslice = P.recs + (size_t(blockIdx.x) * TPB + warp * 32u) * POM_REC_BYTES;
+    if(lane == 0)
+    {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, SLICE_BYTES);
+        bulk_g2s(sslice, gslice, SLICE_BYTES, bar);
+    }
+    uint32_t m = active ? moves[env] : 0u;
+    const uint32_t ep = active ? P.episodes[env] : 0u;
+    const uint32_t draws = pomcore::rng_moves(seed, P.env_offset + env, tick, 5u);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const uint8_t* rec = sslice + lane * POM_REC_BYTES;
+    if(active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_INVALID)))
+    {
+        GlobalAgentStore S{ P.policy + env, P.policy_stride };
+        S.claim(ep);
+        m = pompolicy::simple_moves(rec, mask, m, draws, S);
+        moves[env] = m;
+    }
+}
+
+/* ---------------------------------------------------------------- K2: fused K-tick rollout */
+/* POLICY = false: uniform random agents only (the headline rollout; no policy code in the kernel image).
+ * POLICY = true : the agents in `policy_mask` play SimpleAgent, the others stay uniform random. */
+template<int TPB, bool POLICY> struct RolloutScratch {
+    static constexpr uint32_t OFF_AGENTS = (TileScratch<TPB>::BYTES + 127u) / 128u * 128u;
+    static constexpr uint32_t BYTES = POLICY ? OFF_AGENTS + 8u * TPB * 4u : TileScratch<TPB>::BYTES;
+};
+
+template<int TPB, bool POLICY>
 __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, uint64_t seed, uint32_t tick0,
-                                                uint32_t n_actions, uint32_t no_reset)
+                                                uint32_t n_actions, uint32_t no_reset, uint32_t policy_mask)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
@@ -272,6 +374,15 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
         bulk_g2s(sslice, gslice, SLICE_BYTES, bar);
     }
     uint32_t ep_now = active ? P.episodes[env] : 0u;
+    SharedAgentStore<TPB> agents{ reinterpret_cast<uint32_t*>(smem + RolloutScratch<TPB, POLICY>::OFF_AGENTS) + threadIdx.x };
+    if(POLICY)
+    {
+        /* agent memories: global (SoA, coalesced) -> this thread's column in shared memory, zero if they belong to
+         * an earlier episode */
+        const bool mine = active && P.policy[8 * P.policy_stride + env] == ep_now;
+#pragma unroll
+        for(int k = 0; k < 8; k++) agents.base[k * TPB] = mine ? P.policy[uint64_t(k) * P.policy_stride + env] : 0u;
+    }
     __syncwarp();
     mbar_wait(bar, 0);
 
@@ -289,12 +400,28 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
 #pragma unroll
             for(int a = 0; a < 4; a++)
                 m |= (((uint32_t(h >> (16 * a)) & 0xFFFFu) * n_actions) >> 16) << (8 * a);
+            if(POLICY)
+            {
+                uint32_t draws = 0;
+#pragma unroll
+                for(int a = 0; a < 4; a++)
+                    draws |= (((uint32_t(h >> (16 * a)) & 0xFFFFu) * 5u) >> 16) << (8 * a);
+                m = pompolicy::simple_moves(rec, policy_mask, m, draws, agents);
+            }
             steps++;
         }
         env_tick(rec, m, stepped, false);
-        finish_and_reset(sslice, rec, P, env, active && stepped, !no_reset, ep_now);
+        const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, !no_reset, ep_now);
+        /* a new episode starts with four new agents */
+        if(POLICY && stepped && !no_reset && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID))) agents.clear();
     }
     warp_add(P.stats + ST_STEPS, steps);
+    if(POLICY && active)
+    {
+#pragma unroll
+        for(int k = 0; k < 8; k++) P.policy[uint64_t(k) * P.policy_stride + env] = agents.base[k * TPB];
+        P.policy[8 * P.policy_stride + env] = ep_now;
+    }
 
     fence_proxy_async();
     __syncwarp();
@@ -303,6 +430,25 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
         bulk_s2g(gslice, sslice, SLICE_BYTES);
         bulk_wait_read_all();
     }
+}
+
+/* agent memories <-> array of pom_simple_agent[4] per env (8 words), applying the episode rule */
+__global__ void k_policy_export(BatchParams P, uint64_t first, uint64_t count, uint32_t* __restrict__ out)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(i >= count) return;
+    const uint64_t env = first + i;
+    const bool mine = P.policy[8 * P.policy_stride + env] == P.episodes[env];
+    for(int k = 0; k < 8; k++) out[8 * i + k] = mine ? P.policy[uint64_t(k) * P.policy_stride + env] : 0u;
+}
+
+__global__ void k_policy_import(BatchParams P, uint64_t first, uint64_t count, const uint32_t* __restrict__ in)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(i >= count) return;
+    const uint64_t env = first + i;
+    for(int k = 0; k < 8; k++) P.policy[uint64_t(k) * P.policy_stride + env] = in[8 * i + k];
+    P.policy[8 * P.policy_stride + env] = P.episodes[env];
 }
 
 /* ---------------------------------------------------------------- K3: templates and (re)initialisation */

@@ -281,19 +281,33 @@ POM_HD uint32_t simple_act(const uint8_t* r, int id, SimpleSt& st, uint32_t draw
 
 /* Environment::Step's collection loop (environment.cpp:137-146) for the agents in `mask`: returns `moves` with the
  * bytes of the masked agents replaced (IDLE for a dead agent, whose slot the reference leaves unwritten).
- * `draws` = pom_rng_moves(seed, env, tick, 5): byte a is agent a's uniform{0..4} draw.  st[a] is agent a's state. */
-POM_HD uint32_t simple_moves(const uint8_t* r, uint32_t mask, uint32_t moves, uint32_t draws, SimpleSt* st)
+ * `draws` = pom_rng_moves(seed, env, tick, 5): byte a is agent a's uniform{0..4} draw.  `S` gives access to the
+ * four agent states: S.load(a) / S.store(a, st) (an array on the host, shared or global memory in the kernels). */
+template<class Store>
+POM_HD uint32_t simple_moves(const uint8_t* r, uint32_t mask, uint32_t moves, uint32_t draws, Store& S)
 {
     POM_LOOP
     for(int a = 0; a < 4; a++)
     {
         if(!((mask >> a) & 1u)) continue;
         uint32_t m = POM_MOVE_IDLE;
-        if(!(r[R_AFLAGS + a] & AF_DEAD)) m = simple_act(r, a, st[a], byte_of(draws, a));
+        if(!(r[R_AFLAGS + a] & AF_DEAD))
+        {
+            SimpleSt st = S.load(a);
+            m = simple_act(r, a, st, byte_of(draws, a));
+            S.store(a, st);
+        }
         moves = with_byte(moves, a, m);
     }
     return moves;
 }
+
+/* agent states in a plain array of four */
+struct ArrayStore {
+    SimpleSt* st;
+    POM_HD SimpleSt load(int a) const { return st[a]; }
+    POM_HD void store(int a, const SimpleSt& v) { st[a] = v; }
+};
 
 }
 #endif

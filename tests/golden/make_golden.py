@@ -11,6 +11,11 @@ Outputs
                   per-tick status bytes and the final states.  Moves come from the shared stateless
                   RNG (pom_oracle_rng_moves), so they are regenerated, not stored.
   init.npz      : InitBoardItems boards for the first 64 clean seeds >= 0x1337.
+  simple_agent.npz : games played by four of the reference's agents::SimpleAgent per env (unmodified
+                  simple_agent.cpp / strategy.cpp; the agents' engines are re-seeded before each act so that
+                  their one intDist draw is byte a of pom_oracle_rng_moves(seed, env, tick, 5)): initial
+                  states, the moves of every tick, final states and the agents' final memories.
+                  `python tests/golden/make_golden.py simple` regenerates only this file.
 """
 import os
 import sys
@@ -92,10 +97,44 @@ def write_pomtrc(R, O, path, n, ticks, nact, stress, rs, seeds):
     print("%s: %d envs x %d ticks, %d done, %d bytes" % (os.path.basename(path), n, ticks, int((status & 1).sum()), os.path.getsize(path)))
 
 
+def simple_agent_games(R, O, seeds, n=192, ticks=220, seed=77):
+    S = initial_states(R, n, 0, seeds)
+    half = n // 2          # second half: the boosted regime (kicks, long flames) so that fleeing logic is exercised
+    S["agents"]["canKick"][half:] = 1
+    S["agents"]["maxBombCount"][half:] = 3
+    S["agents"]["bombStrength"][half:] = 3
+    init = S.copy()
+    status = np.zeros(n, np.uint8)
+    shadow, shadow_status, fo = S.copy(), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    agents = R.simple_agents(n)
+    moves = np.zeros((ticks, n, 4), np.uint8)
+    live = np.zeros((ticks, n), np.uint8)
+    excluded = np.zeros(n, np.uint8)
+    for t in range(ticks):
+        draws = O.rng_moves(seed, 0, n, t, 5)
+        mv = np.zeros((n, 4), np.uint8)
+        live[t] = (status & 0x11) == 0
+        agents.moves_batch(S, status, draws, 15, mv)
+        moves[t] = mv
+        O.env_step_batch(shadow, shadow_status, mv, fo)
+        R.env_step_batch(S, status, mv, None, ((fo & 0x20) != 0).astype(np.uint8))
+        excluded |= ((status & 0x10) != 0).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "simple_agent.npz"), init=init.view(np.uint8).reshape(n, 1004),
+                        final=S.view(np.uint8).reshape(n, 1004), moves=moves, live=live, excluded=excluded,
+                        agents=agents.export().view(np.uint8).reshape(n, 32), seed=np.int64(seed), ticks=np.int64(ticks))
+    hist = np.bincount(moves[live.astype(bool)].ravel(), minlength=6)
+    print("simple_agent: %d envs x %d ticks, done %d, excluded %d, move histogram %s, %d bytes" %
+          (n, ticks, int((status & 1).sum()), int(excluded.sum()), hist.tolist(),
+           os.path.getsize(os.path.join(HERE, "simple_agent.npz"))))
+
+
 def main():
     oracle.build()
     R = oracle.reference()
     O = oracle.restatement()
+    if len(sys.argv) > 1 and sys.argv[1] == "simple":
+        simple_agent_games(R, O, oracle.clean_seeds(64))
+        return
 
     # 1. unit-test scenarios
     rec = scenarios.Recorder(R)
@@ -139,6 +178,8 @@ def main():
     # 4. an on-disk trace in the POMTRC1 format (pomcpp_b200/host/pom_trace.hpp) for pom_replay:
     #    96 envs x 120 ticks, boosted kick/bomb regime, produced by the compiled reference
     write_pomtrc(R, O, os.path.join(HERE, "stress96.pomtrc"), 96, 120, 6, 1, 45, seeds)
+    # 5. SimpleAgent games
+    simple_agent_games(R, O, seeds)
     for f in ("scenarios.npz", "init.npz", "traces.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 

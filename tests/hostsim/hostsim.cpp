@@ -69,7 +69,8 @@ void hostsim_simple_moves(const uint8_t* recs, long n, pom_simple_agent* A, uint
         std::memcpy(&m, moves + 4 * e, 4);
         pompolicy::SimpleSt st[4];
         std::memcpy(st, A + 4 * e, sizeof st);
-        m = pompolicy::simple_moves(r, mask, m, pomcore::rng_moves(seed, env0 + uint64_t(e), tick, 5), st);
+        pompolicy::ArrayStore store{ st };
+        m = pompolicy::simple_moves(r, mask, m, pomcore::rng_moves(seed, env0 + uint64_t(e), tick, 5), store);
         std::memcpy(A + 4 * e, st, sizeof st);
         std::memcpy(moves + 4 * e, &m, 4);
     }
