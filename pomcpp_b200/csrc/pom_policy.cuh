@@ -16,11 +16,12 @@
  *   * the agent's persistent members are 8 bytes (pom_simple_agent, include/pom_state.h) instead of a 3 KB object;
  *     its private mt19937_64 is replaced by one caller-supplied draw in 0..4 per act (every path of _Decide
  *     consumes at most one intDist(rng));
- *   * FillRMap's 121-int distance/predecessor map becomes one byte per cell holding the FIRST MOVE of the BFS
- *     path (non-zero = reachable).  MoveTowardsPosition (strategy.cpp:101-124) only ever follows the predecessor
- *     chain back to the cell next to the source, so the label is all it needs; the BFS visiting order
- *     (down, up, right, left; FIFO) is kept because it decides which first move a cell inherits;
- *   * the BFS runs lazily: only the two branches that read the map (danger > 0, enemy within 7) pay for it;
+ *   * FillRMap's queue BFS over a 121-int distance/predecessor map becomes 128-bit bitboard floods in registers
+ *     (see "Bitboards" below): the map is only ever used for "is this cell reachable" and "what is the first move
+ *     towards it", and both follow from flood fills; the tie-breaking of the FIFO queue is reproduced exactly;
+ *   * the floods run lazily: only the two branches that read the map (danger > 0, enemy within 7) pay for them;
+ *   * MoveTowardsSafePlace's double loop with an IsInDanger call per candidate becomes mask intersections and a
+ *     find-first-set;
  *   * IsInDanger for the agent's cell and its four neighbours (the nine calls of _Decide + SafeDirections) is one
  *     pass over the bomb ring.
  *
@@ -92,73 +93,172 @@ POM_HD uint32_t danger5(const uint8_t* r, int x, int y)
 
 POM_HD bool safe_condition(uint32_t danger, uint32_t min) { return danger == 0u || danger >= min; }   /* strategy.cpp:190-193 */
 
-/* FillRMap (strategy.cpp:58-95) as first-move labels.  lab[cell] = 0 unreachable (or the source), else the Move of
- * the first step of the BFS path source -> cell.  `q` is the FIFO of cell ids. */
-struct Reach { uint8_t lab[124]; };
+/* ---------------------------------------------------------------------------------------------
+ * Bitboards: bit (x + 11*y) of a 128-bit word per cell.  FillRMap's queue BFS (strategy.cpp:58-95) visits
+ * neighbours in the order down, up, right, left and is FIFO, so the path its predecessor chain encodes is the
+ * lexicographically smallest (in that direction order) among the SHORTEST paths; MoveTowardsPosition
+ * (strategy.cpp:101-124) only reports that path's first move.  Hence
+ *     first move towards t  =  the first direction k in (down, up, right, left) whose neighbour s_k of the source
+ *                              is nearest to t,
+ * which a level-synchronous flood from t finds without storing distances or predecessors: grow the set from t
+ * through walkable cells until it touches a neighbour of the source.  Every step of the flood is a handful of
+ * 128-bit shifts and masks in registers, identical for all lanes of a warp, instead of a byte queue in local
+ * memory with one divergent iteration per cell.
+ * ------------------------------------------------------------------------------------------- */
+typedef unsigned __int128 bb_t;
 
-POM_HD void fill_reach(const uint8_t* r, uint32_t src_pos, Reach& R)
+POM_HD bb_t bb_make(uint64_t hi, uint64_t lo) { return (bb_t(hi) << 64) | bb_t(lo); }
+POM_HD bb_t bb_bit(int cell) { return bb_t(1) << cell; }
+POM_HD bb_t bb_neighbours(bb_t b)
 {
-    uint8_t q[124];
-    uint32_t* lw = reinterpret_cast<uint32_t*>(R.lab);
-    for(int k = 0; k < 31; k++) lw[k] = 0u;
-    const int sx = int(src_pos & 15u), sy = int(src_pos >> 4);
-    const int src = sx + 11 * sy;
-    int head = 0, tail = 0;
-    q[tail++] = uint8_t(src);
-    POM_LOOP
-    while(head != tail)
-    {
-        const int c = q[head++];
-        const int cx = c % 11, cy = c / 11;
-        const uint32_t inherit = R.lab[c];                     /* 0 only for the source */
-        /* TryAdd order: (x, y+1), (x, y-1), (x+1, y), (x-1, y)  = DOWN, UP, RIGHT, LEFT */
-        POM_LOOP
-        for(int k = 0; k < 4; k++)
-        {
-            const uint32_t mv = 0x03040102u >> (8 * k) & 0xFFu;
-            const int nx = cx + ((k == 2) ? 1 : (k == 3) ? -1 : 0);
-            const int ny = cy + ((k == 0) ? 1 : (k == 1) ? -1 : 0);
-            if(uint32_t(nx) > 10u || uint32_t(ny) > 10u) continue;
-            const int nc = nx + 11 * ny;
-            if(nc == src || R.lab[nc] != 0u) continue;
-            const uint32_t code = r[R_BOARD + nc];
-            const bool agent = c_is_agent(code);
-            if(!(c_is_walkable(code) || agent)) continue;
-            R.lab[nc] = uint8_t(inherit ? inherit : mv);
-            if(!agent) q[tail++] = uint8_t(nc);                /* paths end at agent cells (strategy.cpp:50-52) */
-        }
-    }
+    const bb_t full = bb_make(0x01FFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull);
+    const bb_t not_col0 = bb_make(0x01FFBFF7FEFFDFFBull, 0xFF7FEFFDFFBFF7FEull);
+    const bb_t not_col10 = bb_make(0x00FFDFFBFF7FEFFDull, 0xFFBFF7FEFFDFFBFFull);
+    return (((b << 1) & not_col0) | ((b >> 1) & not_col10) | (b << 11) | (b >> 11)) & full;
+}
+POM_HD int bb_lowest(bb_t b)           /* index of the lowest set bit, b != 0 */
+{
+    const uint64_t lo = uint64_t(b), hi = uint64_t(b >> 64);
+#if defined(__CUDA_ARCH__)
+    return lo ? __ffsll((long long)lo) - 1 : 63 + __ffsll((long long)hi);
+#else
+    return lo ? __builtin_ctzll(lo) : 64 + __builtin_ctzll(hi);
+#endif
 }
 
-/* MoveTowardsPosition (strategy.cpp:101-124) for a target != source */
-POM_HD uint32_t move_towards(const Reach& R, uint32_t src_pos, int tx, int ty)
+/* what the policy needs to know about the board, built once per env and tick for all four agents */
+struct Boards {
+    bb_t walk;      /* IS_WALKABLE: passage or powerup (bboard.hpp:87-90)        */
+    bb_t agent;     /* item >= AGENT0: BFS paths may END here (strategy.cpp:44-52) */
+};
+
+POM_HD Boards make_boards(const uint8_t* r)
 {
-    const uint32_t l = R.lab[tx + 11 * ty];
-    if(l) return l;
+    Boards B;
+    B.walk = 0; B.agent = 0;
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(r + R_BOARD);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 0; i < 31; i++)
+    {
+        const uint32_t w = w32[i];
+        /* per byte b < 0x80: MSB of (b + 0x80 - lo) is set iff b >= lo; flame bytes (MSB set) are masked out at the end */
+        const uint32_t l = w & 0x7F7F7F7Fu, plain = ~w & 0x80808080u;
+        const uint32_t ge1 = l + 0x7F7F7F7Fu, ge9 = l + 0x77777777u, ge12 = l + 0x74747474u, ge13 = l + 0x73737373u, ge17 = l + 0x6F6F6F6Fu;
+        const uint32_t walk = (~ge1 | (ge9 & ~ge12)) & plain;       /* code 0 or 9..11 */
+        const uint32_t agent = ge13 & ~ge17 & plain;                /* code 13..16     */
+        /* the four byte flags -> one nibble (bit k = byte k) */
+        const uint32_t wn = (((walk >> 7) * 0x01020408u) >> 24) & 15u;
+        const uint32_t an = (((agent >> 7) * 0x01020408u) >> 24) & 15u;
+        B.walk |= bb_t(wn) << (4 * i);
+        B.agent |= bb_t(an) << (4 * i);
+    }
+    const bb_t full = bb_make(0x01FFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull);    /* word 30 also holds three non-board bytes */
+    B.walk &= full;
+    B.agent &= full;
+    return B;
+}
+
+/* first move of FillRMap's path from the source cell s to the cell t != s; 0xFF if t cannot be reached */
+POM_HD uint32_t first_move_towards(const Boards& B, int s, int t)
+{
+    const int sx = s % 11, sy = s / 11;
+    const bb_t pass = B.walk & ~bb_bit(s);                        /* the BFS never re-enters its source */
+    const bb_t s_down = sy < 10 ? bb_bit(s + 11) : bb_t(0), s_up = sy > 0 ? bb_bit(s - 11) : bb_t(0);
+    const bb_t s_right = sx < 10 ? bb_bit(s + 1) : bb_t(0), s_left = sx > 0 ? bb_bit(s - 1) : bb_t(0);
+    const bb_t s_any = s_down | s_up | s_right | s_left;
+    bb_t T = bb_bit(t);
+    POM_LOOP
+    for(int guard = 0; guard < 128; guard++)
+    {
+        const bb_t hit = T & s_any;
+        if(hit != 0)
+        {
+            if((hit & s_down) != 0) return POM_MOVE_DOWN;
+            if((hit & s_up) != 0) return POM_MOVE_UP;
+            if((hit & s_right) != 0) return POM_MOVE_RIGHT;
+            return POM_MOVE_LEFT;
+        }
+        const bb_t n = T | (bb_neighbours(T) & pass);
+        if(n == T) break;
+        T = n;
+    }
+    return 0xFFu;
+}
+
+/* MoveTowardsPosition (strategy.cpp:101-124) for a target != source, including what it does on an unreachable one */
+POM_HD uint32_t move_towards(const Boards& B, uint32_t src_pos, int tx, int ty)
+{
+    const uint32_t l = first_move_towards(B, cell_of(src_pos), tx + 11 * ty);
+    if(l != 0xFFu) return l;
     /* unreachable target: its predecessor field is 0 = cell (0,0).  Only a source standing ON (0,0) takes the
      * "predecessor is the source" branch and walks towards the target's side; everybody else gets IDLE. */
     if(src_pos != 0u) return POM_MOVE_IDLE;
     return tx > 0 ? uint32_t(POM_MOVE_RIGHT) : uint32_t(POM_MOVE_DOWN);
 }
 
-/* MoveTowardsSafePlace (strategy.cpp:126-144); the loops stop at `radius`, not at origin + radius (sic) */
-POM_HD uint32_t move_towards_safe_place(const uint8_t* r, const Reach& R, uint32_t src_pos, int radius)
+/* cells in range of a bomb about to explode: IsInDanger(x, y) == 1, i.e. !_safe_condition(.., 2) (strategy.cpp:190-193,225-246) */
+POM_HD bb_t unsafe_cells(const uint8_t* r)
 {
-    const int ox = int(src_pos & 15u), oy = int(src_pos >> 4);
-    const int y0 = oy - radius < 0 ? 0 : oy - radius, y1 = radius < 11 ? radius : 11;
-    const int x0 = ox - radius < 0 ? 0 : ox - radius, x1 = radius < 11 ? radius : 11;
+    const int n = r[R_BCOUNT];
+    uint32_t slot = r[R_BINDEX];
+    bb_t t1 = 0, t0 = 0;
+    const bb_t col0 = bb_make(0x0000400801002004ull, 0x0080100200400801ull);
     POM_LOOP
-    for(int y = y0; y < y1; y++)
+    for(int i = 0; i < n; i++)
     {
-        POM_LOOP
-        for(int x = x0; x < x1; x++)
-        {
-            const int dx = x - ox, dy = y - oy;
-            if((dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy) > radius) continue;
-            if(R.lab[x + 11 * y] != 0u && safe_condition(danger_at(r, x, y), 2u)) return R.lab[x + 11 * y];
-        }
+        const uint32_t b = reinterpret_cast<const uint32_t*>(r + R_BOMBS)[slot];
+        slot = ring_next(slot);
+        const uint32_t t = (b >> 16) & 15u;
+        if(t > 1u) continue;
+        const int bx = int(b & 15u), by = int((b >> 4) & 15u), s = int((b >> 12) & 15u);
+        if(bx > 10 || by > 10) continue;                          /* cannot cover a board cell's row AND column test */
+        const int x0 = bx - s < 0 ? 0 : bx - s, x1 = bx + s > 10 ? 10 : bx + s;
+        const int y0 = by - s < 0 ? 0 : by - s, y1 = by + s > 10 ? 10 : by + s;
+        const bb_t row = bb_t((2u << x1) - (1u << x0)) << (11 * by);
+        const bb_t rows = (bb_bit(11 * (y1 + 1)) - 1) ^ (bb_bit(11 * y0) - 1);
+        const bb_t cross = row | ((col0 << bx) & rows);
+        if(t == 1u) t1 |= cross; else t0 |= cross;
     }
-    return POM_MOVE_IDLE;
+    return t1 & ~t0;                                              /* a covering bomb with time 0 makes the minimum 0 = "no danger" */
+}
+
+/* MoveTowardsSafePlace (strategy.cpp:126-144); the loops stop at `radius`, not at origin + radius (sic) */
+POM_HD uint32_t move_towards_safe_place(const uint8_t* r, const Boards& B, uint32_t src_pos, int radius)
+{
+    const int ox = int(src_pos & 15u), oy = int(src_pos >> 4), s = ox + 11 * oy;
+    /* the cells the double loop looks at: Manhattan distance <= radius, x < radius, y < radius */
+    bb_t region = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int y = 0; y < 11; y++)
+    {
+        const int dy = y < oy ? oy - y : y - oy, h = radius - dy;
+        int x0 = ox - h, x1 = ox + h;
+        if(x0 < 0) x0 = 0;
+        if(x1 > 10) x1 = 10;
+        if(x1 > radius - 1) x1 = radius - 1;
+        if(h >= 0 && y < radius && x0 <= x1) region |= bb_t((2u << x1) - (1u << x0)) << (11 * y);
+    }
+    /* FillRMap's reachable set: flood from the source through walkable cells; agent cells are reached but not left */
+    const bb_t src = bb_bit(s), pass = B.walk & ~src;
+    bb_t E = src;
+    POM_LOOP
+    for(int guard = 0; guard < 128; guard++)
+    {
+        const bb_t n = E | (bb_neighbours(E) & pass);
+        if(n == E) break;
+        E = n;
+    }
+    const bb_t reach = (E | (bb_neighbours(E) & B.agent)) & ~src;
+    bb_t cand = reach & region;
+    if(cand == 0) return POM_MOVE_IDLE;
+    cand &= ~unsafe_cells(r);
+    if(cand == 0) return POM_MOVE_IDLE;
+    const int t = bb_lowest(cand);                                /* scan order of the reference: y outer, x inner */
+    return first_move_towards(B, s, t);                           /* reachable by construction */
 }
 
 /* the 3-bit slots of moveQueue.queue */
@@ -207,17 +307,15 @@ POM_HD uint32_t pick_safe_direction(const uint8_t* r, uint32_t pos, uint32_t dg,
 }
 
 /* _Decide, simple_agent.cpp:52-127 */
-POM_HD uint32_t simple_decide(const uint8_t* r, int id, SimpleSt& st, uint32_t draw)
+POM_HD uint32_t simple_decide(const uint8_t* r, const Boards& B, int id, SimpleSt& st, uint32_t draw)
 {
     const uint32_t pos = r[R_APOS + id];
     const int x = int(pos & 15u), y = int(pos >> 4);
     const uint32_t dg = danger5(r, x, y);
     const uint32_t danger = dg & 15u;
-    Reach R;
     if(danger > 0u)
     {
-        fill_reach(r, pos, R);
-        const uint32_t m = move_towards_safe_place(r, R, pos, int(danger));
+        const uint32_t m = move_towards_safe_place(r, B, pos, int(danger));
         const uint32_t p = pos_step(pos, m);
         if(!pos_oob(p) && c_is_walkable(r[R_BOARD + cell_of(p)]) && safe_condition((dg >> (4u * m)) & 15u, 2u)) return m;
         return pick_safe_direction(r, pos, dg, st, draw);
@@ -246,11 +344,7 @@ POM_HD uint32_t simple_decide(const uint8_t* r, int id, SimpleSt& st, uint32_t d
                 loop = loop && byte_of(st.w0, int((rp_index + i) & 3u)) == byte_of(st.w0, int((rp_index + i + 2u) & 3u));
             if(loop) return draw & 3u;                          /* Move(intDist(rng) % 4) */
             uint32_t m = POM_MOVE_IDLE;
-            if(target >= 0)
-            {
-                fill_reach(r, pos, R);
-                m = move_towards(R, pos, int(r[R_APOS + target] & 15u), int(r[R_APOS + target] >> 4));
-            }
+            if(target >= 0) m = move_towards(B, pos, int(r[R_APOS + target] & 15u), int(r[R_APOS + target] >> 4));
             const uint32_t p = pos_step(pos, m);
             if(!pos_oob(p) && c_is_walkable(r[R_BOARD + cell_of(p)]) && safe_condition((dg >> (4u * m)) & 15u, 5u)) return m;
         }
@@ -267,9 +361,9 @@ POM_HD uint32_t simple_decide(const uint8_t* r, int id, SimpleSt& st, uint32_t d
 }
 
 /* SimpleAgent::act, simple_agent.cpp:128-141 */
-POM_HD uint32_t simple_act(const uint8_t* r, int id, SimpleSt& st, uint32_t draw)
+POM_HD uint32_t simple_act(const uint8_t* r, const Boards& B, int id, SimpleSt& st, uint32_t draw)
 {
-    const uint32_t m = simple_decide(r, id, st, draw);
+    const uint32_t m = simple_decide(r, B, id, st, draw);
     const uint32_t p = pos_step(r[R_APOS + id], m);            /* BOMB and IDLE remember the agent's own cell */
     uint32_t idx = st.w1 & 0xFFu, cnt = (st.w1 >> 8) & 0xFFu;
     if(cnt == 4u) { idx = (idx + 1u) & 3u; cnt = 3u; }          /* PopElem when full */
@@ -286,6 +380,7 @@ POM_HD uint32_t simple_act(const uint8_t* r, int id, SimpleSt& st, uint32_t draw
 template<class Store>
 POM_HD uint32_t simple_moves(const uint8_t* r, uint32_t mask, uint32_t moves, uint32_t draws, Store& S)
 {
+    const Boards B = make_boards(r);
     POM_LOOP
     for(int a = 0; a < 4; a++)
     {
@@ -294,7 +389,7 @@ POM_HD uint32_t simple_moves(const uint8_t* r, uint32_t mask, uint32_t moves, ui
         if(!(r[R_AFLAGS + a] & AF_DEAD))
         {
             SimpleSt st = S.load(a);
-            m = simple_act(r, a, st, byte_of(draws, a));
+            m = simple_act(r, B, a, st, byte_of(draws, a));
             S.store(a, st);
         }
         moves = with_byte(moves, a, m);
