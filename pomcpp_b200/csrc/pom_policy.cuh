@@ -101,7 +101,7 @@ POM_HD bool safe_condition(uint32_t danger, uint32_t min) { return danger == 0u 
  *     first move towards t  =  the first direction k in (down, up, right, left) whose neighbour s_k of the source
  *                              is nearest to t,
  * which a level-synchronous flood from t finds without storing distances or predecessors: grow the set from t
- * through walkable cells until it touches a neighbour of the source.  Every step of the flood is a handful of
+ * through walkable cells until it touches a neighbour of the source (stage B of simple_decide).  Every step of the flood is a handful of
  * 128-bit shifts and masks in registers, identical for all lanes of a warp, instead of a byte queue in local
  * memory with one divergent iteration per cell.
  * ------------------------------------------------------------------------------------------- */
@@ -109,13 +109,6 @@ typedef unsigned __int128 bb_t;
 
 POM_HD bb_t bb_make(uint64_t hi, uint64_t lo) { return (bb_t(hi) << 64) | bb_t(lo); }
 POM_HD bb_t bb_bit(int cell) { return bb_t(1) << cell; }
-POM_HD bb_t bb_neighbours(bb_t b)
-{
-    const bb_t full = bb_make(0x01FFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull);
-    const bb_t not_col0 = bb_make(0x01FFBFF7FEFFDFFBull, 0xFF7FEFFDFFBFF7FEull);
-    const bb_t not_col10 = bb_make(0x00FFDFFBFF7FEFFDull, 0xFFBFF7FEFFDFFBFFull);
-    return (((b << 1) & not_col0) | ((b >> 1) & not_col10) | (b << 11) | (b >> 11)) & full;
-}
 POM_HD int bb_lowest(bb_t b)           /* index of the lowest set bit, b != 0 */
 {
     const uint64_t lo = uint64_t(b), hi = uint64_t(b >> 64);
@@ -160,42 +153,22 @@ POM_HD Boards make_boards(const uint8_t* r)
     return B;
 }
 
-/* first move of FillRMap's path from the source cell s to the cell t != s; 0xFF if t cannot be reached */
-POM_HD uint32_t first_move_towards(const Boards& B, int s, int t)
+/* one flood step: everything in `pass` next to X joins X.  The column masks of the two horizontal shifts are folded
+ * into pre-masked copies of `pass`, so a step is four 128-bit shifts, three ANDs and four ORs. */
+struct Passable {
+    bb_t any, from_left, from_right;   /* enterable at all / by a step to the right (not column 0) / to the left (not column 10) */
+};
+POM_HD Passable make_passable(bb_t pass)
 {
-    const int sx = s % 11, sy = s / 11;
-    const bb_t pass = B.walk & ~bb_bit(s);                        /* the BFS never re-enters its source */
-    const bb_t s_down = sy < 10 ? bb_bit(s + 11) : bb_t(0), s_up = sy > 0 ? bb_bit(s - 11) : bb_t(0);
-    const bb_t s_right = sx < 10 ? bb_bit(s + 1) : bb_t(0), s_left = sx > 0 ? bb_bit(s - 1) : bb_t(0);
-    const bb_t s_any = s_down | s_up | s_right | s_left;
-    bb_t T = bb_bit(t);
-    POM_LOOP
-    for(int guard = 0; guard < 128; guard++)
-    {
-        const bb_t hit = T & s_any;
-        if(hit != 0)
-        {
-            if((hit & s_down) != 0) return POM_MOVE_DOWN;
-            if((hit & s_up) != 0) return POM_MOVE_UP;
-            if((hit & s_right) != 0) return POM_MOVE_RIGHT;
-            return POM_MOVE_LEFT;
-        }
-        const bb_t n = T | (bb_neighbours(T) & pass);
-        if(n == T) break;
-        T = n;
-    }
-    return 0xFFu;
+    Passable P;
+    P.any = pass;
+    P.from_left = pass & bb_make(0x01FFBFF7FEFFDFFBull, 0xFF7FEFFDFFBFF7FEull);
+    P.from_right = pass & bb_make(0x00FFDFFBFF7FEFFDull, 0xFFBFF7FEFFDFFBFFull);
+    return P;
 }
-
-/* MoveTowardsPosition (strategy.cpp:101-124) for a target != source, including what it does on an unreachable one */
-POM_HD uint32_t move_towards(const Boards& B, uint32_t src_pos, int tx, int ty)
+POM_HD bb_t flood_step(bb_t X, const Passable& P)
 {
-    const uint32_t l = first_move_towards(B, cell_of(src_pos), tx + 11 * ty);
-    if(l != 0xFFu) return l;
-    /* unreachable target: its predecessor field is 0 = cell (0,0).  Only a source standing ON (0,0) takes the
-     * "predecessor is the source" branch and walks towards the target's side; everybody else gets IDLE. */
-    if(src_pos != 0u) return POM_MOVE_IDLE;
-    return tx > 0 ? uint32_t(POM_MOVE_RIGHT) : uint32_t(POM_MOVE_DOWN);
+    return X | ((X << 1) & P.from_left) | ((X >> 1) & P.from_right) | (((X << 11) | (X >> 11)) & P.any);
 }
 
 /* cells in range of a bomb about to explode: IsInDanger(x, y) == 1, i.e. !_safe_condition(.., 2) (strategy.cpp:190-193,225-246) */
@@ -224,11 +197,10 @@ POM_HD bb_t unsafe_cells(const uint8_t* r)
     return t1 & ~t0;                                              /* a covering bomb with time 0 makes the minimum 0 = "no danger" */
 }
 
-/* MoveTowardsSafePlace (strategy.cpp:126-144); the loops stop at `radius`, not at origin + radius (sic) */
-POM_HD uint32_t move_towards_safe_place(const uint8_t* r, const Boards& B, uint32_t src_pos, int radius)
+/* the cells MoveTowardsSafePlace's double loop looks at (strategy.cpp:130-135): Manhattan distance <= radius and,
+ * because the loops stop at `radius` instead of origin + radius (sic), x < radius and y < radius */
+POM_HD bb_t safe_place_region(int ox, int oy, int radius)
 {
-    const int ox = int(src_pos & 15u), oy = int(src_pos >> 4), s = ox + 11 * oy;
-    /* the cells the double loop looks at: Manhattan distance <= radius, x < radius, y < radius */
     bb_t region = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -242,23 +214,7 @@ POM_HD uint32_t move_towards_safe_place(const uint8_t* r, const Boards& B, uint3
         if(x1 > radius - 1) x1 = radius - 1;
         if(h >= 0 && y < radius && x0 <= x1) region |= bb_t((2u << x1) - (1u << x0)) << (11 * y);
     }
-    /* FillRMap's reachable set: flood from the source through walkable cells; agent cells are reached but not left */
-    const bb_t src = bb_bit(s), pass = B.walk & ~src;
-    bb_t E = src;
-    POM_LOOP
-    for(int guard = 0; guard < 128; guard++)
-    {
-        const bb_t n = E | (bb_neighbours(E) & pass);
-        if(n == E) break;
-        E = n;
-    }
-    const bb_t reach = (E | (bb_neighbours(E) & B.agent)) & ~src;
-    bb_t cand = reach & region;
-    if(cand == 0) return POM_MOVE_IDLE;
-    cand &= ~unsafe_cells(r);
-    if(cand == 0) return POM_MOVE_IDLE;
-    const int t = bb_lowest(cand);                                /* scan order of the reference: y outer, x inner */
-    return first_move_towards(B, s, t);                           /* reachable by construction */
+    return region;
 }
 
 /* the 3-bit slots of moveQueue.queue */
@@ -271,6 +227,11 @@ POM_HD uint32_t pick_safe_direction(const uint8_t* r, uint32_t pos, uint32_t dg,
 {
     uint32_t mq = st.w1 >> 16;
     int count = 0;
+    /* live slots of recentPositions: the ring only starts to turn once it is full, so with fewer than four entries
+     * they are the physical slots 0 .. count-1 */
+    const uint32_t rp_count = (st.w1 >> 8) & 0xFFu;
+    const uint32_t live = rp_count >= 4u ? 0x80808080u : (0x80808080u & ((1u << (8u * rp_count)) - 1u));
+    uint32_t seen = 0;                                         /* bit mv: DesiredPosition(mv) was visited recently */
     POM_LOOP
     for(int k = 0; k < 4; k++)
     {
@@ -281,21 +242,18 @@ POM_HD uint32_t pick_safe_direction(const uint8_t* r, uint32_t pos, uint32_t dg,
         if(!safe_condition((dg >> (4u * mv)) & 15u, 2u)) continue;
         mq = mq_set(mq, count, mv);
         count++;
+        if(bytes_equal(st.w0, p) & live) seen |= 1u << mv;
     }
     const int moves = count;
-    const uint32_t rp_index = st.w1 & 0xFFu, rp_count = (st.w1 >> 8) & 0xFFu;
     int removes = 0;
     POM_LOOP
     for(int i = 0; i < moves && removes < 4; i++)
     {
-        const uint32_t p = pos_step(pos, mq_get(mq, i));
-        bool seen = false;
-        for(uint32_t j = 0; j < rp_count; j++) seen = seen || byte_of(st.w0, int((rp_index + j) & 3u)) == p;
-        if(seen)
+        if((seen >> mq_get(mq, i)) & 1u)
         {
             for(int k = i + 1; k < count; k++) mq = mq_set(mq, k - 1, mq_get(mq, k));   /* RemoveAt(i) */
             count--;
-            mq = mq_set(mq, count, mq_get(mq, i));                                      /* AddElem(q[i]) */
+            mq = mq_set(mq, count, mq_get(mq, i));                                      /* AddElem(q[i]): the element AFTER it (sic) */
             count++;
             i--;
             removes++;
@@ -306,21 +264,27 @@ POM_HD uint32_t pick_safe_direction(const uint8_t* r, uint32_t pos, uint32_t dg,
     return mq_get(mq, int(draw & 1u));
 }
 
-/* _Decide, simple_agent.cpp:52-127 */
+/*
+ * _Decide, simple_agent.cpp:52-127, laid out as stages that all lanes of a warp pass through together: the flood
+ * loops are the expensive part, so there is exactly ONE copy of each in the code and every lane that needs one
+ * reaches it at the same time, whichever branch of _Decide it is in.
+ *   FLEE  danger > 0:            MoveTowardsSafePlace (flood A: reachable set -> first safe cell t; flood B: first move to t)
+ *   HUNT  enemy within 7 cells:  MoveTowardsEnemy     (flood B: first move to the enemy's cell)
+ */
 POM_HD uint32_t simple_decide(const uint8_t* r, const Boards& B, int id, SimpleSt& st, uint32_t draw)
 {
+    enum { NONE = 0, FLEE = 1, HUNT = 2 };
     const uint32_t pos = r[R_APOS + id];
-    const int x = int(pos & 15u), y = int(pos >> 4);
+    const int x = int(pos & 15u), y = int(pos >> 4), s = x + 11 * y;
     const uint32_t dg = danger5(r, x, y);
     const uint32_t danger = dg & 15u;
-    if(danger > 0u)
-    {
-        const uint32_t m = move_towards_safe_place(r, B, pos, int(danger));
-        const uint32_t p = pos_step(pos, m);
-        if(!pos_oob(p) && c_is_walkable(r[R_BOARD + cell_of(p)]) && safe_condition((dg >> (4u * m)) & 15u, 2u)) return m;
-        return pick_safe_direction(r, pos, dg, st, draw);
-    }
-    if(int(int8_t(r[R_ABCNT + id])) < int(r[R_AMAX + id]))
+
+    /* ---- stage 0: which branch of _Decide is this agent in */
+    uint32_t result = 0xFFu;            /* decided move, 0xFF = not yet */
+    int kind = NONE, t = -1;            /* t = cell to walk towards */
+    bool wood_next = false;             /* "bomb the wood next to me" is still to be tried (:107-110) */
+    if(danger > 0u) kind = FLEE;
+    else if(int(int8_t(r[R_ABCNT + id])) < int(r[R_AMAX + id]))
     {
         /* IsAdjacentEnemy (strategy.cpp:296-312): nearest live enemy, Manhattan */
         int dmin = 99, target = -1;
@@ -334,30 +298,101 @@ POM_HD uint32_t simple_decide(const uint8_t* r, const Boards& B, int id, SimpleS
              * the source's cell */
             if(target < 0 && d <= 7 && d != 0) target = i;
         }
-        if(dmin <= 1) return POM_MOVE_BOMB;
-        if(dmin <= 7)
+        if(dmin <= 1) result = POM_MOVE_BOMB;
+        else
         {
-            /* _HasRPLoop, simple_agent.cpp:24-35 */
-            const uint32_t rp_index = st.w1 & 0xFFu, rp_count = (st.w1 >> 8) & 0xFFu;
-            bool loop = true;
-            for(uint32_t i = 0; i < rp_count / 2u; i++)
-                loop = loop && byte_of(st.w0, int((rp_index + i) & 3u)) == byte_of(st.w0, int((rp_index + i + 2u) & 3u));
-            if(loop) return draw & 3u;                          /* Move(intDist(rng) % 4) */
-            uint32_t m = POM_MOVE_IDLE;
-            if(target >= 0) m = move_towards(B, pos, int(r[R_APOS + target] & 15u), int(r[R_APOS + target] >> 4));
-            const uint32_t p = pos_step(pos, m);
-            if(!pos_oob(p) && c_is_walkable(r[R_BOARD + cell_of(p)]) && safe_condition((dg >> (4u * m)) & 15u, 5u)) return m;
+            wood_next = true;
+            if(dmin <= 7)
+            {
+                /* _HasRPLoop, simple_agent.cpp:24-35 */
+                const uint32_t rp_index = st.w1 & 0xFFu, rp_count = (st.w1 >> 8) & 0xFFu;
+                bool loop = true;
+                for(uint32_t i = 0; i < rp_count / 2u; i++)
+                    loop = loop && byte_of(st.w0, int((rp_index + i) & 3u)) == byte_of(st.w0, int((rp_index + i + 2u) & 3u));
+                if(loop) result = draw & 3u;                    /* Move(intDist(rng) % 4) */
+                else
+                {
+                    kind = HUNT;
+                    if(target >= 0) t = int(r[R_APOS + target] & 15u) + 11 * int(r[R_APOS + target] >> 4);
+                }
+            }
         }
+    }
+
+    const bb_t src = bb_bit(s);
+    const Passable P = make_passable(B.walk & ~src);           /* the BFS never re-enters its source */
+
+    /* ---- stage A (FLEE): FillRMap's reachable set, then the first cell of MoveTowardsSafePlace's scan that is
+     *      reachable and not about to blow up (strategy.cpp:126-144) */
+    if(kind == FLEE)
+    {
+        bb_t E = src;
+        POM_LOOP
+        for(int guard = 0; guard < 128; guard++)
+        {
+            const bb_t n = flood_step(E, P);
+            if(n == E) break;
+            E = n;
+        }
+        /* agent cells next to the flooded area are reached but not left (strategy.cpp:44-52) */
+        const bb_t edge = ((E << 1) & bb_make(0x01FFBFF7FEFFDFFBull, 0xFF7FEFFDFFBFF7FEull)) |
+                          ((E >> 1) & bb_make(0x00FFDFFBFF7FEFFDull, 0xFFBFF7FEFFDFFBFFull)) | (E << 11) | (E >> 11);
+        bb_t cand = (E | (edge & B.agent)) & ~src & safe_place_region(x, y, int(danger));
+        if(cand != 0) cand &= ~unsafe_cells(r);
+        if(cand != 0) t = bb_lowest(cand);                       /* scan order of the reference: y outer, x inner */
+    }
+
+    /* ---- stage B (FLEE with a safe place, HUNT with an enemy): MoveTowardsPosition (strategy.cpp:101-124).
+     *      Grow a set from t through walkable cells until it touches a neighbour of the source: the neighbours
+     *      touched first are the nearest to t, and the first of them in the order down, up, right, left is where
+     *      FillRMap's path starts. */
+    uint32_t m = POM_MOVE_IDLE;
+    if(t >= 0)
+    {
+        const bb_t s_down = y < 10 ? src << 11 : bb_t(0), s_up = y > 0 ? src >> 11 : bb_t(0);
+        const bb_t s_right = x < 10 ? src << 1 : bb_t(0), s_left = x > 0 ? src >> 1 : bb_t(0);
+        const bb_t s_any = s_down | s_up | s_right | s_left;
+        bb_t T = bb_bit(t);
+        uint32_t found = 0xFFu;
+        POM_LOOP
+        for(int guard = 0; guard < 128; guard++)
+        {
+            const bb_t hit = T & s_any;
+            if(hit != 0)
+            {
+                found = (hit & s_down) != 0 ? POM_MOVE_DOWN : (hit & s_up) != 0 ? POM_MOVE_UP : (hit & s_right) != 0 ? POM_MOVE_RIGHT : POM_MOVE_LEFT;
+                break;
+            }
+            const bb_t n = flood_step(T, P);
+            if(n == T) break;
+            T = n;
+        }
+        /* unreachable target (HUNT only): its predecessor field is 0 = cell (0,0); a source standing ON (0,0) takes the
+         * "predecessor is the source" branch and walks towards the target's side, everybody else gets IDLE */
+        if(found == 0xFFu) found = s != 0 ? uint32_t(POM_MOVE_IDLE) : (t % 11 > 0 ? uint32_t(POM_MOVE_RIGHT) : uint32_t(POM_MOVE_DOWN));
+        m = found;
+    }
+
+    /* ---- stage C: take the move if its destination is walkable and safe enough (:62-66, :93-98) */
+    if(kind != NONE)
+    {
+        const uint32_t p = pos_step(pos, m);
+        if(!pos_oob(p) && c_is_walkable(r[R_BOARD + cell_of(p)]) && safe_condition((dg >> (4u * m)) & 15u, kind == FLEE ? 2u : 5u)) result = m;
+    }
+    if(result == 0xFFu && wood_next)
+    {
         /* IsAdjacentItem(state, id, 1, WOOD), strategy.cpp:314-338: own cell and the four neighbours */
-        bool wood = c_is_wood(r[R_BOARD + x + 11 * y]);
+        bool wood = c_is_wood(r[R_BOARD + s]);
         for(uint32_t mv = 1; mv <= 4u; mv++)
         {
             const uint32_t p = pos_step(pos, mv);
             if(!pos_oob(p)) wood = wood || c_is_wood(r[R_BOARD + cell_of(p)]);
         }
-        if(wood) return POM_MOVE_BOMB;
+        if(wood) result = POM_MOVE_BOMB;
     }
-    return pick_safe_direction(r, pos, dg, st, draw);
+    /* ---- stage D: everybody who is still undecided moves one safe step (:68, :113-126) */
+    if(result == 0xFFu) result = pick_safe_direction(r, pos, dg, st, draw);
+    return result;
 }
 
 /* SimpleAgent::act, simple_agent.cpp:128-141 */
