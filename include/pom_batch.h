@@ -127,6 +127,9 @@ int  pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t
 int  pom_batch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_t tick, uint32_t agent_mask);
 /* same with HOST moves (n_envs x 4 bytes, read and written): upload, act, download, synchronise */
 int  pom_batch_policy_moves_host(pom_batch* b, uint8_t* moves_host, uint64_t seed, uint32_t tick, uint32_t agent_mask);
+/* SimpleAgent::act (simple_agent.cpp:128-141) for ONE agent of ONE env with the caller's own draw (0..4); the move
+ * (0..5) goes to *move_out, the agent's memory on the device is updated.  For the bboard host mirror and tests. */
+int  pom_batch_policy_act(pom_batch* b, uint64_t env, int agent, int draw, int* move_out);
 int  pom_batch_policy_reset(pom_batch* b);                          /* all agents forget (new SimpleAgent objects) */
 /* agent memories of envs [first, first+count) as count x 4 pom_simple_agent (HOST memory) */
 int  pom_batch_policy_download(pom_batch* b, uint64_t first, uint64_t count, pom_simple_agent* out);

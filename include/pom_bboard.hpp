@@ -8,8 +8,9 @@
  * path and its tests use (:356-506), Agent (:517-533), Environment (:541-644), InitBoardItems / InitState /
  * Step (:651-668).  Names, argument meaning and the State layout (1004 bytes, same offsets) are the
  * reference's, so agent code written against it compiles unchanged and States can be exchanged with the
- * reference by plain copy.  Printing (PrintState/PrintItem, StartGame's console rendering) and the
- * SimpleAgent/strategy code are out of scope.
+ * reference by plain copy.  Printing (PrintState/PrintItem, StartGame's console rendering) is out of scope
+ * (SURVEY §2 rows 7, 14).  agents::SimpleAgent lives in pomcpp_b200/host/pom_agents.hpp; like Step it runs on the
+ * device.
  *
  * What is different: nothing in here simulates on the CPU.  Field setters (PutItem, PutAgent, Kill,
  * PlantBomb, queue look-ups) are plain host writes/reads, exactly as in the reference; every function that
@@ -184,6 +185,10 @@ void InitBoardItems(State& state, int seed = 0x1337);
 void InitState(State* state, int a0, int a1, int a2, int a3);
 void Step(State* state, Move* moves);
 
+/* agents::SimpleAgent::act for agent `id` on `state`, executed by the device policy code; `memory` is the agent's
+ * persistent part, `draw` (0..4) its one random number.  Used by agents::SimpleAgent (pom_agents.hpp). */
+int SimpleActOnDevice(const State* state, int id, pom_simple_agent* memory, int draw);
+
 /* Many states at once: states[i] is advanced with moves[4*i .. 4*i+3]; one upload, one kernel, one download. */
 void StepBatch(State* states, const Move* moves, size_t n);
 
@@ -241,8 +246,13 @@ public:
     /* one tick with actions from `agents` (shared by all games, called as agents[a]->act(&state_i) for every
      * live agent a of every running game i) */
     size_t Step(std::array<Agent*, AGENT_COUNT> agents);
-    /* `ticks` fused ticks on the device with uniform random actions and auto-reset; returns the counters */
-    pom_stats Rollout(uint32_t ticks, uint64_t seed, bool harmless = false);
+    /* one tick in which the agents in simpleMask (bit a) are played by the device-side SimpleAgent
+     * (simple_agent.cpp:12-141; their draws come from the shared counter RNG keyed by `seed`) and the others
+     * take their move from `moves` (n x 4, host memory; entries of masked agents are ignored) */
+    size_t Step(const Move* moves, unsigned simpleMask, uint64_t seed);
+    /* `ticks` fused ticks on the device with auto-reset; agents in simpleMask play SimpleAgent, the others draw
+     * uniformly (from {0..4} if harmless, else {0..5}); returns the counters */
+    pom_stats Rollout(uint32_t ticks, uint64_t seed, bool harmless = false, unsigned simpleMask = 0);
     /* host copies */
     const std::vector<State>& States();
     const std::vector<uint8_t>& Status();          /* POM_STATUS_* per game */

@@ -92,6 +92,7 @@ def lib():
         L.pom_batch_rollout.argtypes = [vp, u32, u64, u32, u32]
         L.pom_batch_policy_moves.argtypes = [vp, vp, u64, u32, u32]
         L.pom_batch_policy_moves_host.argtypes = [vp, vp, u64, u32, u32]
+        L.pom_batch_policy_act.argtypes = [vp, u64, i32, i32, C.POINTER(C.c_int)]
         L.pom_batch_policy_reset.argtypes = [vp]
         L.pom_batch_policy_download.argtypes = [vp, u64, u64, vp]
         L.pom_batch_policy_upload.argtypes = [vp, u64, u64, vp]
@@ -210,6 +211,11 @@ class Batch:
     def policy_moves_host(self, moves, seed, tick, agent_mask=15):
         assert moves.dtype == np.uint8 and moves.size == 4 * self.n and moves.flags.c_contiguous
         _ck(lib().pom_batch_policy_moves_host(self.h, _p(moves), seed, tick, agent_mask))
+
+    def policy_act(self, env, agent, draw):
+        m = C.c_int(0)
+        _ck(lib().pom_batch_policy_act(self.h, env, agent, draw, C.byref(m)))
+        return m.value
 
     def policy_reset(self): _ck(lib().pom_batch_policy_reset(self.h))
 

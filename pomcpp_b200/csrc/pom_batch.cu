@@ -515,6 +515,25 @@ int pom_batch_policy_moves_host(pom_batch* b, uint8_t* moves_host, uint64_t seed
     return POM_OK;
 }
 
+int pom_batch_policy_act(pom_batch* b, uint64_t env, int agent, int draw, int* move_out)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!move_out) return fail(POM_E_ARG, "pom_batch_policy_act: null output");
+    if(env >= b->n_envs) return fail(POM_E_RANGE, "pom_batch_policy_act: env outside the batch");
+    if(agent < 0 || agent > 3 || draw < 0 || draw > 4) return fail(POM_E_ARG, "pom_batch_policy_act: agent must be 0..3 and draw 0..4");
+    rc = ensure_policy(b); if(rc) return rc;
+    int* dev = nullptr;
+    CK(cudaMalloc(&dev, sizeof(int)));
+    pomk::k_policy_act<<<1, 1, 0, b->stream>>>(b->params(), env, agent, uint32_t(draw), dev);
+    b->launches++;
+    cudaError_t ce = cudaGetLastError();
+    if(ce == cudaSuccess) ce = cudaMemcpyAsync(move_out, dev, sizeof(int), cudaMemcpyDeviceToHost, b->stream);
+    if(ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
+    cudaFree(dev);
+    if(ce != cudaSuccess) return fail(POM_E_CUDA, "pom_batch_policy_act", ce);
+    return POM_OK;
+}
+
 int pom_batch_policy_reset(pom_batch* b)
 {
     int rc = use(b); if(rc) return rc;

@@ -432,6 +432,18 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
     }
 }
 
+/* SimpleAgent::act for ONE agent of ONE env with a caller-chosen draw (the host mirror's agents::SimpleAgent) */
+__global__ void k_policy_act(BatchParams P, uint64_t env, int agent, uint32_t draw, int* move_out)
+{
+    const uint8_t* rec = P.recs + env * POM_REC_BYTES;
+    GlobalAgentStore S{ P.policy + env, P.policy_stride };
+    S.claim(P.episodes[env]);
+    const pompolicy::Boards B = pompolicy::make_boards(rec);
+    pompolicy::SimpleSt st = S.load(agent);
+    *move_out = int(pompolicy::simple_act(rec, B, agent, st, draw));
+    S.store(agent, st);
+}
+
 /* agent memories <-> array of pom_simple_agent[4] per env (8 words), applying the episode rule */
 __global__ void k_policy_export(BatchParams P, uint64_t first, uint64_t count, uint32_t* __restrict__ out)
 {

@@ -265,25 +265,41 @@ POM_HD uint32_t pick_safe_direction(const uint8_t* r, uint32_t pos, uint32_t dg,
 }
 
 /*
- * _Decide, simple_agent.cpp:52-127, laid out as stages that all lanes of a warp pass through together: the flood
- * loops are the expensive part, so there is exactly ONE copy of each in the code and every lane that needs one
- * reaches it at the same time, whichever branch of _Decide it is in.
- *   FLEE  danger > 0:            MoveTowardsSafePlace (flood A: reachable set -> first safe cell t; flood B: first move to t)
- *   HUNT  enemy within 7 cells:  MoveTowardsEnemy     (flood B: first move to the enemy's cell)
+ * _Decide (simple_agent.cpp:52-127) for the four agents of an env, laid out so that the lanes of a warp stay
+ * together where it is expensive.  The flood loops dominate the cost and only some agents need one (FLEE: danger > 0,
+ * MoveTowardsSafePlace; HUNT: an enemy within 7 cells, MoveTowardsEnemy), with very different lengths.  So:
+ *   phase 1  per agent: classify (plan_agent) — cheap, no floods;
+ *   phase 2  ONE loop runs all flood jobs of the env back to back: a lane whose agent 0 needs no flood is already
+ *            working on agent 2's while its neighbour still floods for agent 0.  The sum of an env's jobs varies far
+ *            less between lanes than any single job, and there is exactly one copy of the flood step in the code;
+ *   phase 3  per agent: finish the decision (finish_agent) and update the agent's memory (SimpleAgent::act).
+ * The agents only read the state, so the order in which their decisions are evaluated does not matter.
  */
-POM_HD uint32_t simple_decide(const uint8_t* r, const Boards& B, int id, SimpleSt& st, uint32_t draw)
-{
-    enum { NONE = 0, FLEE = 1, HUNT = 2 };
-    const uint32_t pos = r[R_APOS + id];
-    const int x = int(pos & 15u), y = int(pos >> 4), s = x + 11 * y;
-    const uint32_t dg = danger5(r, x, y);
-    const uint32_t danger = dg & 15u;
+enum { K_NONE = 0, K_FLEE = 1, K_HUNT = 2 };
 
-    /* ---- stage 0: which branch of _Decide is this agent in */
-    uint32_t result = 0xFFu;            /* decided move, 0xFF = not yet */
-    int kind = NONE, t = -1;            /* t = cell to walk towards */
-    bool wood_next = false;             /* "bomb the wood next to me" is still to be tried (:107-110) */
-    if(danger > 0u) kind = FLEE;
+struct Plan {
+    uint32_t dg;            /* IsInDanger at the agent's cell and its four neighbours, nibble per Move (danger5) */
+    uint8_t  kind;          /* K_*                                                                              */
+    uint8_t  target;        /* HUNT: cell of the enemy to walk towards, FLEE: filled by phase 2; 0xFF = none    */
+    uint8_t  result;        /* move decided in phase 1, 0xFF = not yet                                          */
+    uint8_t  wood_next;     /* "bomb the wood next to me" is still to be tried (:107-110)                        */
+    uint8_t  move;          /* phase 2: first move towards the target (IDLE if there is none)                   */
+    bb_t     region;        /* FLEE: the cells MoveTowardsSafePlace scans                                        */
+};
+
+/* phase 1: which branch of _Decide is agent `id` in */
+POM_HD Plan plan_agent(const uint8_t* r, int id, const SimpleSt& st, uint32_t draw)
+{
+    Plan pl;
+    const uint32_t pos = r[R_APOS + id];
+    const int x = int(pos & 15u), y = int(pos >> 4);
+    pl.dg = danger5(r, x, y);
+    pl.kind = K_NONE; pl.target = 0xFFu; pl.result = 0xFFu; pl.wood_next = 0; pl.move = POM_MOVE_IDLE;
+    if((pl.dg & 15u) > 0u)
+    {
+        pl.kind = K_FLEE;
+        pl.region = safe_place_region(x, y, int(pl.dg & 15u));
+    }
     else if(int(int8_t(r[R_ABCNT + id])) < int(r[R_AMAX + id]))
     {
         /* IsAdjacentEnemy (strategy.cpp:296-312): nearest live enemy, Manhattan */
@@ -298,10 +314,10 @@ POM_HD uint32_t simple_decide(const uint8_t* r, const Boards& B, int id, SimpleS
              * the source's cell */
             if(target < 0 && d <= 7 && d != 0) target = i;
         }
-        if(dmin <= 1) result = POM_MOVE_BOMB;
+        if(dmin <= 1) pl.result = POM_MOVE_BOMB;
         else
         {
-            wood_next = true;
+            pl.wood_next = 1;
             if(dmin <= 7)
             {
                 /* _HasRPLoop, simple_agent.cpp:24-35 */
@@ -309,80 +325,110 @@ POM_HD uint32_t simple_decide(const uint8_t* r, const Boards& B, int id, SimpleS
                 bool loop = true;
                 for(uint32_t i = 0; i < rp_count / 2u; i++)
                     loop = loop && byte_of(st.w0, int((rp_index + i) & 3u)) == byte_of(st.w0, int((rp_index + i + 2u) & 3u));
-                if(loop) result = draw & 3u;                    /* Move(intDist(rng) % 4) */
+                if(loop) pl.result = uint8_t(draw & 3u);        /* Move(intDist(rng) % 4) */
                 else
                 {
-                    kind = HUNT;
-                    if(target >= 0) t = int(r[R_APOS + target] & 15u) + 11 * int(r[R_APOS + target] >> 4);
+                    pl.kind = K_HUNT;
+                    if(target >= 0) pl.target = uint8_t(int(r[R_APOS + target] & 15u) + 11 * int(r[R_APOS + target] >> 4));
                 }
             }
         }
     }
+    return pl;
+}
 
-    const bb_t src = bb_bit(s);
-    const Passable P = make_passable(B.walk & ~src);           /* the BFS never re-enters its source */
+/* phase 2: the flood jobs of one env.
+ *   job A (FLEE)  FillRMap's reachable set = flood from the source to a fixpoint (the BFS never re-enters its source,
+ *                 and neither does the flood: the source is in the set from the start); then the first cell of
+ *                 MoveTowardsSafePlace's scan (strategy.cpp:126-144) that is reachable and not about to blow up
+ *                 becomes the target of a job B;
+ *   job B         MoveTowardsPosition (strategy.cpp:101-124): grow a set from the target through walkable cells
+ *                 until it touches a neighbour of the source; the neighbours touched first are the nearest to the
+ *                 target, and the first of them in the order down, up, right, left is where FillRMap's path starts. */
+POM_HD bool bb_test(bb_t b, int cell) { return (uint32_t(b >> (cell & 96)) >> (cell & 31)) & 1u; }
 
-    /* ---- stage A (FLEE): FillRMap's reachable set, then the first cell of MoveTowardsSafePlace's scan that is
-     *      reachable and not about to blow up (strategy.cpp:126-144) */
-    if(kind == FLEE)
+POM_HD void run_floods(const uint8_t* r, const Boards& B, Plan* pl, uint32_t jobs)
+{
+    /* jobs: bit a = agent a has a flood to run (FLEE, or HUNT with an enemy to walk to) */
+    bb_t unsafe = 0;
+    bool have_unsafe = false;
+    int a = -1;
+    bool mode_b = false;
+    bb_t X = 0, src = 0;
+    Passable P = make_passable(0);
+    for(;;)
     {
-        bb_t E = src;
-        POM_LOOP
-        for(int guard = 0; guard < 128; guard++)
+        if(a >= 0)
         {
-            const bb_t n = flood_step(E, P);
-            if(n == E) break;
-            E = n;
-        }
-        /* agent cells next to the flooded area are reached but not left (strategy.cpp:44-52) */
-        const bb_t edge = ((E << 1) & bb_make(0x01FFBFF7FEFFDFFBull, 0xFF7FEFFDFFBFF7FEull)) |
-                          ((E >> 1) & bb_make(0x00FFDFFBFF7FEFFDull, 0xFFBFF7FEFFDFFBFFull)) | (E << 11) | (E >> 11);
-        bb_t cand = (E | (edge & B.agent)) & ~src & safe_place_region(x, y, int(danger));
-        if(cand != 0) cand &= ~unsafe_cells(r);
-        if(cand != 0) t = bb_lowest(cand);                       /* scan order of the reference: y outer, x inner */
-    }
-
-    /* ---- stage B (FLEE with a safe place, HUNT with an enemy): MoveTowardsPosition (strategy.cpp:101-124).
-     *      Grow a set from t through walkable cells until it touches a neighbour of the source: the neighbours
-     *      touched first are the nearest to t, and the first of them in the order down, up, right, left is where
-     *      FillRMap's path starts. */
-    uint32_t m = POM_MOVE_IDLE;
-    if(t >= 0)
-    {
-        const bb_t s_down = y < 10 ? src << 11 : bb_t(0), s_up = y > 0 ? src >> 11 : bb_t(0);
-        const bb_t s_right = x < 10 ? src << 1 : bb_t(0), s_left = x > 0 ? src >> 1 : bb_t(0);
-        const bb_t s_any = s_down | s_up | s_right | s_left;
-        bb_t T = bb_bit(t);
-        uint32_t found = 0xFFu;
-        POM_LOOP
-        for(int guard = 0; guard < 128; guard++)
-        {
-            const bb_t hit = T & s_any;
-            if(hit != 0)
+            /* the hot part: one flood step of the current job.  The source cell itself counts as passable: in job A
+             * it is where the flood starts, in job B the flood reaching it is the stop condition. */
+            const bb_t n = flood_step(X, P);
+            const bool hit = mode_b && (n & src) != 0;
+            if(!hit && n != X) { X = n; continue; }
+            /* the job is over, or turns from A into B */
+            const uint32_t pos = r[R_APOS + a];
+            const int x = int(pos & 15u), y = int(pos >> 4), s = x + 11 * y;
+            if(hit)
             {
-                found = (hit & s_down) != 0 ? POM_MOVE_DOWN : (hit & s_up) != 0 ? POM_MOVE_UP : (hit & s_right) != 0 ? POM_MOVE_RIGHT : POM_MOVE_LEFT;
-                break;
+                pl[a].move = uint8_t((y < 10 && bb_test(X, s + 11)) ? POM_MOVE_DOWN : (y > 0 && bb_test(X, s - 11)) ? POM_MOVE_UP :
+                                     (x < 10 && bb_test(X, s + 1)) ? POM_MOVE_RIGHT : POM_MOVE_LEFT);
             }
-            const bb_t n = flood_step(T, P);
-            if(n == T) break;
-            T = n;
+            else if(mode_b)
+            {
+                /* unreachable target (HUNT only): its predecessor field is 0 = cell (0,0); a source standing ON (0,0)
+                 * takes the "predecessor is the source" branch and walks towards the target's side, everybody else idles */
+                pl[a].move = uint8_t(pos != 0u ? POM_MOVE_IDLE : (pl[a].target % 11u > 0u ? POM_MOVE_RIGHT : POM_MOVE_DOWN));
+            }
+            else
+            {
+                /* agent cells next to the flooded area are reached but not left (strategy.cpp:44-52) */
+                const bb_t edge = ((X << 1) & bb_make(0x01FFBFF7FEFFDFFBull, 0xFF7FEFFDFFBFF7FEull)) |
+                                  ((X >> 1) & bb_make(0x00FFDFFBFF7FEFFDull, 0xFFBFF7FEFFDFFBFFull)) | (X << 11) | (X >> 11);
+                bb_t cand = (X | (edge & B.agent)) & ~src & pl[a].region;
+                if(cand != 0)
+                {
+                    if(!have_unsafe) { unsafe = unsafe_cells(r); have_unsafe = true; }
+                    cand &= ~unsafe;
+                }
+                if(cand != 0)
+                {
+                    const int t = bb_lowest(cand);               /* scan order of the reference: y outer, x inner */
+                    pl[a].target = uint8_t(t);
+                    X = bb_bit(t);
+                    mode_b = true;
+                    continue;
+                }
+            }
         }
-        /* unreachable target (HUNT only): its predecessor field is 0 = cell (0,0); a source standing ON (0,0) takes the
-         * "predecessor is the source" branch and walks towards the target's side, everybody else gets IDLE */
-        if(found == 0xFFu) found = s != 0 ? uint32_t(POM_MOVE_IDLE) : (t % 11 > 0 ? uint32_t(POM_MOVE_RIGHT) : uint32_t(POM_MOVE_DOWN));
-        m = found;
+        /* next job */
+        if(jobs == 0u) break;
+        a = (jobs & 1u) ? 0 : (jobs & 2u) ? 1 : (jobs & 4u) ? 2 : 3;
+        jobs &= jobs - 1u;
+        {
+            const uint32_t pos = r[R_APOS + a];
+            src = bb_bit(int(pos & 15u) + 11 * int(pos >> 4));
+            P = make_passable(B.walk | src);
+            mode_b = pl[a].kind == K_HUNT;
+            X = mode_b ? bb_bit(pl[a].target) : src;
+        }
     }
+}
 
-    /* ---- stage C: take the move if its destination is walkable and safe enough (:62-66, :93-98) */
-    if(kind != NONE)
+/* phase 3: the rest of _Decide for agent `id` */
+POM_HD uint32_t finish_agent(const uint8_t* r, int id, const Plan& pl, SimpleSt& st, uint32_t draw)
+{
+    const uint32_t pos = r[R_APOS + id];
+    uint32_t result = pl.result;
+    /* take the move if its destination is walkable and safe enough (:62-66, :93-98) */
+    if(pl.kind != K_NONE)
     {
-        const uint32_t p = pos_step(pos, m);
-        if(!pos_oob(p) && c_is_walkable(r[R_BOARD + cell_of(p)]) && safe_condition((dg >> (4u * m)) & 15u, kind == FLEE ? 2u : 5u)) result = m;
+        const uint32_t m = pl.move, p = pos_step(pos, m);
+        if(!pos_oob(p) && c_is_walkable(r[R_BOARD + cell_of(p)]) && safe_condition((pl.dg >> (4u * m)) & 15u, pl.kind == K_FLEE ? 2u : 5u)) result = m;
     }
-    if(result == 0xFFu && wood_next)
+    if(result == 0xFFu && pl.wood_next)
     {
         /* IsAdjacentItem(state, id, 1, WOOD), strategy.cpp:314-338: own cell and the four neighbours */
-        bool wood = c_is_wood(r[R_BOARD + s]);
+        bool wood = c_is_wood(r[R_BOARD + cell_of(pos)]);
         for(uint32_t mv = 1; mv <= 4u; mv++)
         {
             const uint32_t p = pos_step(pos, mv);
@@ -390,21 +436,31 @@ POM_HD uint32_t simple_decide(const uint8_t* r, const Boards& B, int id, SimpleS
         }
         if(wood) result = POM_MOVE_BOMB;
     }
-    /* ---- stage D: everybody who is still undecided moves one safe step (:68, :113-126) */
-    if(result == 0xFFu) result = pick_safe_direction(r, pos, dg, st, draw);
+    /* everybody who is still undecided moves one safe step (:68, :113-126) */
+    if(result == 0xFFu) result = pick_safe_direction(r, pos, pl.dg, st, draw);
     return result;
 }
 
-/* SimpleAgent::act, simple_agent.cpp:128-141 */
-POM_HD uint32_t simple_act(const uint8_t* r, const Boards& B, int id, SimpleSt& st, uint32_t draw)
+/* SimpleAgent::act's bookkeeping (simple_agent.cpp:128-141): remember where move m leads */
+POM_HD void remember_position(const uint8_t* r, int id, SimpleSt& st, uint32_t m)
 {
-    const uint32_t m = simple_decide(r, B, id, st, draw);
     const uint32_t p = pos_step(r[R_APOS + id], m);            /* BOMB and IDLE remember the agent's own cell */
     uint32_t idx = st.w1 & 0xFFu, cnt = (st.w1 >> 8) & 0xFFu;
     if(cnt == 4u) { idx = (idx + 1u) & 3u; cnt = 3u; }          /* PopElem when full */
     st.w0 = with_byte(st.w0, int((idx + cnt) & 3u), p);
     cnt++;
     st.w1 = (st.w1 & 0xFFFF0000u) | idx | (cnt << 8);
+}
+
+/* SimpleAgent::act for ONE agent */
+POM_HD uint32_t simple_act(const uint8_t* r, const Boards& B, int id, SimpleSt& st, uint32_t draw)
+{
+    Plan pl[4];
+    for(int a = 0; a < 4; a++) pl[a].kind = K_NONE;
+    pl[id] = plan_agent(r, id, st, draw);
+    run_floods(r, B, pl, (pl[id].kind == K_FLEE || pl[id].target != 0xFFu) ? 1u << id : 0u);
+    const uint32_t m = finish_agent(r, id, pl[id], st, draw);
+    remember_position(r, id, st, m);
     return m;
 }
 
@@ -416,6 +472,19 @@ template<class Store>
 POM_HD uint32_t simple_moves(const uint8_t* r, uint32_t mask, uint32_t moves, uint32_t draws, Store& S)
 {
     const Boards B = make_boards(r);
+    Plan pl[4];
+    uint32_t jobs = 0;
+    POM_LOOP
+    for(int a = 0; a < 4; a++)
+    {
+        pl[a].kind = K_NONE;
+        if(((mask >> a) & 1u) && !(r[R_AFLAGS + a] & AF_DEAD))
+        {
+            pl[a] = plan_agent(r, a, S.load(a), byte_of(draws, a));
+            if(pl[a].kind == K_FLEE || pl[a].target != 0xFFu) jobs |= 1u << a;
+        }
+    }
+    run_floods(r, B, pl, jobs);
     POM_LOOP
     for(int a = 0; a < 4; a++)
     {
@@ -424,7 +493,8 @@ POM_HD uint32_t simple_moves(const uint8_t* r, uint32_t mask, uint32_t moves, ui
         if(!(r[R_AFLAGS + a] & AF_DEAD))
         {
             SimpleSt st = S.load(a);
-            m = simple_act(r, B, a, st, byte_of(draws, a));
+            m = finish_agent(r, a, pl[a], st, byte_of(draws, a));
+            remember_position(r, a, st, m);
             S.store(a, st);
         }
         moves = with_byte(moves, a, m);

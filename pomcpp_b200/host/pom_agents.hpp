@@ -1,6 +1,9 @@
 /*
- * pom_agents.hpp — the reference's trivial policies (include/agents.hpp:18-48, src/agents/basic_agents.cpp)
- * as host Agent objects: uniform{0..5}, uniform{0..4}, always IDLE.  Unlike the reference they can be seeded.
+ * pom_agents.hpp — the reference's policies (include/agents.hpp:18-76, src/agents/basic_agents.cpp,
+ * src/agents/simple_agent.cpp) as host Agent objects: uniform{0..5}, uniform{0..4}, always IDLE, and the heuristic
+ * SimpleAgent.  Unlike the reference they can be seeded.  SimpleAgent::act does not run on the host: like
+ * bboard::Step it executes the device code (pom_policy.cuh) on the given State; for throughput use
+ * BatchEnvironment::Rollout / Step with a simpleMask, which keep states and agent memories on the GPU.
  */
 #ifndef POM_AGENTS_HPP_
 #define POM_AGENTS_HPP_
@@ -32,6 +35,20 @@ struct HarmlessAgent : bboard::Agent
 struct LazyAgent : bboard::Agent
 {
     bboard::Move act(const bboard::State*) override { return bboard::Move::IDLE; }
+};
+
+/* agents::SimpleAgent (include/agents.hpp:55-76): same decisions as the reference's, one intDist draw per act */
+struct SimpleAgent : bboard::Agent
+{
+    std::mt19937_64 rng;
+    std::uniform_int_distribution<int> intDist{0, 4};
+    pom_simple_agent memory{};        /* recentPositions + moveQueue (zero = a freshly constructed agent) */
+    SimpleAgent() : rng(std::random_device{}()) {}
+    explicit SimpleAgent(uint64_t seed) : rng(seed) {}
+    bboard::Move act(const bboard::State* state) override
+    {
+        return bboard::Move(bboard::SimpleActOnDevice(state, id, &memory, intDist(rng)));
+    }
 };
 
 }

@@ -66,6 +66,22 @@ void apply(State* s, int op, int a0 = 0, int a1 = 0, int a2 = 0)
 
 }
 
+/* SimpleAgent::act on the device for one host State: upload, act, fetch the move and the agent's memory */
+int SimpleActOnDevice(const State* s, int id, pom_simple_agent* memory, int draw)
+{
+    pom_batch* h = scratch.get(1);
+    check(pom_batch_upload(h, 0, 1, reinterpret_cast<const pom_state*>(s), nullptr), "pom_batch_upload");
+    pom_simple_agent four[4];
+    std::memset(four, 0, sizeof(four));
+    four[id] = *memory;
+    check(pom_batch_policy_upload(h, 0, 1, four), "pom_batch_policy_upload");
+    int move = 0;
+    check(pom_batch_policy_act(h, 0, id, draw, &move), "pom_batch_policy_act");
+    check(pom_batch_policy_download(h, 0, 1, four), "pom_batch_policy_download");
+    *memory = four[id];
+    return move;
+}
+
 /* ---- State: field access (reference bboard.cpp:125-146, 265-333) ---- */
 void State::PutAgent(int x, int y, int agentID)
 {
@@ -315,9 +331,23 @@ size_t BatchEnvironment::Step(std::array<Agent*, AGENT_COUNT> agents)
     return Step(mv.data());
 }
 
-pom_stats BatchEnvironment::Rollout(uint32_t ticks, uint64_t seed, bool harmless)
+size_t BatchEnvironment::Step(const Move* moves, unsigned simpleMask, uint64_t seed)
 {
-    check(pom_batch_rollout(handle, ticks, seed, tick, harmless ? POM_ROLL_HARMLESS : 0), "pom_batch_rollout");
+    for(size_t i = 0; i < 4 * n; i++) movebuf[i] = uint8_t(int(moves[i]));
+    if(simpleMask & 0xFu)
+        check(pom_batch_policy_moves_host(handle, movebuf.data(), seed, tick, simpleMask & 0xFu), "pom_batch_policy_moves_host");
+    status.resize(n);
+    check(pom_batch_step_host(handle, movebuf.data(), status.data(), 0), "pom_batch_step_host");
+    fresh = false;
+    tick++;
+    size_t running = 0;
+    for(size_t i = 0; i < n; i++) running += (status[i] & (POM_STATUS_DONE | POM_STATUS_INVALID)) ? 0 : 1;
+    return running;
+}
+
+pom_stats BatchEnvironment::Rollout(uint32_t ticks, uint64_t seed, bool harmless, unsigned simpleMask)
+{
+    check(pom_batch_rollout(handle, ticks, seed, tick, (harmless ? POM_ROLL_HARMLESS : 0) | POM_ROLL_SIMPLE(simpleMask)), "pom_batch_rollout");
     tick += ticks;
     fresh = false;
     pom_stats s;

@@ -141,6 +141,38 @@ int main()
         REQUIRE(st.env_steps == 512ull * 200ull);
         REQUIRE(st.episodes == st.wins[0] + st.wins[1] + st.wins[2] + st.wins[3] + st.draws + st.truncated + st.invalid);
     }
+    {   /* "Test Simple Agent" (live_testing.cpp:18-36) without the console: four SimpleAgents play a game through
+         * Environment; their first moves on the default board are known: nobody is in danger, no enemy within 7, wood
+         * next to every corner => agents bomb or step safely, never walk into a wall */
+        agents::SimpleAgent a[4] = {agents::SimpleAgent(11), agents::SimpleAgent(12), agents::SimpleAgent(13), agents::SimpleAgent(14)};
+        Environment env;
+        env.MakeGame({&a[0], &a[1], &a[2], &a[3]});
+        for(int t = 0; t < 60 && !env.IsDone(); t++)
+        {
+            const State before = env.GetState();
+            env.Step();
+            for(int i = 0; i < 4; i++)
+            {
+                if(before.agents[i].dead) continue;
+                const Move m = env.GetLastMove(i);
+                REQUIRE(int(m) >= 0 && int(m) <= 5);
+                if(m == Move::BOMB) REQUIRE(before.agents[i].bombCount < before.agents[i].maxBombCount);
+            }
+        }
+        REQUIRE(env.GetState().timeStep > 0);
+        REQUIRE(a[0].memory.rp_count > 0);              /* the agents remember where they went */
+    }
+    {   /* BatchEnvironment with device-side SimpleAgent opponents: per tick (agent 0 host-controlled) and fused */
+        BatchEnvironment be(256, 0, 0, 32, 0x1337, 800);
+        std::vector<Move> mv(4 * 256, Move::IDLE);
+        size_t running = 256;
+        for(int t = 0; t < 30; t++) running = be.Step(mv.data(), 0xE, 99);
+        REQUIRE(running > 0);
+        REQUIRE(be.States()[0].timeStep > 0);
+        pom_stats st = be.Rollout(300, 5, false, 0xF);
+        REQUIRE(st.env_steps > 0);
+        REQUIRE(st.episodes == st.wins[0] + st.wins[1] + st.wins[2] + st.wins[3] + st.draws + st.truncated + st.invalid);
+    }
     std::printf(failures ? "pom_selftest: %d FAILED\n" : "pom_selftest: all passed\n", failures);
     return failures ? 1 : 0;
 }

@@ -172,6 +172,35 @@ def test_golden_simple_agent_games(pb, orc):
     b.close()
 
 
+def test_policy_act_single_agent(pb, orc):
+    """pom_batch_policy_act: the entry point behind the host mirror's agents::SimpleAgent::act"""
+    g = np.load(os.path.join(GOLD, "simple_agent.npz"))
+    init = g["init"].copy().view(oracle.STATE_DT).reshape(-1)[96:104].copy()     # boosted-regime games
+    n = init.shape[0]
+    b = pb.Batch(n, n_templates=1, empty=True)
+    b.upload(init)
+    S, status = init.copy(), np.zeros(n, np.uint8)
+    A = orc.simple_agents(n)
+    rng = np.random.default_rng(5)
+    for t in range(80):
+        mv = np.zeros((n, 4), np.uint8)
+        for e in range(n):
+            if status[e] & 0x11:
+                continue
+            for a in range(4):
+                if S["agents"]["dead"][e, a]:
+                    continue
+                d = int(rng.integers(0, 5))
+                mv[e, a] = orc.simple_act(S[e:e + 1], a, A[e, a:a + 1], d)
+                assert b.policy_act(e, a, d) == mv[e, a], (t, e, a)
+        b.step_host(mv, None, 0)
+        orc.env_step_batch(S, status, mv)
+    assert _same_agents(b.policy_download(), A)
+    G, _ = b.download()
+    assert orc.diff_batch(G, S)[0] == -1
+    b.close()
+
+
 def test_policy_abi_errors(pb):
     b = pb.Batch(64, n_templates=4)
     L = pb.lib()
@@ -181,5 +210,11 @@ def test_policy_abi_errors(pb):
     assert L.pom_batch_policy_moves(b.h, dev, 1, 0, 16) == -1
     assert L.pom_batch_policy_download(b.h, 60, 10, dev) == -4
     assert L.pom_batch_policy_upload(b.h, 0, 65, dev) == -4
+    import ctypes as C
+    m = C.c_int(0)
+    assert L.pom_batch_policy_act(b.h, 64, 0, 0, C.byref(m)) == -4
+    assert L.pom_batch_policy_act(b.h, 0, 4, 0, C.byref(m)) == -1
+    assert L.pom_batch_policy_act(b.h, 0, 0, 5, C.byref(m)) == -1
+    assert L.pom_batch_policy_act(b.h, 0, 0, 0, None) == -1
     b.free(dev)
     b.close()
