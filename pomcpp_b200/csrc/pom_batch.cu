@@ -32,6 +32,14 @@ int fail(int code, const char* what, cudaError_t ce = cudaSuccess)
     return code;
 }
 
+/* temporary device allocation, released on every return path */
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if(p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+    template<typename T> T* as() const { return static_cast<T*>(p); }
+};
+
 #define CK(expr) do { cudaError_t ce_ = (expr); if(ce_ != cudaSuccess) return fail(POM_E_CUDA, #expr, ce_); } while(0)
 
 constexpr uint64_t TILE_ALIGN = 256;           /* records are allocated in whole tiles of the largest TPB */
@@ -68,6 +76,7 @@ struct pom_batch {
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {}, ev_out = nullptr, ev_begin = nullptr;
     std::vector<int32_t> seeds;
     uint64_t  launches = 0;
+    uint32_t  attr_done = 0;                   /* kernels whose shared-memory attribute has been set on this handle's device */
 
     pomk::BatchParams params() const
     {
@@ -89,10 +98,16 @@ int use(const pom_batch* b)
     return POM_OK;
 }
 
-template<int TPB, typename K>
-int set_smem(K kernel)
+/* The dynamic shared-memory limit of a kernel is a per-device attribute: remember it per handle (one handle = one
+ * device), not in a process-wide flag, so that handles on other GPUs and other host threads set it for themselves. */
+enum { ATTR_STEP = 1, ATTR_ROLLOUT = 2, ATTR_ROLLOUT_POLICY = 4, ATTR_POLICY_MOVES = 8, ATTR_EXPAND = 16 };
+
+template<typename K>
+int set_smem(pom_batch* b, uint32_t which, K kernel, uint32_t bytes)
 {
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pomk::TileScratch<TPB>::BYTES)));
+    if(b->attr_done & which) return POM_OK;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+    b->attr_done |= which;
     return POM_OK;
 }
 
@@ -133,9 +148,10 @@ int build_templates_from_seeds(pom_batch* b, int32_t first_seed)
     uint32_t ncand = uint32_t(n * 2.2) + 64;
     for(int attempt = 0; attempt < 6; attempt++, ncand *= 2)
     {
-        uint8_t* cand = nullptr; uint8_t* dirty = nullptr; uint32_t* pick = nullptr;
-        CK(cudaMalloc(&cand, size_t(ncand) * POM_REC_BYTES));
-        CK(cudaMalloc(&dirty, ncand));
+        DevBuf cand_b, dirty_b, pick_b;
+        CK(cand_b.alloc(size_t(ncand) * POM_REC_BYTES));
+        CK(dirty_b.alloc(ncand));
+        uint8_t* cand = cand_b.as<uint8_t>(); uint8_t* dirty = dirty_b.as<uint8_t>();
         pomk::k_make_templates<<<(ncand + 63) / 64, 64, 0, b->stream>>>(cand, dirty, first_seed, ncand);
         b->launches++;
         CK(cudaGetLastError());
@@ -146,7 +162,8 @@ int build_templates_from_seeds(pom_batch* b, int32_t first_seed)
         for(uint32_t i = 0; i < ncand && idx.size() < n; i++) if(!h[i]) idx.push_back(i);
         if(idx.size() == n)
         {
-            CK(cudaMalloc(&pick, n * sizeof(uint32_t)));
+            CK(pick_b.alloc(n * sizeof(uint32_t)));
+            uint32_t* pick = pick_b.as<uint32_t>();
             CK(cudaMemcpyAsync(pick, idx.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
             const uint64_t words = uint64_t(n) * POM_REC_WORDS;
             pomk::k_gather_records<<<unsigned((words + 255) / 256), 256, 0, b->stream>>>(
@@ -156,9 +173,8 @@ int build_templates_from_seeds(pom_batch* b, int32_t first_seed)
             CK(cudaStreamSynchronize(b->stream));
             b->seeds.resize(n);
             for(uint32_t k = 0; k < n; k++) b->seeds[k] = first_seed + int32_t(idx[k]);
+            return POM_OK;
         }
-        cudaFree(cand); cudaFree(dirty); if(pick) cudaFree(pick);
-        if(idx.size() == n) return POM_OK;
     }
     return fail(POM_E_ARG, "could not find enough clean seeds");
 }
@@ -187,8 +203,7 @@ int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, c
 template<int TPB>
 int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* status_dev, uint64_t first = 0, uint64_t count = 0)
 {
-    static bool once = false;
-    if(!once) { int rc = set_smem<TPB>(pomk::k_step<TPB>); if(rc) return rc; once = true; }
+    { int rc = set_smem(b, ATTR_STEP, pomk::k_step<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     /* envs [first, first + count) only (first is a multiple of TPB); count == 0 means the whole batch */
     pomk::BatchParams P = b->params();
     if(count)
@@ -198,9 +213,7 @@ int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t*
         if(status_dev) status_dev += first;
     }
     const unsigned grid = unsigned((P.n_envs + TPB - 1) / TPB);
-    static int pad = -1;
-    if(pad < 0) { const char* e = std::getenv("POM_SMEM_PAD"); pad = e ? std::atoi(e) : 0; if(pad) cudaFuncSetAttribute(pomk::k_step<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pomk::TileScratch<TPB>::BYTES) + pad); }
-    pomk::k_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES + pad, b->stream>>>(P, reinterpret_cast<const uint32_t*>(moves_dev), flags, status_dev);
+    pomk::k_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(P, reinterpret_cast<const uint32_t*>(moves_dev), flags, status_dev);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -214,19 +227,13 @@ int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, 
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
     if(mask)
     {
-        static bool once = false;
-        if(!once)
-        {
-            CK(cudaFuncSetAttribute(pomk::k_rollout<TPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pomk::RolloutScratch<TPB, true>::BYTES)));
-            once = true;
-        }
-        int rc = ensure_policy(b); if(rc) return rc;
+        int rc = set_smem(b, ATTR_ROLLOUT_POLICY, pomk::k_rollout<TPB, true>, pomk::RolloutScratch<TPB, true>::BYTES); if(rc) return rc;
+        rc = ensure_policy(b); if(rc) return rc;
         pomk::k_rollout<TPB, true><<<grid, TPB, pomk::RolloutScratch<TPB, true>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, mask);
     }
     else
     {
-        static bool once = false;
-        if(!once) { int rc = set_smem<TPB>(pomk::k_rollout<TPB, false>); if(rc) return rc; once = true; }
+        int rc = set_smem(b, ATTR_ROLLOUT, pomk::k_rollout<TPB, false>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc;
         pomk::k_rollout<TPB, false><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, 0u);
     }
     b->launches++;
@@ -237,8 +244,7 @@ int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, 
 template<int TPB>
 int launch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_t tick, uint32_t mask)
 {
-    static bool once = false;
-    if(!once) { int rc = set_smem<TPB>(pomk::k_policy_moves<TPB>); if(rc) return rc; once = true; }
+    { int rc = set_smem(b, ATTR_POLICY_MOVES, pomk::k_policy_moves<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
     pomk::k_policy_moves<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), reinterpret_cast<uint32_t*>(moves_dev), seed, tick, mask);
     b->launches++;
@@ -249,8 +255,7 @@ int launch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_
 template<int TPB>
 int launch_expand(pom_batch* dst, const pom_batch* src, const uint32_t* idx_dev, uint64_t n_children, uint32_t fanout, uint32_t flags)
 {
-    static bool once = false;
-    if(!once) { int rc = set_smem<TPB>(pomk::k_expand_step<TPB>); if(rc) return rc; once = true; }
+    { int rc = set_smem(dst, ATTR_EXPAND, pomk::k_expand_step<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     const unsigned grid = unsigned((n_children + TPB - 1) / TPB);
     pomk::k_expand_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, dst->stream>>>(dst->recs, src->recs, idx_dev, n_children, fanout, flags);
     dst->launches++;
@@ -522,15 +527,13 @@ int pom_batch_policy_act(pom_batch* b, uint64_t env, int agent, int draw, int* m
     if(env >= b->n_envs) return fail(POM_E_RANGE, "pom_batch_policy_act: env outside the batch");
     if(agent < 0 || agent > 3 || draw < 0 || draw > 4) return fail(POM_E_ARG, "pom_batch_policy_act: agent must be 0..3 and draw 0..4");
     rc = ensure_policy(b); if(rc) return rc;
-    int* dev = nullptr;
-    CK(cudaMalloc(&dev, sizeof(int)));
-    pomk::k_policy_act<<<1, 1, 0, b->stream>>>(b->params(), env, agent, uint32_t(draw), dev);
+    DevBuf dev;
+    CK(dev.alloc(sizeof(int)));
+    pomk::k_policy_act<<<1, 1, 0, b->stream>>>(b->params(), env, agent, uint32_t(draw), dev.as<int>());
     b->launches++;
-    cudaError_t ce = cudaGetLastError();
-    if(ce == cudaSuccess) ce = cudaMemcpyAsync(move_out, dev, sizeof(int), cudaMemcpyDeviceToHost, b->stream);
-    if(ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
-    cudaFree(dev);
-    if(ce != cudaSuccess) return fail(POM_E_CUDA, "pom_batch_policy_act", ce);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(move_out, dev.p, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
     return POM_OK;
 }
 
@@ -549,15 +552,13 @@ int pom_batch_policy_download(pom_batch* b, uint64_t first, uint64_t count, pom_
     if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_policy_download: range outside the batch");
     if(count == 0) return POM_OK;
     rc = ensure_policy(b); if(rc) return rc;
-    uint32_t* tmp = nullptr;
-    CK(cudaMalloc(&tmp, count * 32));
-    pomk::k_policy_export<<<unsigned((count + 127) / 128), 128, 0, b->stream>>>(b->params(), first, count, tmp);
+    DevBuf tmp;
+    CK(tmp.alloc(count * 32));
+    pomk::k_policy_export<<<unsigned((count + 127) / 128), 128, 0, b->stream>>>(b->params(), first, count, tmp.as<uint32_t>());
     b->launches++;
-    cudaError_t ce = cudaGetLastError();
-    if(ce == cudaSuccess) ce = cudaMemcpyAsync(out, tmp, count * 32, cudaMemcpyDeviceToHost, b->stream);
-    if(ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
-    cudaFree(tmp);
-    if(ce != cudaSuccess) return fail(POM_E_CUDA, "pom_batch_policy_download", ce);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, tmp.p, count * 32, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
     return POM_OK;
 }
 
@@ -568,18 +569,13 @@ int pom_batch_policy_upload(pom_batch* b, uint64_t first, uint64_t count, const 
     if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_policy_upload: range outside the batch");
     if(count == 0) return POM_OK;
     rc = ensure_policy(b); if(rc) return rc;
-    uint32_t* tmp = nullptr;
-    CK(cudaMalloc(&tmp, count * 32));
-    cudaError_t ce = cudaMemcpyAsync(tmp, in, count * 32, cudaMemcpyHostToDevice, b->stream);
-    if(ce == cudaSuccess)
-    {
-        pomk::k_policy_import<<<unsigned((count + 127) / 128), 128, 0, b->stream>>>(b->params(), first, count, tmp);
-        b->launches++;
-        ce = cudaGetLastError();
-    }
-    if(ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
-    cudaFree(tmp);
-    if(ce != cudaSuccess) return fail(POM_E_CUDA, "pom_batch_policy_upload", ce);
+    DevBuf tmp;
+    CK(tmp.alloc(count * 32));
+    CK(cudaMemcpyAsync(tmp.p, in, count * 32, cudaMemcpyHostToDevice, b->stream));
+    pomk::k_policy_import<<<unsigned((count + 127) / 128), 128, 0, b->stream>>>(b->params(), first, count, tmp.as<uint32_t>());
+    b->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(b->stream));
     return POM_OK;
 }
 
@@ -591,18 +587,18 @@ int pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, co
     if(first_dst + n_dst > dst->n_envs) return fail(POM_E_RANGE, "pom_batch_clone: destination range outside the batch");
     for(uint64_t i = 0; i < n_dst; i++) if(src_idx[i] >= src->n_envs) return fail(POM_E_RANGE, "pom_batch_clone: source index outside the batch");
     if(n_dst == 0) return POM_OK;
-    uint32_t* idx_dev = nullptr;
-    CK(cudaMalloc(&idx_dev, n_dst * sizeof(uint32_t)));
+    DevBuf idx_b, snap;
+    CK(idx_b.alloc(n_dst * sizeof(uint32_t)));
+    uint32_t* idx_dev = idx_b.as<uint32_t>();
     CK(cudaMemcpyAsync(idx_dev, src_idx, n_dst * sizeof(uint32_t), cudaMemcpyHostToDevice, dst->stream));
-    if(src != dst) cudaStreamSynchronize(src->stream);
+    if(src != dst) CK(cudaStreamSynchronize(src->stream));
     const uint8_t* from = src->recs;
-    uint8_t* tmp = nullptr;
     if(src == dst)
     {
         /* in-place gather: read from a snapshot so overlapping ranges are well defined */
-        CK(cudaMalloc(&tmp, dst->n_alloc * POM_REC_BYTES));
-        CK(cudaMemcpyAsync(tmp, dst->recs, dst->n_alloc * POM_REC_BYTES, cudaMemcpyDeviceToDevice, dst->stream));
-        from = tmp;
+        CK(snap.alloc(dst->n_alloc * POM_REC_BYTES));
+        CK(cudaMemcpyAsync(snap.p, dst->recs, dst->n_alloc * POM_REC_BYTES, cudaMemcpyDeviceToDevice, dst->stream));
+        from = snap.as<uint8_t>();
     }
     const uint64_t words = n_dst * POM_REC_WORDS;
     pomk::k_gather_records<<<unsigned((words + 255) / 256), 256, 0, dst->stream>>>(
@@ -610,8 +606,6 @@ int pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, co
     dst->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(dst->stream));
-    cudaFree(idx_dev);
-    if(tmp) cudaFree(tmp);
     return POM_OK;
 }
 
@@ -625,15 +619,14 @@ int pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* 
     if(n_children > dst->n_envs) return fail(POM_E_RANGE, "pom_batch_expand_step: destination too small");
     for(uint64_t i = 0; i < n_roots; i++) if(src_idx[i] >= src->n_envs) return fail(POM_E_RANGE, "pom_batch_expand_step: root index outside the batch");
     if(n_roots == 0) return POM_OK;
-    uint32_t* idx_dev = nullptr;
-    CK(cudaMalloc(&idx_dev, n_roots * sizeof(uint32_t)));
+    DevBuf idx_b;
+    CK(idx_b.alloc(n_roots * sizeof(uint32_t)));
+    uint32_t* idx_dev = idx_b.as<uint32_t>();
     CK(cudaMemcpyAsync(idx_dev, src_idx, n_roots * sizeof(uint32_t), cudaMemcpyHostToDevice, dst->stream));
-    cudaStreamSynchronize(src->stream);
+    CK(cudaStreamSynchronize(src->stream));
     rc = [&]() -> int { POM_DISPATCH(dst, launch_expand, dst, src, idx_dev, n_children, fanout, flags); }();
-    cudaError_t ce = cudaStreamSynchronize(dst->stream);
-    cudaFree(idx_dev);
     if(rc) return rc;
-    if(ce != cudaSuccess) return fail(POM_E_CUDA, "pom_batch_expand_step", ce);
+    CK(cudaStreamSynchronize(dst->stream));             /* idx_dev must outlive the kernel */
     return POM_OK;
 }
 
@@ -664,18 +657,16 @@ int pom_make_board(int device, int32_t seed, pom_state* out, int* dirty)
     if(ce != cudaSuccess || ndev == 0) return fail(POM_E_CUDA, "no CUDA device: the step path has no CPU fallback", ce);
     if(device < 0 || device >= ndev) return fail(POM_E_ARG, "pom_make_board: no such device");
     CK(cudaSetDevice(device));
-    uint8_t* rec = nullptr; uint8_t* d = nullptr; pom_state* aos = nullptr; uint8_t* st = nullptr;
-    CK(cudaMalloc(&rec, POM_REC_BYTES));
-    CK(cudaMalloc(&d, 1));
-    CK(cudaMalloc(&aos, sizeof(pom_state)));
-    CK(cudaMalloc(&st, 1));
-    pomk::k_make_board<<<1, 1>>>(rec, d, seed);
-    pomk::k_unpack<<<1, 1>>>(rec, aos, st, 0, 1);
+    DevBuf rec, d, aos, st;
+    CK(rec.alloc(POM_REC_BYTES));
+    CK(d.alloc(1));
+    CK(aos.alloc(sizeof(pom_state)));
+    CK(st.alloc(1));
+    pomk::k_make_board<<<1, 1>>>(rec.as<uint8_t>(), d.as<uint8_t>(), seed);
+    pomk::k_unpack<<<1, 1>>>(rec.as<uint8_t>(), aos.as<pom_state>(), st.as<uint8_t>(), 0, 1);
     uint8_t hd = 0;
-    ce = cudaMemcpy(out, aos, sizeof(pom_state), cudaMemcpyDeviceToHost);
-    if(ce == cudaSuccess) ce = cudaMemcpy(&hd, d, 1, cudaMemcpyDeviceToHost);
-    cudaFree(rec); cudaFree(d); cudaFree(aos); cudaFree(st);
-    if(ce != cudaSuccess) return fail(POM_E_CUDA, "pom_make_board", ce);
+    CK(cudaMemcpy(out, aos.p, sizeof(pom_state), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&hd, d.p, 1, cudaMemcpyDeviceToHost));
     if(dirty) *dirty = hd;
     return POM_OK;
 }

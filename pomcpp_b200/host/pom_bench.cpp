@@ -4,12 +4,14 @@
  * sharded contiguously over the GPUs with no collective on the data path; the only collective is one
  * ncclAllReduce of the episode counters after the run.
  *
- *   pom_bench [--gpus N] [--envs-per-gpu E] [--steps K] [--warmup W] [--mode step|rollout] [--ticks T]
+ *   pom_bench [--gpus N] [--envs-per-gpu E] [--steps K] [--warmup W] [--mode step|rollout|expand] [--ticks T] [--simple MASK]
  *
  * mode step    : K launches of the per-tick kernel (pom_batch_step, auto-reset), moves pre-generated on device
  * mode rollout : K launches of the fused kernel (pom_batch_rollout), T ticks each, in-kernel RNG + auto-reset
  * mode expand  : tree-search expansion (BASELINE config 5): --roots R root states (taken from a 16-tick pre-roll)
  *                x 6^4 joint actions, one Step each, K repetitions of pom_batch_expand_step (GPU 0 only)
+ * --simple MASK : the agents in MASK (bit a) are played by the device-side SimpleAgent (pom_batch_policy_moves before
+ *                every step / POM_ROLL_SIMPLE in the rollout); 15 = the reference's own benchmark setting
  * Prints one JSON line.  (The CPU reference baseline is reported by bench.py, which alone may load oracle/.)
  */
 #include <chrono>
@@ -30,7 +32,7 @@
 namespace
 {
 
-struct Args { int gpus = 1; uint64_t envs = 1u << 20; int steps = 200; int warmup = 10; std::string mode = "step"; uint32_t ticks = 800; uint64_t roots = 4096; };
+struct Args { int gpus = 1; uint64_t envs = 1u << 20; int steps = 200; int warmup = 10; std::string mode = "step"; uint32_t ticks = 800; uint64_t roots = 4096; uint32_t simple = 0; };
 
 struct Shard { pom_batch* h = nullptr; void* moves = nullptr; float ms = 0.f; pom_stats stats; int rc = 0; std::string err; };
 
@@ -52,6 +54,7 @@ int main(int argc, char** argv)
         else if(k == "--mode") a.mode = next();
         else if(k == "--ticks") a.ticks = uint32_t(std::atoi(next()));
         else if(k == "--roots") a.roots = std::strtoull(next(), nullptr, 10);
+        else if(k == "--simple") a.simple = uint32_t(std::atoi(next())) & 0xFu;
     }
     if(a.mode == "expand")
     {
@@ -110,7 +113,12 @@ int main(int argc, char** argv)
         Shard& s = sh[size_t(g)];
         auto one = [&](int k) -> int
         {
-            if(rollout) return pom_batch_rollout(s.h, a.ticks, seed, uint32_t(k) * a.ticks, 0);
+            if(rollout) return pom_batch_rollout(s.h, a.ticks, seed, uint32_t(k) * a.ticks, POM_ROLL_SIMPLE(a.simple));
+            if(a.simple)
+            {
+                const int rc = pom_batch_policy_moves(s.h, static_cast<uint8_t*>(s.moves) + 4 * a.envs * size_t(k % ring), seed, uint32_t(k), a.simple);
+                if(rc) return rc;
+            }
             return pom_batch_step(s.h, static_cast<uint8_t*>(s.moves) + 4 * a.envs * size_t(k % ring), POM_STEP_AUTORESET | POM_STEP_COUNT);
         };
         for(int w = 0; w < a.warmup && !s.rc; w++) s.rc = one(w);
@@ -174,7 +182,7 @@ int main(int argc, char** argv)
                 "\"envs_per_gpu\": %llu, \"steps\": %d, \"warmup\": %d, \"ticks_per_step\": %u, \"ms_per_step\": %.6g, \"wall_s\": %.4g, "
                 "\"hbm_gbs_algorithmic_per_gpu\": %.6g, \"episode_stats\": {\"env_steps\": %llu, \"episodes\": %llu, \"wins\": [%llu, %llu, %llu, %llu], "
                 "\"draws\": %llu, \"truncated\": %llu, \"sum_episode_len\": %llu, \"invalid\": %llu, \"reduced_with\": \"%s\"}}\n",
-                value, a.gpus, a.mode.c_str(), (unsigned long long)a.envs, a.steps, a.warmup, rollout ? a.ticks : 1u, double(ms_max) / a.steps, wall,
+                value, a.gpus, a.mode.c_str(), a.simple, (unsigned long long)a.envs, a.steps, a.warmup, rollout ? a.ticks : 1u, double(ms_max) / a.steps, wall,
                 rollout ? 0.0 : 582.0 * double(a.envs) / (double(ms_max) / a.steps * 1e-3) / 1e9,
                 total[0], total[1], total[2], total[3], total[4], total[5], total[6], total[7], total[8], total[9], reduced);
     for(int g = 0; g < a.gpus; g++)

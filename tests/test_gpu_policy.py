@@ -218,3 +218,25 @@ def test_policy_abi_errors(pb):
     assert L.pom_batch_policy_act(b.h, 0, 0, 0, None) == -1
     b.free(dev)
     b.close()
+
+
+def test_rollout_with_simple_agents_at_scale(pb, orc):
+    """BASELINE config-3 size (1 Mi envs) with four SimpleAgents: counters are consistent, and a contiguous slice of
+    envs in the middle of the batch, replayed on the oracle from the same counter RNG, matches field by field."""
+    n, ticks, seed = 1 << 20, 120, 2024
+    b = pb.Batch(n, n_templates=512, max_ticks=100)
+    T, _ = b.templates()
+    b.rollout(ticks, seed, 0, pb.ROLL_SIMPLE(15))
+    st = b.stats()
+    assert st.env_steps == n * ticks
+    assert st.episodes == sum(st.wins) + st.draws + st.truncated + st.invalid and st.episodes >= n
+    lo, cnt = 777_001, 192
+    S = np.stack([T[(lo + e) % 512] for e in range(cnt)]).astype(oracle.STATE_DT)
+    A = orc.simple_agents(cnt)
+    status, _ = _oracle_policy_rollout(orc, S, T, A, lo, ticks, seed, 6, 100, 15)
+    G, gst = b.download(lo, cnt)
+    e, why = orc.diff_batch(G, S)
+    assert e == -1, "env %d field group %d" % (lo + e, why)
+    assert (gst == status).all()
+    assert _same_agents(b.policy_download(lo, cnt), A)
+    b.close()
