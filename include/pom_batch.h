@@ -42,7 +42,11 @@ enum {
     POM_STEP_RAW       = 0x1, /* bare bboard::Step (step.cpp:9): no timeStep++, no done/winner, finished envs are stepped too */
     POM_STEP_AUTORESET = 0x2, /* an env that finishes is counted in the stats and re-initialised from the
                                  template pool at the end of the finishing tick (not in the reference)  */
-    POM_STEP_COUNT     = 0x4  /* add the number of envs stepped to stats.env_steps                       */
+    POM_STEP_COUNT     = 0x4, /* add the number of envs stepped to stats.env_steps                       */
+    POM_STEP_OVERLAP   = 0x8  /* pom_batch_step only: step the two halves of the batch on two internal streams so that
+                                 consecutive ticks overlap at their edges.  Every other call on the handle first waits
+                                 for both halves; work the caller enqueues DIRECTLY on pom_batch_stream() is ordered after
+                                 the first half only - call pom_batch_sync or any other entry point first. */
 };
 
 /* flags of pom_batch_rollout: actions per agent come from the shared stateless RNG

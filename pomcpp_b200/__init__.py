@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libpom_b200.so")
 REC_BYTES = 292
 ALGO_BYTES_PER_ENV_STEP = 2 * 289 + 4      # packed state in + out + 4 move bytes
 
-STEP_RAW, STEP_AUTORESET, STEP_COUNT = 1, 2, 4
+STEP_RAW, STEP_AUTORESET, STEP_COUNT, STEP_OVERLAP = 1, 2, 4, 8
 ROLL_HARMLESS, ROLL_NO_RESET = 1, 2
 
 

@@ -178,7 +178,7 @@ int main(int argc, char** argv)
     for(int g = 0; g < a.gpus; g++) ms_max = sh[size_t(g)].ms > ms_max ? sh[size_t(g)].ms : ms_max;
     const double env_steps_timed = double(a.gpus) * double(a.envs) * double(a.steps) * (rollout ? double(a.ticks) : 1.0);
     const double value = env_steps_timed / (double(ms_max) * 1e-3);
-    std::printf("{\"metric\": \"env-steps/sec\", \"value\": %.6g, \"unit\": \"env-steps/s\", \"n_gpus\": %d, \"mode\": \"%s\", "
+    std::printf("{\"metric\": \"env-steps/sec\", \"value\": %.6g, \"unit\": \"env-steps/s\", \"n_gpus\": %d, \"mode\": \"%s\", \"simple_agent_mask\": %u, "
                 "\"envs_per_gpu\": %llu, \"steps\": %d, \"warmup\": %d, \"ticks_per_step\": %u, \"ms_per_step\": %.6g, \"wall_s\": %.4g, "
                 "\"hbm_gbs_algorithmic_per_gpu\": %.6g, \"episode_stats\": {\"env_steps\": %llu, \"episodes\": %llu, \"wins\": [%llu, %llu, %llu, %llu], "
                 "\"draws\": %llu, \"truncated\": %llu, \"sum_episode_len\": %llu, \"invalid\": %llu, \"reduced_with\": \"%s\"}}\n",

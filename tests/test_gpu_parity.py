@@ -502,3 +502,45 @@ def test_config5_expansion_full_size(pb, orc):
         assert (gst == est).all()
     src.close()
     dst.close()
+
+
+@pytest.mark.parametrize("n", [70_001, 300_000])
+def test_step_host_chunked_pipeline_with_pinned_buffers(pb, orc, n):
+    """pom_batch_step_host with pinned buffers: one chunk below 2^18 envs, six chunks on two compute streams above"""
+    b = pb.Batch(n, n_templates=64)
+    S, _ = b.download()
+    status = np.zeros(n, np.uint8)
+    bufs = [(pb.pinned_array((n, 4), np.uint8), pb.pinned_array((n,), np.uint8)) for _ in range(2)]
+    for t in range(24):
+        (mv, _o1), (out, _o2) = bufs[t % 2]
+        mv[:] = orc.rng_moves(5, 0, n, t, 6)
+        b.step_host(mv, out, 0)
+        orc.env_step_batch(S, status, np.ascontiguousarray(mv))
+        assert (out == status).all(), "tick %d" % t
+    G, gst = b.download()
+    assert orc.diff_batch(G, S)[0] == -1 and (gst == status).all()
+    b.close()
+
+
+def test_step_overlap_flag_matches_oracle(pb, orc):
+    """POM_STEP_OVERLAP: the two halves of the batch are stepped on two internal streams, ticks overlap at their edges;
+    results, status bytes and counters must be those of the plain per-tick path (auto-reset rule included)"""
+    n, ticks, seed = (1 << 18) + 1500, 36, 13
+    b = pb.Batch(n, n_templates=32, max_ticks=0)
+    T, _ = b.templates()
+    S, _ = b.download()
+    moves_dev = b.alloc(4 * n * ticks)
+    for t in range(ticks):
+        b.generate_moves(moves_dev.value + 4 * n * t, seed, t, 6)
+    for t in range(ticks):
+        b.step(moves_dev.value + 4 * n * t, pb.STEP_AUTORESET | pb.STEP_COUNT | pb.STEP_OVERLAP)
+        if t == 17:
+            mid = b.stats()                 # any other call joins both halves first
+            assert mid.env_steps == n * 18
+    G, gst = b.download()
+    status, stats = _oracle_rollout(orc, S, T, 0, ticks, seed, 6, 0)
+    assert orc.diff_batch(G, S)[0] == -1
+    assert (gst == status).all()
+    assert (b.stats().as_array() == stats).all(), (b.stats().as_dict(), stats)
+    b.free(moves_dev)
+    b.close()
