@@ -464,13 +464,18 @@ int pom_batch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
      * caller's moves, the first half of the previous tick) and, by stream order, for its own previous tick; the first
      * half of the NEXT tick does not wait for it.  So the last, partly filled wave of one kernel runs next to the first
      * wave of the other, tick after tick; use() joins the streams before any other operation. */
-    const uint64_t half = ((b->n_envs + 1) / 2 + 1023) / 1024 * 1024;
+    static int parts = -1;
+    if(parts < 0) { const char* e = std::getenv("POM_STEP_PARTS"); parts = e ? std::atoi(e) : 2; if(parts < 2 || parts > 16) parts = 2; }
+    const uint64_t per = ((b->n_envs + parts - 1) / parts + 1023) / 1024 * 1024;
     CK(cudaEventRecord(b->ev_begin, b->stream));
     CK(cudaStreamWaitEvent(b->s_k2, b->ev_begin, 0));
-    rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, moves_dev, flags, nullptr, 0, half, b->stream); }();
-    if(rc) return rc;
-    rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, moves_dev, flags, nullptr, half, b->n_envs - half, b->s_k2); }();
-    if(rc) return rc;
+    int c = 0;
+    for(uint64_t first = 0; first < b->n_envs; first += per, c++)
+    {
+        const uint64_t count = first + per <= b->n_envs ? per : b->n_envs - first;
+        rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, moves_dev, flags, nullptr, first, count, (c & 1) ? b->s_k2 : b->stream); }();
+        if(rc) return rc;
+    }
     b->forked = true;
     return POM_OK;
 }

@@ -10,6 +10,7 @@
  * mode rollout : K launches of the fused kernel (pom_batch_rollout), T ticks each, in-kernel RNG + auto-reset
  * mode expand  : tree-search expansion (BASELINE config 5): --roots R root states (taken from a 16-tick pre-roll)
  *                x 6^4 joint actions, one Step each, K repetitions of pom_batch_expand_step (GPU 0 only)
+ * --no-overlap  : mode step without POM_STEP_OVERLAP (one launch per tick; default: two half-batch launches on two streams)
  * --simple MASK : the agents in MASK (bit a) are played by the device-side SimpleAgent (pom_batch_policy_moves before
  *                every step / POM_ROLL_SIMPLE in the rollout); 15 = the reference's own benchmark setting
  * Prints one JSON line.  (The CPU reference baseline is reported by bench.py, which alone may load oracle/.)
@@ -32,7 +33,7 @@
 namespace
 {
 
-struct Args { int gpus = 1; uint64_t envs = 1u << 20; int steps = 200; int warmup = 10; std::string mode = "step"; uint32_t ticks = 800; uint64_t roots = 4096; uint32_t simple = 0; };
+struct Args { int gpus = 1; uint64_t envs = 1u << 20; int steps = 200; int warmup = 10; std::string mode = "step"; uint32_t ticks = 800; uint64_t roots = 4096; uint32_t simple = 0; bool overlap = true; };
 
 struct Shard { pom_batch* h = nullptr; void* moves = nullptr; float ms = 0.f; pom_stats stats; int rc = 0; std::string err; };
 
@@ -55,6 +56,7 @@ int main(int argc, char** argv)
         else if(k == "--ticks") a.ticks = uint32_t(std::atoi(next()));
         else if(k == "--roots") a.roots = std::strtoull(next(), nullptr, 10);
         else if(k == "--simple") a.simple = uint32_t(std::atoi(next())) & 0xFu;
+        else if(k == "--no-overlap") a.overlap = false;
     }
     if(a.mode == "expand")
     {
@@ -119,7 +121,7 @@ int main(int argc, char** argv)
                 const int rc = pom_batch_policy_moves(s.h, static_cast<uint8_t*>(s.moves) + 4 * a.envs * size_t(k % ring), seed, uint32_t(k), a.simple);
                 if(rc) return rc;
             }
-            return pom_batch_step(s.h, static_cast<uint8_t*>(s.moves) + 4 * a.envs * size_t(k % ring), POM_STEP_AUTORESET | POM_STEP_COUNT);
+            return pom_batch_step(s.h, static_cast<uint8_t*>(s.moves) + 4 * a.envs * size_t(k % ring), POM_STEP_AUTORESET | POM_STEP_COUNT | (a.overlap && !a.simple ? POM_STEP_OVERLAP : 0));
         };
         for(int w = 0; w < a.warmup && !s.rc; w++) s.rc = one(w);
         if(!s.rc) s.rc = pom_batch_sync(s.h);
