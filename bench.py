@@ -288,7 +288,8 @@ def run_own(args):
                                            "what": "one launch per tick over the whole batch, no overlap between ticks"}},
             "e2e": {"value": world * n * E2E_STEPS / e2e_max, "unit": "env-steps/s",
                     "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": n, "steps": E2E_STEPS,
-                    "api": "pom_batch_step_host (pinned host moves in, status bytes out, sync per step)"},
+                    "api": "pom_batch_step_host (pinned host moves in, status bytes out, sync per step; the step kernel reads the moves "
+                           "from and writes the status bytes to the pinned host buffers over PCIe itself)"},
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
             "episode_stats": {"env_steps": int(counters[0]), "episodes": int(counters[1]),

@@ -112,7 +112,9 @@ int  pom_batch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags);
 /* same with HOST buffers: copies moves in, steps, copies the status bytes out (may be NULL), synchronises.
  * status_host[e] is the env's status at the END of this tick; with POM_STEP_AUTORESET it is the status of the
  * episode that just ended (done / winner / draw / truncated / invalid) even though the env itself has already
- * been re-initialised — the "done" signal an RL loop needs.                                              */
+ * been re-initialised — the "done" signal an RL loop needs.
+ * Buffers from pom_host_alloc (or any page-locked, device-mapped memory) are read and written by the kernel directly
+ * over PCIe; pageable buffers are staged through chunked asynchronous copies.                             */
 int  pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags);
 /* `ticks` fused ticks with the boards resident in shared memory; actions from pom_rng_moves(rng_seed,
  * global env index, tick0 + k); auto-reset unless POM_ROLL_NO_RESET.  Replaces the loop of

@@ -526,7 +526,26 @@ int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status
     int rc = use(b); if(rc) return rc;
     if(!moves_host) return fail(POM_E_ARG, "pom_batch_step_host: null moves");
     const uint64_t n = b->n_envs;
-    /* POM_CHUNKS is a tuning knob for experiments; the default is the measured best for 1 Mi envs (6 chunks on two
+    /* Pinned (page-locked, mapped) host buffers: the kernel reads the move bytes from and writes the status bytes to host
+     * memory itself (its one coalesced load per warp is issued before the wait for the bulk state copy, so the PCIe
+     * latency hides behind it); no staging copies, no chunks.  POM_ZEROCOPY=0 forces the copy pipeline. */
+    static int zerocopy = -1;
+    if(zerocopy < 0) { const char* e = std::getenv("POM_ZEROCOPY"); zerocopy = e ? std::atoi(e) : 1; }
+    if(zerocopy)
+    {
+        void* mdev = nullptr; void* sdev = nullptr;
+        bool ok = cudaHostGetDevicePointer(&mdev, const_cast<uint8_t*>(moves_host), 0) == cudaSuccess;
+        if(ok && status_host) ok = cudaHostGetDevicePointer(&sdev, status_host, 0) == cudaSuccess;
+        if(!ok) cudaGetLastError();                          /* pageable memory: fall through to the copy pipeline */
+        else
+        {
+            rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, static_cast<const uint8_t*>(mdev), flags, static_cast<uint8_t*>(sdev)); }();
+            if(rc) return rc;
+            CK(cudaStreamSynchronize(b->stream));
+            return POM_OK;
+        }
+    }
+    /* Pageable buffers: staged copies.  POM_CHUNKS is a tuning knob for experiments; the default is the measured best for 1 Mi envs (6 chunks on two
      * compute streams: 175 us per tick against 219 us for 3 chunks on one stream; submitting the same pipeline as a
      * CUDA graph was measured too and is slower than the direct calls, 182 us) */
     static int want = -1;

@@ -504,13 +504,17 @@ def test_config5_expansion_full_size(pb, orc):
     dst.close()
 
 
-@pytest.mark.parametrize("n", [70_001, 300_000])
-def test_step_host_chunked_pipeline_with_pinned_buffers(pb, orc, n):
-    """pom_batch_step_host with pinned buffers: one chunk below 2^18 envs, six chunks on two compute streams above"""
+@pytest.mark.parametrize("n,pinned", [(70_001, True), (300_000, True), (300_000, False)])
+def test_step_host_large_batches(pb, orc, n, pinned):
+    """pom_batch_step_host at sizes where it pipelines: pinned buffers are read and written by the kernel directly
+    (zero-copy), pageable ones go through the copy pipeline (six chunks on two compute streams above 2^18 envs)"""
     b = pb.Batch(n, n_templates=64)
     S, _ = b.download()
     status = np.zeros(n, np.uint8)
-    bufs = [(pb.pinned_array((n, 4), np.uint8), pb.pinned_array((n,), np.uint8)) for _ in range(2)]
+    if pinned:
+        bufs = [(pb.pinned_array((n, 4), np.uint8), pb.pinned_array((n,), np.uint8)) for _ in range(2)]
+    else:
+        bufs = [((np.zeros((n, 4), np.uint8), None), (np.zeros(n, np.uint8), None)) for _ in range(2)]
     for t in range(24):
         (mv, _o1), (out, _o2) = bufs[t % 2]
         mv[:] = orc.rng_moves(5, 0, n, t, 6)
@@ -520,6 +524,10 @@ def test_step_host_chunked_pipeline_with_pinned_buffers(pb, orc, n):
     G, gst = b.download()
     assert orc.diff_batch(G, S)[0] == -1 and (gst == status).all()
     b.close()
+    if pinned:
+        for (_, o1), (_, o2) in bufs:
+            pb.pinned_free(o1)
+            pb.pinned_free(o2)
 
 
 def test_step_overlap_flag_matches_oracle(pb, orc):
