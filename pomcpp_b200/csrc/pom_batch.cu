@@ -369,6 +369,7 @@ int pom_batch_destroy(pom_batch* b)
 {
     if(!b) return POM_OK;
     cudaSetDevice(b->device);
+    if(b->s_k2) cudaStreamSynchronize(b->s_k2);
     if(b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->recs); cudaFree(b->templates); cudaFree(b->episodes); cudaFree(b->stats);
     cudaFree(b->moves_buf); cudaFree(b->status_buf); cudaFree(b->aos_stage); cudaFree(b->st_stage);
@@ -658,6 +659,7 @@ int pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, co
     int rc = use(dst); if(rc) return rc;
     if(!src || !src_idx) return fail(POM_E_ARG, "pom_batch_clone: null argument");
     if(src->device != dst->device) return fail(POM_E_ARG, "pom_batch_clone: handles live on different devices");
+    if(src != dst) { rc = use(src); if(rc) return rc; }         /* joins src's second compute stream if a step is in flight there */
     if(first_dst + n_dst > dst->n_envs) return fail(POM_E_RANGE, "pom_batch_clone: destination range outside the batch");
     for(uint64_t i = 0; i < n_dst; i++) if(src_idx[i] >= src->n_envs) return fail(POM_E_RANGE, "pom_batch_clone: source index outside the batch");
     if(n_dst == 0) return POM_OK;
@@ -688,6 +690,7 @@ int pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* 
     int rc = use(dst); if(rc) return rc;
     if(!src || !src_idx || src == dst) return fail(POM_E_ARG, "pom_batch_expand_step: bad argument");
     if(src->device != dst->device) return fail(POM_E_ARG, "pom_batch_expand_step: handles live on different devices");
+    rc = use(src); if(rc) return rc;                              /* joins src's second compute stream if a step is in flight there */
     if(fanout == 0 || fanout > 1296) return fail(POM_E_ARG, "pom_batch_expand_step: fanout must be 1..1296");
     const uint64_t n_children = n_roots * fanout;
     if(n_children > dst->n_envs) return fail(POM_E_RANGE, "pom_batch_expand_step: destination too small");
