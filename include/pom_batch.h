@@ -101,6 +101,12 @@ const char* pom_last_error(void);
 /* ---- AoS <-> packed exchange (there is no reference call: State is passed by pointer) ---- */
 int  pom_batch_upload(pom_batch* b, uint64_t first, uint64_t count, const pom_state* states, const uint8_t* status /* may be NULL */);
 int  pom_batch_download(pom_batch* b, uint64_t first, uint64_t count, pom_state* states /* may be NULL */, uint8_t* status /* may be NULL */);
+/* like pom_batch_download, but every State is what agent `agent` observes through a square window of `view` cells
+ * around its position (Pommerman: 4): cells outside are Item::FOG (bboard.hpp:62), agents / bombs / flames outside are
+ * not exposed (bboard.hpp:218-226: "if someone is out of sight we simply don't expose their AgentInfo"; hidden agents
+ * keep only `dead`, x = y = -1).  The reference declares this ("potentially fogged board state", bboard.hpp:529) but
+ * never implements it.  The result is what Agent::act(const State*) is meant to receive. */
+int  pom_batch_observe(pom_batch* b, uint64_t first, uint64_t count, int agent, int view, pom_state* states, uint8_t* status);
 int  pom_batch_reset(pom_batch* b);   /* all envs back to their template, counters and episode numbers cleared */
 int  pom_batch_templates(pom_batch* b, pom_state* out /* n_templates */, int32_t* seeds_out /* may be NULL */);
 

@@ -253,6 +253,13 @@ public:
     /* `ticks` fused ticks on the device with auto-reset; agents in simpleMask play SimpleAgent, the others draw
      * uniformly (from {0..4} if harmless, else {0..5}); returns the counters */
     pom_stats Rollout(uint32_t ticks, uint64_t seed, bool harmless = false, unsigned simpleMask = 0);
+    /* fog of war for the host agents of Step(agents): with view >= 0 every agent's act() receives the State as it sees it
+     * through a square window of `view` cells (Pommerman: 4) — Item::FOG outside, agents / bombs / flames outside not
+     * exposed (the "potentially fogged board state" of bboard.hpp:529, which the reference never implements);
+     * view < 0 (default) = full observability, as in the reference */
+    void SetViewRange(int view) { viewRange = view; }
+    /* the State of every game as agent `agentID` observes it */
+    std::vector<State> Observe(int agentID, int view);
     /* host copies */
     const std::vector<State>& States();
     const std::vector<uint8_t>& Status();          /* POM_STATUS_* per game */
@@ -270,6 +277,7 @@ private:
     std::vector<uint8_t> movebuf;
     bool fresh = false;
     uint32_t tick = 0;
+    int viewRange = -1;
 };
 
 }

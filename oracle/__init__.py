@@ -139,6 +139,11 @@ class Restatement:
         self.lib.pom_oracle_rng_moves_batch(seed, env0, n, tick, n_actions, _ptr(out))
         return out
 
+    def fog_batch(self, S, agent, view=4):
+        """in place: every State as `agent` observes it (pom_oracle_fog)"""
+        self.lib.pom_oracle_fog_batch(_ptr(S), C.c_long(S.shape[0]), agent, view)
+        return S
+
     # --- agents::SimpleAgent / bboard::strategy (oracle/pom_oracle_agent.c) ---
     def simple_agents(self, n_envs):
         return np.zeros((n_envs, 4), dtype=SIMPLE_DT)

@@ -809,3 +809,44 @@ void pom_oracle_rng_moves_batch(uint64_t seed, uint64_t env0, long n, uint32_t t
         memcpy(moves_out + 4 * e, &m, 4);
     }
 }
+
+/* ---- partial observability: the State as agent `agent` sees it through a square window of `view` cells.
+ * The reference only reserves the vocabulary (Item::FOG, bboard.hpp:62; "potentially fogged board state", :529; hidden
+ * AgentInfo, :218-226); the rule is Pommerman's.  Written independently of the device code: a visibility map first,
+ * then every component is filtered through it. */
+void pom_oracle_fog(pom_state* s, int agent, int view)
+{
+    unsigned char vis[BS][BS];
+    for (int y = 0; y < BS; y++)
+        for (int x = 0; x < BS; x++) {
+            int dx = x - s->agents[agent].x, dy = y - s->agents[agent].y;
+            if (dx < 0) dx = -dx;
+            if (dy < 0) dy = -dy;
+            vis[y][x] = (unsigned char)((dx > dy ? dx : dy) <= view);
+            if (!vis[y][x]) s->board[y][x] = POM_ITEM_FOG;
+        }
+    for (int i = 0; i < POM_AGENT_COUNT; i++) {
+        pom_agent* g = &s->agents[i];
+        if (i == agent) continue;
+        int seen = !g->dead && !oob(g->x, g->y) && vis[g->y][g->x];
+        if (!seen) { int d = g->dead; memset(g, 0, sizeof *g); g->x = -1; g->y = -1; g->dead = (uint8_t)d; }
+    }
+    pom_state t = *s;
+    memset(s->bombs, 0, sizeof s->bombs);
+    s->bombs_index = 0; s->bombs_count = 0;
+    for (int i = 0; i < t.bombs_count && i < NB; i++) {
+        int b = t.bombs[(t.bombs_index + i) % NB];
+        if (!oob(b_x(b), b_y(b)) && vis[b_y(b)][b_x(b)]) s->bombs[s->bombs_count++] = b;
+    }
+    memset(s->flames, 0, sizeof s->flames);
+    s->flames_index = 0; s->flames_count = 0;
+    for (int i = 0; i < t.flames_count && i < NB; i++) {
+        pom_flame f = t.flames[(t.flames_index + i) % NB];
+        if (!oob(f.x, f.y) && vis[f.y][f.x]) s->flames[s->flames_count++] = f;
+    }
+}
+
+void pom_oracle_fog_batch(pom_state* S, long n, int agent, int view)
+{
+    for (long e = 0; e < n; e++) pom_oracle_fog(&S[e], agent, view);
+}

@@ -85,6 +85,12 @@ long pom_oracle_diff_batch(const pom_state* A, const pom_state* B, long n, const
 void pom_oracle_hash_batch(const pom_state* S, long n, uint64_t* out);
 void pom_oracle_rng_moves_batch(uint64_t seed, uint64_t env0, long n, uint32_t tick, uint32_t n_actions, uint8_t* moves_out);
 
+/* the State as agent `agent` observes it through a square window of `view` cells: Item::FOG outside (bboard.hpp:62),
+ * agents / bombs / flames outside not exposed (bboard.hpp:218-226).  Declared but not implemented by the reference
+ * (bboard.hpp:529), so this is the definition the device code is checked against, not a restatement. */
+void pom_oracle_fog(pom_state* s, int agent, int view);
+void pom_oracle_fog_batch(pom_state* S, long n, int agent, int view);
+
 /* ---- agents::SimpleAgent + bboard::strategy (pom_oracle_agent.c) ----
  * act() of the reference's heuristic agent `id` on state s (simple_agent.cpp:128-141); `st` holds the
  * agent's persistent members, `draw` (0..4) replaces its one intDist(rng) call.  Returns the Move. */

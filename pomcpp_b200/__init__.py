@@ -85,6 +85,7 @@ def lib():
         L.pom_batch_sync.argtypes = [vp]
         L.pom_batch_upload.argtypes = [vp, u64, u64, vp, vp]
         L.pom_batch_download.argtypes = [vp, u64, u64, vp, vp]
+        L.pom_batch_observe.argtypes = [vp, u64, u64, i32, i32, vp, vp]
         L.pom_batch_reset.argtypes = [vp]
         L.pom_batch_templates.argtypes = [vp, vp, vp]
         L.pom_batch_step.argtypes = [vp, vp, u32]
@@ -187,6 +188,14 @@ class Batch:
         S = np.zeros(count, STATE_DT) if with_states else None
         st = np.zeros(count, np.uint8)
         _ck(lib().pom_batch_download(self.h, first, count, _p(S), _p(st)))
+        return S, st
+
+    def observe(self, agent, view=4, first=0, count=None):
+        """States as `agent` sees them through a (2*view+1)^2 window (fog of war)"""
+        count = self.n - first if count is None else count
+        S = np.zeros(count, STATE_DT)
+        st = np.zeros(count, np.uint8)
+        _ck(lib().pom_batch_observe(self.h, first, count, agent, view, _p(S), _p(st)))
         return S, st
 
     def templates(self):

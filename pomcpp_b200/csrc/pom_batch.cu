@@ -425,6 +425,26 @@ int pom_batch_download(pom_batch* b, uint64_t first, uint64_t count, pom_state* 
     return POM_OK;
 }
 
+int pom_batch_observe(pom_batch* b, uint64_t first, uint64_t count, int agent, int view, pom_state* states, uint8_t* status)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!states) return fail(POM_E_ARG, "pom_batch_observe: null output");
+    if(agent < 0 || agent > 3 || view < 0) return fail(POM_E_ARG, "pom_batch_observe: agent must be 0..3 and view >= 0");
+    if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_observe: range outside the batch");
+    rc = ensure_stage(b); if(rc) return rc;
+    for(uint64_t done = 0; done < count; done += XFER_CHUNK)
+    {
+        const uint64_t c = count - done < XFER_CHUNK ? count - done : XFER_CHUNK;
+        pomk::k_observe<<<unsigned((c + 127) / 128), 128, 0, b->stream>>>(b->recs, b->aos_stage, b->st_stage, first + done, c, agent, view);
+        b->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(states + done, b->aos_stage, c * sizeof(pom_state), cudaMemcpyDeviceToHost, b->stream));
+        if(status) CK(cudaMemcpyAsync(status + done, b->st_stage, c, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    return POM_OK;
+}
+
 int pom_batch_reset(pom_batch* b)
 {
     int rc = use(b); if(rc) return rc;

@@ -1097,6 +1097,61 @@ POM_HD uint8_t unpack(const uint8_t* r, pom_state* s)
     return r[R_STATUS];
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * Partial observability.  The reference reserves Item::FOG (bboard.hpp:62) and says that
+ * Agent::act receives a "(potentially fogged) board state" (bboard.hpp:529) in which the AgentInfo of agents out of
+ * sight is simply not exposed (bboard.hpp:218-226), but it never implements the fogging.  This is Pommerman's rule
+ * (a square window of `view` cells around the observer, 4 in the game) applied to a State:
+ *   board     cells outside the window become FOG
+ *   agents    the observer's own entry is kept; another agent that is dead or stands outside the window keeps only
+ *             its `dead` flag: x = y = -1, the other fields 0 (who is alive is public in Pommerman)
+ *   bombs     entries outside the window are dropped, the ring is rewritten from slot 0 in logical order
+ *   flames    entries whose origin is outside the window are dropped likewise
+ *   timeStep, aliveAgents are public
+ * ------------------------------------------------------------------------------------------- */
+POM_HD void fog_state(pom_state* s, int agent, int view)
+{
+    const int ax = s->agents[agent].x, ay = s->agents[agent].y;
+    const int x0 = ax - view, x1 = ax + view, y0 = ay - view, y1 = ay + view;
+    for(int y = 0; y < POM_BOARD_SIZE; y++)
+        for(int x = 0; x < POM_BOARD_SIZE; x++)
+            if(x < x0 || x > x1 || y < y0 || y > y1) s->board[y][x] = POM_ITEM_FOG;
+    for(int i = 0; i < POM_AGENT_COUNT; i++)
+    {
+        pom_agent& g = s->agents[i];
+        if(i == agent) continue;
+        if(g.dead || g.x < x0 || g.x > x1 || g.y < y0 || g.y > y1)
+        {
+            g.x = -1; g.y = -1; g.bombCount = 0; g.maxBombCount = 0; g.bombStrength = 0; g.canKick = 0;
+        }
+    }
+    int32_t keep[POM_MAX_BOMBS];
+    int nb = 0;
+    for(int i = 0; i < s->bombs_count && i < POM_MAX_BOMBS; i++)
+    {
+        const int32_t b = s->bombs[(s->bombs_index + i) % POM_MAX_BOMBS];
+        const int bx = b & 15, by = (b >> 4) & 15;
+        if(bx >= x0 && bx <= x1 && by >= y0 && by <= y1) keep[nb++] = b;
+    }
+    for(int i = 0; i < POM_MAX_BOMBS; i++) s->bombs[i] = i < nb ? keep[i] : 0;
+    s->bombs_index = 0;
+    s->bombs_count = nb;
+    pom_flame fk[POM_MAX_BOMBS];
+    int nf = 0;
+    for(int i = 0; i < s->flames_count && i < POM_MAX_BOMBS; i++)
+    {
+        const pom_flame f = s->flames[(s->flames_index + i) % POM_MAX_BOMBS];
+        if(f.x >= x0 && f.x <= x1 && f.y >= y0 && f.y <= y1) fk[nf++] = f;
+    }
+    for(int i = 0; i < POM_MAX_BOMBS; i++)
+    {
+        if(i < nf) s->flames[i] = fk[i];
+        else { s->flames[i].x = 0; s->flames[i].y = 0; s->flames[i].timeLeft = 0; s->flames[i].strength = 0; }
+    }
+    s->flames_index = 0;
+    s->flames_count = nf;
+}
+
 /* the shared stateless action source (same arithmetic as oracle/pom_oracle.c pom_oracle_rng_moves) */
 POM_HD uint64_t splitmix64(uint64_t z)
 {

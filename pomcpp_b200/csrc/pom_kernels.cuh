@@ -13,7 +13,7 @@
  *                   template pool inside the kernel.
  *  K3 k_make_templates / k_fill_from_templates   board generation on the device and env (re)initialisation.
  *  K4 k_clone / k_expand_step                    state copy and tree-search fan-out (+ one Step, fused).
- *  K5 k_pack / k_unpack                          AoS bboard::State <-> packed record.
+ *  K5 k_pack / k_unpack / k_observe              AoS bboard::State <-> packed record; the State as one agent sees it (fog).
  *  K7 k_policy_moves / k_rollout<TPB, true>   the reference's SimpleAgent (pom_policy.cuh) as the action source: per tick
  *                                                 into a moves buffer, or inside the fused rollout with the agents'
  *                                                 8-byte memories resident in shared memory.
@@ -561,6 +561,16 @@ __global__ void k_unpack(const uint8_t* __restrict__ recs, pom_state* aos, uint8
         if(status) status[i] = st;
     }
     else if(status) status[i] = recs[(first + i) * POM_REC_BYTES + R_STATUS];
+}
+
+/* the State of env first + i as agent `agent` sees it through a window of `view` cells (pomcore::fog_state) */
+__global__ void k_observe(const uint8_t* __restrict__ recs, pom_state* aos, uint8_t* status, uint64_t first, uint64_t count, int agent, int view)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(i >= count) return;
+    const uint8_t st = pomcore::unpack(recs + (first + i) * POM_REC_BYTES, aos + i);
+    pomcore::fog_state(aos + i, agent, view);
+    if(status) status[i] = st;
 }
 
 /* ---------------------------------------------------------------- misc */

@@ -312,20 +312,26 @@ size_t BatchEnvironment::Step(const Move* moves)
     return running;
 }
 
+std::vector<State> BatchEnvironment::Observe(int agentID, int view)
+{
+    std::vector<State> out(n);
+    check(pom_batch_observe(handle, 0, n, agentID, view, reinterpret_cast<pom_state*>(out.data()), nullptr), "pom_batch_observe");
+    return out;
+}
+
 size_t BatchEnvironment::Step(std::array<Agent*, AGENT_COUNT> agents)
 {
     Refresh();
     std::vector<Move> mv(4 * n, Move::IDLE);
-    for(size_t i = 0; i < n; i++)
+    for(int a = 0; a < AGENT_COUNT; a++)
     {
-        if(status[i] & (POM_STATUS_DONE | POM_STATUS_INVALID)) continue;
-        for(int a = 0; a < AGENT_COUNT; a++)
+        std::vector<State> fogged;
+        if(viewRange >= 0) fogged = Observe(a, viewRange);
+        agents[size_t(a)]->id = a;
+        for(size_t i = 0; i < n; i++)
         {
-            if(!host[i].agents[a].dead)
-            {
-                agents[size_t(a)]->id = a;
-                mv[4 * i + size_t(a)] = agents[size_t(a)]->act(&host[i]);
-            }
+            if(status[i] & (POM_STATUS_DONE | POM_STATUS_INVALID)) continue;
+            if(!host[i].agents[a].dead) mv[4 * i + size_t(a)] = agents[size_t(a)]->act(viewRange >= 0 ? &fogged[i] : &host[i]);
         }
     }
     return Step(mv.data());

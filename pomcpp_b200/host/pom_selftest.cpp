@@ -173,6 +173,27 @@ int main()
         REQUIRE(st.env_steps > 0);
         REQUIRE(st.episodes == st.wins[0] + st.wins[1] + st.wins[2] + st.wins[3] + st.draws + st.truncated + st.invalid);
     }
+    {   /* fog of war: host agents see a 9x9 window; what lies outside is Item::FOG and hidden agents have no position */
+        struct Peek : Agent
+        {
+            int fogCells = 0, hidden = 0, calls = 0;
+            Move act(const State* s) override
+            {
+                calls++;
+                for(int y = 0; y < BOARD_SIZE; y++) for(int x = 0; x < BOARD_SIZE; x++) fogCells += s->board[y][x] == Item::FOG;
+                for(int i = 0; i < AGENT_COUNT; i++) hidden += (i != id && s->agents[i].x < 0);
+                return Move::IDLE;
+            }
+        } peek;
+        BatchEnvironment be(64, 0, 0, 8);
+        be.SetViewRange(4);
+        be.Step({&peek, &peek, &peek, &peek});
+        REQUIRE(peek.calls == 64 * 4);
+        REQUIRE(peek.fogCells == 64 * 4 * (121 - 25));       /* from a corner only 5 x 5 cells are in the window */
+        REQUIRE(peek.hidden == 64 * 4 * 3);                   /* the other corners are 10 cells away */
+        std::vector<State> all = be.Observe(0, 10);
+        REQUIRE(all[0].agents[2].x == 10 && all[0].agents[2].y == 10);
+    }
     std::printf(failures ? "pom_selftest: %d FAILED\n" : "pom_selftest: all passed\n", failures);
     return failures ? 1 : 0;
 }

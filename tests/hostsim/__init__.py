@@ -40,6 +40,7 @@ class HostSim:
         L.hostsim_rng_moves.restype = C.c_uint32
         L.hostsim_rng_moves.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.hostsim_simple_moves.argtypes = [vp, C.c_long, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp]
+        L.hostsim_fog_batch.argtypes = [vp, C.c_long, C.c_int, C.c_int]
         assert L.hostsim_record_bytes() == REC
 
     def pack(self, S, status=None):
@@ -63,6 +64,10 @@ class HostSim:
 
     def spawn_flame(self, rec, x, y, s):
         self.lib.hostsim_spawn_flame(_p(rec), x, y, s)
+
+    def fog_batch(self, S, agent, view):
+        self.lib.hostsim_fog_batch(_p(S), S.shape[0], agent, view)
+        return S
 
     def simple_moves(self, recs, A, seed, env0, tick, mask, moves):
         self.lib.hostsim_simple_moves(_p(recs), recs.shape[0], _p(A), seed, env0, tick, mask, _p(moves))

@@ -76,6 +76,12 @@ void hostsim_simple_moves(const uint8_t* recs, long n, pom_simple_agent* A, uint
     }
 }
 
+/* the device fog code (pomcore::fog_state) on AoS states */
+void hostsim_fog_batch(pom_state* S, long n, int agent, int view)
+{
+    for(long e = 0; e < n; e++) pomcore::fog_state(&S[e], agent, view);
+}
+
 uint32_t hostsim_rng_moves(uint64_t seed, uint64_t env, uint32_t tick, uint32_t n_actions)
 {
     return pomcore::rng_moves(seed, env, tick, n_actions);

@@ -1,0 +1,77 @@
+"""Fog of war: pom_batch_observe / pomcore::fog_state against the oracle's definition
+(oracle/pom_oracle.c pom_oracle_fog).  The reference only declares the feature (bboard.hpp:62,218-226,529), so the
+checks are: device code == independent C definition, plus the properties that define fog."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+FOG = 5
+
+
+def _mid_game_states(orc, n=256, ticks=40, seed=21):
+    seeds = oracle.clean_seeds(32)
+    S = orc.zero_state(n)
+    for i in range(n):
+        orc.init_state(S[i:i + 1], seeds[i % 32])
+    S["agents"]["maxBombCount"] = 3
+    S["agents"]["bombStrength"] = 3
+    status = np.zeros(n, np.uint8)
+    for t in range(ticks):
+        orc.env_step_batch(S, status, orc.rng_moves(seed, 0, n, t, 6))
+    return S
+
+
+def _check_properties(full, obs, agent, view):
+    ax, ay = full["agents"]["x"][:, agent], full["agents"]["y"][:, agent]
+    yy, xx = np.mgrid[0:11, 0:11]
+    vis = (np.abs(xx[None] - ax[:, None, None]) <= view) & (np.abs(yy[None] - ay[:, None, None]) <= view)
+    assert (obs["board"][vis] == full["board"][vis]).all()
+    assert (obs["board"][~vis] == FOG).all()
+    assert (obs["agents"][:, agent] == full["agents"][:, agent]).all()
+    assert (obs["agents"]["dead"] == full["agents"]["dead"]).all()
+    assert (obs["timeStep"] == full["timeStep"]).all() and (obs["aliveAgents"] == full["aliveAgents"]).all()
+    assert (obs["bombs_count"] <= full["bombs_count"]).all() and (obs["flames_count"] <= full["flames_count"]).all()
+    for e in range(full.shape[0]):
+        for k in range(int(obs["bombs_count"][e])):
+            b = int(obs["bombs"][e, k])
+            assert vis[e, (b >> 4) & 15, b & 15]
+        for i in range(4):
+            g = obs["agents"][e, i]
+            if i != agent and g["x"] >= 0:
+                assert vis[e, g["y"], g["x"]] and not g["dead"]
+
+
+@pytest.mark.parametrize("agent,view", [(0, 4), (2, 4), (3, 1), (1, 0), (1, 10)])
+def test_fog_definition_and_device_code_on_host(orc, agent, view):
+    from hostsim import HostSim
+    hs = HostSim()
+    full = _mid_game_states(orc)
+    a = orc.fog_batch(full.copy(), agent, view)
+    b = hs.fog_batch(full.copy(), agent, view)
+    assert orc.diff_batch(a, b)[0] == -1
+    _check_properties(full, a, agent, view)
+    if view >= 10:
+        assert (a["board"] == full["board"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("agent,view", [(0, 4), (3, 2)])
+def test_observe_on_gpu(orc, agent, view):
+    import pomcpp_b200 as pb
+    n = 5000
+    b = pb.Batch(n, n_templates=64)
+    b.rollout(45, 3, 0, pb.ROLL_NO_RESET)
+    full, st = b.download()
+    obs, st2 = b.observe(agent, view)
+    assert (st == st2).all()
+    assert orc.diff_batch(obs, orc.fog_batch(full.copy(), agent, view))[0] == -1
+    _check_properties(full[:300], obs[:300], agent, view)
+    part, _ = b.observe(agent, view, first=1234, count=77)
+    assert orc.diff_batch(part, obs[1234:1234 + 77])[0] == -1
+    L = pb.lib()
+    assert L.pom_batch_observe(b.h, 0, 1, 4, 4, obs.ctypes.data, None) == -1
+    assert L.pom_batch_observe(b.h, 0, n + 1, 0, 4, obs.ctypes.data, None) == -4
+    b.close()
