@@ -12,7 +12,7 @@
  *                   from the stateless counter RNG, truncation, episode statistics and auto-reset from the
  *                   template pool inside the kernel.
  *  K3 k_make_templates / k_fill_from_templates   board generation on the device and env (re)initialisation.
- *  K4 k_clone / k_expand_step                    state copy and tree-search fan-out (+ one Step, fused).
+ *  K4 k_gather_records / k_expand_step           state copy (pom_batch_clone) and tree-search fan-out (+ one Step, fused).
  *  K5 k_pack / k_unpack / k_observe              AoS bboard::State <-> packed record; the State as one agent sees it (fog).
  *  K7 k_policy_moves / k_rollout<TPB, true>   the reference's SimpleAgent (pom_policy.cuh) as the action source: per tick
  *                                                 into a moves buffer, or inside the fused rollout with the agents'
