@@ -14,23 +14,19 @@
 namespace agents
 {
 
-struct RandomAgent : bboard::Agent
+/* uniform{0 .. N_ACTIONS-1}; the members keep the reference's names (rng, intDist) */
+template<int N_ACTIONS>
+struct UniformAgent : bboard::Agent
 {
     std::mt19937_64 rng;
-    std::uniform_int_distribution<int> intDist{0, 5};
-    RandomAgent() : rng(std::random_device{}()) {}
-    explicit RandomAgent(uint64_t seed) : rng(seed) {}
+    std::uniform_int_distribution<int> intDist{0, N_ACTIONS - 1};
+    UniformAgent() : rng(std::random_device{}()) {}
+    explicit UniformAgent(uint64_t seed) : rng(seed) {}
     bboard::Move act(const bboard::State*) override { return bboard::Move(intDist(rng)); }
 };
 
-struct HarmlessAgent : bboard::Agent
-{
-    std::mt19937_64 rng;
-    std::uniform_int_distribution<int> intDist{0, 4};
-    HarmlessAgent() : rng(std::random_device{}()) {}
-    explicit HarmlessAgent(uint64_t seed) : rng(seed) {}
-    bboard::Move act(const bboard::State*) override { return bboard::Move(intDist(rng)); }
-};
+struct RandomAgent : UniformAgent<6> { using UniformAgent<6>::UniformAgent; };      /* basic_agents.cpp:12-22: moves and bombs */
+struct HarmlessAgent : UniformAgent<5> { using UniformAgent<5>::UniformAgent; };    /* basic_agents.cpp:28-38: never plants a bomb */
 
 struct LazyAgent : bboard::Agent
 {
