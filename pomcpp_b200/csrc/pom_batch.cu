@@ -835,7 +835,8 @@ int pom_device_free(int device, void* p)
 int pom_host_alloc(uint64_t bytes, void** out)
 {
     if(!out) return fail(POM_E_ARG, "pom_host_alloc: null output");
-    if(cudaHostAlloc(out, bytes, cudaHostAllocDefault) != cudaSuccess) return fail(POM_E_NOMEM, "pom_host_alloc", cudaGetLastError());
+    /* page-locked for every device of the process and mapped into their address spaces (zero-copy step_host) */
+    if(cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) return fail(POM_E_NOMEM, "pom_host_alloc", cudaGetLastError());
     return POM_OK;
 }
 
