@@ -239,9 +239,9 @@ int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, 
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
     if(mask)
     {
-        int rc = set_smem(b, ATTR_ROLLOUT_POLICY, pomk::k_rollout<TPB, true>, pomk::RolloutScratch<TPB, true>::BYTES); if(rc) return rc;
+        int rc = set_smem(b, ATTR_ROLLOUT_POLICY, pomk::k_rollout<TPB, true>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc;
         rc = ensure_policy(b); if(rc) return rc;
-        pomk::k_rollout<TPB, true><<<grid, TPB, pomk::RolloutScratch<TPB, true>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, mask);
+        pomk::k_rollout<TPB, true><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, mask);
     }
     else
     {

@@ -15,8 +15,8 @@
  *  K4 k_gather_records / k_expand_step           state copy (pom_batch_clone) and tree-search fan-out (+ one Step, fused).
  *  K5 k_pack / k_unpack / k_observe              AoS bboard::State <-> packed record; the State as one agent sees it (fog).
  *  K7 k_policy_moves / k_rollout<TPB, true>   the reference's SimpleAgent (pom_policy.cuh) as the action source: per tick
- *                                                 into a moves buffer, or inside the fused rollout with the agents'
- *                                                 8-byte memories resident in shared memory.
+ *                                                 into a moves buffer, or inside the fused rollout; the agents' 8-byte
+ *                                                 memories live in global memory, word-major (coalesced, L1/L2-resident).
  *  K6 stats                                      nine counters packed into three warp reductions, then one atomicAdd
  *                                                 per warp and non-zero counter; warp-cooperative reset (cp.async).
  */
@@ -278,36 +278,15 @@ struct GlobalAgentStore {
         base[uint64_t(2 * a) * stride] = v.w0;
         base[uint64_t(2 * a + 1) * stride] = v.w1;
     }
+    __device__ __forceinline__ void clear(uint32_t episode)
+    {
+#pragma unroll
+        for(int k = 0; k < 8; k++) base[uint64_t(k) * stride] = 0u;
+        base[8 * stride] = episode;
+    }
     __device__ __forceinline__ void claim(uint32_t episode)
     {
-        if(base[8 * stride] != episode)
-        {
-#pragma unroll
-            for(int k = 0; k < 8; k++) base[uint64_t(k) * stride] = 0u;
-            base[8 * stride] = episode;
-        }
-    }
-};
-
-/* the same eight words in shared memory, [word][thread] so that the lanes of a warp never share a bank */
-template<int TPB> struct SharedAgentStore {
-    uint32_t* base;           /* &words[threadIdx.x] */
-    __device__ __forceinline__ pompolicy::SimpleSt load(int a) const
-    {
-        pompolicy::SimpleSt s;
-        s.w0 = base[(2 * a) * TPB];
-        s.w1 = base[(2 * a + 1) * TPB];
-        return s;
-    }
-    __device__ __forceinline__ void store(int a, const pompolicy::SimpleSt& v)
-    {
-        base[(2 * a) * TPB] = v.w0;
-        base[(2 * a + 1) * TPB] = v.w1;
-    }
-    __device__ __forceinline__ void clear()
-    {
-#pragma unroll
-        for(int k = 0; k < 8; k++) base[k * TPB] = 0u;
+        if(base[8 * stride] != episode) clear(episode);
     }
 };
 
@@ -349,11 +328,6 @@ __global__ void __launch_bounds__(TPB) k_policy_moves(BatchParams P, uint32_t* _
 /* ---------------------------------------------------------------- K2: fused K-tick rollout */
 /* POLICY = false: uniform random agents only (the headline rollout; no policy code in the kernel image).
  * POLICY = true : the agents in `policy_mask` play SimpleAgent, the others stay uniform random. */
-template<int TPB, bool POLICY> struct RolloutScratch {
-    static constexpr uint32_t OFF_AGENTS = (TileScratch<TPB>::BYTES + 127u) / 128u * 128u;
-    static constexpr uint32_t BYTES = POLICY ? OFF_AGENTS + 8u * TPB * 4u : TileScratch<TPB>::BYTES;
-};
-
 template<int TPB, bool POLICY>
 __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, uint64_t seed, uint32_t tick0,
                                                 uint32_t n_actions, uint32_t no_reset, uint32_t policy_mask)
@@ -374,15 +348,10 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
         bulk_g2s(sslice, gslice, SLICE_BYTES, bar);
     }
     uint32_t ep_now = active ? P.episodes[env] : 0u;
-    SharedAgentStore<TPB> agents{ reinterpret_cast<uint32_t*>(smem + RolloutScratch<TPB, POLICY>::OFF_AGENTS) + threadIdx.x };
-    if(POLICY)
-    {
-        /* agent memories: global (SoA, coalesced) -> this thread's column in shared memory, zero if they belong to
-         * an earlier episode */
-        const bool mine = active && P.policy[8 * P.policy_stride + env] == ep_now;
-#pragma unroll
-        for(int k = 0; k < 8; k++) agents.base[k * TPB] = mine ? P.policy[uint64_t(k) * P.policy_stride + env] : 0u;
-    }
+    /* agent memories stay in global memory (word-major, so every access of a warp is one coalesced 128-byte line that
+     * lives in L1/L2 for the whole rollout): keeping them in shared memory would cost one resident CTA per SM */
+    GlobalAgentStore agents{ P.policy + (active ? env : 0), P.policy_stride };
+    if(POLICY && active) agents.claim(ep_now);
     __syncwarp();
     mbar_wait(bar, 0);
 
@@ -413,15 +382,9 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
         env_tick(rec, m, stepped, false);
         const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, !no_reset, ep_now);
         /* a new episode starts with four new agents */
-        if(POLICY && stepped && !no_reset && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID))) agents.clear();
+        if(POLICY && stepped && !no_reset && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID))) agents.clear(ep_now);
     }
     warp_add(P.stats + ST_STEPS, steps);
-    if(POLICY && active)
-    {
-#pragma unroll
-        for(int k = 0; k < 8; k++) P.policy[uint64_t(k) * P.policy_stride + env] = agents.base[k * TPB];
-        P.policy[8 * P.policy_stride + env] = ep_now;
-    }
 
     fence_proxy_async();
     __syncwarp();
