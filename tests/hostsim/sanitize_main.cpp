@@ -1,7 +1,8 @@
 /*
- * sanitize_main.cpp — TEST-ONLY.  Runs the kernel body (pom_core.cuh, host build) and the plain-C restatement
- * side by side under AddressSanitizer + UndefinedBehaviorSanitizer on seeded random traces (incl. the all-kick
- * stress regime), comparing every field after every tick.  compute-sanitizer is not available on the GPU pool,
+ * sanitize_main.cpp — TEST-ONLY.  Runs the kernel body (pom_core.cuh, host build) and the plain-C restatement side by
+ * side under AddressSanitizer + UndefinedBehaviorSanitizer on seeded random traces (random agents, the all-kick stress
+ * regime, and games in which agents 1-3 are played by the device policy code, pom_policy.cuh, against the oracle's
+ * SimpleAgent), comparing every field after every tick.  compute-sanitizer is not available on the GPU pool,
  * so this is the memory-safety check of the exact code the CUDA kernels run: every record access of the tick
  * happens inside a 292-byte heap block of its own, so an out-of-bounds ring / board / stack index trips ASan.
  *
@@ -13,6 +14,7 @@
 #include <vector>
 
 #include "pom_core.cuh"
+#include "pom_policy.cuh"
 extern "C" {
 #include "pom_oracle.h"
 }
@@ -22,8 +24,12 @@ int main(int argc, char** argv)
     const int n = argc > 1 ? std::atoi(argv[1]) : 512;
     const int ticks = argc > 2 ? std::atoi(argv[2]) : 200;
     long steps = 0, invalid = 0;
-    for(int stress = 0; stress < 2; stress++)
+    for(int stress = 0; stress < 3; stress++)      /* 0 random agents, 1 all-kick stress, 2 SimpleAgent opponents (policy code + its oracle) */
     {
+        const bool simple = stress == 2;
+        std::vector<pom_simple_agent> A(static_cast<size_t>(4 * n)), B(static_cast<size_t>(4 * n));
+        std::memset(A.data(), 0, A.size() * sizeof(pom_simple_agent));
+        std::memset(B.data(), 0, B.size() * sizeof(pom_simple_agent));
         std::vector<pom_state> S(static_cast<size_t>(n)), T(static_cast<size_t>(n));
         std::vector<uint8_t*> recs(static_cast<size_t>(n));
         std::vector<uint8_t> st(static_cast<size_t>(n), 0);
@@ -31,7 +37,7 @@ int main(int argc, char** argv)
         for(int e = 0; e < n; e++)
         {
             do { pom_oracle_zero_state(&S[size_t(e)]); } while(pom_oracle_init_state(&S[size_t(e)], seed++, 0, 1, 2, 3));
-            if(stress)
+            if(stress == 1)
             {
                 for(int a = 0; a < 4; a++) { S[size_t(e)].agents[a].canKick = 1; S[size_t(e)].agents[a].maxBombCount = 5; S[size_t(e)].agents[a].bombStrength = 4; }
                 S[size_t(e)].bombs_index = (e * 3) % 20;       /* rings that wrap */
@@ -45,9 +51,25 @@ int main(int argc, char** argv)
         {
             for(int e = 0; e < n; e++)
             {
-                const uint32_t m = pom_oracle_rng_moves(99 + uint64_t(stress), uint64_t(e), uint32_t(t), 6);
+                uint32_t m = pom_oracle_rng_moves(99 + uint64_t(stress), uint64_t(e), uint32_t(t), 6);
                 uint8_t mv[4];
                 std::memcpy(mv, &m, 4);
+                if(simple && !(st[size_t(e)] & 0x11))
+                {
+                    /* agents 1-3: the device policy code on the packed record vs the oracle's SimpleAgent on the AoS state */
+                    const uint32_t draws = pom_oracle_rng_moves(7, uint64_t(e), uint32_t(t), 5);
+                    pompolicy::ArrayStore store{ reinterpret_cast<pompolicy::SimpleSt*>(&B[size_t(4 * e)]) };
+                    m = pompolicy::simple_moves(recs[size_t(e)], 0xEu, m, draws, store);
+                    for(int a = 1; a < 4; a++)
+                        mv[a] = S[size_t(e)].agents[a].dead ? uint8_t(0) : uint8_t(pom_oracle_simple_act(&S[size_t(e)], a, &A[size_t(4 * e + a)], int((draws >> (8 * a)) & 0xFFu)));
+                    uint32_t m2;
+                    std::memcpy(&m2, mv, 4);
+                    if(m2 != m || std::memcmp(&A[size_t(4 * e)], &B[size_t(4 * e)], 4 * sizeof(pom_simple_agent)))
+                    {
+                        std::printf("POLICY MISMATCH tick %d env %d\n", t, e);
+                        return 1;
+                    }
+                }
                 if(!(st[size_t(e)] & 0x11)) steps++;
                 pom_oracle_env_step(&S[size_t(e)], &st[size_t(e)], mv);
                 pomcore::env_step(recs[size_t(e)], m);
@@ -62,6 +84,8 @@ int main(int argc, char** argv)
                     if(st[size_t(e)] & 0x10) invalid++;
                     S[size_t(e)] = S0[size_t(e)];
                     st[size_t(e)] = 0;
+                    std::memset(&A[size_t(4 * e)], 0, 4 * sizeof(pom_simple_agent));
+                    std::memset(&B[size_t(4 * e)], 0, 4 * sizeof(pom_simple_agent));
                     pomcore::pack(&S[size_t(e)], 0, recs[size_t(e)]);
                 }
             }
