@@ -282,7 +282,8 @@ def run_own(args):
                          "traffic": load_traffic(), "algorithmic_bytes_per_env_step": ALGO_BYTES,
                          "peak_source": peak_src, "kernel": "k_step<128>", "step_ms": ms / K,
                          "launches_per_step": 2 if flags & pb.STEP_OVERLAP else 1,
-                         "note": "achieved = 582 B x envs / time per tick over the timed region (CUDA events bracket both streams)",
+                         "note": "achieved = 582 B x envs / time per tick over the timed region (CUDA events bracket both streams); traffic = DRAM bytes "
+                                 "per tick from the ncu capture of one whole-batch launch (the two half-batch launches move the same bytes)",
                          "single_launch": {"launch_ms": single_ms, "achieved": ALGO_BYTES * n / (single_ms * 1e-3) / 1e9,
                                            "frac": ALGO_BYTES * n / (single_ms * 1e-3) / 1e9 / peak, "steps": SINGLE_STEPS,
                                            "what": "one launch per tick over the whole batch, no overlap between ticks"}},
