@@ -240,25 +240,56 @@ def run_own(args):
     assert stats.env_steps == n * (K + W), "kernel did not step every env on every tick"
 
     # ---- e2e: host buffers through pom_batch_step_host, copies inside the timed region
-    E2E_RING = 4
+    #      (a) one batch, pom_batch_step_host: launch, wait, launch, ... ; (b) the same envs as two half-batches stepped
+    #      alternately through pom_batch_step_host_async + pom_batch_sync, the way an actor loop with two env groups
+    #      runs: while the host consumes the results of one half, the GPU steps the other.  In both, every tick moves
+    #      all 4 move bytes/env host -> device and the status byte/env device -> host, and the host waits for them.
+    E2E_RING = 32                                        # distinct move sets: a short ring would make the games periodic
     mv_ring = [pb.pinned_array((n, 4), np.uint8) for _ in range(E2E_RING)]
     st_host, st_owner = pb.pinned_array((n,), np.uint8)
     rng = np.random.default_rng(RNG_SEED + rank)
     for arr, _ in mv_ring:
         arr[:] = rng.integers(0, 6, size=(n, 4), dtype=np.uint8)      # the policy's output, already in pinned memory
-    e2e_flags = flags & ~pb.STEP_OVERLAP               # pom_batch_step_host synchronises every tick
-    for w in range(2 * E2E_RING):     
+    e2e_flags = flags & ~pb.STEP_OVERLAP               # every tick is waited for
+    for w in range(8):
         b.step_host(mv_ring[w % E2E_RING][0], st_host, e2e_flags)
     barrier()
     t0 = time.perf_counter()
     for k in range(E2E_STEPS):
         b.step_host(mv_ring[k % E2E_RING][0], st_host, e2e_flags)
+    e2e_single_s = time.perf_counter() - t0
+    barrier()
+
+    h = n // 2
+    halves = [pb.Batch(h, device=local_rank, env_offset=plan["first"] + i * h, n_templates=N_TEMPLATES, max_ticks=800) for i in range(2)]
+    for x in halves:
+        x.rollout(PREROLL_TICKS, RNG_SEED, 0, 0)
+        x.sync()
+    mv_half = [[arr[i * h:(i + 1) * h] for arr, _ in mv_ring] for i in range(2)]
+    st_half = [st_host[i * h:(i + 1) * h] for i in range(2)]
+
+    def double_buffered(steps):
+        halves[0].step_host_async(mv_half[0][0], st_half[0], e2e_flags)
+        for k in range(steps):
+            halves[1].step_host_async(mv_half[1][k % E2E_RING], st_half[1], e2e_flags)
+            halves[0].sync()                   # results of half 0 are on the host now; its next moves are written here
+            if k + 1 < steps:
+                halves[0].step_host_async(mv_half[0][(k + 1) % E2E_RING], st_half[0], e2e_flags)
+            halves[1].sync()                   # results of half 1
+
+    double_buffered(8)
+    barrier()
+    t0 = time.perf_counter()
+    double_buffered(E2E_STEPS)
     e2e_s = time.perf_counter() - t0
     barrier()
+    e2e_launches = halves[0].launch_count() + halves[1].launch_count()
+    for x in halves:
+        x.close()
 
     # ---- aggregate over ranks
     dev = "cuda" if dist is not None else "cpu"
-    ms_max, e2e_max = [float(v) for v in shard.max_over_ranks([ms, e2e_s], dist, dev)]
+    ms_max, e2e_max, e2e_single_max = [float(v) for v in shard.max_over_ranks([ms, e2e_s, e2e_single_s], dist, dev)]
     # the one collective of the run: final NCCL reduce of the episode counters
     counters = shard.reduce_counters(b.stats().as_array(), dist, dev)
 
@@ -289,8 +320,11 @@ def run_own(args):
                                            "what": "one launch per tick over the whole batch, no overlap between ticks"}},
             "e2e": {"value": world * n * E2E_STEPS / e2e_max, "unit": "env-steps/s",
                     "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": n, "steps": E2E_STEPS,
-                    "api": "pom_batch_step_host (pinned host moves in, status bytes out, sync per step; the step kernel reads the moves "
-                           "from and writes the status bytes to the pinned host buffers over PCIe itself)"},
+                    "api": "two half-batches stepped alternately with pom_batch_step_host_async + pom_batch_sync (pinned host moves in, "
+                           "status bytes out, the host waits for every half-batch every tick; the step kernel reads the moves from and "
+                           "writes the status bytes to the pinned host buffers over PCIe itself)",
+                    "single_batch": {"value": world * n * E2E_STEPS / e2e_single_max, "unit": "env-steps/s",
+                                     "api": "one batch, pom_batch_step_host: launch and wait, tick after tick"}},
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
             "episode_stats": {"env_steps": int(counters[0]), "episodes": int(counters[1]),

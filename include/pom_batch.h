@@ -122,6 +122,10 @@ int  pom_batch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags);
  * Buffers from pom_host_alloc (or any page-locked, device-mapped memory) are read and written by the kernel directly
  * over PCIe; pageable buffers are staged through chunked asynchronous copies.                             */
 int  pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags);
+/* the same without the final synchronisation, for page-locked mapped buffers only (pom_host_alloc): returns as soon as
+ * the step is queued; status_host (and moves_host) belong to the device until pom_batch_sync(b) returns.  Lets a caller
+ * that runs two batches alternately keep the GPU busy while it consumes the results of the other batch. */
+int  pom_batch_step_host_async(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags);
 /* `ticks` fused ticks with the boards resident in shared memory; actions from pom_rng_moves(rng_seed,
  * global env index, tick0 + k); auto-reset unless POM_ROLL_NO_RESET.  Replaces the loop of
  * Environment::StartGame (environment.cpp:68-88) with RandomAgent/HarmlessAgent::act (bboard.hpp:517-533), or with

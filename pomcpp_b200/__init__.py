@@ -90,6 +90,7 @@ def lib():
         L.pom_batch_templates.argtypes = [vp, vp, vp]
         L.pom_batch_step.argtypes = [vp, vp, u32]
         L.pom_batch_step_host.argtypes = [vp, vp, vp, u32]
+        L.pom_batch_step_host_async.argtypes = [vp, vp, vp, u32]
         L.pom_batch_rollout.argtypes = [vp, u32, u64, u32, u32]
         L.pom_batch_policy_moves.argtypes = [vp, vp, u64, u32, u32]
         L.pom_batch_policy_moves_host.argtypes = [vp, vp, u64, u32, u32]
@@ -210,6 +211,11 @@ class Batch:
     def step_host(self, moves, status_out=None, flags=0):
         assert moves.dtype == np.uint8 and moves.size == 4 * self.n and moves.flags.c_contiguous
         _ck(lib().pom_batch_step_host(self.h, _p(moves), _p(status_out), flags))
+
+    def step_host_async(self, moves, status_out=None, flags=0):
+        """pinned buffers only; results are valid after sync()"""
+        assert moves.dtype == np.uint8 and moves.size == 4 * self.n and moves.flags.c_contiguous
+        _ck(lib().pom_batch_step_host_async(self.h, _p(moves), _p(status_out), flags))
 
     def rollout(self, ticks, seed, tick0=0, flags=0):
         _ck(lib().pom_batch_rollout(self.h, ticks, seed, tick0, flags))

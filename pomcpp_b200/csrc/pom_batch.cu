@@ -542,6 +542,26 @@ static int enqueue_step_pipeline(pom_batch* b, const uint8_t* moves_host, uint8_
     return POM_OK;
 }
 
+/* zero-copy launch shared by pom_batch_step_host (pinned buffers) and pom_batch_step_host_async; returns 1 if the buffers
+ * are not page-locked/mapped (nothing launched), 0 on success, a negative POM_E_* on error */
+static int launch_step_zero_copy(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags)
+{
+    void* mdev = nullptr; void* sdev = nullptr;
+    bool ok = cudaHostGetDevicePointer(&mdev, const_cast<uint8_t*>(moves_host), 0) == cudaSuccess;
+    if(ok && status_host) ok = cudaHostGetDevicePointer(&sdev, status_host, 0) == cudaSuccess;
+    if(!ok) { cudaGetLastError(); return 1; }
+    return [&]() -> int { POM_DISPATCH(b, launch_step, b, static_cast<const uint8_t*>(mdev), flags, static_cast<uint8_t*>(sdev)); }();
+}
+
+int pom_batch_step_host_async(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!moves_host) return fail(POM_E_ARG, "pom_batch_step_host_async: null moves");
+    rc = launch_step_zero_copy(b, moves_host, status_host, flags);
+    if(rc == 1) return fail(POM_E_ARG, "pom_batch_step_host_async: the buffers must be page-locked, device-mapped memory (pom_host_alloc)");
+    return rc;
+}
+
 int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags)
 {
     int rc = use(b); if(rc) return rc;
@@ -554,17 +574,14 @@ int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status
     if(zerocopy < 0) { const char* e = std::getenv("POM_ZEROCOPY"); zerocopy = e ? std::atoi(e) : 1; }
     if(zerocopy)
     {
-        void* mdev = nullptr; void* sdev = nullptr;
-        bool ok = cudaHostGetDevicePointer(&mdev, const_cast<uint8_t*>(moves_host), 0) == cudaSuccess;
-        if(ok && status_host) ok = cudaHostGetDevicePointer(&sdev, status_host, 0) == cudaSuccess;
-        if(!ok) cudaGetLastError();                          /* pageable memory: fall through to the copy pipeline */
-        else
+        rc = launch_step_zero_copy(b, moves_host, status_host, flags);
+        if(rc < 0) return rc;
+        if(rc == 0)
         {
-            rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, static_cast<const uint8_t*>(mdev), flags, static_cast<uint8_t*>(sdev)); }();
-            if(rc) return rc;
             CK(cudaStreamSynchronize(b->stream));
             return POM_OK;
         }
+        /* pageable memory: fall through to the copy pipeline */
     }
     /* Pageable buffers: staged copies.  POM_CHUNKS is a tuning knob for experiments; the default is the measured best for 1 Mi envs (6 chunks on two
      * compute streams: 175 us per tick against 219 us for 3 chunks on one stream; submitting the same pipeline as a

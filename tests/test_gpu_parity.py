@@ -552,3 +552,39 @@ def test_step_overlap_flag_matches_oracle(pb, orc):
     assert (b.stats().as_array() == stats).all(), (b.stats().as_dict(), stats)
     b.free(moves_dev)
     b.close()
+
+
+def test_step_host_async_double_buffered(pb, orc):
+    """two batches stepped alternately through pom_batch_step_host_async + sync (the e2e pattern of bench.py)"""
+    h, ticks = 40_000, 30
+    B = [pb.Batch(h, env_offset=i * h, n_templates=32) for i in range(2)]
+    S = [x.download()[0] for x in B]
+    status = [np.zeros(h, np.uint8) for _ in range(2)]
+    mv = [pb.pinned_array((h, 4), np.uint8) for _ in range(2)]
+    out = [pb.pinned_array((h,), np.uint8) for _ in range(2)]
+
+    def launch(i, t):
+        mv[i][0][:] = orc.rng_moves(8, i * h, h, t, 6)
+        B[i].step_host_async(mv[i][0], out[i][0], 0)
+
+    def check(i, t):
+        B[i].sync()
+        orc.env_step_batch(S[i], status[i], np.ascontiguousarray(mv[i][0]))
+        assert (out[i][0] == status[i]).all(), "half %d tick %d" % (i, t)
+
+    launch(0, 0)
+    for t in range(ticks):
+        launch(1, t)
+        check(0, t)
+        if t + 1 < ticks:
+            launch(0, t + 1)
+        check(1, t)
+    for i in range(2):
+        G, gst = B[i].download()
+        assert orc.diff_batch(G, S[i])[0] == -1 and (gst == status[i]).all()
+    # pageable buffers are refused (the call could not be asynchronous)
+    assert pb.lib().pom_batch_step_host_async(B[0].h, np.zeros((h, 4), np.uint8).ctypes.data, None, 0) == -1
+    for x in B:
+        x.close()
+    for a, o in mv + out:
+        pb.pinned_free(o)
