@@ -4,12 +4,14 @@
  * sharded contiguously over the GPUs with no collective on the data path; the only collective is one
  * ncclAllReduce of the episode counters after the run.
  *
- *   pom_bench [--gpus N] [--envs-per-gpu E] [--steps K] [--warmup W] [--mode step|rollout|expand] [--ticks T] [--simple MASK]
+ *   pom_bench [--gpus N] [--envs-per-gpu E] [--steps K] [--warmup W] [--mode step|rollout|expand|host] [--ticks T] [--simple MASK]
  *
  * mode step    : K launches of the per-tick kernel (pom_batch_step, auto-reset), moves pre-generated on device
  * mode rollout : K launches of the fused kernel (pom_batch_rollout), T ticks each, in-kernel RNG + auto-reset
  * mode expand  : tree-search expansion (BASELINE config 5): --roots R root states (taken from a 16-tick pre-roll)
  *                x 6^4 joint actions, one Step each, K repetitions of pom_batch_expand_step (GPU 0 only)
+ * mode host    : end to end from host buffers (GPU 0): the envs as two half-batches stepped alternately with
+ *                pom_batch_step_host_async + pom_batch_sync from pinned move / status buffers (what bench.py reports as e2e)
  * --no-overlap  : mode step without POM_STEP_OVERLAP (one launch per tick; default: two half-batch launches on two streams)
  * --simple MASK : the agents in MASK (bit a) are played by the device-side SimpleAgent (pom_batch_policy_moves before
  *                every step / POM_ROLL_SIMPLE in the rollout); 15 = the reference's own benchmark setting
@@ -80,6 +82,54 @@ int main(int argc, char** argv)
                     "\"fanout\": 1296, \"steps\": %d, \"ms_per_step\": %.6g, \"hbm_write_gbs\": %.6g}\n",
                     children / s, (unsigned long long)a.roots, a.steps, 1e3 * s / a.steps, children * 292.0 / s / 1e9);
         pom_batch_destroy(src); pom_batch_destroy(dst);
+        return 0;
+    }
+    if(a.mode == "host")
+    {
+        /* every tick: 4 move bytes/env host -> device, 1 status byte/env device -> host, and the host waits for them */
+        const uint64_t h = a.envs / 2;
+        const int ring = 16;
+        pom_batch* B[2] = { nullptr, nullptr };
+        uint8_t* mv[2] = { nullptr, nullptr }; uint8_t* st[2] = { nullptr, nullptr };
+        for(int i = 0; i < 2; i++)
+        {
+            pom_init_desc d;
+            std::memset(&d, 0, sizeof(d));
+            d.env_offset = uint64_t(i) * h; d.n_templates = 4096; d.first_seed = 0x1337; d.max_ticks = 800;
+            if(pom_batch_init(&B[i], 0, h, &d)) die("pom_batch_init");
+            if(pom_batch_rollout(B[i], 96, 20240229, 0, 0)) die("preroll");
+            if(pom_host_alloc(4 * h * ring, reinterpret_cast<void**>(&mv[i])) || pom_host_alloc(h, reinterpret_cast<void**>(&st[i]))) die("pom_host_alloc");
+            for(int t = 0; t < ring; t++)
+                for(uint64_t e = 0; e < h; e++)
+                {
+                    const uint32_t m = pom_rng_moves(77, uint64_t(i) * h + e, uint32_t(t), 6);
+                    std::memcpy(mv[i] + (size_t(t) * h + e) * 4, &m, 4);
+                }
+            if(pom_batch_sync(B[i])) die("sync");
+        }
+        unsigned long long done_seen = 0;
+        auto run = [&](int steps)
+        {
+            if(pom_batch_step_host_async(B[0], mv[0], st[0], POM_STEP_AUTORESET)) die("step_host_async");
+            for(int k = 0; k < steps; k++)
+            {
+                if(pom_batch_step_host_async(B[1], mv[1] + size_t(k % ring) * h * 4, st[1], POM_STEP_AUTORESET)) die("step_host_async");
+                if(pom_batch_sync(B[0])) die("sync");
+                done_seen += st[0][size_t(k) % h] & 1u;                 /* the host reads the results */
+                if(k + 1 < steps && pom_batch_step_host_async(B[0], mv[0] + size_t((k + 1) % ring) * h * 4, st[0], POM_STEP_AUTORESET)) die("step_host_async");
+                if(pom_batch_sync(B[1])) die("sync");
+                done_seen += st[1][size_t(k) % h] & 1u;
+            }
+        };
+        run(a.warmup);
+        auto t0 = std::chrono::steady_clock::now();
+        run(a.steps);
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("{\"metric\": \"env-steps/sec\", \"mode\": \"host\", \"value\": %.6g, \"unit\": \"env-steps/s\", \"envs\": %llu, \"steps\": %d, "
+                    "\"us_per_step\": %.4g, \"h2d_bytes_per_step\": %llu, \"d2h_bytes_per_step\": %llu, \"done_flags_sampled\": %llu}\n",
+                    double(2 * h) * a.steps / s, (unsigned long long)(2 * h), a.steps, 1e6 * s / a.steps,
+                    (unsigned long long)(8 * h), (unsigned long long)(2 * h), done_seen);
+        for(int i = 0; i < 2; i++) { pom_batch_destroy(B[i]); pom_host_free(mv[i]); pom_host_free(st[i]); }
         return 0;
     }
     if(a.gpus < 1 || a.gpus > pom_device_count()) { std::fprintf(stderr, "pom_bench: %d GPUs requested, %d present\n", a.gpus, pom_device_count()); return 2; }

@@ -345,6 +345,14 @@ def test_cpp_bench_driver_runs(pb):
     assert out.returncode == 0, out.stdout + out.stderr
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["episode_stats"]["env_steps"] == 65536 * 23 and d["value"] > 1e8
+    # the other modes: fused rollout with device-side SimpleAgent opponents, host-buffer (e2e) stepping, expansion
+    for extra in (["--mode", "rollout", "--simple", "14", "--ticks", "50", "--steps", "2", "--warmup", "1"],
+                  ["--mode", "step", "--simple", "15", "--steps", "10", "--warmup", "2"],
+                  ["--mode", "host", "--steps", "10", "--warmup", "2"],
+                  ["--mode", "expand", "--roots", "64", "--steps", "2", "--warmup", "1"]):
+        out = subprocess.run([exe, "--gpus", "1", "--envs-per-gpu", "65536"] + extra, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, " ".join(extra) + "\n" + out.stdout + out.stderr
+        assert json.loads(out.stdout.strip().splitlines()[-1])["value"] > 1e6
 
 
 def test_state_primitives_on_device(pb, orc):
