@@ -64,3 +64,16 @@ def test_rng_is_shared_with_oracle(lib, orc):
         for tick in (0, 5, 799):
             for na in (5, 6):
                 assert lib.pom_rng_moves(42, env, tick, na) == orc.lib.pom_oracle_rng_moves(42, env, tick, na)
+
+
+def test_examples_build_and_fail_loudly_without_gpu(lib):
+    """examples/ compile against include/ and the in-tree library; without a device they stop with the library's error"""
+    import subprocess
+    import pomcpp_b200 as pb
+    ex = os.path.join(ROOT, "examples")
+    out = subprocess.run(["make", "-C", ex], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    if pb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    run = subprocess.run([os.path.join(ex, "actor_loop"), "64", "2"], capture_output=True, text=True, timeout=60)
+    assert run.returncode != 0 and "no CPU fallback" in run.stderr

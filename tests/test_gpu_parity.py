@@ -596,3 +596,14 @@ def test_step_host_async_double_buffered(pb, orc):
         x.close()
     for a, o in mv + out:
         pb.pinned_free(o)
+
+
+def test_examples_run(pb):
+    """examples/: plain C against the C ABI (actor loop with device opponents, double-buffered) and C++ against the bboard
+    mirror (Environment + SimpleAgent, then one ply of tree search)"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(pb.LIB_PATH))
+    out = subprocess.run([os.path.join(root, "examples", "actor_loop"), "4096", "60"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "491520 env-steps" in out.stdout, out.stdout + out.stderr
+    out = subprocess.run([os.path.join(root, "examples", "tree_search")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.count("continuations") == 6, out.stdout + out.stderr
