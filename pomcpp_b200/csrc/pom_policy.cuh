@@ -409,7 +409,10 @@ POM_HD void run_floods(const uint8_t* r, const Boards& B, Plan* pl, uint32_t job
             src = bb_bit(int(pos & 15u) + 11 * int(pos >> 4));
             P = make_passable(B.walk | src);
             mode_b = pl[a].kind == K_HUNT;
-            X = mode_b ? bb_bit(pl[a].target) : src;
+            /* FillRMap only ever enters walkable cells and agent cells (strategy.cpp:44-46): a target on anything else
+             * (possible for an enemy only in hand-made states whose board and agent list disagree) is unreachable,
+             * which an empty start set reports right away */
+            X = !mode_b ? src : (bb_test(B.walk | B.agent, pl[a].target) ? bb_bit(pl[a].target) : bb_t(0));
         }
     }
 }

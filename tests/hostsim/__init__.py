@@ -41,6 +41,8 @@ class HostSim:
         L.hostsim_rng_moves.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.hostsim_simple_moves.argtypes = [vp, C.c_long, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp]
         L.hostsim_fog_batch.argtypes = [vp, C.c_long, C.c_int, C.c_int]
+        L.hostsim_move_towards.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        L.hostsim_move_towards_safe_place.argtypes = [vp, C.c_int, C.c_int]
         assert L.hostsim_record_bytes() == REC
 
     def pack(self, S, status=None):
@@ -64,6 +66,12 @@ class HostSim:
 
     def spawn_flame(self, rec, x, y, s):
         self.lib.hostsim_spawn_flame(_p(rec), x, y, s)
+
+    def move_towards(self, rec, agent, tx, ty):
+        return self.lib.hostsim_move_towards(_p(rec), agent, tx, ty)
+
+    def move_towards_safe_place(self, rec, agent, radius):
+        return self.lib.hostsim_move_towards_safe_place(_p(rec), agent, radius)
 
     def fog_batch(self, S, agent, view):
         self.lib.hostsim_fog_batch(_p(S), S.shape[0], agent, view)

@@ -76,6 +76,36 @@ void hostsim_simple_moves(const uint8_t* recs, long n, pom_simple_agent* A, uint
     }
 }
 
+/* MoveTowardsPosition as the device policy code computes it (a HUNT flood job towards cell (tx, ty)), for direct
+ * comparison with the queue BFS of the oracle / the reference on arbitrary boards; returns the Move */
+int hostsim_move_towards(const uint8_t* rec, int agent, int tx, int ty)
+{
+    const pompolicy::Boards B = pompolicy::make_boards(rec);
+    pompolicy::Plan pl[4];
+    for(int a = 0; a < 4; a++) pl[a].kind = pompolicy::K_NONE;
+    pl[agent].kind = pompolicy::K_HUNT;
+    pl[agent].target = uint8_t(tx + 11 * ty);
+    pl[agent].move = POM_MOVE_IDLE;
+    pompolicy::run_floods(rec, B, pl, 1u << agent);
+    return pl[agent].move;
+}
+
+/* MoveTowardsSafePlace as the device policy code computes it (a FLEE job with the given radius) */
+int hostsim_move_towards_safe_place(const uint8_t* rec, int agent, int radius)
+{
+    const pompolicy::Boards B = pompolicy::make_boards(rec);
+    pompolicy::Plan pl[4];
+    for(int a = 0; a < 4; a++) pl[a].kind = pompolicy::K_NONE;
+    const uint32_t pos = rec[R_APOS + agent];
+    pl[agent].kind = pompolicy::K_FLEE;
+    pl[agent].target = 0xFFu;
+    pl[agent].move = POM_MOVE_IDLE;
+    pl[agent].dg = uint32_t(radius) & 15u;
+    pl[agent].region = pompolicy::safe_place_region(int(pos & 15u), int(pos >> 4), radius);
+    pompolicy::run_floods(rec, B, pl, 1u << agent);
+    return pl[agent].move;
+}
+
 /* the device fog code (pomcore::fog_state) on AoS states */
 void hostsim_fog_batch(pom_state* S, long n, int agent, int view)
 {

@@ -214,3 +214,65 @@ def test_unreachable_enemy_from_the_origin_corner(orc, hs):
         assert not bad.any()
         hs.simple_moves(recs, B, 5, 0, 0, 1, mv2)
         assert (mv == mv2).all() and A.tobytes() == B.tobytes()
+
+
+# ---- the path-finding pieces on arbitrary boards (far more varied than what full games reach) ---------------
+def _random_positions(orc, n, seed):
+    """mid-game states with extra random walls / passages / powerups / bombs so that reachability is non-trivial"""
+    rng = np.random.default_rng(seed)
+    seeds = oracle.clean_seeds(48)
+    S = orc.zero_state(n)
+    for i in range(n):
+        orc.init_state(S[i:i + 1], seeds[i % 48])
+    S["agents"]["maxBombCount"] = 3
+    S["agents"]["bombStrength"] = 2
+    st = np.zeros(n, np.uint8)
+    for t in range(int(rng.integers(5, 40))):
+        orc.env_step_batch(S, st, orc.rng_moves(seed, 0, n, t, 6))
+    for i in range(n):                       # open up / close random cells (never an agent's, a bomb's or a flame's cell)
+        for _ in range(int(rng.integers(0, 40))):
+            x, y = int(rng.integers(0, 11)), int(rng.integers(0, 11))
+            c = int(S["board"][i, y, x])
+            if c in (0, 1) or (c >> 8) == 2 or c in (6, 7, 8):
+                S["board"][i, y, x] = int(rng.choice([0, 0, 0, 1, 2 << 8, 6, 7, 8]))
+    return S, rng
+
+
+def test_fill_rmap_and_move_towards_match_compiled_reference_on_random_boards(orc, ref):
+    S, rng = _random_positions(orc, 300, 5)
+    for i in range(S.shape[0]):
+        s = S[i:i + 1]
+        for a in range(4):
+            if s["agents"]["dead"][0, a]:
+                continue
+            assert (orc.fill_rmap(s, a) == ref.fill_rmap(s, a)).all(), (i, a)
+            tx, ty = int(rng.integers(0, 11)), int(rng.integers(0, 11))
+            if (tx, ty) != (int(s["agents"]["x"][0, a]), int(s["agents"]["y"][0, a])):
+                assert orc.move_towards(s, a, 0, tx, ty) == ref.move_towards(s, a, 0, tx, ty)
+            for kind in (1, 2, 3):
+                radius = int(rng.integers(1, 11))
+                assert orc.move_towards(s, a, kind, radius) == ref.move_towards(s, a, kind, radius), (i, a, kind, radius)
+
+
+def test_device_floods_equal_the_queue_bfs_on_random_boards(orc, hs):
+    """the bitboard floods of pom_policy.cuh against the oracle's FillRMap + MoveTowardsPosition / MoveTowardsSafePlace:
+    every cell of the board as a target, every radius"""
+    S, rng = _random_positions(orc, 160, 6)
+    recs, bad = hs.pack(S)
+    assert not bad.any()
+    checked = 0
+    for i in range(S.shape[0]):
+        s = S[i:i + 1]
+        for a in range(4):
+            if s["agents"]["dead"][0, a]:
+                continue
+            ax, ay = int(s["agents"]["x"][0, a]), int(s["agents"]["y"][0, a])
+            for ty in range(11):
+                for tx in range(11):
+                    if (tx, ty) == (ax, ay):
+                        continue
+                    assert hs.move_towards(recs[i], a, tx, ty) == orc.move_towards(s, a, 0, tx, ty), (i, a, tx, ty)
+                    checked += 1
+            for radius in range(1, 11):
+                assert hs.move_towards_safe_place(recs[i], a, radius) == orc.move_towards(s, a, 3, radius), (i, a, radius)
+    assert checked > 20000
