@@ -227,10 +227,10 @@ POM_HD uint32_t pick_safe_direction(const uint8_t* r, uint32_t pos, uint32_t dg,
 {
     uint32_t mq = st.w1 >> 16;
     int count = 0;
-    /* live slots of recentPositions: the ring only starts to turn once it is full, so with fewer than four entries
-     * they are the physical slots 0 .. count-1 */
-    const uint32_t rp_count = (st.w1 >> 8) & 0xFFu;
-    const uint32_t live = rp_count >= 4u ? 0x80808080u : (0x80808080u & ((1u << (8u * rp_count)) - 1u));
+    /* live slots of recentPositions: `count` physical slots starting at `index` (a byte mask, rotated into place) */
+    const uint32_t rp_index = st.w1 & 3u, rp_count = (st.w1 >> 8) & 0xFFu;
+    const uint32_t first = rp_count >= 4u ? 0x80808080u : (0x80808080u & ((1u << (8u * rp_count)) - 1u));
+    const uint32_t live = (first << (8u * rp_index)) | (rp_index ? first >> (32u - 8u * rp_index) : 0u);
     uint32_t seen = 0;                                         /* bit mv: DesiredPosition(mv) was visited recently */
     POM_LOOP
     for(int k = 0; k < 4; k++)

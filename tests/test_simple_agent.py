@@ -276,3 +276,33 @@ def test_device_floods_equal_the_queue_bfs_on_random_boards(orc, hs):
             for radius in range(1, 11):
                 assert hs.move_towards_safe_place(recs[i], a, radius) == orc.move_towards(s, a, 3, radius), (i, a, radius)
     assert checked > 20000
+
+
+def test_act_on_arbitrary_states_and_memories(orc, hs):
+    """SimpleAgent::act on random boards with ARBITRARY agent memories (any ring index / count, off-board remembered
+    positions, any stale move-queue content): what pom_batch_policy_upload may hand to the device code"""
+    S, rng = _random_positions(orc, 400, 7)
+    n = S.shape[0]
+    recs, bad = hs.pack(S)
+    assert not bad.any()
+    for rep in range(6):
+        A = orc.simple_agents(n)
+        nib = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 15], np.uint8)          # -1 .. 11
+        A["recent"] = nib[rng.integers(0, 13, (n, 4, 4))] | (nib[rng.integers(0, 13, (n, 4, 4))] << 4)
+        A["rp_index"] = rng.integers(0, 4, (n, 4))
+        A["rp_count"] = rng.integers(0, 5, (n, 4))
+        A["move_queue"] = (rng.integers(0, 6, (n, 4)) | (rng.integers(0, 6, (n, 4)) << 3) |
+                           (rng.integers(0, 6, (n, 4)) << 6) | (rng.integers(0, 6, (n, 4)) << 9)).astype(np.uint16)
+        # some agents remember cells next to them, so that SortDirections has something to reorder
+        for e in range(0, n, 3):
+            for a in range(4):
+                x, y = int(S["agents"]["x"][e, a]), int(S["agents"]["y"][e, a])
+                A["recent"][e, a, rep % 4] = ((x + 1) & 15) | ((y & 15) << 4)
+                A["recent"][e, a, (rep + 1) % 4] = (x & 15) | (((y + 1) & 15) << 4)
+        B = A.copy()
+        mv = np.zeros((n, 4), np.uint8)
+        mv2 = mv.copy()
+        orc.simple_moves_batch(S, None, A, 40 + rep, 0, rep, 15, mv)
+        hs.simple_moves(recs, B, 40 + rep, 0, rep, 15, mv2)
+        assert (mv == mv2).all(), np.argwhere(mv != mv2)[:3]
+        assert A.tobytes() == B.tobytes()
