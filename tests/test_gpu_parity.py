@@ -607,3 +607,30 @@ def test_examples_run(pb):
     assert out.returncode == 0 and "491520 env-steps" in out.stdout, out.stdout + out.stderr
     out = subprocess.run([os.path.join(root, "examples", "tree_search")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.count("continuations") == 6, out.stdout + out.stderr
+
+
+def test_inconsistent_uploaded_states_on_gpu(pb, orc):
+    """the states of tests/test_fuzz_states.py (random, mutually inconsistent edits of mid-game states) uploaded through
+    the C ABI and stepped on the GPU"""
+    from hostsim import HostSim
+    from test_fuzz_states import mutated_states
+    S = mutated_states(orc, 301, 6000)
+    _, bad = HostSim().pack(S, np.zeros(S.shape[0], np.uint8))
+    S = S[bad == 0].copy()
+    n = S.shape[0]
+    assert n > 3000
+    b = pb.Batch(n, n_templates=1, empty=True)
+    b.upload(S)
+    status = np.zeros(n, np.uint8)
+    out = np.zeros(n, np.uint8)
+    for t in range(12):
+        mv = orc.rng_moves(1301, 0, n, t, 6)
+        b.step_host(mv, out, 0)
+        fl = np.zeros(n, np.uint8)
+        orc.env_step_batch(S, status, mv, fl)
+        status[(fl & 0x3E) != 0] |= 0x10
+        assert ((out & 0x11) == (status & 0x11)).all(), "tick %d" % t
+        G, _ = b.download()
+        e, why = orc.diff_batch(G, S, ((status & 0x10) != 0).astype(np.uint8))
+        assert e == -1, "tick %d env %d field group %d" % (t, e, why)
+    b.close()
