@@ -29,7 +29,7 @@ def mutated_states(orc, seed, n):
     S = S[(st & 0x11) == 0].copy()
     for i in range(S.shape[0]):
         for _ in range(int(rng.integers(0, 8))):
-            m = int(rng.integers(0, 9))
+            m = int(rng.integers(0, 12))
             x, y = int(rng.integers(0, 11)), int(rng.integers(0, 11))
             cnt, lo = int(S["bombs_count"][i]), int(S["bombs_index"][i])
             if m == 0:
@@ -61,6 +61,16 @@ def mutated_states(orc, seed, n):
             elif m == 8:
                 S["agents"]["dead"][i, int(rng.integers(0, 4))] = int(rng.integers(0, 2))
                 S["aliveAgents"][i] = int(4 - S["agents"]["dead"][i].sum())
+            elif m == 9 and S["flames_count"][i] > 0:          # a live flame with another time left / strength
+                sl = (int(S["flames_index"][i]) + int(rng.integers(0, S["flames_count"][i]))) % 20
+                S["flames"]["timeLeft"][i, sl] = int(rng.integers(1, 6))
+                S["flames"]["strength"][i, sl] = int(rng.integers(0, 7))
+            elif m == 10:                                      # a flame cell without queue entry (origin id 0, board_logic.cpp:504)
+                S["board"][i, y, x] = (4 << 16) + int(rng.integers(0, 4))
+            elif m == 11 and S["flames_count"][i] > 0:         # a flame cell pointing at a live flame from anywhere on the board
+                sl = (int(S["flames_index"][i]) + int(rng.integers(0, S["flames_count"][i]))) % 20
+                fx, fy = int(S["flames"]["x"][i, sl]), int(S["flames"]["y"][i, sl])
+                S["board"][i, y, x] = (4 << 16) + ((fx + 11 * fy) << 3) + int(rng.integers(0, 4))
     return S
 
 
