@@ -92,6 +92,29 @@ int main(int argc, char** argv)
         }
         for(int e = 0; e < n; e++) std::free(recs[size_t(e)]);
     }
+    /* the deepest explosion the rings allow: 20 bombs, each in range of the next, set off by the first (nesting depth 20
+     * on the explosion machine's explicit stack) */
+    for(int layout = 0; layout < 2; layout++)
+    {
+        pom_state s, t;
+        pom_oracle_zero_state(&s);
+        pom_oracle_kill(&s, 1); pom_oracle_kill(&s, 2); pom_oracle_kill(&s, 3);
+        pom_oracle_put_agent(&s, 5, 5, 0);
+        s.agents[0].maxBombCount = 30; s.agents[0].bombStrength = 2;
+        for(int k = 0; k < 20; k++)
+        {
+            const int a = k < 11 ? k : 10, b = k < 11 ? 0 : k - 10;
+            pom_oracle_plant_bomb(&s, layout ? b : a, layout ? a : b, 0, k ? 10 : 1, 1);
+        }
+        uint8_t* rec = static_cast<uint8_t*>(std::malloc(POM_REC_BYTES));
+        if(pomcore::pack(&s, 0, rec)) { std::printf("pack failed\n"); return 1; }
+        const uint8_t idle[4] = {0, 0, 0, 0};
+        pom_oracle_step(&s, idle);
+        pomcore::step(rec, 0u);
+        pomcore::unpack(rec, &t);
+        std::free(rec);
+        if(pom_oracle_state_diff(&s, &t) || s.bombs_count != 0 || s.flames_count != 20) { std::printf("CHAIN MISMATCH layout %d\n", layout); return 1; }
+    }
     std::printf("sanitize_main: %ld env-steps, %ld aborted episodes, clean\n", steps, invalid);
     return 0;
 }
