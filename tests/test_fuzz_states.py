@@ -115,3 +115,26 @@ def test_restatement_vs_compiled_reference_on_inconsistent_states(orc, ref, seed
         st2[(st & 0x10) != 0] |= 0x10
         e, why = orc.diff_batch(S, S2, ((st & 0x10) != 0).astype(np.uint8))
         assert e == -1, "tick %d env %d field group %d" % (t, e, why)
+
+
+def test_simple_agent_on_inconsistent_states(orc):
+    """SimpleAgent::act on the same kind of states: restatement vs the device policy code (host build), and vs the compiled
+    reference agent where available"""
+    from hostsim import HostSim
+    hs = HostSim()
+    R = oracle.reference() if oracle.have_reference() else None
+    S = mutated_states(orc, 401, 3000)
+    recs, bad = hs.pack(S, np.zeros(S.shape[0], np.uint8))
+    S, recs = S[bad == 0].copy(), recs[bad == 0].copy()
+    n = S.shape[0]
+    A = orc.simple_agents(n)
+    B = A.copy()
+    C_ = R.simple_agents(n) if R is not None else None
+    for t in range(3):
+        mv, mv2, mv3 = (np.zeros((n, 4), np.uint8) for _ in range(3))
+        orc.simple_moves_batch(S, None, A, 401, 0, t, 15, mv)
+        hs.simple_moves(recs, B, 401, 0, t, 15, mv2)
+        assert (mv == mv2).all() and A.tobytes() == B.tobytes(), "device policy code, act %d" % t
+        if C_ is not None:
+            C_.moves_batch(S, None, orc.rng_moves(401, 0, n, t, 5), 15, mv3)
+            assert (mv == mv3).all() and A.tobytes() == C_.export().tobytes(), "compiled reference agent, act %d" % t
