@@ -634,3 +634,17 @@ def test_inconsistent_uploaded_states_on_gpu(pb, orc):
         e, why = orc.diff_batch(G, S, ((status & 0x10) != 0).astype(np.uint8))
         assert e == -1, "tick %d env %d field group %d" % (t, e, why)
     b.close()
+
+
+def test_make_board_extreme_seeds(pb, orc):
+    """InitBoardItems on the device for negative and extreme seeds (std::mt19937_64(int) sign-extends the seed)"""
+    checked = 0
+    for seed in list(range(-12, 0)) + [-2 ** 31, -2 ** 31 + 1, 2 ** 31 - 1, 2 ** 31 - 2, 0, 1]:
+        s = orc.zero_state()
+        dirty = orc.init_board_items(s, seed)
+        board, d = pb.make_board(seed)
+        assert bool(d) == bool(dirty), seed
+        if not dirty:
+            assert (board["board"][0] == s["board"][0]).all(), seed
+            checked += 1
+    assert checked >= 6
