@@ -944,7 +944,10 @@ POM_HD void env_post(uint8_t* r)
 {
     uint32_t st = r[R_STATUS];
     uint16_t* ts = reinterpret_cast<uint16_t*>(r + R_TIME);
-    *ts = uint16_t(*ts + 1);
+    /* timeStep is 16 bits in the record (an int in the reference): a game that would pass 65535 ticks leaves what the
+     * record can carry, exactly like an upload with timeStep > 65535 (pack) */
+    if(*ts == 0xFFFFu) st |= POM_STATUS_INVALID;
+    else *ts = uint16_t(*ts + 1);
     const int alive = int(int8_t(r[R_ALIVE]));
     if(alive == 1)
     {

@@ -20,7 +20,7 @@
  *  212     4      agent maxBombCount
  *  216     4      agent bombStrength
  *  220     4      agent flags: bit0 canKick, bit1 dead
- *  224     2      timeStep (u16)
+ *  224     2      timeStep (u16; an env about to pass 65535 is marked POM_STATUS_INVALID instead of wrapping)
  *  226     1      aliveAgents (signed byte)
  *  227     1      status (POM_STATUS_* of include/pom_state.h; the reference keeps these in Environment)
  *  228     20     flames.queue[20].position, x | y<<4, PHYSICAL ring order

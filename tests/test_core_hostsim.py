@@ -115,3 +115,24 @@ def test_core_rng_matches_oracle(orc, hs):
         for tick in (0, 1, 799):
             for na in (5, 6):
                 assert hs.lib.hostsim_rng_moves(99, env, tick, na) == orc.lib.pom_oracle_rng_moves(99, env, tick, na)
+
+
+def test_time_step_does_not_wrap(orc):
+    """timeStep is 16 bits in the record: the tick that would pass 65535 marks the env INVALID instead of wrapping"""
+    from hostsim import HostSim
+    hs = HostSim()
+    s = orc.zero_state()
+    orc.init_state(s)
+    s["timeStep"] = 65534
+    recs, bad = hs.pack(s)
+    assert not bad.any()
+    idle = np.zeros((1, 4), np.uint8)
+    hs.step_records(recs, idle, False)
+    out, st = hs.unpack(recs)
+    assert out["timeStep"][0] == 65535 and st[0] == 0
+    hs.step_records(recs, idle, False)
+    out, st = hs.unpack(recs)
+    assert out["timeStep"][0] == 65535 and (st[0] & 0x10)
+    hs.step_records(recs, idle, False)                 # frozen from now on
+    out2, st2 = hs.unpack(recs)
+    assert orc.diff_batch(out, out2)[0] == -1 and st2[0] == st[0]
