@@ -45,7 +45,8 @@ enum {
     F_FLAME_OVF      = 0x08,
     F_BAD_MOVE       = 0x10,
     F_LOOP_GUARD     = 0x20,   /* D5: AgentBombChainReversion would recurse forever (also: internal loop guards) */
-    F_INVALID_MASK   = 0x3E
+    F_RANGE          = 0x40,   /* device only: a field left what the packed record can carry (maxBombCount / bombStrength > 255) */
+    F_INVALID_MASK   = 0x7E
 };
 
 /* the four agents, one byte per agent in each word */
@@ -511,8 +512,9 @@ POM_HD void move_agent(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, uint32
     if(bytes_equal(dq, d) & ~(A.flg << 6) & ~(0x80u << (8 * i))) return;
     if(c_is_powerup(item))                                           /* ConsumePowerup, step_utility.cpp:247-262 */
     {
-        if(item == uint32_t(C_EXTRABOMB)) A.amax = with_byte(A.amax, i, byte_of(A.amax, i) + 1u);
-        else if(item == uint32_t(C_INCRRANGE)) A.astr = with_byte(A.astr, i, byte_of(A.astr, i) + 1u);
+        /* the reference counts these up in ints without bound; the record holds bytes */
+        if(item == uint32_t(C_EXTRABOMB)) { if(byte_of(A.amax, i) == 255u) flags |= F_RANGE; A.amax = with_byte(A.amax, i, byte_of(A.amax, i) + 1u); }
+        else if(item == uint32_t(C_INCRRANGE)) { if(byte_of(A.astr, i) == 255u) flags |= F_RANGE; A.astr = with_byte(A.astr, i, byte_of(A.astr, i) + 1u); }
         else A.flg |= uint32_t(AF_CANKICK) << (8 * i);
         item = C_PASSAGE;
     }

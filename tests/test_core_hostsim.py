@@ -136,3 +136,25 @@ def test_time_step_does_not_wrap(orc):
     hs.step_records(recs, idle, False)                 # frozen from now on
     out2, st2 = hs.unpack(recs)
     assert orc.diff_batch(out, out2)[0] == -1 and st2[0] == st[0]
+
+
+def test_powerup_counters_do_not_wrap(orc):
+    """maxBombCount / bombStrength are bytes in the record: the pickup that would pass 255 marks the env INVALID"""
+    from hostsim import HostSim
+    hs = HostSim()
+    for item, field in ((6, "maxBombCount"), (7, "bombStrength")):
+        s = orc.zero_state()
+        orc.kill(s, 1, 2, 3)
+        orc.put_agent(s, 0, 0, 0)
+        orc.put_item(s, 1, 0, item)
+        s["agents"][field][0, 0] = 255
+        recs, bad = hs.pack(s)
+        assert not bad.any()
+        hs.step_records(recs, np.array([[4, 0, 0, 0]], np.uint8), False)
+        _, st = hs.unpack(recs)
+        assert st[0] & 0x10
+        s["agents"][field][0, 0] = 254
+        recs, _ = hs.pack(s)
+        hs.step_records(recs, np.array([[4, 0, 0, 0]], np.uint8), False)
+        out, st = hs.unpack(recs)
+        assert not (st[0] & 0x10) and out["agents"][field][0, 0] == 255
