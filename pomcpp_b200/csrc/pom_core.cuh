@@ -1001,7 +1001,8 @@ POM_HD int pack(const pom_state* s, uint8_t status, uint8_t* r)
     for(int a = 0; a < 4; a++)
     {
         const pom_agent& g = s->agents[a];
-        if(uint32_t(g.x) > 10u || uint32_t(g.y) > 10u || g.bombCount < -128 || g.bombCount > 127 ||
+        /* bombCount moves by one per plant / explosion and the ring holds 20 bombs: +-64 leaves the signed byte ample room */
+        if(uint32_t(g.x) > 10u || uint32_t(g.y) > 10u || g.bombCount < -64 || g.bombCount > 64 ||
                 uint32_t(g.maxBombCount) > 255u || uint32_t(g.bombStrength) > 255u) bad = 4;
         r[R_APOS + a] = uint8_t((g.x & 15) | ((g.y & 15) << 4));
         r[R_ABCNT + a] = uint8_t(g.bombCount);
