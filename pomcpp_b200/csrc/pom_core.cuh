@@ -218,7 +218,12 @@ POM_HD bool flames_age(uint8_t* r)
         uint8_t* t = r + R_FTIME + slot;
         *t = uint8_t(*t - 1);
     }
-    return r[R_FTIME + r[R_FINDEX]] == 0;
+    /* a front flame whose timer is already negative never pops (in the reference either, Q10) and counts down for ever:
+     * before the signed byte would wrap, the env leaves what the record can carry.  (pack() accepts timers in
+     * [-16, 100], so no other entry can get near the limit while it waits for the front.) */
+    const uint32_t front = r[R_FTIME + r[R_FINDEX]];
+    if(front == 0x80u) r[R_STATUS] |= POM_STATUS_INVALID;
+    return front == 0u;
 }
 
 POM_HD void flames_pop_due(uint8_t* r)
@@ -993,7 +998,7 @@ POM_HD int pack(const pom_state* s, uint8_t status, uint8_t* r)
     for(int k = 0; k < 20; k++)
     {
         const pom_flame& f = s->flames[k];
-        if(uint32_t(f.x) > 10u || uint32_t(f.y) > 10u || f.timeLeft < -128 || f.timeLeft > 127 || uint32_t(f.strength) > 255u) bad = 3;
+        if(uint32_t(f.x) > 10u || uint32_t(f.y) > 10u || f.timeLeft < -16 || f.timeLeft > 100 || uint32_t(f.strength) > 255u) bad = 3;
         r[R_FPOS + k] = uint8_t((f.x & 15) | ((f.y & 15) << 4));
         r[R_FTIME + k] = uint8_t(f.timeLeft);
         r[R_FSTR + k] = uint8_t(f.strength);

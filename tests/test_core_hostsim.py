@@ -158,3 +158,32 @@ def test_powerup_counters_do_not_wrap(orc):
         hs.step_records(recs, np.array([[4, 0, 0, 0]], np.uint8), False)
         out, st = hs.unpack(recs)
         assert not (st[0] & 0x10) and out["agents"][field][0, 0] == 255
+
+
+def test_stuck_flame_queue_does_not_wrap(orc):
+    """a front flame with a negative timer never pops (reference: TickFlames tests `== 0`); its byte-sized timer must not
+    wrap around into a positive one"""
+    from hostsim import HostSim
+    hs = HostSim()
+    s = orc.zero_state()
+    orc.kill(s, 2, 3)
+    orc.put_agent(s, 10, 10, 0)
+    orc.put_agent(s, 0, 10, 1)
+    orc.spawn_flame(s, 3, 3, 1)
+    s["flames"]["timeLeft"][0, 0] = -10
+    ref_copy = s.copy()
+    recs, bad = hs.pack(s)
+    assert not bad.any()
+    idle = np.zeros((1, 4), np.uint8)
+    st_o = np.zeros(1, np.uint8)
+    for t in range(130):
+        hs.step_records(recs, idle, False)
+        out, st = hs.unpack(recs)
+        if st[0] & 0x10:
+            break
+        orc.env_step_batch(ref_copy, st_o, idle)
+        assert orc.diff_batch(out, ref_copy)[0] == -1, t
+    assert (st[0] & 0x10) and out["flames"]["timeLeft"][0, 0] == -128 and t > 100
+    # timers outside [-16, 100] are refused at upload
+    s["flames"]["timeLeft"][0, 0] = -17
+    assert hs.pack(s)[1][0] != 0
