@@ -1,7 +1,9 @@
 """TEST INFRASTRUCTURE ONLY — ctypes loaders for the CPU checkers.
 
-``restatement()`` -> oracle/_build/libpom_oracle.so  (plain-C restatement, oracle/pom_oracle.c)
-``reference()``   -> oracle/_ref/libpomref.so        (the UNMODIFIED reference + oracle/ref_shim.cpp)
+``restatement()`` -> oracle/_build/libpom_oracle.so  (plain-C restatement: oracle/pom_oracle.c, the step path;
+                                                     oracle/pom_oracle_agent.c, SimpleAgent + strategy)
+``reference()``   -> oracle/_ref/libpomref.so        (the UNMODIFIED reference sources bboard / step / step_utility /
+                                                     strategy / simple_agent + oracle/ref_shim.cpp)
 
 Only tests/, ``__graft_entry__.smoke()`` and bench.py's cpu_baseline / ``--impl reference`` legs
 may import this module.  The product package ``pomcpp_b200`` never does.

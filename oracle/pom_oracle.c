@@ -15,6 +15,10 @@
  *   D5: unbounded AgentBombChainReversion recursion (found by this project's differential runs: the
  *       compiled reference hangs at -O3 and overflows the stack at -O0): flagged, chain stopped.
  * An env whose tick raised D3/D4/D5/overflow/bad-move is marked POM_STATUS_INVALID and frozen.
+ *
+ * Also here: InitBoardItems with libstdc++'s mt19937_64 / uniform_int_distribution restated, the shared counter RNG, the
+ * multi-threaded "port" CPU baseline, and pom_oracle_fog (the DEFINITION of the fogged view, which the reference only
+ * declares).  The heuristic agent (SimpleAgent + strategy) is restated in pom_oracle_agent.c.
  */
 #include "pom_oracle.h"
 
