@@ -131,6 +131,12 @@ int  pom_batch_step_host_async(pom_batch* b, const uint8_t* moves_host, uint8_t*
  * Environment::StartGame (environment.cpp:68-88) with RandomAgent/HarmlessAgent::act (bboard.hpp:517-533), or with
  * SimpleAgent::act for the agents named by POM_ROLL_SIMPLE(mask) (their draw: byte a of pom_rng_moves(.., 5)). */
 int  pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t tick0, uint32_t flags);
+/* the fused kernel with the CALLER's moves: `ticks` ticks in one launch, moves_dev = DEVICE pointer to ticks x n_envs x 4
+ * bytes, tick-major (tick k, env e, agent a at ((k * n_envs) + e) * 4 + a).  The boards stay in shared memory for the
+ * whole sequence, so the state crosses HBM once per launch instead of once per tick: the way to replay traces or to
+ * evaluate fixed action plans in a search.  Same episode rule as the rollout: truncation at max_ticks, statistics,
+ * auto-reset unless POM_ROLL_NO_RESET (the only flag accepted). */
+int  pom_batch_step_seq(pom_batch* b, const uint8_t* moves_dev, uint32_t ticks, uint32_t flags);
 
 /* ---- the reference's heuristic agent as a device-side action source (agents::SimpleAgent, simple_agent.cpp:12-141;
  *      bboard::strategy, strategy.cpp:37-338): the caller of the step path in Environment::Step

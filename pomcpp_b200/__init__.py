@@ -92,6 +92,7 @@ def lib():
         L.pom_batch_step_host.argtypes = [vp, vp, vp, u32]
         L.pom_batch_step_host_async.argtypes = [vp, vp, vp, u32]
         L.pom_batch_rollout.argtypes = [vp, u32, u64, u32, u32]
+        L.pom_batch_step_seq.argtypes = [vp, vp, u32, u32]
         L.pom_batch_policy_moves.argtypes = [vp, vp, u64, u32, u32]
         L.pom_batch_policy_moves_host.argtypes = [vp, vp, u64, u32, u32]
         L.pom_batch_policy_act.argtypes = [vp, u64, i32, i32, C.POINTER(C.c_int)]
@@ -211,6 +212,10 @@ class Batch:
     def step_host(self, moves, status_out=None, flags=0):
         assert moves.dtype == np.uint8 and moves.size == 4 * self.n and moves.flags.c_contiguous
         _ck(lib().pom_batch_step_host(self.h, _p(moves), _p(status_out), flags))
+
+    def step_seq(self, moves_dev, ticks, flags=0):
+        """`ticks` ticks in one launch with the caller's moves (device pointer, ticks x n x 4 bytes, tick-major)"""
+        _ck(lib().pom_batch_step_seq(self.h, moves_dev, ticks, flags))
 
     def step_host_async(self, moves, status_out=None, flags=0):
         """pinned buffers only; results are valid after sync()"""

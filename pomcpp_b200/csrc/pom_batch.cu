@@ -232,7 +232,7 @@ int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t*
 }
 
 template<int TPB>
-int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, uint32_t flags)
+int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, uint32_t flags, const uint8_t* move_seq = nullptr)
 {
     const uint32_t n_actions = (flags & POM_ROLL_HARMLESS) ? 5u : 6u, no_reset = (flags & POM_ROLL_NO_RESET) ? 1u : 0u;
     const uint32_t mask = (flags >> POM_ROLL_SIMPLE_SHIFT) & 0xFu;
@@ -241,12 +241,12 @@ int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, 
     {
         int rc = set_smem(b, ATTR_ROLLOUT_POLICY, pomk::k_rollout<TPB, true>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc;
         rc = ensure_policy(b); if(rc) return rc;
-        pomk::k_rollout<TPB, true><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, mask);
+        pomk::k_rollout<TPB, true><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, mask, nullptr);
     }
     else
     {
         int rc = set_smem(b, ATTR_ROLLOUT, pomk::k_rollout<TPB, false>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc;
-        pomk::k_rollout<TPB, false><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, 0u);
+        pomk::k_rollout<TPB, false><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, 0u, reinterpret_cast<const uint32_t*>(move_seq));
     }
     b->launches++;
     CK(cudaGetLastError());
@@ -609,6 +609,14 @@ int pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t 
 {
     int rc = use(b); if(rc) return rc;
     POM_DISPATCH(b, launch_rollout, b, ticks, rng_seed, tick0, flags);
+}
+
+int pom_batch_step_seq(pom_batch* b, const uint8_t* moves_dev, uint32_t ticks, uint32_t flags)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!moves_dev) return fail(POM_E_ARG, "pom_batch_step_seq: null moves");
+    if(flags & ~uint32_t(POM_ROLL_NO_RESET)) return fail(POM_E_ARG, "pom_batch_step_seq: only POM_ROLL_NO_RESET is accepted");
+    POM_DISPATCH(b, launch_rollout, b, ticks, 0, 0, flags, moves_dev);
 }
 
 int pom_batch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_t tick, uint32_t agent_mask)

@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(TPB) k_policy_moves(BatchParams P, uint32_t* _
  * POLICY = true : the agents in `policy_mask` play SimpleAgent, the others stay uniform random. */
 template<int TPB, bool POLICY>
 __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, uint64_t seed, uint32_t tick0,
-                                                uint32_t n_actions, uint32_t no_reset, uint32_t policy_mask)
+                                                uint32_t n_actions, uint32_t no_reset, uint32_t policy_mask,
+                                                const uint32_t* __restrict__ move_seq)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
@@ -363,7 +364,13 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
     {
         const bool stepped = active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID));
         uint32_t m = 0;
-        if(stepped)
+        if(stepped && move_seq)
+        {
+            /* pom_batch_step_seq: the caller's moves, tick-major; one coalesced 4-byte load per env and tick */
+            m = __ldg(move_seq + uint64_t(k) * P.n_envs + env);
+            steps++;
+        }
+        else if(stepped)
         {
             const uint64_t h = pomcore::splitmix64(key + uint64_t(tick0 + k));
 #pragma unroll

@@ -648,3 +648,28 @@ def test_make_board_extreme_seeds(pb, orc):
             assert (board["board"][0] == s["board"][0]).all(), seed
             checked += 1
     assert checked >= 6
+
+
+@pytest.mark.parametrize("no_reset", [False, True])
+def test_step_seq_fused_ticks_with_given_moves(pb, orc, no_reset):
+    """pom_batch_step_seq: the fused kernel fed with the caller's moves (tick-major device buffer) = the per-tick path with
+    the same moves, episode rule included"""
+    n, ticks, seed, env0 = 3000, 70, 19, 40
+    b = pb.Batch(n, env_offset=env0, n_templates=24, max_ticks=50)
+    T, _ = b.templates()
+    S, _ = b.download()
+    seq = b.alloc(4 * n * ticks)
+    for t in range(ticks):
+        b.generate_moves(seq.value + 4 * n * t, seed, t, 6)
+    fl = pb.ROLL_NO_RESET if no_reset else 0
+    b.step_seq(seq, 30, fl)
+    b.step_seq(seq.value + 4 * n * 30, ticks - 30, fl)
+    G, gst = b.download()
+    status, stats = _oracle_rollout(orc, S, T, env0, ticks, seed, 6, 50, no_reset=no_reset)
+    assert orc.diff_batch(G, S)[0] == -1
+    assert (gst == status).all()
+    assert (b.stats().as_array() == stats).all(), (b.stats().as_dict(), stats)
+    assert pb.lib().pom_batch_step_seq(b.h, None, 1, 0) == -1
+    assert pb.lib().pom_batch_step_seq(b.h, seq, 1, pb.ROLL_HARMLESS) == -1
+    b.free(seq)
+    b.close()
