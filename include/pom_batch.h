@@ -135,7 +135,8 @@ int  pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t
  * bytes, tick-major (tick k, env e, agent a at ((k * n_envs) + e) * 4 + a).  The boards stay in shared memory for the
  * whole sequence, so the state crosses HBM once per launch instead of once per tick: the way to replay traces or to
  * evaluate fixed action plans in a search.  Same episode rule as the rollout: truncation at max_ticks, statistics,
- * auto-reset unless POM_ROLL_NO_RESET (the only flag accepted). */
+ * auto-reset unless POM_ROLL_NO_RESET (the only flag accepted).  moves_dev may also point into page-locked mapped host
+ * memory (pom_host_alloc): the kernel then fetches the moves over PCIe while it runs. */
 int  pom_batch_step_seq(pom_batch* b, const uint8_t* moves_dev, uint32_t ticks, uint32_t flags);
 
 /* ---- the reference's heuristic agent as a device-side action source (agents::SimpleAgent, simple_agent.cpp:12-141;

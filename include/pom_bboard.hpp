@@ -250,6 +250,9 @@ public:
      * (simple_agent.cpp:12-141; their draws come from the shared counter RNG keyed by `seed`) and the others
      * take their move from `moves` (n x 4, host memory; entries of masked agents are ignored) */
     size_t Step(const Move* moves, unsigned simpleMask, uint64_t seed);
+    /* `ticks` ticks in ONE launch with the given moves (ticks x n x 4, tick-major, host memory); finished games freeze.
+     * Returns the number of games still running.  For replaying traces and evaluating fixed action plans. */
+    size_t StepSequence(const Move* moves, uint32_t ticks);
     /* `ticks` fused ticks on the device with auto-reset; agents in simpleMask play SimpleAgent, the others draw
      * uniformly (from {0..4} if harmless, else {0..5}); returns the counters */
     pom_stats Rollout(uint32_t ticks, uint64_t seed, bool harmless = false, unsigned simpleMask = 0);

@@ -351,6 +351,25 @@ size_t BatchEnvironment::Step(const Move* moves, unsigned simpleMask, uint64_t s
     return running;
 }
 
+size_t BatchEnvironment::StepSequence(const Move* moves, uint32_t ticks)
+{
+    const size_t bytes = size_t(ticks) * n * 4;
+    void* pinned = nullptr;
+    check(pom_host_alloc(bytes, &pinned), "pom_host_alloc");
+    uint8_t* mv = static_cast<uint8_t*>(pinned);
+    for(size_t i = 0; i < bytes; i++) mv[i] = uint8_t(int(moves[i]));
+    int rc = pom_batch_step_seq(handle, mv, ticks, POM_ROLL_NO_RESET);     /* the kernel reads the pinned buffer directly */
+    if(rc == POM_OK) rc = pom_batch_sync(handle);
+    pom_host_free(pinned);
+    check(rc, "pom_batch_step_seq");
+    tick += ticks;
+    fresh = false;
+    Refresh();
+    size_t running = 0;
+    for(size_t i = 0; i < n; i++) running += (status[i] & (POM_STATUS_DONE | POM_STATUS_INVALID | POM_STATUS_TRUNCATED)) ? 0 : 1;
+    return running;
+}
+
 pom_stats BatchEnvironment::Rollout(uint32_t ticks, uint64_t seed, bool harmless, unsigned simpleMask)
 {
     check(pom_batch_rollout(handle, ticks, seed, tick, (harmless ? POM_ROLL_HARMLESS : 0) | POM_ROLL_SIMPLE(simpleMask)), "pom_batch_rollout");

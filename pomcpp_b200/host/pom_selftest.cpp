@@ -6,7 +6,9 @@
  * compiles and behaves the same when pointed at this library.  Exit code 0 = all passed.
  */
 #include <cstdio>
+#include <cstring>
 #include <memory>
+#include <random>
 
 #include "bboard.hpp"
 #include "pom_agents.hpp"
@@ -172,6 +174,22 @@ int main()
         pom_stats st = be.Rollout(300, 5, false, 0xF);
         REQUIRE(st.env_steps > 0);
         REQUIRE(st.episodes == st.wins[0] + st.wins[1] + st.wins[2] + st.wins[3] + st.draws + st.truncated + st.invalid);
+    }
+    {   /* StepSequence (one launch, given moves) == the same moves tick by tick */
+        const size_t n = 200; const uint32_t ticks = 25;
+        BatchEnvironment a(n, 0, 0, 16), b(n, 0, 0, 16);
+        std::vector<Move> seq(size_t(ticks) * n * 4);
+        std::mt19937 rng(5);
+        for(auto& m : seq) m = Move(int(rng() % 6));
+        size_t ra = 0;
+        for(uint32_t t = 0; t < ticks; t++) ra = a.Step(seq.data() + size_t(t) * n * 4);
+        const size_t rb = b.StepSequence(seq.data(), ticks);
+        REQUIRE(ra == rb);
+        bool same = true;
+        for(size_t i = 0; i < n; i++)
+            same = same && std::memcmp(a.States()[i].board, b.States()[i].board, sizeof(a.States()[i].board)) == 0 &&
+                   a.States()[i].timeStep == b.States()[i].timeStep && a.Status()[i] == b.Status()[i];
+        REQUIRE(same);
     }
     {   /* fog of war: host agents see a 9x9 window; what lies outside is Item::FOG and hidden agents have no position */
         struct Peek : Agent
