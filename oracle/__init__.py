@@ -146,6 +146,11 @@ class Restatement:
         self.lib.pom_oracle_fog_batch(_ptr(S), C.c_long(S.shape[0]), agent, view)
         return S
 
+    def observe_planes_batch(self, S, agent, view=4):
+        out = np.zeros((S.shape[0], 496), np.uint8)
+        self.lib.pom_oracle_observe_planes_batch(_ptr(S), C.c_long(S.shape[0]), agent, view, _ptr(out))
+        return out
+
     # --- agents::SimpleAgent / bboard::strategy (oracle/pom_oracle_agent.c) ---
     def simple_agents(self, n_envs):
         return np.zeros((n_envs, 4), dtype=SIMPLE_DT)

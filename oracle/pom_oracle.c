@@ -854,3 +854,47 @@ void pom_oracle_fog_batch(pom_state* S, long n, int agent, int view)
 {
     for (long e = 0; e < n; e++) pom_oracle_fog(&S[e], agent, view);
 }
+
+/* ---- observation planes: the DEFINITION the device code is checked against (the reference has no counterpart).
+ * Built from the AoS State through pom_oracle_fog, i.e. independently of the packed record. */
+void pom_oracle_observe_planes(const pom_state* full, int agent, int view, uint8_t out[496])
+{
+    pom_state s = *full;
+    pom_oracle_fog(&s, agent, view);
+    memset(out, 0, 496);
+    for (int y = 0; y < BS; y++)
+        for (int x = 0; x < BS; x++) {
+            int v = s.board[y][x], id;
+            if (is_agent(v)) id = 10 + (v - POM_ITEM_AGENT0);
+            else if (is_flame(v)) id = 4;
+            else if (is_wood(v)) id = 2;
+            else id = v;                                   /* 0 1 3 5 6 7 8 9 keep the reference's ids */
+            out[x + BS * y] = (uint8_t)id;
+            if (is_flame(v)) {
+                int o = flame_id(v), t = 0;
+                for (int i = 0; i < full->flames_count && i < NB; i++) {       /* first entry of the FULL queue with this origin */
+                    const pom_flame* f = &full->flames[(full->flames_index + i) % NB];
+                    if (f->x + BS * f->y == o) { t = f->timeLeft; break; }
+                }
+                out[363 + x + BS * y] = (uint8_t)(t < 0 ? 0 : t);
+            }
+        }
+    for (int i = 0; i < s.bombs_count; i++) {              /* the fogged queue: visible bombs only, in order */
+        int b = s.bombs[i];
+        out[121 + b_x(b) + BS * b_y(b)] = (uint8_t)b_str(b);
+        out[242 + b_x(b) + BS * b_y(b)] = (uint8_t)b_time(b);
+    }
+    const pom_agent* a = &full->agents[agent];
+    int ammo = a->maxBombCount - a->bombCount, alive = 0;
+    for (int i = 0; i < 4; i++) alive |= full->agents[i].dead ? 0 : (1 << i);
+    out[484] = (uint8_t)a->x; out[485] = (uint8_t)a->y;
+    out[486] = (uint8_t)(ammo < 0 ? 0 : ammo > 255 ? 255 : ammo);
+    out[487] = (uint8_t)a->bombStrength; out[488] = (uint8_t)(a->canKick ? 1 : 0); out[489] = (uint8_t)alive;
+    out[490] = (uint8_t)(full->timeStep & 0xFF); out[491] = (uint8_t)((full->timeStep >> 8) & 0xFF);
+    out[492] = (uint8_t)((alive >> agent) & 1);
+}
+
+void pom_oracle_observe_planes_batch(const pom_state* S, long n, int agent, int view, uint8_t* out)
+{
+    for (long e = 0; e < n; e++) pom_oracle_observe_planes(&S[e], agent, view, out + 496 * e);
+}

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpom_b200.so")
 
 REC_BYTES = 292
+OBS_BYTES = 496
 ALGO_BYTES_PER_ENV_STEP = 2 * 289 + 4      # packed state in + out + 4 move bytes
 
 STEP_RAW, STEP_AUTORESET, STEP_COUNT, STEP_OVERLAP = 1, 2, 4, 8
@@ -86,6 +87,10 @@ def lib():
         L.pom_batch_upload.argtypes = [vp, u64, u64, vp, vp]
         L.pom_batch_download.argtypes = [vp, u64, u64, vp, vp]
         L.pom_batch_observe.argtypes = [vp, u64, u64, i32, i32, vp, vp]
+        L.pom_batch_obs_stride.restype = u64
+        L.pom_batch_obs_stride.argtypes = [vp]
+        L.pom_batch_observe_planes.argtypes = [vp, vp, u32, i32]
+        L.pom_device_copy.argtypes = [i32, vp, vp, u64]
         L.pom_batch_reset.argtypes = [vp]
         L.pom_batch_templates.argtypes = [vp, vp, vp]
         L.pom_batch_step.argtypes = [vp, vp, u32]
@@ -199,6 +204,22 @@ class Batch:
         st = np.zeros(count, np.uint8)
         _ck(lib().pom_batch_observe(self.h, first, count, agent, view, _p(S), _p(st)))
         return S, st
+
+    def observe_planes(self, agent_mask=15, view=4, obs_dev=None):
+        """observation planes of the agents in agent_mask, computed and kept on the device; returns a host copy
+        [n_agents, n_envs, 496] (and leaves obs_dev filled if the caller passed its own buffer)"""
+        k = bin(agent_mask & 15).count("1")
+        stride = int(lib().pom_batch_obs_stride(self.h))
+        own = obs_dev is None
+        if own:
+            obs_dev = self.alloc(k * stride * OBS_BYTES)
+        _ck(lib().pom_batch_observe_planes(self.h, obs_dev, agent_mask, view))
+        self.sync()
+        host = np.zeros((k, stride, OBS_BYTES), np.uint8)
+        _ck(lib().pom_device_copy(self.device, _p(host), obs_dev, host.nbytes))
+        if own:
+            self.free(obs_dev)
+        return host[:, :self.n]
 
     def templates(self):
         T = np.zeros(self.n_templates, STATE_DT)

@@ -112,7 +112,7 @@ int use(const pom_batch* cb, bool join = true)
 
 /* The dynamic shared-memory limit of a kernel is a per-device attribute: remember it per handle (one handle = one
  * device), not in a process-wide flag, so that handles on other GPUs and other host threads set it for themselves. */
-enum { ATTR_STEP = 1, ATTR_ROLLOUT = 2, ATTR_ROLLOUT_POLICY = 4, ATTR_POLICY_MOVES = 8, ATTR_EXPAND = 16 };
+enum { ATTR_STEP = 1, ATTR_ROLLOUT = 2, ATTR_ROLLOUT_POLICY = 4, ATTR_POLICY_MOVES = 8, ATTR_EXPAND = 16, ATTR_OBS = 32 };
 
 template<typename K>
 int set_smem(pom_batch* b, uint32_t which, K kernel, uint32_t bytes)
@@ -259,6 +259,17 @@ int launch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_
     { int rc = set_smem(b, ATTR_POLICY_MOVES, pomk::k_policy_moves<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
     pomk::k_policy_moves<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), reinterpret_cast<uint32_t*>(moves_dev), seed, tick, mask);
+    b->launches++;
+    CK(cudaGetLastError());
+    return POM_OK;
+}
+
+template<int TPB>
+int launch_observe_planes(pom_batch* b, uint8_t* obs_dev, uint32_t mask, int view)
+{
+    { int rc = set_smem(b, ATTR_OBS, pomk::k_observe_planes<TPB>, pomk::ObsScratch<TPB>::BYTES); if(rc) return rc; }
+    const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
+    pomk::k_observe_planes<TPB><<<grid, TPB, pomk::ObsScratch<TPB>::BYTES, b->stream>>>(b->params(), obs_dev, b->n_alloc, mask, view);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -442,6 +453,24 @@ int pom_batch_observe(pom_batch* b, uint64_t first, uint64_t count, int agent, i
         if(status) CK(cudaMemcpyAsync(status + done, b->st_stage, c, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
     }
+    return POM_OK;
+}
+
+uint64_t pom_batch_obs_stride(const pom_batch* b) { return b ? b->n_alloc : 0; }
+
+int pom_batch_observe_planes(pom_batch* b, uint8_t* obs_dev, uint32_t agent_mask, int view)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!obs_dev) return fail(POM_E_ARG, "pom_batch_observe_planes: null output");
+    if(agent_mask == 0 || agent_mask > 0xFu || view < 0) return fail(POM_E_ARG, "pom_batch_observe_planes: agent_mask must be 1..15 and view >= 0");
+    POM_DISPATCH(b, launch_observe_planes, b, obs_dev, agent_mask, view);
+}
+
+int pom_device_copy(int device, void* dst, const void* src, uint64_t bytes)
+{
+    if(!dst || !src) return fail(POM_E_ARG, "pom_device_copy: null pointer");
+    CK(cudaSetDevice(device));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
     return POM_OK;
 }
 

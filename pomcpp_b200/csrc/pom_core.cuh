@@ -1163,6 +1163,86 @@ POM_HD void fog_state(pom_state* s, int agent, int view)
     s->flames_count = nf;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * Observation planes: what agent `agent` sees through a window of `view` cells, as POM_OBS_BYTES
+ * bytes ready for a network input (include/pom_batch.h describes the layout).  Same visibility rule as fog_state; the
+ * board plane uses the reference's Item order (bboard.hpp:54-71) with wood / flame powerup flags hidden, as in the game.
+ * ------------------------------------------------------------------------------------------- */
+POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
+{
+    const uint32_t ap = r[R_APOS + agent];
+    const int ax = int(ap & 15u), ay = int(ap >> 4);
+    const int x0 = ax - view, x1 = ax + view, y0 = ay - view, y1 = ay + view;
+    const int fc = r[R_FCOUNT];
+    const uint32_t fi = r[R_FINDEX];
+    int c = 0;
+    for(int y = 0; y < POM_BOARD_SIZE; y++)
+    {
+        for(int x = 0; x < POM_BOARD_SIZE; x++, c++)
+        {
+            uint32_t item = 5u, flife = 0u;                                  /* FOG */
+            if(x >= x0 && x <= x1 && y >= y0 && y <= y1)
+            {
+                const uint32_t code = r[R_BOARD + c];
+                if(code & 0x80u)
+                {
+                    item = 4u;
+                    /* the flame-queue entry this cell belongs to: the first one, in queue order, with the cell's origin
+                     * (the rule State::PopFlame matches cells by, bboard.cpp:160-176) */
+                    const uint32_t origin = flame_origin(r, code);
+                    uint32_t slot = fi;
+                    for(int k = 0; k < fc && k < 20; k++, slot = ring_next(slot))
+                    {
+                        if(r[R_FPOS + slot] == origin)
+                        {
+                            const int t = int(int8_t(r[R_FTIME + slot]));
+                            flife = uint32_t(t < 0 ? 0 : t);
+                            break;
+                        }
+                    }
+                }
+                else if(code <= 1u) item = code;
+                else if(code <= 6u) item = 2u;
+                else if(code == uint32_t(C_BOMB)) item = 3u;
+                else if(code == uint32_t(C_FOG)) item = 5u;
+                else if(code <= 11u) item = code - 3u;                       /* 9,10,11 -> 6,7,8 */
+                else if(code == uint32_t(C_AGENTDUMMY)) item = 9u;
+                else item = code - 3u;                                       /* 13..16 -> 10..13 */
+            }
+            out[c] = uint8_t(item);
+            out[121 + c] = 0;
+            out[242 + c] = 0;
+            out[363 + c] = uint8_t(flife);
+        }
+    }
+    /* visible bombs: blast strength and timer at their cell; a later queue entry on the same cell overwrites an earlier one */
+    {
+        const int bc = r[R_BCOUNT];
+        uint32_t slot = r[R_BINDEX];
+        for(int k = 0; k < bc && k < 20; k++, slot = ring_next(slot))
+        {
+            const uint32_t b = reinterpret_cast<const uint32_t*>(r + R_BOMBS)[slot];
+            const int bx = int(b & 15u), by = int((b >> 4) & 15u);
+            if(bx > 10 || by > 10 || bx < x0 || bx > x1 || by < y0 || by > y1) continue;
+            out[121 + bx + 11 * by] = uint8_t((b >> 12) & 15u);
+            out[242 + bx + 11 * by] = uint8_t((b >> 16) & 15u);
+        }
+    }
+    const int ammo = int(r[R_AMAX + agent]) - int(int8_t(r[R_ABCNT + agent]));
+    uint32_t alive = 0;
+    for(int i = 0; i < 4; i++) alive |= (r[R_AFLAGS + i] & AF_DEAD) ? 0u : (1u << i);
+    out[484] = uint8_t(ax);
+    out[485] = uint8_t(ay);
+    out[486] = uint8_t(ammo < 0 ? 0 : (ammo > 255 ? 255 : ammo));
+    out[487] = r[R_ASTR + agent];
+    out[488] = uint8_t((r[R_AFLAGS + agent] & AF_CANKICK) ? 1 : 0);
+    out[489] = uint8_t(alive);
+    out[490] = r[R_TIME];
+    out[491] = r[R_TIME + 1];
+    out[492] = uint8_t((alive >> agent) & 1u);
+    out[493] = 0; out[494] = 0; out[495] = 0;
+}
+
 /* the shared stateless action source (same arithmetic as oracle/pom_oracle.c pom_oracle_rng_moves) */
 POM_HD uint64_t splitmix64(uint64_t z)
 {

@@ -14,6 +14,7 @@
  *  K3 k_make_templates / k_fill_from_templates   board generation on the device and env (re)initialisation.
  *  K4 k_gather_records / k_expand_step           state copy (pom_batch_clone) and tree-search fan-out (+ one Step, fused).
  *  K5 k_pack / k_unpack / k_observe              AoS bboard::State <-> packed record; the State as one agent sees it (fog).
+ *     k_observe_planes                            the same view as byte planes for a network input, written with bulk stores.
  *  K7 k_policy_moves / k_rollout<TPB, true>   the reference's SimpleAgent (pom_policy.cuh) as the action source: per tick
  *                                                 into a moves buffer, or inside the fused rollout; the agents' 8-byte
  *                                                 memories live in global memory, word-major (coalesced, L1/L2-resident).
@@ -541,6 +542,53 @@ __global__ void k_observe(const uint8_t* __restrict__ recs, pom_state* aos, uint
     const uint8_t st = pomcore::unpack(recs + (first + i) * POM_REC_BYTES, aos + i);
     pomcore::fog_state(aos + i, agent, view);
     if(status) status[i] = st;
+}
+
+/* observation planes (pomcore::observe_planes) for the agents in `mask`, written as POM_OBS_BYTES records into one slab
+ * per agent: out[((k * stride) + env) * POM_OBS_BYTES], k = rank of the agent within the mask.  Same per-warp staging as
+ * k_step: the warp's 32 records come in with one bulk load; every lane writes its env's observation into the warp's
+ * 32 x 496-byte tile in shared memory, which leaves with ONE bulk store per agent (15.9 KB, contiguous in the slab). */
+template<int TPB> struct ObsScratch {
+    static constexpr uint32_t OFF_OBS = (TileScratch<TPB>::BYTES + 127u) / 128u * 128u;
+    static constexpr uint32_t BYTES = OFF_OBS + uint32_t(TPB) * POM_OBS_BYTES;
+};
+
+template<int TPB>
+__global__ void __launch_bounds__(TPB) k_observe_planes(BatchParams P, uint8_t* __restrict__ out, uint64_t stride, uint32_t mask, int view)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint64_t env0 = uint64_t(blockIdx.x) * TPB + warp * 32u;            /* first env of this warp's slice */
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR) + warp;
+    uint8_t* sslice = smem + warp * SLICE_BYTES;
+    uint8_t* otile = smem + ObsScratch<TPB>::OFF_OBS + warp * (32u * POM_OBS_BYTES);
+    if(lane == 0)
+    {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, SLICE_BYTES);
+        bulk_g2s(sslice, P.recs + env0 * POM_REC_BYTES, SLICE_BYTES, bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const uint8_t* rec = sslice + lane * POM_REC_BYTES;
+    uint32_t k = 0;
+    for(int a = 0; a < 4; a++)
+    {
+        if(!((mask >> a) & 1u)) continue;
+        /* lanes past n_envs read the zeroed tail of the record array and write into the padded tail of the slab */
+        pomcore::observe_planes(rec, a, view, otile + lane * POM_OBS_BYTES);
+        fence_proxy_async();
+        __syncwarp();
+        if(lane == 0)
+        {
+            bulk_s2g(out + (uint64_t(k) * stride + env0) * POM_OBS_BYTES, otile, 32u * POM_OBS_BYTES);
+            bulk_wait_read_all();                                 /* the tile is rewritten for the next agent */
+        }
+        __syncwarp();
+        k++;
+    }
 }
 
 /* ---------------------------------------------------------------- misc */

@@ -41,6 +41,7 @@ class HostSim:
         L.hostsim_rng_moves.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.hostsim_simple_moves.argtypes = [vp, C.c_long, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp]
         L.hostsim_fog_batch.argtypes = [vp, C.c_long, C.c_int, C.c_int]
+        L.hostsim_observe_planes.argtypes = [vp, C.c_long, C.c_int, C.c_int, vp]
         L.hostsim_move_towards.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         L.hostsim_move_towards_safe_place.argtypes = [vp, C.c_int, C.c_int]
         assert L.hostsim_record_bytes() == REC
@@ -72,6 +73,11 @@ class HostSim:
 
     def move_towards_safe_place(self, rec, agent, radius):
         return self.lib.hostsim_move_towards_safe_place(_p(rec), agent, radius)
+
+    def observe_planes(self, recs, agent, view):
+        out = np.zeros((recs.shape[0], 496), np.uint8)
+        self.lib.hostsim_observe_planes(_p(recs), recs.shape[0], agent, view, _p(out))
+        return out
 
     def fog_batch(self, S, agent, view):
         self.lib.hostsim_fog_batch(_p(S), S.shape[0], agent, view)

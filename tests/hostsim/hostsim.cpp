@@ -112,6 +112,12 @@ void hostsim_fog_batch(pom_state* S, long n, int agent, int view)
     for(long e = 0; e < n; e++) pomcore::fog_state(&S[e], agent, view);
 }
 
+/* the device observation code (pomcore::observe_planes) on packed records */
+void hostsim_observe_planes(const uint8_t* recs, long n, int agent, int view, uint8_t* out)
+{
+    for(long e = 0; e < n; e++) pomcore::observe_planes(recs + e * POM_REC_BYTES, agent, view, out + 496 * e);
+}
+
 uint32_t hostsim_rng_moves(uint64_t seed, uint64_t env, uint32_t tick, uint32_t n_actions)
 {
     return pomcore::rng_moves(seed, env, tick, n_actions);

@@ -75,3 +75,71 @@ def test_observe_on_gpu(orc, agent, view):
     assert L.pom_batch_observe(b.h, 0, 1, 4, 4, obs.ctypes.data, None) == -1
     assert L.pom_batch_observe(b.h, 0, n + 1, 0, 4, obs.ctypes.data, None) == -4
     b.close()
+
+
+@pytest.mark.parametrize("agent,view", [(0, 4), (3, 4), (1, 2), (2, 10)])
+def test_observation_planes_device_code_on_host(orc, agent, view):
+    """pomcore::observe_planes on packed records vs the oracle's definition built from the AoS State, on mid-game states
+    and on the mutually inconsistent states of tests/test_fuzz_states.py"""
+    from hostsim import HostSim
+    from test_fuzz_states import mutated_states
+    hs = HostSim()
+    for S in (mutated_states(orc, 77 + agent, 1500), _mid_game_states(orc)):
+        recs, bad = hs.pack(S, np.zeros(S.shape[0], np.uint8))
+        S, recs = S[bad == 0].copy(), recs[bad == 0].copy()
+        a = orc.observe_planes_batch(S, agent, view)
+        b = hs.observe_planes(recs, agent, view)
+        assert (a == b).all(), np.argwhere(a != b)[:5]
+        # the board plane is the fogged board with the game's item ids
+        fog = orc.fog_batch(S.copy(), agent, view)
+        assert ((a[:, :121].reshape(-1, 11, 11) == 5) == (fog["board"] == FOG)).all()
+        assert (a[:, 484] == S["agents"]["x"][:, agent]).all() and (a[:, 489] == (1 - S["agents"]["dead"]) @ np.array([1, 2, 4, 8])).all()
+        assert a[:, 121:242].any()
+    assert a[:, 363:484].any() or view < 10     # flame lives show up once bombs have gone off
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mask,view", [(15, 4), (0b0101, 2)])
+def test_observation_planes_on_gpu(orc, mask, view):
+    import pomcpp_b200 as pb
+    n = 5000 + 17
+    b = pb.Batch(n, n_templates=64)
+    b.rollout(45, 3, 0, pb.ROLL_NO_RESET)
+    full, _ = b.download()
+    obs = b.observe_planes(mask, view)
+    agents = [a for a in range(4) if (mask >> a) & 1]
+    assert obs.shape == (len(agents), n, 496)
+    for k, a in enumerate(agents):
+        want = orc.observe_planes_batch(full, a, view)
+        assert (obs[k] == want).all(), (a, np.argwhere(obs[k] != want)[:4])
+    L = pb.lib()
+    dev = b.alloc(496 * 256)
+    assert L.pom_batch_observe_planes(b.h, None, 1, 4) == -1
+    assert L.pom_batch_observe_planes(b.h, dev, 0, 4) == -1
+    assert L.pom_batch_observe_planes(b.h, dev, 16, 4) == -1
+    assert L.pom_batch_observe_planes(b.h, dev, 1, -1) == -1
+    b.free(dev)
+    b.close()
+
+
+@pytest.mark.gpu
+def test_observation_planes_throughput_smoke():
+    """1 Mi envs x 4 agents (2 GB of planes per call) stays on the device; just check it runs and is not absurdly slow"""
+    import time
+    import pomcpp_b200 as pb
+    n = 1 << 20
+    b = pb.Batch(n, n_templates=256)
+    stride = int(pb.lib().pom_batch_obs_stride(b.h))
+    dev = b.alloc(4 * stride * 496)
+    pb._ck(pb.lib().pom_batch_observe_planes(b.h, dev, 15, 4))
+    b.sync()
+    b.event(0)
+    for _ in range(5):
+        pb._ck(pb.lib().pom_batch_observe_planes(b.h, dev, 15, 4))
+    b.event(1)
+    b.sync()
+    ms = b.elapsed_ms() / 5
+    print("observe_planes: %.3f ms per 1 Mi envs x 4 agents, %.0f GB/s written" % (ms, 4 * n * 496 / ms / 1e6))
+    assert ms < 20
+    b.free(dev)
+    b.close()
