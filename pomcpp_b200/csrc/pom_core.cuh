@@ -1168,51 +1168,59 @@ POM_HD void fog_state(pom_state* s, int agent, int view)
  * bytes ready for a network input (include/pom_batch.h describes the layout).  Same visibility rule as fog_state; the
  * board plane uses the reference's Item order (bboard.hpp:54-71) with wood / flame powerup flags hidden, as in the game.
  * ------------------------------------------------------------------------------------------- */
-POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
+POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)   /* out: 4-byte aligned */
 {
     const uint32_t ap = r[R_APOS + agent];
     const int ax = int(ap & 15u), ay = int(ap >> 4);
     const int x0 = ax - view, x1 = ax + view, y0 = ay - view, y1 = ay + view;
-    const int fc = r[R_FCOUNT];
-    const uint32_t fi = r[R_FINDEX];
-    int c = 0;
-    for(int y = 0; y < POM_BOARD_SIZE; y++)
+    uint32_t* ow = reinterpret_cast<uint32_t*>(out);
+    /* planes 1-3 start out empty: bytes 124..483 = words 31..120 (bytes 121..123 are written with board word 30) */
+    for(int w = 31; w < 121; w++) ow[w] = 0u;
+    /* board plane, four cells per word: the item ids come from byte-parallel range tests on the cell codes
+     * (0,1 keep; 2..6 wood -> 2; 7 bomb -> 3; 8.. -> code - 3, i.e. fog 5, powerups 6..8, dummy 9, agents 10..13;
+     * flame codes have the top bit set -> 4), then cells outside the window are overwritten with 5 (fog) */
+    const uint32_t* bw = reinterpret_cast<const uint32_t*>(r + R_BOARD);
+    int x = 0, y = 0;
+    for(int w = 0; w < 31; w++)
     {
-        for(int x = 0; x < POM_BOARD_SIZE; x++, c++)
+        const uint32_t codes = bw[w];
+        uint32_t vis = 0u;                                     /* 0xFF in the bytes of visible cells */
+        for(int j = 0; j < 4; j++)
         {
-            uint32_t item = 5u, flife = 0u;                                  /* FOG */
-            if(x >= x0 && x <= x1 && y >= y0 && y <= y1)
+            const bool cell = w < 30 || j == 0;                /* word 30: only its first byte is a board cell */
+            if(cell && x >= x0 && x <= x1 && y >= y0 && y <= y1) vis |= 0xFFu << (8 * j);
+            if(++x == POM_BOARD_SIZE) { x = 0; y++; }
+        }
+        const uint32_t l = codes & 0x7F7F7F7Fu, flame = codes & 0x80808080u, plain = ~codes & 0x80808080u;
+        const uint32_t ge2 = (l + 0x7E7E7E7Eu) & 0x80808080u, ge7 = (l + 0x79797979u) & 0x80808080u, ge8 = (l + 0x78787878u) & 0x80808080u;
+        const uint32_t keep = ((plain & ~ge2) >> 7) * 0xFFu, wood = ((plain & ge2 & ~ge7) >> 7) * 0xFFu;
+        const uint32_t bomb = ((plain & ge7 & ~ge8) >> 7) * 0xFFu, high = ((plain & ge8) >> 7) * 0xFFu, burn = (flame >> 7) * 0xFFu;
+        const uint32_t minus3 = ((l | 0x80808080u) - 0x03030303u) & 0x7F7F7F7Fu;       /* per byte, no borrow between bytes */
+        uint32_t ids = (codes & keep) | (0x02020202u & wood) | (0x03030303u & bomb) | (minus3 & high) | (0x04040404u & burn);
+        ids = (ids & vis) | (0x05050505u & ~vis);
+        if(w == 30) ids &= 0xFFu;                              /* bytes 121..123: the first cells of the bomb-strength plane */
+        ow[w] = ids;
+        uint32_t lit = burn & vis;                             /* visible flame cells: how long they still burn */
+        if(lit)
+        {
+            const int fc = r[R_FCOUNT];
+            for(int j = 0; j < 4; j++)
             {
-                const uint32_t code = r[R_BOARD + c];
-                if(code & 0x80u)
+                if(!((lit >> (8 * j)) & 0xFFu)) continue;
+                /* the flame-queue entry the cell belongs to: the first one, in queue order, with the cell's origin
+                 * (the rule State::PopFlame matches cells by, bboard.cpp:160-176) */
+                const uint32_t origin = flame_origin(r, (codes >> (8 * j)) & 0xFFu);
+                uint32_t slot = r[R_FINDEX];
+                for(int k = 0; k < fc && k < 20; k++, slot = ring_next(slot))
                 {
-                    item = 4u;
-                    /* the flame-queue entry this cell belongs to: the first one, in queue order, with the cell's origin
-                     * (the rule State::PopFlame matches cells by, bboard.cpp:160-176) */
-                    const uint32_t origin = flame_origin(r, code);
-                    uint32_t slot = fi;
-                    for(int k = 0; k < fc && k < 20; k++, slot = ring_next(slot))
+                    if(r[R_FPOS + slot] == origin)
                     {
-                        if(r[R_FPOS + slot] == origin)
-                        {
-                            const int t = int(int8_t(r[R_FTIME + slot]));
-                            flife = uint32_t(t < 0 ? 0 : t);
-                            break;
-                        }
+                        const int t = int(int8_t(r[R_FTIME + slot]));
+                        out[363 + 4 * w + j] = uint8_t(t < 0 ? 0 : t);
+                        break;
                     }
                 }
-                else if(code <= 1u) item = code;
-                else if(code <= 6u) item = 2u;
-                else if(code == uint32_t(C_BOMB)) item = 3u;
-                else if(code == uint32_t(C_FOG)) item = 5u;
-                else if(code <= 11u) item = code - 3u;                       /* 9,10,11 -> 6,7,8 */
-                else if(code == uint32_t(C_AGENTDUMMY)) item = 9u;
-                else item = code - 3u;                                       /* 13..16 -> 10..13 */
             }
-            out[c] = uint8_t(item);
-            out[121 + c] = 0;
-            out[242 + c] = 0;
-            out[363 + c] = uint8_t(flife);
         }
     }
     /* visible bombs: blast strength and timer at their cell; a later queue entry on the same cell overwrites an earlier one */
@@ -1231,16 +1239,9 @@ POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
     const int ammo = int(r[R_AMAX + agent]) - int(int8_t(r[R_ABCNT + agent]));
     uint32_t alive = 0;
     for(int i = 0; i < 4; i++) alive |= (r[R_AFLAGS + i] & AF_DEAD) ? 0u : (1u << i);
-    out[484] = uint8_t(ax);
-    out[485] = uint8_t(ay);
-    out[486] = uint8_t(ammo < 0 ? 0 : (ammo > 255 ? 255 : ammo));
-    out[487] = r[R_ASTR + agent];
-    out[488] = uint8_t((r[R_AFLAGS + agent] & AF_CANKICK) ? 1 : 0);
-    out[489] = uint8_t(alive);
-    out[490] = r[R_TIME];
-    out[491] = r[R_TIME + 1];
-    out[492] = uint8_t((alive >> agent) & 1u);
-    out[493] = 0; out[494] = 0; out[495] = 0;
+    ow[121] = uint32_t(ax) | (uint32_t(ay) << 8) | (uint32_t(ammo < 0 ? 0 : (ammo > 255 ? 255 : ammo)) << 16) | (uint32_t(r[R_ASTR + agent]) << 24);
+    ow[122] = ((r[R_AFLAGS + agent] & AF_CANKICK) ? 1u : 0u) | (alive << 8) | (uint32_t(r[R_TIME]) << 16) | (uint32_t(r[R_TIME + 1]) << 24);
+    ow[123] = (alive >> agent) & 1u;
 }
 
 /* the shared stateless action source (same arithmetic as oracle/pom_oracle.c pom_oracle_rng_moves) */
