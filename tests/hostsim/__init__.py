@@ -46,6 +46,10 @@ class HostSim:
         L.hostsim_move_towards_safe_place.argtypes = [vp, C.c_int, C.c_int]
         assert L.hostsim_record_bytes() == REC
 
+    def set_by_rays(self, on):
+        """True: step_records runs the tick in the warp-cooperative kernels' decomposition (pomcore::step_by_rays)"""
+        self.lib.hostsim_set_by_rays(int(bool(on)))
+
     def pack(self, S, status=None):
         n = S.shape[0]
         recs = np.zeros((n, REC), np.uint8)

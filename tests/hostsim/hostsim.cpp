@@ -34,7 +34,12 @@ void hostsim_unpack_batch(const uint8_t* recs, long n, pom_state* S, uint8_t* st
     }
 }
 
-/* raw != 0: bboard::Step only; raw == 0: Environment::Step semantics */
+/* raw != 0: bboard::Step only; raw == 0: Environment::Step semantics.
+ * by_rays != 0: the tick in the form the warp-cooperative kernels run it (ray-parallel explosions, arm-parallel flame
+ * pops: the lanes' work done one after the other), so that the scan / commit decomposition itself is checked on the CPU */
+static int g_by_rays = 0;
+void hostsim_set_by_rays(int on) { g_by_rays = on; }
+
 void hostsim_step_records(uint8_t* recs, long n, const uint8_t* moves, int raw, uint8_t* flags_out)
 {
     for(long e = 0; e < n; e++)
@@ -42,7 +47,17 @@ void hostsim_step_records(uint8_t* recs, long n, const uint8_t* moves, int raw, 
         uint32_t m;
         std::memcpy(&m, moves + 4 * e, 4);
         uint8_t* r = recs + e * POM_REC_BYTES;
-        int f = raw ? pomcore::step(r, m) : pomcore::env_step(r, m);
+        int f = 0;
+        if(!g_by_rays) f = raw ? pomcore::step(r, m) : pomcore::env_step(r, m);
+        else if(raw || !(r[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_INVALID)))
+        {
+            f = pomcore::step_by_rays(r, m);
+            if(!raw)
+            {
+                if(f & pomcore::F_INVALID_MASK) r[R_STATUS] |= POM_STATUS_INVALID;
+                pomcore::env_post(r);
+            }
+        }
         if(flags_out) flags_out[e] = uint8_t(f);
     }
 }
