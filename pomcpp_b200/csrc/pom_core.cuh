@@ -486,6 +486,9 @@ struct TickCtx {
                                agent's start-of-tick cell; kept exact when bombs are planted this tick)            */
     uint32_t anyDir;        /* non-zero iff some bomb in the queue has a direction: start-of-tick directions, kicks
                                and stale direction bits inherited by bombs planted this tick           */
+    uint32_t dstBomb;       /* 0x80 in byte a: a start-of-tick bomb queue entry sits on agent a's DESTINATION      */
+    uint32_t needRevert;    /* non-zero iff an agent may stand on a queue entry's cell after moving there this
+                               tick: only then can the bomb pre-pass (step.cpp:195-227) bounce anyone back         */
 };
 
 /* leave the cell an agent stood on: BOMB if a queue entry sits there, else PASSAGE (step.cpp:89-96,127-134) */
@@ -624,7 +627,36 @@ POM_HD bool move_agents_fast(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, 
     const uint32_t c1 = bytes_equal2(dq, rot_bytes(dq, 1)), c2 = bytes_equal2(dq, rot_bytes(dq, 2));
     const uint32_t coll = (c1 & l1) | (c2 & l2) | (rot_bytes(c1, 3) & l3);               /* HasDPCollision */
     const uint32_t die = mv & flame;                                                      /* :84-99 */
-    const uint32_t go = mv & ~flame & ~coll & (passage | pwr | bombc);                    /* :101-184 */
+    uint32_t go = mv & ~flame & ~coll & (passage | pwr | bombc);                          /* :101-184 */
+
+    uint32_t pl = isBomb & live;                                                          /* PlantBombModifiedLife, as in move_agent */
+    POM_LOOP
+    while(pl)
+    {
+        const int a = first_set_byte(pl);
+        pl &= pl - 1u;
+        if(int(int8_t(byte_of(A.bcnt, a))) >= int(byte_of(A.amax, a))) continue;
+        const uint32_t cnt = r[R_BCOUNT];
+        if(cnt >= 20u) flags |= F_D4_BOMB_OVF;
+        uint32_t& b = bomb_slot(r, ring20(r[R_BINDEX] + cnt));
+        b = (b & ~0xF00u) + (uint32_t(a) << 8);
+        b = (b & ~0xFFu) + byte_of(A.pos, a);
+        b = (b & ~0xF000u) + (byte_of(A.astr, a) << 12);
+        b = (b & ~0xF0000u) + (uint32_t(POM_BOMB_LIFETIME + 1) << 16);
+        A.bcnt = with_byte(A.bcnt, a, byte_of(A.bcnt, a) + 1u);
+        r[R_BCOUNT] = uint8_t(cnt + 1u);
+        T.onBomb |= 0x80u << (8 * a);
+        T.anyDir |= b & 0xF00000u;
+    }
+    uint32_t kick = go & bombc & (A.flg << 7);                                            /* :147-184 with canKick */
+    /* Q2: an agent that cannot kick still steps onto the bomb and is bounced back by the bomb pre-pass
+     * (step.cpp:170-184,195-227).  When no bomb has or gets a direction this tick, that round trip changes nothing: the
+     * agent's cell and the bomb's cell end as they started, no one else reads either cell in between (no other live agent
+     * has this agent's old cell or its destination as destination).  So such an agent simply stays.  With a direction
+     * somewhere the general bomb phase may see the agent on the bomb: then it does step there. */
+    if((T.anyDir | kick) == 0u) go &= ~(bombc & T.dstBomb);
+    T.needRevert = go & T.dstBomb;
+
     const uint32_t vac = die | go;
     const uint32_t vacv = (T.onBomb >> 7) * uint32_t(C_BOMB);                             /* vacate(): BOMB or PASSAGE */
 #if defined(__CUDACC__)
@@ -647,7 +679,6 @@ POM_HD bool move_agents_fast(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, 
         A.astr = ((A.astr & 0x7F7F7F7Fu) + (ir >> 7)) ^ (A.astr & H);
         A.flg |= kk >> 7;                                                                  /* AF_CANKICK */
     }
-    uint32_t kick = go & bombc & (A.flg << 7);                                            /* :147-184 with canKick */
     POM_LOOP
     while(kick)
     {
@@ -666,25 +697,6 @@ POM_HD bool move_agents_fast(uint8_t* r, Agents& A, TickCtx& T, uint32_t moves, 
     {
         A.flg |= die >> 6;                                                                 /* AF_DEAD */
         A.alive -= popcount32(die);
-    }
-    uint32_t pl = isBomb & live;                                                          /* PlantBombModifiedLife, as in move_agent */
-    POM_LOOP
-    while(pl)
-    {
-        const int a = first_set_byte(pl);
-        pl &= pl - 1u;
-        if(int(int8_t(byte_of(A.bcnt, a))) >= int(byte_of(A.amax, a))) continue;
-        const uint32_t cnt = r[R_BCOUNT];
-        if(cnt >= 20u) flags |= F_D4_BOMB_OVF;
-        uint32_t& b = bomb_slot(r, ring20(r[R_BINDEX] + cnt));
-        b = (b & ~0xF00u) + (uint32_t(a) << 8);
-        b = (b & ~0xFFu) + byte_of(A.pos, a);
-        b = (b & ~0xF000u) + (byte_of(A.astr, a) << 12);
-        b = (b & ~0xF0000u) + (uint32_t(POM_BOMB_LIFETIME + 1) << 16);
-        A.bcnt = with_byte(A.bcnt, a, byte_of(A.bcnt, a) + 1u);
-        r[R_BCOUNT] = uint8_t(cnt + 1u);
-        T.onBomb |= 0x80u << (8 * a);
-        T.anyDir |= b & 0xF00000u;
     }
     return true;
 }
@@ -882,10 +894,18 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
     const uint32_t oldPos = A.pos;                                   /* FillPositions :24 */
     const uint32_t posq = A.pos + 0x11111111u;
 
-    /* which agents stand on a bomb queue entry (State::HasBomb of their cell, used when they leave it) */
+    /* destinations, one biased byte per agent (kept in a register: a dynamically indexed array would
+     * live in local memory) */
+    uint32_t dq = 0u;
+    for(int a = 0; a < 4; a++)                                       /* FillDestPos :25 */
+        dq |= (uint32_t(int(byte_of(posq, a)) + move_delta(byte_of(moves, a))) & 0xFFu) << (8 * a);
+
+    /* which agents stand on a bomb queue entry (State::HasBomb of their cell, used when they leave it), and which
+     * are heading for one */
     TickCtx T;
     T.onBomb = 0u;
     T.anyDir = 0u;
+    T.dstBomb = 0u;
     {
         const int bc0 = r[R_BCOUNT];
         uint32_t slot = r[R_BINDEX];
@@ -893,16 +913,12 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
         for(int k = 0; k < bc0; k++, slot = ring_next(slot))
         {
             const uint32_t b = bomb_slot(r, slot);
-            T.onBomb |= bytes_equal(A.pos, b & 0xFFu);
+            const uint32_t bq = ((b & 0xFFu) + 0x11u) * 0x01010101u;
+            T.onBomb |= bytes_equal2(posq, bq);
+            T.dstBomb |= bytes_equal2(dq, bq);
             T.anyDir |= b & 0xF00000u;
         }
     }
-
-    /* destinations, one biased byte per agent (kept in a register: a dynamically indexed array would
-     * live in local memory) */
-    uint32_t dq = 0u;
-    for(int a = 0; a < 4; a++)                                       /* FillDestPos :25 */
-        dq |= (uint32_t(int(byte_of(posq, a)) + move_delta(byte_of(moves, a))) & 0xFFu) << (8 * a);
     if(!move_agents_fast(r, A, T, moves, dq, posq, flags))
     {
     /* tgt[a]: 0x80 in byte b iff agent a's destination is agent b's cell.  The same four masks serve
@@ -965,6 +981,7 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
             i = byte_of(dep, int(i));
         }
     }
+    T.needRevert = A.pos ^ oldPos;
     }
 
     int bc = r[R_BCOUNT];
@@ -988,7 +1005,7 @@ POM_HD int step_body(uint8_t* r, uint32_t moves, bool& explode_due, bool explode
              * loop (:230-278) has anything to do: it only re-stamps / explodes bombs whose cell reads PASSAGE / FLAMES.
              * Reversions write AGENT or BOMB codes only, so they cannot create such a cell behind the pass. */
             bool needMove = false;
-            const bool anyAgentMoved = A.pos != oldPos;
+            const bool anyAgentMoved = T.needRevert != 0u;
             uint32_t slot = r[R_BINDEX];
             POM_LOOP
             for(int k = 0; k < bc; k++, slot = ring_next(slot))
@@ -1082,6 +1099,58 @@ POM_HD int step_explode_due(uint8_t* r)
     return flags;
 }
 
+/* ray d of a spawn at p (order +x, -x, +y, -y, :220-262): cells up to the border or `strength`; sets the cell stride */
+POM_HD uint32_t ray_length(uint32_t p, uint32_t strength, uint32_t d, int& stride)
+{
+    const uint32_t x = p & 15u, y = p >> 4;
+    const uint32_t rooms = (10u - x) | (x << 8) | ((10u - y) << 16) | (y << 24);
+    const uint32_t room = (rooms >> (8u * d)) & 0xFFu;
+    stride = int(int8_t(0xF50BFF01u >> (8u * d)));                    /* +1, -1, +11, -11 */
+    return strength < room ? strength : room;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Arm-parallel form of State::PopFlame (bboard.cpp:148-180) for the warp-cooperative tick (warp_pop_due): the cross of
+ * +-strength cells is four arms and a centre; every cell is cleared from its own old value and the (unchanged) flame
+ * positions alone, so the arms need no order.  The ring is popped after all arms are done.
+ * ------------------------------------------------------------------------------------------- */
+POM_HD void pop_flame_cell(uint8_t* r, uint32_t ci, uint32_t own, uint32_t p)
+{
+    uint8_t* cell = r + R_BOARD + ci;
+    const uint32_t c = *cell;
+    if(c_is_flame(c) && ((c & 0xFCu) == own || flame_origin(r, c) == p))
+    {
+        const uint32_t pw = c & 3u;                                   /* FlagItem, bboard.cpp:182-189 */
+        *cell = uint8_t(pw ? 8u + pw : 0u);
+    }
+}
+
+/* arm d (+x, -x, +y, -y) of the front flame's cross; d == 0 also clears the centre */
+POM_HD void pop_flame_arm(uint8_t* r, uint32_t d)
+{
+    const uint32_t fi = r[R_FINDEX];
+    const uint32_t p = r[R_FPOS + fi];
+    uint32_t s = r[R_FSTR + fi];
+    if(s > 10u) s = 10u;
+    const uint32_t own = uint32_t(C_FLAME) | (fi << 2);
+    int stride;
+    const uint32_t len = ray_length(p, s, d, stride);
+    uint32_t ci = uint32_t(cell_of(p));
+    if(d == 0u) pop_flame_cell(r, ci, own, p);
+    POM_LOOP
+    for(uint32_t k = 0; k < len; k++)
+    {
+        ci = uint32_t(int(ci) + stride);
+        pop_flame_cell(r, ci, own, p);
+    }
+}
+
+POM_HD void pop_flame_ring(uint8_t* r)                               /* PopElem, bboard.hpp:131-137 */
+{
+    r[R_FINDEX] = uint8_t(ring20(r[R_FINDEX] + 1u));
+    r[R_FCOUNT] = uint8_t(r[R_FCOUNT] - 1);
+}
+
 /* ---------------------------------------------------------------------------------------------
  * Ray-parallel form of ExplodeTopBomb (bboard.cpp:191-196) -> SpawnFlame (:198-263) for the warp-cooperative
  * tick (pom_kernels.cuh, warp_explode_due): four lanes own the four rays of one explosion.
@@ -1097,16 +1166,6 @@ POM_HD int step_explode_due(uint8_t* r)
  * (its powerup flag travels into the flame cell, :46-50), bits 8-11 agents killed, bit 12 chain.
  * ------------------------------------------------------------------------------------------- */
 enum { RAY_N_MASK = 0xF, RAY_WOOD_SHIFT = 4, RAY_KILL_SHIFT = 8, RAY_KILL_MASK = 0xF00, RAY_CHAIN = 0x1000 };
-
-/* ray d of a spawn at p (order +x, -x, +y, -y, :220-262): cells up to the border or `strength`; sets the cell stride */
-POM_HD uint32_t ray_length(uint32_t p, uint32_t strength, uint32_t d, int& stride)
-{
-    const uint32_t x = p & 15u, y = p >> 4;
-    const uint32_t rooms = (10u - x) | (x << 8) | ((10u - y) << 16) | (y << 24);
-    const uint32_t room = (rooms >> (8u * d)) & 0xFFu;
-    stride = int(int8_t(0xF50BFF01u >> (8u * d)));                    /* +1, -1, +11, -11 */
-    return strength < room ? strength : room;
-}
 
 POM_HD uint32_t ray_scan(uint8_t* r, uint32_t ci, int stride, uint32_t len)
 {
@@ -1213,7 +1272,15 @@ POM_HD bool explode_top_by_rays(uint8_t* r, int& flags)
 /* bboard::Step with the explosion loop in the ray-parallel form (host emulation of the warp-cooperative tick) */
 POM_HD int step_by_rays(uint8_t* r, uint32_t moves)
 {
-    tick_flames(r);
+    if(flames_age(r))
+    {
+        const int n = r[R_FCOUNT];
+        for(int i = 0; i < n && r[R_FTIME + r[R_FINDEX]] == 0; i++)
+        {
+            for(uint32_t d = 0; d < 4; d++) pop_flame_arm(r, d);
+            pop_flame_ring(r);
+        }
+    }
     bool due;
     int flags = step_body(r, moves, due, false);
     if(due)

@@ -193,13 +193,120 @@ __device__ __forceinline__ uint32_t finish_and_reset(uint8_t* warp_recs, uint8_t
     return st;
 }
 
-/* ---------------------------------------------------------------- one tick of one env */
-__device__ __forceinline__ void env_tick(uint8_t* rec, uint32_t m, bool step, bool raw)
+/* ---------------------------------------------------------------- one tick of the warp's 32 envs */
+/* The tick runs one env per lane (pom_core.cuh) except for its two rare, long, divergent pieces: the flame pops at the
+ * start (TickFlames -> PopFlame) and the explosions at the end (TickBombs -> ExplodeTopBomb -> SpawnFlame).  An env
+ * needs them in 11 % / 16 % of its ticks, so with one env per lane nearly every warp ran them with 2-3 of 32 lanes
+ * active (profiles/k_step_by_function_r1.txt).  Here the warp votes which envs are due (__ballot_sync), and every
+ * group of four lanes takes one due env, one lane per ray / arm: flame reach is resolved by four lanes walking the
+ * four rays at once, the kills and the chain test are combined with __shfl_xor_sync inside the group. */
+constexpr uint32_t FULL_WARP = 0xFFFFFFFFu;
+
+/* lane index of the n-th (0-based, n < 8) set bit of mask; 32 if there is none */
+__device__ __forceinline__ uint32_t nth_set_lane(uint32_t mask, uint32_t n)
 {
+#pragma unroll
+    for(uint32_t i = 0; i < 7; i++)
+        if(i < n) mask &= mask - 1u;
+    return mask ? uint32_t(__ffs(int(mask))) - 1u : 32u;
+}
+
+/* the pop loop of util::TickFlames (step_utility.cpp:216-222); `due` = this lane's front flame has expired.
+ * Called by all 32 lanes. */
+__device__ __forceinline__ void warp_pop_due(uint8_t* sslice, const uint8_t* rec, bool due)
+{
+    const uint32_t lane = threadIdx.x & 31u, quad = lane >> 2, arm = lane & 3u;
+    int turns = due ? int(rec[R_FCOUNT]) : 0;                 /* flameCount turns at most */
+    for(;;)
+    {
+        const uint32_t mask = __ballot_sync(FULL_WARP, due);
+        if(mask == 0u) break;
+        const uint32_t e = nth_set_lane(mask, quad);
+        uint8_t* r = sslice + e * POM_REC_BYTES;
+        if(e < 32u) pomcore::pop_flame_arm(r, arm);
+        __syncwarp();                                         /* every arm has read the front entry */
+        if(e < 32u && arm == 0u) pomcore::pop_flame_ring(r);
+        __syncwarp();
+        if(due && __popc(mask & ((1u << lane) - 1u)) < 8)
+        {
+            turns--;
+            due = turns > 0 && rec[R_FTIME + rec[R_FINDEX]] == 0;
+        }
+    }
+}
+
+/* the explosion loop of util::TickBombs (step_utility.cpp:231-244); `due` = this lane's bombs[0] has timed out.
+ * Called by all 32 lanes.  A group scans its four rays without writing; if no ray meets a bomb the rays are committed
+ * and lane 0 of the group does the rest of ExplodeTopBomb; else the env's own lane runs the serial machine. */
+__device__ __forceinline__ void warp_explode_due(uint8_t* sslice, uint8_t* rec, bool due, int& flags)
+{
+    const uint32_t lane = threadIdx.x & 31u, quad = lane >> 2, ray = lane & 3u;
+    int turns = due ? int(rec[R_BCOUNT]) : 0;                 /* bombCount turns at most */
+    for(;;)
+    {
+        const uint32_t mask = __ballot_sync(FULL_WARP, due);
+        if(mask == 0u) break;
+        const uint32_t e = nth_set_lane(mask, quad);
+        uint8_t* r = sslice + e * POM_REC_BYTES;
+        uint32_t plan = 0u, ci0 = 0u, slot = 0u;
+        int stride = 0;
+        if(e < 32u)
+        {
+            const uint32_t c = pomcore::bomb_slot(r, r[R_BINDEX]);
+            const uint32_t p = c & 0xFFu;
+            ci0 = uint32_t(pomcore::cell_of(p));
+            slot = pomcore::ring20(uint32_t(r[R_FINDEX]) + r[R_FCOUNT]);
+            const uint32_t len = pomcore::ray_length(p, (c >> 12) & 15u, ray, stride);
+            plan = pomcore::ray_scan(r, ci0, stride, len);
+        }
+        uint32_t all = plan | __shfl_xor_sync(FULL_WARP, plan, 1);
+        all |= __shfl_xor_sync(FULL_WARP, all, 2);
+        const bool chain = (all & pomcore::RAY_CHAIN) != 0u;
+        if(e < 32u && !chain)
+        {
+            pomcore::ray_commit(r, ci0, stride, plan, slot);  /* rays and origin are disjoint cells */
+            if(ray == 0u)
+            {
+                int f = 0;
+                pomcore::top_bomb_commit(r, all, f);
+                if(f & pomcore::F_INVALID_MASK) r[R_STATUS] |= POM_STATUS_INVALID;
+            }
+        }
+        const uint32_t chained = __ballot_sync(FULL_WARP, chain);   /* bit 4q: the explosion served by group q chains */
+        __syncwarp();                                         /* the groups' writes are visible to the envs' own lanes */
+        if(due)
+        {
+            const uint32_t rank = uint32_t(__popc(mask & ((1u << lane) - 1u)));
+            if(rank < 8u)
+            {
+                if((chained >> (4u * rank)) & 1u)
+                {
+                    flags |= pomcore::step_explode_due(rec);  /* finishes the loop for this env */
+                    due = false;
+                }
+                else
+                {
+                    turns--;
+                    due = turns > 0 && pomcore::top_bomb_due(rec);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+/* bboard::Step (+ Environment::Step's bookkeeping unless raw) for the env of every lane with `step` set */
+__device__ __forceinline__ void warp_tick(uint8_t* sslice, uint8_t* rec, uint32_t m, bool step, bool raw)
+{
+    const bool pops = step && pomcore::flames_age(rec);       /* TickFlames, step.cpp:15 */
+    warp_pop_due(sslice, rec, pops);
+    int flags = 0;
+    bool due = false;
+    if(step) flags = pomcore::step_body(rec, m, due, false);
+    warp_explode_due(sslice, rec, due, flags);
     if(step)
     {
-        const int f = pomcore::step(rec, m);
-        if(f & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+        if(flags & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
         if(!raw) pomcore::env_post(rec);
     }
 }
@@ -242,7 +349,7 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
     uint8_t* rec = sslice + lane * POM_REC_BYTES;
     /* finished envs are skipped (environment.cpp:125) unless raw; invalid envs always freeze */
     const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
-    env_tick(rec, m, stepped, raw);
+    warp_tick(sslice, rec, m, stepped, raw);
     if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
     uint32_t st_end = active ? rec[R_STATUS] : 0u;
     if(flags & POM_STEP_AUTORESET)
@@ -387,7 +494,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
             }
             steps++;
         }
-        env_tick(rec, m, stepped, false);
+        warp_tick(sslice, rec, m, stepped, false);
         const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, !no_reset, ep_now);
         /* a new episode starts with four new agents */
         if(POLICY && stepped && !no_reset && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID))) agents.clear(ep_now);
@@ -502,7 +609,7 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
     {
         for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = 0u;
     }
-    env_tick(rec, m, stepped, raw);
+    warp_tick(sslice, rec, m, stepped, raw);
     fence_proxy_async();
     __syncwarp();
     if(lane == 0)

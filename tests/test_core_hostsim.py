@@ -58,10 +58,16 @@ def _trace(orc, hs, n, ticks, nact, stress, seed, restart=True, ring_start=None)
     B = orc.zero_state(n)
     for e in range(n):
         assert orc.init_state(B[e:e + 1], seeds[e % len(seeds)]) == 0
-    if stress:
+    if stress == 1:
         B["agents"]["canKick"] = 1
         B["agents"]["maxBombCount"] = 5
         B["agents"]["bombStrength"] = 4
+    elif stress == 2:
+        # mixed: some agents kick, some do not (they step onto bombs and are bounced back), several bombs each
+        rng = np.random.default_rng(seed)
+        B["agents"]["canKick"] = rng.integers(0, 2, (n, 4))
+        B["agents"]["maxBombCount"] = rng.integers(1, 5, (n, 4))
+        B["agents"]["bombStrength"] = rng.integers(1, 4, (n, 4))
     if ring_start is not None:
         # empty rings that start near the end of the physical array: every queue operation wraps
         # (FixedQueue index arithmetic, reference general_test.cpp:41-61 "Index 5 / Index 2")
@@ -106,8 +112,48 @@ def test_core_stress(orc, hs):
     assert _trace(orc, hs, 2048, 250, 6, 1, 2003) > 300000
 
 
+def test_core_mixed_kickers(orc, hs):
+    assert _trace(orc, hs, 2048, 250, 6, 2, 2005) > 300000
+
+
 def test_core_ring_wraparound(orc, hs):
     assert _trace(orc, hs, 2048, 150, 6, 1, 2004, ring_start=15) > 200000
+
+
+@pytest.fixture()
+def hs_rays():
+    """the host build with the tick decomposed the way the warp-cooperative kernels run it (pomcore::step_by_rays):
+    explosions scanned and committed ray by ray (serial machine only when a ray meets a bomb), flame pops arm by arm"""
+    h = HostSim()
+    h.set_by_rays(True)
+    yield h
+    h.set_by_rays(False)
+
+
+def test_core_by_rays_random(orc, hs_rays):
+    assert _trace(orc, hs_rays, 2048, 100, 6, 0, 2011) > 150000
+
+
+def test_core_by_rays_stress(orc, hs_rays):
+    assert _trace(orc, hs_rays, 2048, 250, 6, 1, 2013) > 300000
+
+
+def test_core_by_rays_mixed_kickers(orc, hs_rays):
+    assert _trace(orc, hs_rays, 2048, 250, 6, 2, 2015) > 300000
+
+
+def test_core_by_rays_ring_wraparound(orc, hs_rays):
+    assert _trace(orc, hs_rays, 2048, 150, 6, 1, 2014, ring_start=15) > 200000
+
+
+@pytest.mark.parametrize("fn", scenarios.STEP_SCENARIOS, ids=lambda f: f.__name__)
+def test_scenarios_core_by_rays(orc, fn):
+    b = HostSimBackend(orc)
+    b.h.set_by_rays(True)
+    try:
+        fn(b)
+    finally:
+        b.h.set_by_rays(False)
 
 
 def test_core_rng_matches_oracle(orc, hs):

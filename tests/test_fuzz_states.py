@@ -74,10 +74,13 @@ def mutated_states(orc, seed, n):
     return S
 
 
+@pytest.mark.parametrize("by_rays", [False, True], ids=["one-lane", "by-rays"])
 @pytest.mark.parametrize("seed", [101, 102, 103])
-def test_kernel_body_on_inconsistent_states(orc, seed):
+def test_kernel_body_on_inconsistent_states(orc, seed, by_rays):
+    """by_rays: the tick in the decomposition the warp-cooperative kernels use (ray-parallel explosions, arm-parallel pops)"""
     from hostsim import HostSim
     hs = HostSim()
+    hs.set_by_rays(by_rays)
     S = mutated_states(orc, seed, 3000)
     recs, bad = hs.pack(S, np.zeros(S.shape[0], np.uint8))
     S, recs = S[bad == 0].copy(), recs[bad == 0].copy()
