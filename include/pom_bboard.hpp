@@ -27,6 +27,7 @@
 #include <array>
 #include <cstdint>
 #include <functional>
+#include <iostream>
 #include <memory>
 #include <vector>
 
@@ -98,6 +99,7 @@ struct FixedQueue
 
 struct Position { int x; int y; };
 inline bool operator==(const Position& a, const Position& b) { return a.x == b.x && a.y == b.y; }
+inline std::ostream& operator<<(std::ostream& out, const Position& p) { return out << '(' << p.x << ", " << p.y << ')'; }   /* bboard.hpp:203-207 */
 
 struct AgentInfo
 {
@@ -184,6 +186,9 @@ struct Agent
 void InitBoardItems(State& state, int seed = 0x1337);
 void InitState(State* state, int a0, int a1, int a2, int a3);
 void Step(State* state, Move* moves);
+/* bboard.hpp:677, bboard.cpp:384-401: `timeSteps` ticks of act() x 4 -> Step.  The reference also clears the console,
+ * prints the board and sleeps 80 ms per tick; rendering is out of scope here, the game itself is identical. */
+void StartGame(State* state, Agent* agents[AGENT_COUNT], int timeSteps);
 
 /* agents::SimpleAgent::act for agent `id` on `state`, executed by the device policy code; `memory` is the agent's
  * persistent part, `draw` (0..4) its one random number.  Used by agents::SimpleAgent (pom_agents.hpp). */
@@ -283,6 +288,14 @@ private:
     int viewRange = -1;
 };
 
+}
+
+namespace std
+{
+template<> struct hash<bboard::Position>                              /* bboard.hpp:694-703 */
+{
+    size_t operator()(const bboard::Position& p) const { return hash<int>()(p.x + p.y * bboard::BOARD_SIZE); }
+};
 }
 
 #endif

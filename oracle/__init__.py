@@ -185,8 +185,8 @@ class Restatement:
 class Reference:
     """oracle/_ref/libpomref.so: the unmodified reference behind oracle/ref_shim.cpp."""
 
-    def __init__(self, flavour=""):
-        path = os.path.join(HERE, "_ref", "libpomref%s.so" % flavour)
+    def __init__(self, flavour="", stem="libpomref"):
+        path = os.path.join(HERE, "_ref", "%s%s.so" % (stem, flavour))
         if not os.path.exists(path) and os.path.exists("/root/reference/src/bboard/step.cpp"):
             build()
         if not os.path.exists(path):
@@ -329,6 +329,23 @@ def reference(flavour=""):
     if k not in _cache:
         _cache[k] = Reference(flavour)
     return _cache[k]
+
+
+def dropin():
+    """oracle/_ref/libpomdrop.so: the same shim + the unmodified reference simple_agent.cpp compiled against THIS repo's
+    include/ and linked with the product's host layer.  Host-only entry points (agents, strategy, util, field setters)
+    work anywhere; the stepping ones run on the GPU through the bboard mirror."""
+    if "drop" not in _cache:
+        _cache["drop"] = Reference(stem="libpomdrop")
+    return _cache["drop"]
+
+
+def have_dropin():
+    try:
+        dropin()
+        return True
+    except (FileNotFoundError, OSError):
+        return False
 
 
 def have_reference():

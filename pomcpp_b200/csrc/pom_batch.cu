@@ -56,6 +56,10 @@ struct pom_batch {
     uint32_t  n_templates = 0;
     uint32_t  max_ticks = 0;
     int       tpb = 128;
+    int       n_sms = 1;
+    int       ws_nw = 20;
+    uint32_t  attr_ws = 0;
+    int       step_kernel = 0;                 /* 0 = k_step_ws (persistent, warp-specialised), 1 = k_step (one CTA per tile); POM_STEP_KERNEL=tile */
     uint8_t*  recs = nullptr;
     uint8_t*  templates = nullptr;
     uint32_t* episodes = nullptr;
@@ -212,10 +216,31 @@ int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, c
     return POM_OK;
 }
 
+/* geometry of the persistent per-tick kernel (k_step_ws): compute warps and slice buffers per CTA (= per SM) */
+constexpr int WS_NW = 20, WS_NBUF = 24;
+
+template<int NW>
+int launch_step_ws(pom_batch* b, const pomk::BatchParams& P, const uint8_t* moves_dev, uint32_t flags, uint8_t* status_dev, cudaStream_t on)
+{
+    typedef pomk::RingScratch<WS_NBUF> R;
+    if(!(b->attr_ws & (1u << NW)))
+    {
+        CK(cudaFuncSetAttribute(pomk::k_step_ws<NW, WS_NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(R::BYTES)));
+        b->attr_ws |= 1u << NW;
+    }
+    const uint64_t n_slices = (P.n_envs + 31) / 32;
+    const unsigned grid = unsigned(n_slices < uint64_t(b->n_sms) ? n_slices : uint64_t(b->n_sms));
+    const uint32_t moves_bulk = (reinterpret_cast<uintptr_t>(moves_dev) & 15u) == 0u ? 1u : 0u;   /* TMA needs 16-byte alignment */
+    pomk::k_step_ws<NW, WS_NBUF><<<grid, (NW + 1) * 32, R::BYTES, on ? on : b->stream>>>(
+        P, reinterpret_cast<const uint32_t*>(moves_dev), flags, status_dev, moves_bulk);
+    b->launches++;
+    CK(cudaGetLastError());
+    return POM_OK;
+}
+
 template<int TPB>
 int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* status_dev, uint64_t first = 0, uint64_t count = 0, cudaStream_t on = nullptr)
 {
-    { int rc = set_smem(b, ATTR_STEP, pomk::k_step<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     /* envs [first, first + count) only (first is a multiple of TPB); count == 0 means the whole batch */
     pomk::BatchParams P = b->params();
     if(count)
@@ -224,6 +249,19 @@ int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t*
         moves_dev += 4 * first;
         if(status_dev) status_dev += first;
     }
+    if(b->step_kernel == 0)
+    {
+        /* persistent, warp-specialised: one CTA per SM; POM_WS_NW picks the number of compute warps (experiments) */
+        switch(b->ws_nw)
+        {
+        case 12: return launch_step_ws<12>(b, P, moves_dev, flags, status_dev, on);
+        case 14: return launch_step_ws<14>(b, P, moves_dev, flags, status_dev, on);
+        case 16: return launch_step_ws<16>(b, P, moves_dev, flags, status_dev, on);
+        case 18: return launch_step_ws<18>(b, P, moves_dev, flags, status_dev, on);
+        default: return launch_step_ws<WS_NW>(b, P, moves_dev, flags, status_dev, on);
+        }
+    }
+    { int rc = set_smem(b, ATTR_STEP, pomk::k_step<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     const unsigned grid = unsigned((P.n_envs + TPB - 1) / TPB);
     pomk::k_step<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, on ? on : b->stream>>>(P, reinterpret_cast<const uint32_t*>(moves_dev), flags, status_dev);
     b->launches++;
@@ -325,6 +363,10 @@ int pom_batch_init(pom_batch** out, int device, uint64_t n_envs, const pom_init_
     b->env_offset = desc->env_offset;
     b->n_templates = desc->n_templates;
     b->max_ticks = desc->max_ticks;
+    cudaDeviceGetAttribute(&b->n_sms, cudaDevAttrMultiProcessorCount, device);
+    if(b->n_sms < 1) b->n_sms = 1;
+    if(const char* e = std::getenv("POM_STEP_KERNEL")) b->step_kernel = std::strcmp(e, "tile") == 0 ? 1 : 0;
+    if(const char* e = std::getenv("POM_WS_NW")) b->ws_nw = std::atoi(e);
     if(const char* e = std::getenv("POM_TPB"))
     {
         const int t = std::atoi(e);

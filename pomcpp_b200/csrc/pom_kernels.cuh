@@ -69,6 +69,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     asm volatile(
@@ -365,6 +369,109 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
         bulk_s2g(gslice, sslice, SLICE_BYTES);
         bulk_wait_read_all();                                 /* smem must stay valid until it has been read */
     }
+}
+
+/* ---------------------------------------------------------------- K1, persistent form: k_step_ws */
+/* One CTA per SM for the whole launch.  Shared memory is a ring of NBUF slice buffers (32 records + the slice's 32 x 4
+ * move bytes each); warp NW is the PRODUCER: it keeps every free buffer filled with the CTA's next slice (TMA bulk load,
+ * completion on the buffer's `full` mbarrier).  Warps 0..NW-1 COMPUTE: a warp takes the next ticket (shared-memory
+ * counter), waits for that buffer to be full, runs the tick on it in place, bulk-stores it and hands the buffer back
+ * (`empty` mbarrier) once the store has read it.  NBUF > NW, so NBUF - NW loads are always in flight ahead of the
+ * compute warps: they never wait for HBM, and nothing is relaunched or drained between slices.
+ * With k_step every warp did load -> tick -> store itself; once the tick got cheap (vectorised movement, shared-out
+ * explosions) ncu showed 4 long-scoreboard stall cycles per issue and 45 % issue utilisation: the 24 resident warps
+ * spent 40 % of their time waiting for their own loads (profiles/k_step_ncu_summary_r2b.json).
+ * Slices are dealt round-robin over the CTAs (slice = blockIdx.x + ticket * gridDim.x): at any time the CTAs work on a
+ * window of neighbouring slices, and a warp knows its slice from its ticket alone. */
+template<int NBUF> struct RingScratch {
+    static constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
+    static constexpr uint32_t SLOT = SLICE_BYTES + 128;
+    static constexpr uint32_t OFF_FULL = NBUF * SLOT;
+    static constexpr uint32_t OFF_EMPTY = OFF_FULL + 8 * NBUF;
+    static constexpr uint32_t OFF_TICKET = OFF_EMPTY + 8 * NBUF;
+    static constexpr uint32_t BYTES = OFF_TICKET + 16;
+};
+
+template<int NW, int NBUF>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, const uint32_t* __restrict__ moves, uint32_t flags,
+                                                               uint8_t* __restrict__ status_out, uint32_t moves_bulk)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    typedef RingScratch<NBUF> R;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + R::OFF_FULL);
+    uint64_t* empty = reinterpret_cast<uint64_t*>(smem + R::OFF_EMPTY);
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(smem + R::OFF_TICKET);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint64_t n_slices = (P.n_envs + 31u) / 32u;
+    /* this CTA's slices: blockIdx.x, blockIdx.x + gridDim.x, ... */
+    const uint32_t T = blockIdx.x < n_slices ? uint32_t((n_slices - blockIdx.x + gridDim.x - 1u) / gridDim.x) : 0u;
+    if(threadIdx.x == 0)
+    {
+        for(int b = 0; b < NBUF; b++) { mbar_init(full + b, 1); mbar_init(empty + b, 1); }
+        *ticket = 0u;
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if(warp == NW)
+    {
+        if(lane != 0) return;
+        for(uint32_t t = 0; t < T; t++)
+        {
+            const uint32_t b = t % NBUF, use = t / NBUF;
+            if(use) mbar_wait(empty + b, (use - 1u) & 1u);               /* the buffer's previous slice has been stored */
+            const uint64_t s = blockIdx.x + uint64_t(t) * gridDim.x;
+            const bool whole = (s + 1u) * 32u <= P.n_envs;                /* the last slice's moves may end early: per-lane loads */
+            const uint32_t mbytes = (moves_bulk && whole) ? 128u : 0u;
+            mbar_expect_tx(full + b, R::SLICE_BYTES + mbytes);
+            bulk_g2s(smem + b * R::SLOT, P.recs + s * R::SLICE_BYTES, R::SLICE_BYTES, full + b);
+            if(mbytes) bulk_g2s(smem + b * R::SLOT + R::SLICE_BYTES, moves + s * 32u, 128u, full + b);
+        }
+        return;
+    }
+
+    const bool raw = (flags & POM_STEP_RAW) != 0u;
+    uint32_t stepped_total = 0u;
+    for(;;)
+    {
+        uint32_t t = 0u;
+        if(lane == 0) t = atomicAdd(ticket, 1u);
+        t = __shfl_sync(FULL_WARP, t, 0);
+        if(t >= T) break;
+        const uint32_t b = t % NBUF, use = t / NBUF;
+        const uint64_t s = blockIdx.x + uint64_t(t) * gridDim.x;
+        const uint64_t env = s * 32u + lane;
+        const bool active = env < P.n_envs;
+        const bool whole = (s + 1u) * 32u <= P.n_envs;
+        uint8_t* sslice = smem + b * R::SLOT;
+        uint32_t m = 0u;
+        if(!(moves_bulk && whole) && active) m = __ldg(moves + env);      /* overlaps the wait below */
+        uint32_t ep_now = (active && (flags & POM_STEP_AUTORESET)) ? P.episodes[env] : 0u;
+        mbar_wait(full + b, use & 1u);
+        if(moves_bulk && whole) m = reinterpret_cast<const uint32_t*>(sslice + R::SLICE_BYTES)[lane];
+
+        uint8_t* rec = sslice + lane * POM_REC_BYTES;
+        const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
+        warp_tick(sslice, rec, m, stepped, raw);
+        stepped_total += stepped ? 1u : 0u;
+        uint32_t st_end = active ? rec[R_STATUS] : 0u;
+        if(flags & POM_STEP_AUTORESET)
+        {
+            const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, true, ep_now);
+            if(active && stepped) st_end = st;
+        }
+        if(status_out && active) status_out[env] = uint8_t(st_end);
+        fence_proxy_async();
+        __syncwarp();
+        if(lane == 0)
+        {
+            bulk_s2g(P.recs + s * R::SLICE_BYTES, sslice, R::SLICE_BYTES);
+            bulk_wait_read_all();
+            mbar_arrive(empty + b);
+        }
+        __syncwarp();
+    }
+    if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped_total);
 }
 
 /* ---------------------------------------------------------------- K7: agent memories of the SimpleAgent policy */

@@ -70,7 +70,19 @@ void apply(State* s, int op, int a0 = 0, int a1 = 0, int a2 = 0)
 int SimpleActOnDevice(const State* s, int id, pom_simple_agent* memory, int draw)
 {
     pom_batch* h = scratch.get(1);
-    check(pom_batch_upload(h, 0, 1, reinterpret_cast<const pom_state*>(s), nullptr), "pom_batch_upload");
+    /* A fogged State (BatchEnvironment::SetViewRange, pom_batch_observe) carries x = y = -1 for agents out of sight or
+     * dead, which the packed record cannot hold.  Such an agent is not exposed to the observer (bboard.hpp:218-226), so
+     * for the policy it is absent: marked dead at (0, 0), where nothing of the policy looks at it. */
+    State seen = *s;
+    for(int a = 0; a < AGENT_COUNT; a++)
+    {
+        AgentInfo& g = seen.agents[a];
+        if(a != id && (g.x < 0 || g.y < 0 || g.x >= BOARD_SIZE || g.y >= BOARD_SIZE))
+        {
+            g.x = 0; g.y = 0; g.dead = true;
+        }
+    }
+    check(pom_batch_upload(h, 0, 1, reinterpret_cast<const pom_state*>(&seen), nullptr), "pom_batch_upload");
     pom_simple_agent four[4];
     std::memset(four, 0, sizeof(four));
     four[id] = *memory;
@@ -202,6 +214,18 @@ void StepBatch(State* states, const Move* moves, size_t n)
 }
 
 void Step(State* state, Move* moves) { StepBatch(state, moves, 1); }
+
+/* bboard.cpp:384-401 without the console output and the 80 ms sleep: every agent acts on the shared State (dead ones
+ * too, as in the reference), then one Step; no early exit */
+void StartGame(State* state, Agent* agents[AGENT_COUNT], int timeSteps)
+{
+    Move moves[AGENT_COUNT];
+    for(int t = 0; t < timeSteps; t++)
+    {
+        for(int a = 0; a < AGENT_COUNT; a++) moves[a] = agents[a]->act(state);
+        Step(state, moves);
+    }
+}
 
 /* ---- Environment (reference environment.cpp:48-213) ---- */
 Environment::Environment() : state(new State()), agents{{nullptr, nullptr, nullptr, nullptr}} {}

@@ -12,6 +12,8 @@
 
 #include "bboard.hpp"
 #include "pom_agents.hpp"
+#include "strategy.hpp"
+#include "step_utility.hpp"
 
 using namespace bboard;
 
@@ -162,7 +164,7 @@ int main()
             }
         }
         REQUIRE(env.GetState().timeStep > 0);
-        REQUIRE(a[0].memory.rp_count > 0);              /* the agents remember where they went */
+        REQUIRE(a[0].recentPositions.count > 0);              /* the agents remember where they went */
     }
     {   /* BatchEnvironment with device-side SimpleAgent opponents: per tick (agent 0 host-controlled) and fused */
         BatchEnvironment be(256, 0, 0, 32, 0x1337, 800);
@@ -211,6 +213,52 @@ int main()
         REQUIRE(peek.hidden == 64 * 4 * 3);                   /* the other corners are 10 cells away */
         std::vector<State> all = be.Observe(0, 10);
         REQUIRE(all[0].agents[2].x == 10 && all[0].agents[2].y == 10);
+    }
+    {   /* fog of war + SimpleAgent (runs on the device): hidden agents (x = y = -1) are simply absent for the policy */
+        agents::SimpleAgent a[4] = {agents::SimpleAgent(21), agents::SimpleAgent(22), agents::SimpleAgent(23), agents::SimpleAgent(24)};
+        BatchEnvironment be(4, 0, 0, 4);
+        be.SetViewRange(4);
+        size_t running = 4;
+        for(int t = 0; t < 25; t++) running = be.Step({&a[0], &a[1], &a[2], &a[3]});
+        REQUIRE(running <= 4);
+        REQUIRE(be.States()[0].timeStep > 0);
+    }
+    {   /* bboard::StartGame(State*, Agent*[], int) (bboard.hpp:677): act x 4 -> Step, `timeSteps` times */
+        auto s = std::make_unique<State>();
+        InitState(s.get(), 0, 1, 2, 3);
+        agents::HarmlessAgent h[4] = {agents::HarmlessAgent(1), agents::HarmlessAgent(2), agents::HarmlessAgent(3), agents::HarmlessAgent(4)};
+        Agent* four[4] = {&h[0], &h[1], &h[2], &h[3]};
+        for(int i = 0; i < 4; i++) four[i]->id = i;
+        StartGame(s.get(), four, 12);
+        REQUIRE(s->aliveAgents == 4);
+        int onBoard = 0;
+        for(int i = 0; i < 4; i++) onBoard += s->board[s->agents[i].y][s->agents[i].x] == Item::AGENT0 + i;
+        REQUIRE(onBoard == 4);
+    }
+    {   /* the host helpers of include/strategy.hpp / step_utility.hpp, as agent code calls them (strategy_test.cpp:16-37,
+         * step_utility_test.cpp): known answers on a small fixture */
+        auto s = std::make_unique<State>();
+        s->PutAgentsInCorners(0, 1, 2, 3);
+        s->PutItem(1, 0, Item::RIGID);
+        strategy::RMap r;
+        strategy::FillRMap(*s, r, 0);
+        REQUIRE(r.GetDistance(0, 1) == 1 && r.GetDistance(1, 1) == 2 && r.GetDistance(1, 0) == 0);
+        REQUIRE(r.GetDistance(10, 10) == 20);                 /* paths end AT agent cells */
+        REQUIRE(strategy::MoveTowardsPosition(r, {3, 1}) == Move::DOWN);
+        REQUIRE(strategy::IsAdjacentEnemy(*s, 0, 9) == false && strategy::IsAdjacentEnemy(*s, 0, 10) == true);
+        s->PlantBomb(0, 3, 1, true);
+        REQUIRE(strategy::IsInDanger(*s, 0, 2) == BOMB_LIFETIME && strategy::IsInDanger(*s, 1, 2) == 0);
+        Position d[4];
+        Move m[4] = {Move::RIGHT, Move::LEFT, Move::IDLE, Move::IDLE};
+        s->PutAgent(4, 4, 0); s->PutAgent(5, 4, 1);
+        util::FillDestPos(s.get(), m, d);
+        REQUIRE((d[0] == Position{5, 4}) && (d[1] == Position{4, 4}));
+        util::FixSwitchMove(s.get(), d);
+        REQUIRE((d[0] == Position{4, 4}) && (d[1] == Position{5, 4}));
+        int dep[4] = {-1, -1, -1, -1}, chain[4] = {-1, -1, -1, -1};
+        m[1] = Move::IDLE;
+        util::FillDestPos(s.get(), m, d);
+        REQUIRE(util::ResolveDependencies(s.get(), d, dep, chain) == 3 && dep[1] == 0 && chain[0] == 1);
     }
     std::printf(failures ? "pom_selftest: %d FAILED\n" : "pom_selftest: all passed\n", failures);
     return failures ? 1 : 0;
