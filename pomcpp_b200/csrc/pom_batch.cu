@@ -88,7 +88,8 @@ struct pom_batch {
     {
         pomk::BatchParams P;
         P.recs = recs; P.n_envs = n_envs; P.env_offset = env_offset; P.templates = templates;
-        P.n_templates = n_templates; P.max_ticks = max_ticks; P.episodes = episodes; P.stats = stats;
+        P.n_templates = n_templates; P.max_ticks = max_ticks;
+        P.tmpl_mask = (n_templates & (n_templates - 1u)) == 0u ? n_templates - 1u : 0u; P.episodes = episodes; P.stats = stats;
         P.policy = policy; P.policy_stride = n_alloc;
         return P;
     }

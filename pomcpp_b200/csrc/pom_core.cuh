@@ -1157,8 +1157,8 @@ POM_HD void pop_flame_ring(uint8_t* r)                               /* PopElem,
  * The rays of one spawn touch disjoint cells, so they only interact through a chained explosion
  * (SpawnFlameItem finds a bomb queue entry on the cell, :30-39): the nested spawn writes cells that later
  * rays of the parent - or rays of a grand-child - may cross.  So every ray is first SCANNED without writing
- * (ray_scan); when no ray meets a bomb the four rays are COMMITTED independently (ray_commit) and one lane
- * does the spawn's prologue, the kills and PopBomb (top_bomb_commit); otherwise nothing has been written and
+ * (ray_scan); when no ray meets a bomb the four rays are COMMITTED independently (ray_commit) and three lanes
+ * share the spawn's prologue, the kills and PopBomb (top_bomb_commit_part); otherwise nothing has been written and
  * the explosion runs on the serial machine (`explode`).  In the bench workload 0.2 % of the explosions chain;
  * in the kick/bomb stress regime most do.
  *
@@ -1207,38 +1207,52 @@ POM_HD void ray_commit(uint8_t* r, uint32_t ci, int stride, uint32_t plan, uint3
     if(plan & (1u << RAY_WOOD_SHIFT)) r[R_BOARD + ci] = uint8_t(code | ((plan >> (RAY_WOOD_SHIFT + 1)) & 3u));
 }
 
-/* the part of a chain-free ExplodeTopBomb that is not a ray: SpawnFlame's prologue (:200-218), the kills of the
- * whole spawn (State::Kill, bboard.hpp:474-481; `ray_kills` = the four plans OR-ed) and PopBomb (:93-97).
- * `slot` = the flame-ring slot the spawn takes (the same value every ray was committed with). */
-POM_HD void top_bomb_commit(uint8_t* r, uint32_t ray_kills, int& flags)
+/* The part of a chain-free ExplodeTopBomb that is not a ray, in three pieces that touch disjoint fields of the record,
+ * so that three lanes of the group can run them at once:
+ *   part 0  SpawnFlame's prologue (bboard.cpp:200-208): the flame-queue entry
+ *   part 1  the origin cell (:210-217) and the kills of the whole spawn (State::Kill, bboard.hpp:474-481;
+ *           `ray_kills` = the four ray plans OR-ed)
+ *   part 2  PopBomb (:93-97)
+ * `c` = the top bomb word and `slot` = the flame-ring slot the spawn takes, both read before any part ran.
+ * Returns true when the flame ring was already full (F_FLAME_OVF). */
+POM_HD bool top_bomb_commit_part(uint8_t* r, uint32_t c, uint32_t ray_kills, uint32_t part, uint32_t slot)
 {
-    const uint32_t c = bomb_slot(r, r[R_BINDEX]);
     const uint32_t p = c & 0xFFu;
-    const uint32_t fc = r[R_FCOUNT];
-    if(fc >= 20u) flags |= F_FLAME_OVF;
-    const uint32_t slot = ring20(r[R_FINDEX] + fc);
-    r[R_FPOS + slot] = uint8_t(p);
-    r[R_FSTR + slot] = uint8_t((c >> 12) & 15u);
-    r[R_FTIME + slot] = uint8_t(POM_FLAME_LIFETIME);
-    r[R_FCOUNT] = uint8_t(fc + 1u);
-    uint8_t* cell = r + R_BOARD + cell_of(p);
-    uint32_t kills = (ray_kills & RAY_KILL_MASK) >> RAY_KILL_SHIFT;
-    const uint32_t co = *cell;
-    if(c_is_agent(co)) kills |= 1u << (co - uint32_t(C_AGENT0));
-    *cell = uint8_t(C_FLAME | (slot << 2));
-    uint32_t* aw = reinterpret_cast<uint32_t*>(r + R_APOS);
-    if(kills)
+    bool overflow = false;
+    if(part == 0u)
     {
-        /* bit a of kills -> AF_DEAD in byte a; agents already dead are not counted twice */
-        const uint32_t deadBits = ((kills & 1u) << 1) | ((kills & 2u) << 8) | ((kills & 4u) << 15) | ((kills & 8u) << 22);
-        const uint32_t fresh = deadBits & ~aw[4];
-        aw[4] |= fresh;
-        r[R_ALIVE] = uint8_t(r[R_ALIVE] - popcount32(fresh));
+        const uint32_t fc = r[R_FCOUNT];
+        overflow = fc >= 20u;
+        r[R_FPOS + slot] = uint8_t(p);
+        r[R_FSTR + slot] = uint8_t((c >> 12) & 15u);
+        r[R_FTIME + slot] = uint8_t(POM_FLAME_LIFETIME);
+        r[R_FCOUNT] = uint8_t(fc + 1u);
     }
-    const int id = int((c >> 8) & 3u);                                /* PopBomb */
-    r[R_ABCNT + id] = uint8_t(r[R_ABCNT + id] - 1);
-    r[R_BINDEX] = uint8_t(ring_next(r[R_BINDEX]));
-    r[R_BCOUNT] = uint8_t(r[R_BCOUNT] - 1);
+    else if(part == 1u)
+    {
+        uint8_t* cell = r + R_BOARD + cell_of(p);
+        uint32_t kills = (ray_kills & RAY_KILL_MASK) >> RAY_KILL_SHIFT;
+        const uint32_t co = *cell;
+        if(c_is_agent(co)) kills |= 1u << (co - uint32_t(C_AGENT0));
+        *cell = uint8_t(C_FLAME | (slot << 2));
+        if(kills)
+        {
+            /* bit a of kills -> AF_DEAD in byte a; agents already dead are not counted twice */
+            uint32_t* aw = reinterpret_cast<uint32_t*>(r + R_APOS);
+            const uint32_t deadBits = ((kills & 1u) << 1) | ((kills & 2u) << 8) | ((kills & 4u) << 15) | ((kills & 8u) << 22);
+            const uint32_t fresh = deadBits & ~aw[4];
+            aw[4] |= fresh;
+            r[R_ALIVE] = uint8_t(r[R_ALIVE] - popcount32(fresh));
+        }
+    }
+    else if(part == 2u)
+    {
+        const int id = int((c >> 8) & 3u);
+        r[R_ABCNT + id] = uint8_t(r[R_ABCNT + id] - 1);
+        r[R_BINDEX] = uint8_t(ring_next(r[R_BINDEX]));
+        r[R_BCOUNT] = uint8_t(r[R_BCOUNT] - 1);
+    }
+    return overflow;
 }
 
 /* whether TickBombs' explosion loop (step_utility.cpp:231-244) has another turn: bombs[0] has timed out */
@@ -1264,8 +1278,11 @@ POM_HD bool explode_top_by_rays(uint8_t* r, int& flags)
         all |= plan[d];
     }
     if(all & RAY_CHAIN) return false;
-    for(uint32_t d = 0; d < 4; d++) ray_commit(r, ci0, stride[d], plan[d], slot);
-    top_bomb_commit(r, all, flags);
+    for(uint32_t d = 0; d < 4; d++)
+    {
+        ray_commit(r, ci0, stride[d], plan[d], slot);
+        if(top_bomb_commit_part(r, c, all, d, slot)) flags |= F_FLAME_OVF;
+    }
     return true;
 }
 

@@ -41,6 +41,7 @@ struct BatchParams {
     uint64_t            env_offset;   /* global index of env 0                                   */
     const uint8_t*      templates;    /* n_templates packed records                              */
     uint32_t            n_templates;
+    uint32_t            tmpl_mask;    /* n_templates - 1 when that is a power of two (template index without a division), else 0 */
     uint32_t            max_ticks;
     uint32_t*           episodes;     /* per-env number of finished episodes                     */
     unsigned long long* stats;        /* POM_STATS_WORDS counters                                */
@@ -110,33 +111,60 @@ __device__ __forceinline__ void warp_add(unsigned long long* dst, uint32_t v)
     if((threadIdx.x & 31u) == 0u && s) atomicAdd(dst, (unsigned long long)s);
 }
 
-/* called by ALL 32 lanes; `fin` = this lane's env finished an episode.  Counters of at most 32 per warp
- * are packed four to a word so that three warp reductions serve all nine counters. */
-__device__ __forceinline__ void account_episodes(unsigned long long* stats, bool fin, uint32_t status, uint32_t len)
+/* Episode statistics are gathered per lane in registers (16-bit counters, two to a word) and added to the global
+ * counters ONCE per warp and launch (acc_flush): one warp reduction and one atomicAdd per counter, instead of three
+ * reductions and up to nine atomics in every tick in which some env of the warp finished (1.3 M warp-instructions per
+ * 1 Mi-env tick, profiles/k_step_by_function_r2.txt). */
+struct EpisodeAcc {
+    uint32_t fin_draw = 0u;      /* episodes | draws << 16      */
+    uint32_t trunc_abort = 0u;   /* truncated | aborted << 16   */
+    uint32_t win01 = 0u, win23 = 0u;
+    uint32_t len = 0u;           /* sum of episode lengths      */
+    uint32_t steps = 0u;         /* env-steps executed          */
+    uint32_t pending = 0u;       /* episodes since the last flush (16-bit counters: flush before 65536) */
+};
+
+__device__ __forceinline__ void acc_add(EpisodeAcc& A, bool fin, uint32_t status, uint32_t len)
 {
+    if(!fin) return;
     /* exactly one outcome per episode: DONE (won | draw) > TRUNCATED > aborted (left the reference's domain) */
-    const bool done = fin && (status & POM_STATUS_DONE);
+    const bool done = (status & POM_STATUS_DONE) != 0u;
     const bool draw = done && (status & POM_STATUS_DRAW);
-    const bool trunc = fin && !done && (status & POM_STATUS_TRUNCATED);
-    const bool won = done && !draw;
-    const bool aborted = fin && !done && !trunc;
+    const bool trunc = !done && (status & POM_STATUS_TRUNCATED);
     const uint32_t w = (status & POM_STATUS_WINNER_MASK) >> POM_STATUS_WINNER_SHIFT;
-    const uint32_t a = (fin ? 1u : 0u) | (draw ? 1u << 8 : 0u) | (trunc ? 1u << 16 : 0u) | (aborted ? 1u << 24 : 0u);
-    const uint32_t b = won ? 1u << (8u * w) : 0u;
-    const uint32_t sa = __reduce_add_sync(0xFFFFFFFFu, a);
-    const uint32_t sb = __reduce_add_sync(0xFFFFFFFFu, b);
-    const uint32_t sl = __reduce_add_sync(0xFFFFFFFFu, fin ? len : 0u);
-    if((threadIdx.x & 31u) == 0u)
+    A.fin_draw += 1u + (draw ? 0x10000u : 0u);
+    A.trunc_abort += (trunc ? 1u : 0u) + ((!done && !trunc) ? 0x10000u : 0u);
+    if(done && !draw)
     {
-        atomicAdd(stats + ST_EPISODES, (unsigned long long)(sa & 0xFFu));
-        if((sa >> 8) & 0xFFu) atomicAdd(stats + ST_DRAWS, (unsigned long long)((sa >> 8) & 0xFFu));
-        if((sa >> 16) & 0xFFu) atomicAdd(stats + ST_TRUNC, (unsigned long long)((sa >> 16) & 0xFFu));
-        if(sa >> 24) atomicAdd(stats + ST_INVALID, (unsigned long long)(sa >> 24));
-        atomicAdd(stats + ST_SUMLEN, (unsigned long long)sl);
-#pragma unroll
-        for(uint32_t k = 0; k < 4; k++)
-            if((sb >> (8u * k)) & 0xFFu) atomicAdd(stats + ST_WIN0 + k, (unsigned long long)((sb >> (8u * k)) & 0xFFu));
+        const uint32_t inc = (w & 1u) ? 0x10000u : 1u;
+        if(w & 2u) A.win23 += inc; else A.win01 += inc;
     }
+    A.len += len;
+    A.pending++;
+}
+
+/* called by ALL 32 lanes */
+__device__ __forceinline__ void acc_flush(unsigned long long* stats, EpisodeAcc& A, bool count_steps)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    if(__reduce_or_sync(0xFFFFFFFFu, A.pending))
+    {
+        const uint32_t v[9] = { A.fin_draw & 0xFFFFu, A.win01 & 0xFFFFu, A.win01 >> 16, A.win23 & 0xFFFFu, A.win23 >> 16,
+                                A.fin_draw >> 16, A.trunc_abort & 0xFFFFu, A.len, A.trunc_abort >> 16 };
+        /* ST_EPISODES = 1, ST_WIN0..3 = 2..5, ST_DRAWS = 6, ST_TRUNC = 7, ST_SUMLEN = 8, ST_INVALID = 9 */
+#pragma unroll
+        for(int k = 0; k < 9; k++)
+        {
+            const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, v[k]);
+            if(lane == 0u && sum) atomicAdd(stats + 1 + k, (unsigned long long)sum);
+        }
+    }
+    if(count_steps)
+    {
+        const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, A.steps);
+        if(lane == 0u && sum) atomicAdd(stats + ST_STEPS, (unsigned long long)sum);
+    }
+    A = EpisodeAcc();
 }
 
 /* end-of-tick episode handling shared by K1 (auto-reset flag) and K2: truncate, count, reset.
@@ -156,7 +184,7 @@ __device__ __forceinline__ void cp_async_wait_all()
  * the reset path does not expose a dependent global load.  Returns the env's end-of-tick status byte as it was
  * BEFORE a reset (what an RL loop needs to see: done / winner / truncated of the episode that just ended). */
 __device__ __forceinline__ uint32_t finish_and_reset(uint8_t* warp_recs, uint8_t* rec, const BatchParams& P, uint64_t env, bool active, bool do_reset,
-                                                 uint32_t& ep_now)
+                                                 uint32_t& ep_now, EpisodeAcc& acc)
 {
     uint32_t st = active ? rec[R_STATUS] : 0u;
     const uint32_t len = active ? *reinterpret_cast<const uint16_t*>(rec + R_TIME) : 0u;
@@ -164,7 +192,7 @@ __device__ __forceinline__ uint32_t finish_and_reset(uint8_t* warp_recs, uint8_t
     const bool fin = active && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID)) != 0u;
     uint32_t pending = __ballot_sync(0xFFFFFFFFu, fin);
     if(pending == 0u) return st;
-    account_episodes(P.stats, fin, st, len);
+    acc_add(acc, fin, st, len);
     if(!do_reset)
     {
         if(fin) rec[R_STATUS] = uint8_t(st);
@@ -177,7 +205,7 @@ __device__ __forceinline__ uint32_t finish_and_reset(uint8_t* warp_recs, uint8_t
         P.episodes[env] = ep;
         /* (env_offset + env + ep) % n_templates without 64-bit division on the common path */
         const uint64_t g = P.env_offset + env + ep;
-        tmpl = g < 0xFFFFFFFFull ? uint32_t(g) % P.n_templates : uint32_t(g % P.n_templates);
+        tmpl = P.tmpl_mask ? (uint32_t(g) & P.tmpl_mask) : (g < 0xFFFFFFFFull ? uint32_t(g) % P.n_templates : uint32_t(g % P.n_templates));
     }
     const uint32_t lane = threadIdx.x & 31u;
     while(pending)
@@ -206,18 +234,22 @@ __device__ __forceinline__ uint32_t finish_and_reset(uint8_t* warp_recs, uint8_t
  * four rays at once, the kills and the chain test are combined with __shfl_xor_sync inside the group. */
 constexpr uint32_t FULL_WARP = 0xFFFFFFFFu;
 
-/* lane index of the n-th (0-based, n < 8) set bit of mask; 32 if there is none */
-__device__ __forceinline__ uint32_t nth_set_lane(uint32_t mask, uint32_t n)
+/* Which env does group `quad` serve this round?  The due lanes write their lane index into an 8-byte list in shared
+ * memory at the position of their rank among the due lanes (ranks 8.. wait for the next round); group q reads entry q.
+ * Returns 32 when the group has nothing to do.  `wlist`: 8 bytes of shared memory owned by this warp. */
+__device__ __forceinline__ uint32_t due_env_of_group(uint8_t* wlist, uint32_t mask, bool due, uint32_t lane, uint32_t quad, uint32_t& rank)
 {
-#pragma unroll
-    for(uint32_t i = 0; i < 7; i++)
-        if(i < n) mask &= mask - 1u;
-    return mask ? uint32_t(__ffs(int(mask))) - 1u : 32u;
+    rank = uint32_t(__popc(mask & ((1u << lane) - 1u)));
+    if(due && rank < 8u) wlist[rank] = uint8_t(lane);
+    __syncwarp();
+    const uint32_t e = quad < uint32_t(__popc(mask)) ? wlist[quad] : 32u;
+    __syncwarp();                                             /* the list is rewritten next round */
+    return e;
 }
 
 /* the pop loop of util::TickFlames (step_utility.cpp:216-222); `due` = this lane's front flame has expired.
  * Called by all 32 lanes. */
-__device__ __forceinline__ void warp_pop_due(uint8_t* sslice, const uint8_t* rec, bool due)
+__device__ __forceinline__ void warp_pop_due(uint8_t* sslice, const uint8_t* rec, bool due, uint8_t* wlist)
 {
     const uint32_t lane = threadIdx.x & 31u, quad = lane >> 2, arm = lane & 3u;
     int turns = due ? int(rec[R_FCOUNT]) : 0;                 /* flameCount turns at most */
@@ -225,13 +257,14 @@ __device__ __forceinline__ void warp_pop_due(uint8_t* sslice, const uint8_t* rec
     {
         const uint32_t mask = __ballot_sync(FULL_WARP, due);
         if(mask == 0u) break;
-        const uint32_t e = nth_set_lane(mask, quad);
+        uint32_t rank;
+        const uint32_t e = due_env_of_group(wlist, mask, due, lane, quad, rank);
         uint8_t* r = sslice + e * POM_REC_BYTES;
         if(e < 32u) pomcore::pop_flame_arm(r, arm);
         __syncwarp();                                         /* every arm has read the front entry */
         if(e < 32u && arm == 0u) pomcore::pop_flame_ring(r);
         __syncwarp();
-        if(due && __popc(mask & ((1u << lane) - 1u)) < 8)
+        if(due && rank < 8u)
         {
             turns--;
             due = turns > 0 && rec[R_FTIME + rec[R_FINDEX]] == 0;
@@ -242,7 +275,7 @@ __device__ __forceinline__ void warp_pop_due(uint8_t* sslice, const uint8_t* rec
 /* the explosion loop of util::TickBombs (step_utility.cpp:231-244); `due` = this lane's bombs[0] has timed out.
  * Called by all 32 lanes.  A group scans its four rays without writing; if no ray meets a bomb the rays are committed
  * and lane 0 of the group does the rest of ExplodeTopBomb; else the env's own lane runs the serial machine. */
-__device__ __forceinline__ void warp_explode_due(uint8_t* sslice, uint8_t* rec, bool due, int& flags)
+__device__ __forceinline__ void warp_explode_due(uint8_t* sslice, uint8_t* rec, bool due, int& flags, uint8_t* wlist)
 {
     const uint32_t lane = threadIdx.x & 31u, quad = lane >> 2, ray = lane & 3u;
     int turns = due ? int(rec[R_BCOUNT]) : 0;                 /* bombCount turns at most */
@@ -250,13 +283,14 @@ __device__ __forceinline__ void warp_explode_due(uint8_t* sslice, uint8_t* rec, 
     {
         const uint32_t mask = __ballot_sync(FULL_WARP, due);
         if(mask == 0u) break;
-        const uint32_t e = nth_set_lane(mask, quad);
+        uint32_t rank;
+        const uint32_t e = due_env_of_group(wlist, mask, due, lane, quad, rank);
         uint8_t* r = sslice + e * POM_REC_BYTES;
-        uint32_t plan = 0u, ci0 = 0u, slot = 0u;
+        uint32_t plan = 0u, ci0 = 0u, slot = 0u, c = 0u;
         int stride = 0;
         if(e < 32u)
         {
-            const uint32_t c = pomcore::bomb_slot(r, r[R_BINDEX]);
+            c = pomcore::bomb_slot(r, r[R_BINDEX]);
             const uint32_t p = c & 0xFFu;
             ci0 = uint32_t(pomcore::cell_of(p));
             slot = pomcore::ring20(uint32_t(r[R_FINDEX]) + r[R_FCOUNT]);
@@ -266,33 +300,27 @@ __device__ __forceinline__ void warp_explode_due(uint8_t* sslice, uint8_t* rec, 
         uint32_t all = plan | __shfl_xor_sync(FULL_WARP, plan, 1);
         all |= __shfl_xor_sync(FULL_WARP, all, 2);
         const bool chain = (all & pomcore::RAY_CHAIN) != 0u;
+        __syncwarp();                                         /* all four lanes have read the top bomb and the flame ring */
         if(e < 32u && !chain)
         {
             pomcore::ray_commit(r, ci0, stride, plan, slot);  /* rays and origin are disjoint cells */
-            if(ray == 0u)
-            {
-                int f = 0;
-                pomcore::top_bomb_commit(r, all, f);
-                if(f & pomcore::F_INVALID_MASK) r[R_STATUS] |= POM_STATUS_INVALID;
-            }
+            /* the rest of ExplodeTopBomb, shared out: lane 0 the flame entry and the origin cell, lane 1 the kills,
+             * lane 2 PopBomb (three disjoint sets of fields) */
+            if(pomcore::top_bomb_commit_part(r, c, all, ray, slot)) r[R_STATUS] |= POM_STATUS_INVALID;
         }
         const uint32_t chained = __ballot_sync(FULL_WARP, chain);   /* bit 4q: the explosion served by group q chains */
         __syncwarp();                                         /* the groups' writes are visible to the envs' own lanes */
-        if(due)
+        if(due && rank < 8u)
         {
-            const uint32_t rank = uint32_t(__popc(mask & ((1u << lane) - 1u)));
-            if(rank < 8u)
+            if((chained >> (4u * rank)) & 1u)
             {
-                if((chained >> (4u * rank)) & 1u)
-                {
-                    flags |= pomcore::step_explode_due(rec);  /* finishes the loop for this env */
-                    due = false;
-                }
-                else
-                {
-                    turns--;
-                    due = turns > 0 && pomcore::top_bomb_due(rec);
-                }
+                flags |= pomcore::step_explode_due(rec);      /* finishes the loop for this env */
+                due = false;
+            }
+            else
+            {
+                turns--;
+                due = turns > 0 && pomcore::top_bomb_due(rec);
             }
         }
         __syncwarp();
@@ -300,14 +328,14 @@ __device__ __forceinline__ void warp_explode_due(uint8_t* sslice, uint8_t* rec, 
 }
 
 /* bboard::Step (+ Environment::Step's bookkeeping unless raw) for the env of every lane with `step` set */
-__device__ __forceinline__ void warp_tick(uint8_t* sslice, uint8_t* rec, uint32_t m, bool step, bool raw)
+__device__ __forceinline__ void warp_tick(uint8_t* sslice, uint8_t* rec, uint32_t m, bool step, bool raw, uint8_t* wlist)
 {
     const bool pops = step && pomcore::flames_age(rec);       /* TickFlames, step.cpp:15 */
-    warp_pop_due(sslice, rec, pops);
+    warp_pop_due(sslice, rec, pops, wlist);
     int flags = 0;
     bool due = false;
     if(step) flags = pomcore::step_body(rec, m, due, false);
-    warp_explode_due(sslice, rec, due, flags);
+    warp_explode_due(sslice, rec, due, flags, wlist);
     if(step)
     {
         if(flags & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
@@ -318,7 +346,8 @@ __device__ __forceinline__ void warp_tick(uint8_t* sslice, uint8_t* rec, uint32_
 /* dynamic shared memory of the tile kernels: TPB records + one mbarrier per warp */
 template<int TPB> struct TileScratch {
     static constexpr uint32_t OFF_BAR = TPB * POM_REC_BYTES;
-    static constexpr uint32_t BYTES = OFF_BAR + 64;
+    static constexpr uint32_t OFF_LIST = OFF_BAR + 64;        /* 8 bytes per warp: due_env_of_group */
+    static constexpr uint32_t BYTES = OFF_LIST + 8 * (TPB / 32);
 };
 
 /* ---------------------------------------------------------------- K1: per-tick kernel */
@@ -353,14 +382,16 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
     uint8_t* rec = sslice + lane * POM_REC_BYTES;
     /* finished envs are skipped (environment.cpp:125) unless raw; invalid envs always freeze */
     const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
-    warp_tick(sslice, rec, m, stepped, raw);
-    if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped ? 1u : 0u);
+    warp_tick(sslice, rec, m, stepped, raw, smem + TileScratch<TPB>::OFF_LIST + 8u * warp);
+    EpisodeAcc acc;
+    acc.steps = stepped ? 1u : 0u;
     uint32_t st_end = active ? rec[R_STATUS] : 0u;
     if(flags & POM_STEP_AUTORESET)
     {
-        const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, true, ep_now);
+        const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, true, ep_now, acc);
         if(active && stepped) st_end = st;
     }
+    acc_flush(P.stats, acc, (flags & POM_STEP_COUNT) != 0u);
     if(status_out && active) status_out[env] = uint8_t(st_end);   /* one coalesced byte per env */
     fence_proxy_async();                                      /* generic-proxy writes -> visible to the bulk store */
     __syncwarp();
@@ -385,7 +416,7 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
  * window of neighbouring slices, and a warp knows its slice from its ticket alone. */
 template<int NBUF> struct RingScratch {
     static constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
-    static constexpr uint32_t SLOT = SLICE_BYTES + 128;
+    static constexpr uint32_t SLOT = SLICE_BYTES + 128 + 16;      /* records, the slice's moves, the warp's due list */
     static constexpr uint32_t OFF_FULL = NBUF * SLOT;
     static constexpr uint32_t OFF_EMPTY = OFF_FULL + 8 * NBUF;
     static constexpr uint32_t OFF_TICKET = OFF_EMPTY + 8 * NBUF;
@@ -431,7 +462,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, con
     }
 
     const bool raw = (flags & POM_STEP_RAW) != 0u;
-    uint32_t stepped_total = 0u;
+    EpisodeAcc acc;
     for(;;)
     {
         uint32_t t = 0u;
@@ -447,17 +478,23 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, con
         uint32_t m = 0u;
         if(!(moves_bulk && whole) && active) m = __ldg(moves + env);      /* overlaps the wait below */
         uint32_t ep_now = (active && (flags & POM_STEP_AUTORESET)) ? P.episodes[env] : 0u;
+        /* A parity wait can only tell the current phase from the one before it.  In quiet ticks the compute warps are
+         * faster than HBM: with one slow load outstanding they can take 24 further tickets and come back to the same
+         * buffer while its barrier is still in the phase of that load - the parity of the NEXT use then reads as
+         * "complete".  So a warp first waits until the buffer's previous user has handed it back (the producer cannot
+         * have re-armed `full` before that); from then on `full` is at most one phase behind. */
+        if(use) mbar_wait(empty + b, (use - 1u) & 1u);
         mbar_wait(full + b, use & 1u);
         if(moves_bulk && whole) m = reinterpret_cast<const uint32_t*>(sslice + R::SLICE_BYTES)[lane];
 
         uint8_t* rec = sslice + lane * POM_REC_BYTES;
         const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
-        warp_tick(sslice, rec, m, stepped, raw);
-        stepped_total += stepped ? 1u : 0u;
+        warp_tick(sslice, rec, m, stepped, raw, sslice + R::SLICE_BYTES + 128u);
+        acc.steps += stepped ? 1u : 0u;
         uint32_t st_end = active ? rec[R_STATUS] : 0u;
         if(flags & POM_STEP_AUTORESET)
         {
-            const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, true, ep_now);
+            const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, true, ep_now, acc);
             if(active && stepped) st_end = st;
         }
         if(status_out && active) status_out[env] = uint8_t(st_end);
@@ -471,7 +508,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, con
         }
         __syncwarp();
     }
-    if(flags & POM_STEP_COUNT) warp_add(P.stats + ST_STEPS, stepped_total);
+    acc_flush(P.stats, acc, (flags & POM_STEP_COUNT) != 0u);
 }
 
 /* ---------------------------------------------------------------- K7: agent memories of the SimpleAgent policy */
@@ -574,16 +611,17 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
     uint8_t* rec = sslice + lane * POM_REC_BYTES;
     /* per-env RNG key hoisted out of the tick loop (first splitmix64 of pom_rng_moves) */
     const uint64_t key = pomcore::splitmix64(seed ^ ((P.env_offset + env) * 0xD6E8FEB86659FD93ull));
-    uint32_t steps = 0;
+    EpisodeAcc acc;
     for(uint32_t k = 0; k < ticks; k++)
     {
+        if((k & 0x3FFFu) == 0x3FFFu) acc_flush(P.stats, acc, true);   /* the per-lane counters are 16 bits wide */
         const bool stepped = active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID));
         uint32_t m = 0;
         if(stepped && move_seq)
         {
             /* pom_batch_step_seq: the caller's moves, tick-major; one coalesced 4-byte load per env and tick */
             m = __ldg(move_seq + uint64_t(k) * P.n_envs + env);
-            steps++;
+            acc.steps++;
         }
         else if(stepped)
         {
@@ -599,14 +637,14 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
                     draws |= (((uint32_t(h >> (16 * a)) & 0xFFFFu) * 5u) >> 16) << (8 * a);
                 m = pompolicy::simple_moves(rec, policy_mask, m, draws, agents);
             }
-            steps++;
+            acc.steps++;
         }
-        warp_tick(sslice, rec, m, stepped, false);
-        const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, !no_reset, ep_now);
+        warp_tick(sslice, rec, m, stepped, false, smem + TileScratch<TPB>::OFF_LIST + 8u * warp);
+        const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, !no_reset, ep_now, acc);
         /* a new episode starts with four new agents */
         if(POLICY && stepped && !no_reset && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID))) agents.clear(ep_now);
     }
-    warp_add(P.stats + ST_STEPS, steps);
+    acc_flush(P.stats, acc, true);
 
     fence_proxy_async();
     __syncwarp();
@@ -716,7 +754,7 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
     {
         for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = 0u;
     }
-    warp_tick(sslice, rec, m, stepped, raw);
+    warp_tick(sslice, rec, m, stepped, raw, smem + TileScratch<TPB>::OFF_LIST + 8u * warp);
     fence_proxy_async();
     __syncwarp();
     if(lane == 0)
