@@ -40,8 +40,11 @@ enum {
 /* flags of pom_batch_step / pom_batch_expand_step */
 enum {
     POM_STEP_RAW       = 0x1, /* bare bboard::Step (step.cpp:9): no timeStep++, no done/winner, finished envs are stepped too */
-    POM_STEP_AUTORESET = 0x2, /* an env that finishes is counted in the stats and re-initialised from the
-                                 template pool at the end of the finishing tick (not in the reference)  */
+    POM_STEP_AUTORESET = 0x2, /* an env that finishes IN THIS TICK is counted in the stats and re-initialised from the
+                                 template pool at the end of the tick (not in the reference).  An env that is already
+                                 done or invalid when the tick starts (uploaded that way, or finished by an earlier
+                                 step without this flag) is not stepped and therefore stays frozen: use pom_batch_reset,
+                                 or upload a running state */
     POM_STEP_COUNT     = 0x4, /* add the number of envs stepped to stats.env_steps                       */
     POM_STEP_OVERLAP   = 0x8  /* pom_batch_step only: step the two halves of the batch on two internal streams so that
                                  consecutive ticks overlap at their edges.  Every other call on the handle first waits
@@ -143,6 +146,27 @@ int  pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* statu
  * the step is queued; status_host (and moves_host) belong to the device until pom_batch_sync(b) returns.  Lets a caller
  * that runs two batches alternately keep the GPU busy while it consumes the results of the other batch. */
 int  pom_batch_step_host_async(pom_batch* b, const uint8_t* moves_host, uint8_t* status_host, uint32_t flags);
+/* One tick with COMPACT input and output, for actor loops whose bottleneck is the host link (PCIe / host memory), e.g.
+ * eight GPUs fed from one host: 2 bytes in and ~0.3 bytes out per env-step instead of 4 + 1.
+ *   joint      n_envs joint actions, j = a0 + 6*a1 + 36*a2 + 216*a3 with a_k = Move of agent k (the encoding of
+ *              pom_batch_expand_step).  All four moves are always supplied, as the reference's Step reads them all
+ *              (step_utility.cpp:138-144).  j >= 1296 is taken modulo 6 per digit.
+ *   done_bits  (n_envs + 31) / 32 words: bit (e % 32) of word e / 32 = env e ended an episode in this tick
+ *              (done, truncated or invalid; with POM_STEP_AUTORESET the env has already been re-initialised).  May be NULL.
+ *   fin_env, fin_status, fin_count   the same envs as a compacted list in no particular order: env index and status byte
+ *              (as pom_batch_step_host's status_host reports it), *fin_count entries, at most fin_capacity (further
+ *              ones are dropped: size the list for the worst case n_envs, or poll done_bits).  fin_env may be NULL.
+ * Every pointer may be device memory or page-locked mapped host memory (pom_host_alloc / pom_host_alloc_near): the
+ * kernel reads and writes host memory directly.  Enqueues only: results are valid after pom_batch_sync(b). */
+typedef struct pom_step_compact_io {
+    const uint16_t* joint;
+    uint32_t*       done_bits;
+    uint32_t*       fin_env;
+    uint8_t*        fin_status;
+    uint32_t*       fin_count;
+    uint32_t        fin_capacity;
+} pom_step_compact_io;
+int  pom_batch_step_compact(pom_batch* b, const pom_step_compact_io* io, uint32_t flags);
 /* `ticks` fused ticks with the boards resident in shared memory; actions from pom_rng_moves(rng_seed,
  * global env index, tick0 + k); auto-reset unless POM_ROLL_NO_RESET.  Replaces the loop of
  * Environment::StartGame (environment.cpp:68-88) with RandomAgent/HarmlessAgent::act (bboard.hpp:517-533), or with
@@ -180,7 +204,7 @@ int  pom_batch_policy_upload(pom_batch* b, uint64_t first, uint64_t count, const
 int  pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_dst);
 /* tree-search expansion: child c = i * fanout + j of root src_idx[i] gets joint action j with
  * a_k = (j / 6^k) % 6 and is stepped once (clone + Step fused, one HBM write per child).
- * fanout <= 1296; dst needs n_roots * fanout envs.                                                  */
+ * fanout <= 1296; dst needs n_roots * fanout envs; dst envs behind the last child are left untouched.  */
 int  pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_roots, uint32_t fanout, uint32_t flags);
 
 /* ---- State primitives on ONE env, executed by the device code of the step path (fixtures, the
@@ -217,9 +241,19 @@ void*    pom_batch_stats_device_ptr(const pom_batch* b);/* POM_STATS_WORDS x uin
 void*    pom_batch_records_device_ptr(const pom_batch* b);
 int      pom_device_alloc(int device, uint64_t bytes, void** out);
 int      pom_device_free(int device, void* p);
-int      pom_device_copy(int device, void* dst, const void* src, uint64_t bytes);   /* either side may be host or device memory */
+/* either side may be host or device memory.  A plain synchronous cudaMemcpy on the default stream: it is NOT ordered
+ * after work queued on a handle (handles use non-blocking streams) - call pom_batch_sync(b) first when the source is
+ * being written by a queued call such as pom_batch_observe_planes. */
+int      pom_device_copy(int device, void* dst, const void* src, uint64_t bytes);
 int      pom_host_alloc(uint64_t bytes, void** out);    /* pinned host memory for pom_batch_step_host */
 int      pom_host_free(void* p);
+/* pinned host memory placed on the NUMA node of `device` (first touched by a thread bound to the CPUs that
+ * /sys/bus/pci/devices/<gpu>/local_cpulist names), so that the kernel's zero-copy reads and writes do not cross the
+ * inter-socket link; falls back to pom_host_alloc when the topology cannot be read.  Free with pom_host_free. */
+int      pom_host_alloc_near(int device, uint64_t bytes, void** out);
+/* binds the CALLING thread to the CPUs local to `device` (launch latency, polling of mapped buffers); returns POM_OK
+ * also when the topology cannot be read (nothing is changed then) */
+int      pom_bind_thread_near(int device);
 /* timing helper: runs fn-less CUDA-event brackets on the handle's stream */
 int      pom_batch_event_record(pom_batch* b, int which /* 0 = start, 1 = stop */);
 int      pom_batch_event_elapsed_ms(pom_batch* b, float* ms);   /* synchronises on the stop event */

@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(HERE, "libpom_b200.so")
 
 REC_BYTES = 292
 OBS_BYTES = 496
-ALGO_BYTES_PER_ENV_STEP = 2 * 289 + 4      # packed state in + out + 4 move bytes
+ALGO_BYTES_PER_ENV_STEP = 2 * 289 + 4      # packed PAYLOAD in + out + 4 move bytes (what the roofline credits)
+MOVED_BYTES_PER_ENV_STEP = 2 * 292 + 4     # what actually crosses HBM: the record is padded to 292 B
 
 STEP_RAW, STEP_AUTORESET, STEP_COUNT, STEP_OVERLAP = 1, 2, 4, 8
 ROLL_HARMLESS, ROLL_NO_RESET = 1, 2
@@ -46,6 +47,17 @@ assert SIMPLE_DT.itemsize == 8
 class InitDesc(C.Structure):
     _fields_ = [("env_offset", C.c_uint64), ("n_templates", C.c_uint32), ("first_seed", C.c_int32),
                 ("host_templates", C.c_void_p), ("max_ticks", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class StepCompactIO(C.Structure):
+    _fields_ = [("joint", C.c_void_p), ("done_bits", C.c_void_p), ("fin_env", C.c_void_p), ("fin_status", C.c_void_p),
+                ("fin_count", C.c_void_p), ("fin_capacity", C.c_uint32)]
+
+
+def joint_of_moves(moves):
+    """[n, 4] moves (0..5) -> uint16 joint actions j = a0 + 6 a1 + 36 a2 + 216 a3"""
+    m = np.asarray(moves, np.uint16).reshape(-1, 4)
+    return (m[:, 0] + 6 * m[:, 1] + 36 * m[:, 2] + 216 * m[:, 3]).astype(np.uint16)
 
 
 class Stats(C.Structure):
@@ -125,6 +137,9 @@ def lib():
         L.pom_device_free.argtypes = [i32, vp]
         L.pom_host_alloc.argtypes = [u64, C.POINTER(vp)]
         L.pom_host_free.argtypes = [vp]
+        L.pom_host_alloc_near.argtypes = [i32, u64, C.POINTER(vp)]
+        L.pom_bind_thread_near.argtypes = [i32]
+        L.pom_batch_step_compact.argtypes = [vp, vp, u32]
         L.pom_batch_event_record.argtypes = [vp, i32]
         L.pom_batch_event_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.pom_batch_flush_l2.argtypes = [vp]
@@ -234,6 +249,17 @@ class Batch:
         assert moves.dtype == np.uint8 and moves.size == 4 * self.n and moves.flags.c_contiguous
         _ck(lib().pom_batch_step_host(self.h, _p(moves), _p(status_out), flags))
 
+    def step_compact(self, joint, done_bits=None, fin_env=None, fin_status=None, fin_count=None, flags=0):
+        """one tick with compact I/O (pom_batch_step_compact): `joint` = n uint16 joint actions; outputs are optional.
+        Arrays must live in pinned mapped memory (pinned_array) or be raw device pointers (int); enqueue only."""
+        def ptr(a):
+            if a is None:
+                return None
+            return C.c_void_p(a) if isinstance(a, int) else _p(a)
+        io = StepCompactIO(ptr(joint), ptr(done_bits), ptr(fin_env), ptr(fin_status), ptr(fin_count),
+                           0 if fin_env is None else (fin_env.size if hasattr(fin_env, "size") else self.n))
+        _ck(lib().pom_batch_step_compact(self.h, C.byref(io), flags))
+
     def step_seq(self, moves_dev, ticks, flags=0):
         """`ticks` ticks in one launch with the caller's moves (device pointer, ticks x n x 4 bytes, tick-major)"""
         _ck(lib().pom_batch_step_seq(self.h, moves_dev, ticks, flags))
@@ -325,12 +351,21 @@ def make_board(seed, device=0):
     return s, d.value
 
 
-def pinned_array(shape, dtype):
-    """numpy array backed by pinned host memory (pom_host_alloc); keep the returned owner alive."""
+def bind_thread_near(device):
+    """pins the calling thread to the CPUs next to `device` (pom_bind_thread_near)"""
+    _ck(lib().pom_bind_thread_near(device))
+
+
+def pinned_array(shape, dtype, near_device=None):
+    """numpy array backed by pinned host memory (pom_host_alloc, or pom_host_alloc_near when near_device is given: pages
+    on the GPU's NUMA node); keep the returned owner alive."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
     p = C.c_void_p()
-    _ck(lib().pom_host_alloc(n, C.byref(p)))
+    if near_device is None:
+        _ck(lib().pom_host_alloc(n, C.byref(p)))
+    else:
+        _ck(lib().pom_host_alloc_near(near_device, n, C.byref(p)))
     buf = (C.c_uint8 * n).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
     return arr, p

@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <sched.h>
 #include <string>
 #include <vector>
 #include <new>
@@ -69,6 +71,7 @@ struct pom_batch {
     pom_state* aos_stage = nullptr;            /* XFER_CHUNK states                          */
     uint8_t*  st_stage = nullptr;
     uint32_t* bad_count = nullptr;
+    uint32_t* fin_counter = nullptr;           /* device word behind the finished-env list of pom_batch_step_compact */
     uint32_t* policy = nullptr;                /* 9 x n_alloc words: SimpleAgent memories (allocated on first use) */
     void*     flush_buf = nullptr;
     cudaStream_t stream = nullptr;
@@ -162,6 +165,8 @@ int fill_from_templates(pom_batch* b)
 int build_templates_from_seeds(pom_batch* b, int32_t first_seed)
 {
     const uint32_t n = b->n_templates;
+    if(n > (1u << 24)) return fail(POM_E_ARG, "pom_batch_init: at most 2^24 templates");
+    if(int64_t(first_seed) + 16 * int64_t(n) + 4096 > 0x7FFFFFFFll) return fail(POM_E_ARG, "pom_batch_init: first_seed too close to INT_MAX for this many templates");
     uint32_t ncand = uint32_t(n * 2.2) + 64;
     for(int attempt = 0; attempt < 6; attempt++, ncand *= 2)
     {
@@ -221,7 +226,7 @@ int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, c
 constexpr int WS_NW = 20, WS_NBUF = 24;
 
 template<int NW>
-int launch_step_ws(pom_batch* b, const pomk::BatchParams& P, const uint8_t* moves_dev, uint32_t flags, uint8_t* status_dev, cudaStream_t on)
+int launch_step_ws(pom_batch* b, const pomk::BatchParams& P, const pomk::StepIO& io, uint32_t flags, cudaStream_t on)
 {
     typedef pomk::RingScratch<WS_NBUF> R;
     if(!(b->attr_ws & (1u << NW)))
@@ -231,12 +236,24 @@ int launch_step_ws(pom_batch* b, const pomk::BatchParams& P, const uint8_t* move
     }
     const uint64_t n_slices = (P.n_envs + 31) / 32;
     const unsigned grid = unsigned(n_slices < uint64_t(b->n_sms) ? n_slices : uint64_t(b->n_sms));
-    const uint32_t moves_bulk = (reinterpret_cast<uintptr_t>(moves_dev) & 15u) == 0u ? 1u : 0u;   /* TMA needs 16-byte alignment */
-    pomk::k_step_ws<NW, WS_NBUF><<<grid, (NW + 1) * 32, R::BYTES, on ? on : b->stream>>>(
-        P, reinterpret_cast<const uint32_t*>(moves_dev), flags, status_dev, moves_bulk);
+    pomk::k_step_ws<NW, WS_NBUF><<<grid, (NW + 1) * 32, R::BYTES, on ? on : b->stream>>>(P, io, flags);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
+}
+
+int launch_step_io(pom_batch* b, const pomk::BatchParams& P, pomk::StepIO io, uint32_t flags, cudaStream_t on)
+{
+    io.bulk = (reinterpret_cast<uintptr_t>(io.moves) & 15u) == 0u ? 1u : 0u;   /* TMA needs 16-byte alignment */
+    /* persistent, warp-specialised: one CTA per SM; POM_WS_NW picks the number of compute warps (experiments) */
+    switch(b->ws_nw)
+    {
+    case 12: return launch_step_ws<12>(b, P, io, flags, on);
+    case 14: return launch_step_ws<14>(b, P, io, flags, on);
+    case 16: return launch_step_ws<16>(b, P, io, flags, on);
+    case 18: return launch_step_ws<18>(b, P, io, flags, on);
+    default: return launch_step_ws<WS_NW>(b, P, io, flags, on);
+    }
 }
 
 template<int TPB>
@@ -252,15 +269,10 @@ int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t*
     }
     if(b->step_kernel == 0)
     {
-        /* persistent, warp-specialised: one CTA per SM; POM_WS_NW picks the number of compute warps (experiments) */
-        switch(b->ws_nw)
-        {
-        case 12: return launch_step_ws<12>(b, P, moves_dev, flags, status_dev, on);
-        case 14: return launch_step_ws<14>(b, P, moves_dev, flags, status_dev, on);
-        case 16: return launch_step_ws<16>(b, P, moves_dev, flags, status_dev, on);
-        case 18: return launch_step_ws<18>(b, P, moves_dev, flags, status_dev, on);
-        default: return launch_step_ws<WS_NW>(b, P, moves_dev, flags, status_dev, on);
-        }
+        pomk::StepIO io{};
+        io.moves = moves_dev;
+        io.status_out = status_dev;
+        return launch_step_io(b, P, io, flags, on);
     }
     { int rc = set_smem(b, ATTR_STEP, pomk::k_step<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     const unsigned grid = unsigned((P.n_envs + TPB - 1) / TPB);
@@ -325,6 +337,51 @@ int launch_expand(pom_batch* dst, const pom_batch* src, const uint32_t* idx_dev,
     return POM_OK;
 }
 
+}
+
+namespace
+{
+/* a caller's buffer as the device sees it: device memory as is, mapped pinned host memory through its device alias */
+template<typename T>
+int device_view(T* p, T** out, const char* what)
+{
+    *out = nullptr;
+    if(!p) return POM_OK;
+    cudaPointerAttributes a;
+    if(cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return fail(POM_E_ARG, what); }
+    if(a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) { *out = p; return POM_OK; }
+    if(a.type == cudaMemoryTypeHost && a.devicePointer) { *out = static_cast<T*>(a.devicePointer); return POM_OK; }
+    return fail(POM_E_ARG, what);
+}
+}
+
+namespace
+{
+/* CPUs local to the GPU, from sysfs; empty when unknown */
+bool local_cpus(int device, cpu_set_t* set)
+{
+    char bus[32] = {0};
+    if(cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return false; }
+    for(char* c = bus; *c; c++) if(*c >= 'A' && *c <= 'Z') *c = char(*c - 'A' + 'a');
+    std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist");
+    std::string list;
+    if(!f || !std::getline(f, list) || list.empty()) return false;
+    CPU_ZERO(set);
+    int n = 0;
+    size_t i = 0;
+    while(i < list.size())
+    {
+        char* end = nullptr;
+        const long lo = std::strtol(list.c_str() + i, &end, 10);
+        long hi = lo;
+        i = size_t(end - list.c_str());
+        if(i < list.size() && list[i] == '-') { hi = std::strtol(list.c_str() + i + 1, &end, 10); i = size_t(end - list.c_str()); }
+        for(long c = lo; c <= hi && c < CPU_SETSIZE; c++) { CPU_SET(int(c), set); n++; }
+        if(i < list.size() && list[i] == ',') i++;
+        else if(i < list.size() && (list[i] < '0' || list[i] > '9')) break;
+    }
+    return n > 0;
+}
 }
 
 /* tile geometry: threads (= envs) per CTA; tunable through POM_TPB for experiments, default = measured best */
@@ -427,7 +484,7 @@ int pom_batch_destroy(pom_batch* b)
     if(b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->recs); cudaFree(b->templates); cudaFree(b->episodes); cudaFree(b->stats);
     cudaFree(b->moves_buf); cudaFree(b->status_buf); cudaFree(b->aos_stage); cudaFree(b->st_stage);
-    cudaFree(b->bad_count); cudaFree(b->flush_buf); cudaFree(b->policy);
+    cudaFree(b->bad_count); cudaFree(b->flush_buf); cudaFree(b->policy); cudaFree(b->fin_counter);
     if(b->ev[0]) cudaEventDestroy(b->ev[0]);
     if(b->ev[1]) cudaEventDestroy(b->ev[1]);
     for(int i = 0; i < pom_batch::MAX_CHUNKS; i++) { if(b->ev_in[i]) cudaEventDestroy(b->ev_in[i]); if(b->ev_done[i]) cudaEventDestroy(b->ev_done[i]); }
@@ -453,7 +510,7 @@ int pom_batch_upload(pom_batch* b, uint64_t first, uint64_t count, const pom_sta
 {
     int rc = use(b); if(rc) return rc;
     if(!states) return fail(POM_E_ARG, "pom_batch_upload: null states");
-    if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_upload: range outside the batch");
+    if(first > b->n_envs || count > b->n_envs - first) return fail(POM_E_RANGE, "pom_batch_upload: range outside the batch");
     uint32_t bad = 0;
     rc = pack_into(b, b->recs, first, count, states, status, &bad);
     if(rc) return rc;
@@ -464,7 +521,7 @@ int pom_batch_upload(pom_batch* b, uint64_t first, uint64_t count, const pom_sta
 int pom_batch_download(pom_batch* b, uint64_t first, uint64_t count, pom_state* states, uint8_t* status)
 {
     int rc = use(b); if(rc) return rc;
-    if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_download: range outside the batch");
+    if(first > b->n_envs || count > b->n_envs - first) return fail(POM_E_RANGE, "pom_batch_download: range outside the batch");
     rc = ensure_stage(b); if(rc) return rc;
     for(uint64_t done = 0; done < count; done += XFER_CHUNK)
     {
@@ -484,7 +541,7 @@ int pom_batch_observe(pom_batch* b, uint64_t first, uint64_t count, int agent, i
     int rc = use(b); if(rc) return rc;
     if(!states) return fail(POM_E_ARG, "pom_batch_observe: null output");
     if(agent < 0 || agent > 3 || view < 0) return fail(POM_E_ARG, "pom_batch_observe: agent must be 0..3 and view >= 0");
-    if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_observe: range outside the batch");
+    if(first > b->n_envs || count > b->n_envs - first) return fail(POM_E_RANGE, "pom_batch_observe: range outside the batch");
     rc = ensure_stage(b); if(rc) return rc;
     for(uint64_t done = 0; done < count; done += XFER_CHUNK)
     {
@@ -677,6 +734,44 @@ int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status
     return POM_OK;
 }
 
+int pom_batch_step_compact(pom_batch* b, const pom_step_compact_io* io, uint32_t flags)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!io || !io->joint) return fail(POM_E_ARG, "pom_batch_step_compact: null joint actions");
+    if(io->fin_env && (!io->fin_status || !io->fin_count)) return fail(POM_E_ARG, "pom_batch_step_compact: fin_env needs fin_status and fin_count");
+    if(flags & POM_STEP_OVERLAP) return fail(POM_E_ARG, "pom_batch_step_compact: POM_STEP_OVERLAP is not supported");
+    if(b->step_kernel != 0) return fail(POM_E_ARG, "pom_batch_step_compact needs the persistent step kernel (unset POM_STEP_KERNEL)");
+    pomk::StepIO k{};
+    uint16_t* joint = nullptr; uint32_t* count = nullptr;
+    const char* bad = "pom_batch_step_compact: buffers must be device memory or page-locked mapped host memory (pom_host_alloc)";
+    if((rc = device_view(const_cast<uint16_t*>(io->joint), &joint, bad))) return rc;
+    if((rc = device_view(io->done_bits, &k.done_bits, bad))) return rc;
+    if((rc = device_view(io->fin_env, &k.fin_env, bad))) return rc;
+    if((rc = device_view(io->fin_status, &k.fin_status, bad))) return rc;
+    if((rc = device_view(io->fin_count, &count, bad))) return rc;
+    k.moves = joint;
+    k.joint = 1u;
+    k.fin_capacity = io->fin_capacity;
+    if(k.fin_env)
+    {
+        if(!b->fin_counter)
+        {
+            CK(cudaMalloc(&b->fin_counter, sizeof(uint32_t)));
+            CK(cudaMemsetAsync(b->fin_counter, 0, sizeof(uint32_t), b->stream));
+        }
+        k.fin_counter = b->fin_counter;
+    }
+    rc = launch_step_io(b, b->params(), k, flags, b->stream);
+    if(rc) return rc;
+    if(k.fin_env)
+    {
+        pomk::k_publish_count<<<1, 1, 0, b->stream>>>(b->fin_counter, count, io->fin_capacity);
+        b->launches++;
+        CK(cudaGetLastError());
+    }
+    return POM_OK;
+}
+
 int pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t tick0, uint32_t flags)
 {
     int rc = use(b); if(rc) return rc;
@@ -741,7 +836,7 @@ int pom_batch_policy_download(pom_batch* b, uint64_t first, uint64_t count, pom_
 {
     int rc = use(b); if(rc) return rc;
     if(!out) return fail(POM_E_ARG, "pom_batch_policy_download: null output");
-    if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_policy_download: range outside the batch");
+    if(first > b->n_envs || count > b->n_envs - first) return fail(POM_E_RANGE, "pom_batch_policy_download: range outside the batch");
     if(count == 0) return POM_OK;
     rc = ensure_policy(b); if(rc) return rc;
     DevBuf tmp;
@@ -758,7 +853,7 @@ int pom_batch_policy_upload(pom_batch* b, uint64_t first, uint64_t count, const 
 {
     int rc = use(b); if(rc) return rc;
     if(!in) return fail(POM_E_ARG, "pom_batch_policy_upload: null input");
-    if(first + count > b->n_envs) return fail(POM_E_RANGE, "pom_batch_policy_upload: range outside the batch");
+    if(first > b->n_envs || count > b->n_envs - first) return fail(POM_E_RANGE, "pom_batch_policy_upload: range outside the batch");
     if(count == 0) return POM_OK;
     rc = ensure_policy(b); if(rc) return rc;
     DevBuf tmp;
@@ -777,7 +872,7 @@ int pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, co
     if(!src || !src_idx) return fail(POM_E_ARG, "pom_batch_clone: null argument");
     if(src->device != dst->device) return fail(POM_E_ARG, "pom_batch_clone: handles live on different devices");
     if(src != dst) { rc = use(src); if(rc) return rc; }         /* joins src's second compute stream if a step is in flight there */
-    if(first_dst + n_dst > dst->n_envs) return fail(POM_E_RANGE, "pom_batch_clone: destination range outside the batch");
+    if(first_dst > dst->n_envs || n_dst > dst->n_envs - first_dst) return fail(POM_E_RANGE, "pom_batch_clone: destination range outside the batch");
     for(uint64_t i = 0; i < n_dst; i++) if(src_idx[i] >= src->n_envs) return fail(POM_E_RANGE, "pom_batch_clone: source index outside the batch");
     if(n_dst == 0) return POM_OK;
     DevBuf idx_b, snap;
@@ -857,7 +952,9 @@ int pom_make_board(int device, int32_t seed, pom_state* out, int* dirty)
     CK(aos.alloc(sizeof(pom_state)));
     CK(st.alloc(1));
     pomk::k_make_board<<<1, 1>>>(rec.as<uint8_t>(), d.as<uint8_t>(), seed);
+    CK(cudaGetLastError());
     pomk::k_unpack<<<1, 1>>>(rec.as<uint8_t>(), aos.as<pom_state>(), st.as<uint8_t>(), 0, 1);
+    CK(cudaGetLastError());
     uint8_t hd = 0;
     CK(cudaMemcpy(out, aos.p, sizeof(pom_state), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&hd, d.p, 1, cudaMemcpyDeviceToHost));
@@ -935,6 +1032,26 @@ int pom_host_alloc(uint64_t bytes, void** out)
     /* page-locked for every device of the process and mapped into their address spaces (zero-copy step_host) */
     if(cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) return fail(POM_E_NOMEM, "pom_host_alloc", cudaGetLastError());
     return POM_OK;
+}
+
+int pom_bind_thread_near(int device)
+{
+    cpu_set_t set;
+    if(local_cpus(device, &set)) sched_setaffinity(0, sizeof(set), &set);
+    return POM_OK;
+}
+
+int pom_host_alloc_near(int device, uint64_t bytes, void** out)
+{
+    if(!out) return fail(POM_E_ARG, "pom_host_alloc_near: null output");
+    cpu_set_t before, near;
+    const bool have_before = sched_getaffinity(0, sizeof(before), &before) == 0;
+    const bool moved = have_before && local_cpus(device, &near) && sched_setaffinity(0, sizeof(near), &near) == 0;
+    /* the pages are allocated and first touched (pinning touches them) by this thread, now running next to the GPU */
+    const int rc = pom_host_alloc(bytes, out);
+    if(rc == POM_OK) std::memset(*out, 0, bytes);
+    if(moved) sched_setaffinity(0, sizeof(before), &before);
+    return rc;
 }
 
 int pom_host_free(void* p)

@@ -414,6 +414,26 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
  * spent 40 % of their time waiting for their own loads (profiles/k_step_ncu_summary_r2b.json).
  * Slices are dealt round-robin over the CTAs (slice = blockIdx.x + ticket * gridDim.x): at any time the CTAs work on a
  * window of neighbouring slices, and a warp knows its slice from its ticket alone. */
+/* inputs and outputs of one per-tick launch besides the records */
+struct StepIO {
+    const void* moves;         /* n_envs x 4 move bytes (uint32 per env), or n_envs joint actions (uint16 per env) when joint != 0 */
+    uint32_t    joint;         /* j = a0 + 6 a1 + 36 a2 + 216 a3 (the encoding of pom_batch_expand_step) */
+    uint32_t    bulk;          /* moves are 16-byte aligned: fetch them with the slice's TMA load */
+    uint8_t*    status_out;    /* one end-of-tick status byte per env, or null */
+    uint32_t*   done_bits;     /* one word per slice: bit l = env 32 s + l ended an episode this tick, or null */
+    uint32_t*   fin_env;       /* compacted list of those envs ...            (null: no list) */
+    uint8_t*    fin_status;    /* ... and their status bytes (as in status_out) */
+    uint32_t*   fin_counter;   /* DEVICE counter the list is appended through */
+    uint32_t    fin_capacity;
+};
+
+/* four moves from a joint action index */
+__device__ __forceinline__ uint32_t moves_of_joint(uint32_t j)
+{
+    const uint32_t a0 = j % 6u, r1 = j / 6u, a1 = r1 % 6u, r2 = r1 / 6u, a2 = r2 % 6u, a3 = (r2 / 6u) % 6u;
+    return a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
+}
+
 template<int NBUF> struct RingScratch {
     static constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
     static constexpr uint32_t SLOT = SLICE_BYTES + 128 + 16;      /* records, the slice's moves, the warp's due list */
@@ -424,9 +444,13 @@ template<int NBUF> struct RingScratch {
 };
 
 template<int NW, int NBUF>
-__global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, const uint32_t* __restrict__ moves, uint32_t flags,
-                                                               uint8_t* __restrict__ status_out, uint32_t moves_bulk)
+__global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, StepIO io, uint32_t flags)
 {
+    const uint32_t* __restrict__ moves = static_cast<const uint32_t*>(io.moves);
+    const uint16_t* __restrict__ joint = static_cast<const uint16_t*>(io.moves);
+    uint8_t* __restrict__ status_out = io.status_out;
+    const uint32_t moves_bulk = io.bulk;
+    const uint32_t mv_bytes = io.joint ? 64u : 128u;              /* move bytes per slice */
     extern __shared__ __align__(128) uint8_t smem[];
     typedef RingScratch<NBUF> R;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + R::OFF_FULL);
@@ -453,10 +477,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, con
             if(use) mbar_wait(empty + b, (use - 1u) & 1u);               /* the buffer's previous slice has been stored */
             const uint64_t s = blockIdx.x + uint64_t(t) * gridDim.x;
             const bool whole = (s + 1u) * 32u <= P.n_envs;                /* the last slice's moves may end early: per-lane loads */
-            const uint32_t mbytes = (moves_bulk && whole) ? 128u : 0u;
+            const uint32_t mbytes = (moves_bulk && whole) ? mv_bytes : 0u;
             mbar_expect_tx(full + b, R::SLICE_BYTES + mbytes);
             bulk_g2s(smem + b * R::SLOT, P.recs + s * R::SLICE_BYTES, R::SLICE_BYTES, full + b);
-            if(mbytes) bulk_g2s(smem + b * R::SLOT + R::SLICE_BYTES, moves + s * 32u, 128u, full + b);
+            if(mbytes) bulk_g2s(smem + b * R::SLOT + R::SLICE_BYTES, static_cast<const uint8_t*>(io.moves) + s * mv_bytes, mbytes, full + b);
         }
         return;
     }
@@ -476,7 +500,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, con
         const bool whole = (s + 1u) * 32u <= P.n_envs;
         uint8_t* sslice = smem + b * R::SLOT;
         uint32_t m = 0u;
-        if(!(moves_bulk && whole) && active) m = __ldg(moves + env);      /* overlaps the wait below */
+        if(!(moves_bulk && whole) && active) m = io.joint ? uint32_t(__ldg(joint + env)) : __ldg(moves + env);   /* overlaps the wait below */
         uint32_t ep_now = (active && (flags & POM_STEP_AUTORESET)) ? P.episodes[env] : 0u;
         /* A parity wait can only tell the current phase from the one before it.  In quiet ticks the compute warps are
          * faster than HBM: with one slow load outstanding they can take 24 further tickets and come back to the same
@@ -485,7 +509,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, con
          * have re-armed `full` before that); from then on `full` is at most one phase behind. */
         if(use) mbar_wait(empty + b, (use - 1u) & 1u);
         mbar_wait(full + b, use & 1u);
-        if(moves_bulk && whole) m = reinterpret_cast<const uint32_t*>(sslice + R::SLICE_BYTES)[lane];
+        if(moves_bulk && whole)
+            m = io.joint ? uint32_t(reinterpret_cast<const uint16_t*>(sslice + R::SLICE_BYTES)[lane])
+                         : reinterpret_cast<const uint32_t*>(sslice + R::SLICE_BYTES)[lane];
+        if(io.joint) m = moves_of_joint(m);
 
         uint8_t* rec = sslice + lane * POM_REC_BYTES;
         const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
@@ -498,6 +525,24 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, con
             if(active && stepped) st_end = st;
         }
         if(status_out && active) status_out[env] = uint8_t(st_end);
+        if(io.done_bits || io.fin_env)
+        {
+            /* compact results: which envs ended an episode in this tick, as one bit per env and as a list */
+            const bool ended = active && stepped && (st_end & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID)) != 0u;
+            const uint32_t em = __ballot_sync(FULL_WARP, ended);
+            if(io.done_bits && lane == 0) io.done_bits[s] = em;
+            if(io.fin_env && em)
+            {
+                uint32_t base = 0u;
+                if(lane == 0) base = atomicAdd(io.fin_counter, uint32_t(__popc(em)));
+                base = __shfl_sync(FULL_WARP, base, 0) + uint32_t(__popc(em & ((1u << lane) - 1u)));
+                if(ended && base < io.fin_capacity)
+                {
+                    io.fin_env[base] = uint32_t(env);
+                    io.fin_status[base] = uint8_t(st_end);
+                }
+            }
+        }
         fence_proxy_async();
         __syncwarp();
         if(lane == 0)
@@ -509,6 +554,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, con
         __syncwarp();
     }
     acc_flush(P.stats, acc, (flags & POM_STEP_COUNT) != 0u);
+}
+
+/* hands the length of the finished-env list to the caller (host-mapped or device word) and clears the device counter */
+__global__ void k_publish_count(uint32_t* counter, uint32_t* out, uint32_t capacity)
+{
+    const uint32_t n = *counter;
+    *out = n < capacity ? n : capacity;
+    *counter = 0u;
 }
 
 /* ---------------------------------------------------------------- K7: agent memories of the SimpleAgent policy */
@@ -755,12 +808,24 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
         for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = 0u;
     }
     warp_tick(sslice, rec, m, stepped, raw, smem + TileScratch<TPB>::OFF_LIST + 8u * warp);
-    fence_proxy_async();
-    __syncwarp();
-    if(lane == 0)
+    const uint64_t c0 = uint64_t(blockIdx.x) * TPB + warp * 32u;      /* first child of this warp's slice */
+    if(c0 + 32u <= n_children)
     {
-        bulk_s2g(dst + (size_t(blockIdx.x) * TPB + warp * 32u) * POM_REC_BYTES, sslice, SLICE_BYTES);
-        bulk_wait_read_all();
+        fence_proxy_async();
+        __syncwarp();
+        if(lane == 0)
+        {
+            bulk_s2g(dst + c0 * POM_REC_BYTES, sslice, SLICE_BYTES);
+            bulk_wait_read_all();
+        }
+    }
+    else if(c < n_children)
+    {
+        /* the last, partly filled slice: only the children's own records are written - dst envs behind n_children keep
+         * their contents (a bulk store of the whole slice would overwrite up to 31 of them) */
+        uint32_t* out = reinterpret_cast<uint32_t*>(dst + c * POM_REC_BYTES);
+#pragma unroll 1
+        for(int w = 0; w < POM_REC_WORDS; w++) out[w] = rw[w];
     }
 }
 

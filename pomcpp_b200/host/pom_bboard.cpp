@@ -82,6 +82,20 @@ int SimpleActOnDevice(const State* s, int id, pom_simple_agent* memory, int draw
             g.x = 0; g.y = 0; g.dead = true;
         }
     }
+    /* likewise a visible flame cell whose flame started out of sight has lost its queue entry: for the policy it is just
+     * a burning cell (the literal Item::FLAMES, which the record carries as an orphan flame) */
+    for(int y = 0; y < BOARD_SIZE; y++)
+    {
+        for(int x = 0; x < BOARD_SIZE; x++)
+        {
+            const int v = seen.board[y][x];
+            if(!IS_FLAME(v)) continue;
+            const Position origin = { FLAME_ID(v) % BOARD_SIZE, FLAME_ID(v) / BOARD_SIZE };
+            bool listed = false;
+            for(int k = 0; k < seen.flames.count && !listed; k++) listed = seen.flames[k].position == origin;
+            if(!listed) seen.board[y][x] = Item::FLAMES;
+        }
+    }
     check(pom_batch_upload(h, 0, 1, reinterpret_cast<const pom_state*>(&seen), nullptr), "pom_batch_upload");
     pom_simple_agent four[4];
     std::memset(four, 0, sizeof(four));

@@ -1,0 +1,195 @@
+"""GPU tests (-m gpu) added in round 2:
+  * the parity chain closed on the device: the CUDA path against the COMPILED, UNMODIFIED reference (oracle/_ref/libpomref.so)
+    directly, not only against the restatement;
+  * the persistent warp-specialised per-tick kernel (k_step_ws) against the one-CTA-per-tile kernel (k_step) on identical
+    inputs, incl. the quiet-tick regime in which compute warps lap the buffer ring;
+  * compact step I/O (pom_batch_step_compact: uint16 joint actions in, done bits + finished-env list out);
+  * pom_batch_expand_step with a partly filled last slice."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import pomcpp_b200 as pb
+    assert os.path.exists(pb.LIB_PATH) and pb.device_count() > 0
+    return pb
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not oracle.have_reference():
+        pytest.skip("oracle/_ref/libpomref.so not shipped")
+    return oracle.reference()
+
+
+def _gpu_vs_compiled_reference(pb, orc, ref, n, ticks, nact, stress, seed):
+    """every field of every env after every tick, GPU vs the reference's own bboard::Step.  The reference is fenced where
+    it is undefined: ref_env_step_batch excludes D1(>=2)/D3/D4 ticks itself (FenceTick), and envs the GPU marks INVALID
+    in this tick (D5: the reference would hang) are excluded for it; excluded envs leave the comparison for good."""
+    b = pb.Batch(n, n_templates=256)
+    S, _ = b.download()
+    if stress:
+        S["agents"]["canKick"] = 1
+        S["agents"]["maxBombCount"] = 5
+        S["agents"]["bombStrength"] = 4
+        b.upload(S)
+    A = S.copy()
+    sa = np.zeros(n, np.uint8)
+    pre = np.zeros(n, np.uint8)
+    out_of_domain = np.zeros(n, bool)
+    prev_invalid = np.zeros(n, bool)
+    moves_dev = b.alloc(4 * n)
+    compared = 0
+    for t in range(ticks):
+        b.generate_moves(moves_dev, seed, t, nact)
+        b.step(moves_dev, 0)
+        G, gst = b.download()
+        now_invalid = (gst & 0x10) != 0
+        mv = orc.rng_moves(seed, 0, n, t, nact)
+        ref.env_step_batch(A, sa, mv, pre, (now_invalid & ~prev_invalid).astype(np.uint8))
+        prev_invalid = now_invalid
+        out_of_domain |= now_invalid | ((sa & 0x10) != 0)
+        e, why = orc.diff_batch(G, A, out_of_domain.astype(np.uint8))
+        assert e == -1, "tick %d env %d field group %d" % (t, e, why)
+        assert ((((sa ^ gst) & 0x0F) != 0) & ~out_of_domain).sum() == 0, "status, tick %d" % t
+        compared += int((~out_of_domain & ((gst & 1) == 0)).sum())
+    b.free(moves_dev)
+    b.close()
+    return compared, int(out_of_domain.sum())
+
+
+def test_gpu_vs_compiled_reference_config2(pb, orc, ref):
+    """BASELINE config 2 (harmless agents, per-tick kernel) straight against the compiled reference"""
+    compared, excluded = _gpu_vs_compiled_reference(pb, orc, ref, 16384, 400, 5, 0, 42)
+    assert compared > 6_000_000 and excluded < 100
+
+
+def test_gpu_vs_compiled_reference_random(pb, orc, ref):
+    compared, excluded = _gpu_vs_compiled_reference(pb, orc, ref, 32768, 64, 6, 0, 1234)
+    assert compared > 600_000 and excluded < 50
+
+
+def test_gpu_vs_compiled_reference_stress(pb, orc, ref):
+    """all agents kick, five bombs each, strength 4: kicks, chains, moving bombs, ghost bombs"""
+    compared, excluded = _gpu_vs_compiled_reference(pb, orc, ref, 8192, 200, 6, 1, 1003)
+    assert compared > 120_000
+
+
+def _run_kernel(pb, kernel, n, ticks, preroll, misalign=0, flags=None):
+    os.environ["POM_STEP_KERNEL"] = kernel
+    try:
+        b = pb.Batch(n, n_templates=4096, max_ticks=800)
+    finally:
+        os.environ.pop("POM_STEP_KERNEL", None)
+    if preroll:
+        b.rollout(preroll, 5, 0, 0)
+    mv = b.alloc(4 * n + 64)
+    base = mv.value + misalign
+    for t in range(ticks):
+        b.generate_moves(base, 77, t, 6)
+        b.step(base, pb.STEP_AUTORESET | pb.STEP_COUNT if flags is None else flags)
+    st = b.stats().as_dict()
+    S, status = b.download(0, min(n, 150000))
+    b.free(mv)
+    b.close()
+    return st, S, status
+
+
+@pytest.mark.parametrize("n,ticks,preroll,misalign", [(300001, 20, 0, 0), (300001, 12, 30, 4), (1 << 20, 16, 0, 0), (70000, 20, 10, 0)])
+def test_persistent_kernel_equals_tile_kernel(pb, n, ticks, preroll, misalign):
+    """k_step_ws (one CTA per SM, producer warp + slice-buffer ring) == k_step (one CTA per 128-env tile): same records,
+    same status bytes, same counters.  1 Mi fresh envs = quiet ticks: compute warps outrun HBM and lap the ring (the
+    regime that exposed a parity-aliasing bug in the ring's barriers); misalign = moves fetched per lane instead of by TMA."""
+    a = _run_kernel(pb, "ws", n, ticks, preroll, misalign)
+    c = _run_kernel(pb, "tile", n, ticks, preroll, misalign)
+    assert a[0] == c[0], (a[0], c[0])
+    assert a[1].tobytes() == c[1].tobytes() and (a[2] == c[2]).all()
+
+
+@pytest.mark.parametrize("autoreset", [True, False])
+def test_step_compact_matches_step_host(pb, autoreset):
+    """uint16 joint actions in, done bits + finished-env list out == the byte-per-agent API on a twin batch"""
+    n, ticks = 100003, 40
+    flags = (pb.STEP_AUTORESET | pb.STEP_COUNT) if autoreset else 0
+    a = pb.Batch(n, n_templates=512, max_ticks=30)
+    c = pb.Batch(n, n_templates=512, max_ticks=30)
+    mv, o1 = pb.pinned_array((n, 4), np.uint8)
+    st, o2 = pb.pinned_array((n,), np.uint8)
+    joint, o3 = pb.pinned_array((n,), np.uint16, near_device=0)
+    bits, o4 = pb.pinned_array(((n + 31) // 32,), np.uint32, near_device=0)
+    fenv, o5 = pb.pinned_array((n,), np.uint32)
+    fst, o6 = pb.pinned_array((n,), np.uint8)
+    fcnt, o7 = pb.pinned_array((1,), np.uint32)
+    rng = np.random.default_rng(3)
+    ended_total = 0
+    for t in range(ticks):
+        mv[:] = rng.integers(0, 6, (n, 4), dtype=np.uint8)
+        joint[:] = pb.joint_of_moves(mv)
+        a.step_host(mv, st, flags)
+        c.step_compact(joint, bits, fenv, fst, fcnt, flags)
+        c.sync()
+        ended = (st & 0x31) != 0 if autoreset else np.zeros(n, bool)
+        if not autoreset:
+            # without auto-reset an env reports the tick in which it finished; afterwards it is frozen and not stepped
+            ended = ((st & 0x11) != 0) & ~getattr(test_step_compact_matches_step_host, "_prev", np.zeros(n, bool))
+            test_step_compact_matches_step_host._prev = (st & 0x11) != 0
+        got_bits = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert (got_bits == ended).all(), "done bits, tick %d" % t
+        k = int(fcnt[0])
+        assert k == int(ended.sum())
+        order = np.argsort(fenv[:k])
+        assert (fenv[:k][order] == np.nonzero(ended)[0]).all()
+        assert (fst[:k][order] == st[ended]).all()
+        ended_total += k
+    if hasattr(test_step_compact_matches_step_host, "_prev"):
+        del test_step_compact_matches_step_host._prev
+    A, sa = a.download()
+    Cc, sc = c.download()
+    assert A.tobytes() == Cc.tobytes() and (sa == sc).all()
+    assert a.stats().as_dict() == c.stats().as_dict()
+    assert ended_total > 1000
+    # device buffers work too, and a list that is too short is truncated, not overrun
+    jd = c.alloc(2 * n)
+    pb.lib().pom_device_copy(0, jd, joint.ctypes.data_as(__import__("ctypes").c_void_p), 2 * n)
+    small_env, o8 = pb.pinned_array((8,), np.uint32)
+    small_st, o9 = pb.pinned_array((8,), np.uint8)
+    c.step_compact(jd.value, None, small_env, small_st, fcnt, flags)
+    c.sync()
+    assert int(fcnt[0]) <= 8
+    c.free(jd)
+    for o in (o1, o2, o3, o4, o5, o6, o7, o8, o9):
+        pb.pinned_free(o)
+    a.close()
+    c.close()
+
+
+def test_expand_partial_last_slice_keeps_neighbours(pb, orc):
+    """n_children not a multiple of 32: the dst envs behind the last child must survive (they were zero-filled before)"""
+    src = pb.Batch(64, n_templates=16)
+    src.rollout(12, 9, 0, pb.ROLL_NO_RESET)
+    dst = pb.Batch(3000, n_templates=16)
+    before, sb = dst.download()
+    roots = np.array([5, 17], np.uint32)
+    fanout = 1101                                   # 2202 children: the last slice holds 26
+    dst.expand_step_from(src, roots, fanout, 0)
+    after, sa = dst.download()
+    n_children = 2 * fanout
+    assert after[n_children:].tobytes() == before[n_children:].tobytes() and (sa[n_children:] == sb[n_children:]).all()
+    # and the children themselves are right
+    R, rst = src.download()
+    for c in (0, 1100, 1101, n_children - 1):
+        root, j = c // fanout, c % fanout
+        s = R[roots[root]:roots[root] + 1].copy()
+        st = rst[roots[root]:roots[root] + 1].copy()
+        mv = np.array([[j % 6, (j // 6) % 6, (j // 36) % 6, (j // 216) % 6]], np.uint8)
+        orc.env_step_batch(s, st, mv)
+        assert orc.diff_batch(after[c:c + 1], s)[0] == -1 and sa[c] == st[0]
+    src.close()
+    dst.close()
