@@ -158,6 +158,12 @@ int  pom_batch_step_host_async(pom_batch* b, const uint8_t* moves_host, uint8_t*
  *              ones are dropped: size the list for the worst case n_envs, or poll done_bits).  fin_env may be NULL.
  * Every pointer may be device memory or page-locked mapped host memory (pom_host_alloc / pom_host_alloc_near): the
  * kernel reads and writes host memory directly.  Enqueues only: results are valid after pom_batch_sync(b). */
+/* pom_batch_step and pom_batch_observe_planes in ONE kernel: at the end of the tick (after an auto-reset, so that the
+ * planes show the state the next action applies to) every env's observation for the agents in agent_mask is written
+ * from the record the kernel still holds in shared memory - the 306 MB record array of a 1 Mi-env batch is not read a
+ * second time and no second launch is needed.  obs_dev, agent_mask, view and the layout are those of
+ * pom_batch_observe_planes.  Envs that are frozen (done / invalid, no auto-reset) are observed as they are. */
+int  pom_batch_step_observe(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* obs_dev, uint32_t agent_mask, int view);
 typedef struct pom_step_compact_io {
     const uint16_t* joint;
     uint32_t*       done_bits;
@@ -165,6 +171,10 @@ typedef struct pom_step_compact_io {
     uint8_t*        fin_status;
     uint32_t*       fin_count;
     uint32_t        fin_capacity;
+    /* optional: observation planes written by the same kernel (see pom_batch_step_observe): DEVICE buffer, agents, window */
+    uint8_t*        obs_dev;
+    uint32_t        obs_agent_mask;
+    int32_t         obs_view;
 } pom_step_compact_io;
 int  pom_batch_step_compact(pom_batch* b, const pom_step_compact_io* io, uint32_t flags);
 /* `ticks` fused ticks with the boards resident in shared memory; actions from pom_rng_moves(rng_seed,

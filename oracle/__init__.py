@@ -269,6 +269,10 @@ class Reference:
     def hardware_concurrency(self):
         return self.lib.ref_hardware_concurrency()
 
+    def set_fence(self, on):
+        """the per-tick FenceTick of the timed loops on/off (only ever off on traces where it cannot fire)"""
+        self.lib.ref_set_fence(int(bool(on)))
+
     # --- agents::SimpleAgent / bboard::strategy, unmodified reference code ---
     class SimpleAgents:
         """n_envs x 4 reference SimpleAgent objects (zero-initialised memory, engine re-seeded per act)."""

@@ -51,7 +51,8 @@ class InitDesc(C.Structure):
 
 class StepCompactIO(C.Structure):
     _fields_ = [("joint", C.c_void_p), ("done_bits", C.c_void_p), ("fin_env", C.c_void_p), ("fin_status", C.c_void_p),
-                ("fin_count", C.c_void_p), ("fin_capacity", C.c_uint32)]
+                ("fin_count", C.c_void_p), ("fin_capacity", C.c_uint32), ("obs_dev", C.c_void_p),
+                ("obs_agent_mask", C.c_uint32), ("obs_view", C.c_int32)]
 
 
 def joint_of_moves(moves):
@@ -140,6 +141,7 @@ def lib():
         L.pom_host_alloc_near.argtypes = [i32, u64, C.POINTER(vp)]
         L.pom_bind_thread_near.argtypes = [i32]
         L.pom_batch_step_compact.argtypes = [vp, vp, u32]
+        L.pom_batch_step_observe.argtypes = [vp, vp, u32, vp, u32, i32]
         L.pom_batch_event_record.argtypes = [vp, i32]
         L.pom_batch_event_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.pom_batch_flush_l2.argtypes = [vp]
@@ -249,7 +251,26 @@ class Batch:
         assert moves.dtype == np.uint8 and moves.size == 4 * self.n and moves.flags.c_contiguous
         _ck(lib().pom_batch_step_host(self.h, _p(moves), _p(status_out), flags))
 
-    def step_compact(self, joint, done_bits=None, fin_env=None, fin_status=None, fin_count=None, flags=0):
+    def step_observe(self, moves_dev, obs_dev, agent_mask=1, view=4, flags=0):
+        """one tick + observation planes of the agents in agent_mask, one kernel (pom_batch_step_observe)"""
+        _ck(lib().pom_batch_step_observe(self.h, moves_dev, flags, obs_dev, agent_mask, view))
+
+    def compact_io(self, joint, done_bits=None, fin_env=None, fin_status=None, fin_count=None, obs_dev=None,
+                   obs_agent_mask=0, obs_view=4):
+        """a prepared pom_step_compact_io for step_compact_io (an actor loop reuses its buffers: build the struct once)"""
+        def ptr(a):
+            if a is None:
+                return None
+            return C.c_void_p(a) if isinstance(a, int) else _p(a)
+        return StepCompactIO(ptr(joint), ptr(done_bits), ptr(fin_env), ptr(fin_status), ptr(fin_count),
+                             0 if fin_env is None else (fin_env.size if hasattr(fin_env, "size") else self.n),
+                             obs_dev, obs_agent_mask, obs_view)
+
+    def step_compact_io(self, io, flags=0):
+        _ck(lib().pom_batch_step_compact(self.h, C.byref(io), flags))
+
+    def step_compact(self, joint, done_bits=None, fin_env=None, fin_status=None, fin_count=None, flags=0, obs_dev=None,
+                     obs_agent_mask=0, obs_view=4):
         """one tick with compact I/O (pom_batch_step_compact): `joint` = n uint16 joint actions; outputs are optional.
         Arrays must live in pinned mapped memory (pinned_array) or be raw device pointers (int); enqueue only."""
         def ptr(a):
@@ -257,7 +278,8 @@ class Batch:
                 return None
             return C.c_void_p(a) if isinstance(a, int) else _p(a)
         io = StepCompactIO(ptr(joint), ptr(done_bits), ptr(fin_env), ptr(fin_status), ptr(fin_count),
-                           0 if fin_env is None else (fin_env.size if hasattr(fin_env, "size") else self.n))
+                           0 if fin_env is None else (fin_env.size if hasattr(fin_env, "size") else self.n),
+                           obs_dev, obs_agent_mask, obs_view)
         _ck(lib().pom_batch_step_compact(self.h, C.byref(io), flags))
 
     def step_seq(self, moves_dev, ticks, flags=0):

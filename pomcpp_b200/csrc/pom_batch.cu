@@ -318,9 +318,9 @@ int launch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_
 template<int TPB>
 int launch_observe_planes(pom_batch* b, uint8_t* obs_dev, uint32_t mask, int view)
 {
-    { int rc = set_smem(b, ATTR_OBS, pomk::k_observe_planes<TPB>, pomk::ObsScratch<TPB>::BYTES); if(rc) return rc; }
+    { int rc = set_smem(b, ATTR_OBS, pomk::k_observe_planes<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
-    pomk::k_observe_planes<TPB><<<grid, TPB, pomk::ObsScratch<TPB>::BYTES, b->stream>>>(b->params(), obs_dev, b->n_alloc, mask, view);
+    pomk::k_observe_planes<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), obs_dev, b->n_alloc, mask, view);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -734,6 +734,19 @@ int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status
     return POM_OK;
 }
 
+int pom_batch_step_observe(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* obs_dev, uint32_t agent_mask, int view)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!moves_dev || !obs_dev) return fail(POM_E_ARG, "pom_batch_step_observe: null pointer");
+    if(agent_mask == 0 || agent_mask > 0xFu || view < 0) return fail(POM_E_ARG, "pom_batch_step_observe: agent_mask must be 1..15 and view >= 0");
+    if(flags & POM_STEP_OVERLAP) return fail(POM_E_ARG, "pom_batch_step_observe: POM_STEP_OVERLAP is not supported");
+    if(b->step_kernel != 0) return fail(POM_E_ARG, "pom_batch_step_observe needs the persistent step kernel (unset POM_STEP_KERNEL)");
+    pomk::StepIO k{};
+    k.moves = moves_dev;
+    k.obs = obs_dev; k.obs_stride = b->n_alloc; k.obs_mask = agent_mask; k.obs_view = view;
+    return launch_step_io(b, b->params(), k, flags, b->stream);
+}
+
 int pom_batch_step_compact(pom_batch* b, const pom_step_compact_io* io, uint32_t flags)
 {
     int rc = use(b); if(rc) return rc;
@@ -752,24 +765,22 @@ int pom_batch_step_compact(pom_batch* b, const pom_step_compact_io* io, uint32_t
     k.moves = joint;
     k.joint = 1u;
     k.fin_capacity = io->fin_capacity;
+    if(io->obs_dev)
+    {
+        if(io->obs_agent_mask == 0 || io->obs_agent_mask > 0xFu || io->obs_view < 0) return fail(POM_E_ARG, "pom_batch_step_compact: obs_agent_mask must be 1..15 and obs_view >= 0");
+        k.obs = io->obs_dev; k.obs_stride = b->n_alloc; k.obs_mask = io->obs_agent_mask; k.obs_view = io->obs_view;
+    }
     if(k.fin_env)
     {
         if(!b->fin_counter)
         {
-            CK(cudaMalloc(&b->fin_counter, sizeof(uint32_t)));
-            CK(cudaMemsetAsync(b->fin_counter, 0, sizeof(uint32_t), b->stream));
+            CK(cudaMalloc(&b->fin_counter, 2 * sizeof(uint32_t)));
+            CK(cudaMemsetAsync(b->fin_counter, 0, 2 * sizeof(uint32_t), b->stream));
         }
         k.fin_counter = b->fin_counter;
+        k.fin_count_out = count;
     }
-    rc = launch_step_io(b, b->params(), k, flags, b->stream);
-    if(rc) return rc;
-    if(k.fin_env)
-    {
-        pomk::k_publish_count<<<1, 1, 0, b->stream>>>(b->fin_counter, count, io->fin_capacity);
-        b->launches++;
-        CK(cudaGetLastError());
-    }
-    return POM_OK;
+    return launch_step_io(b, b->params(), k, flags, b->stream);
 }
 
 int pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t tick0, uint32_t flags)

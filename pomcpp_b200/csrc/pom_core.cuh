@@ -1545,57 +1545,104 @@ POM_HD void fog_state(pom_state* s, int agent, int view)
  * bytes ready for a network input (include/pom_batch.h describes the layout).  Same visibility rule as fog_state; the
  * board plane uses the reference's Item order (bboard.hpp:54-71) with wood / flame powerup flags hidden, as in the game.
  * ------------------------------------------------------------------------------------------- */
-POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)   /* out: 4-byte aligned */
+/* 16 bytes of an observation at once: one STG.128 / STS.128 on the device */
+POM_HD void obs_store16(uint8_t* out, int chunk, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<uint4*>(out)[chunk] = make_uint4(a, b, c, d);
+#else
+    uint32_t* w = reinterpret_cast<uint32_t*>(out) + 4 * chunk;
+    w[0] = a; w[1] = b; w[2] = c; w[3] = d;
+#endif
+}
+
+/* `out` is 16-byte aligned and may be global memory: the record is written in 31 chunks of 16 bytes (whole chunks,
+ * nothing is read back), then the few bytes of visible bombs and flames are patched in by the same thread.  So a lane
+ * can write its env's observation straight to its place in HBM from the record it holds in shared memory - the L2
+ * merges the 16-byte pieces of a 32-byte sector - and no staging tile is needed. */
+POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
 {
     const uint32_t ap = r[R_APOS + agent];
     const int ax = int(ap & 15u), ay = int(ap >> 4);
     const int x0 = ax - view, x1 = ax + view, y0 = ay - view, y1 = ay + view;
-    uint32_t* ow = reinterpret_cast<uint32_t*>(out);
-    /* planes 1-3 start out empty: bytes 124..483 = words 31..120 (bytes 121..123 are written with board word 30) */
-    for(int w = 31; w < 121; w++) ow[w] = 0u;
+    /* planes 1-3 start out empty: bytes 128..479 = chunks 8..29 (bytes 121..127 leave with board chunk 7) */
+    for(int q = 8; q < 30; q++) obs_store16(out, q, 0u, 0u, 0u, 0u);
     /* board plane, four cells per word: the item ids come from byte-parallel range tests on the cell codes
      * (0,1 keep; 2..6 wood -> 2; 7 bomb -> 3; 8.. -> code - 3, i.e. fog 5, powerups 6..8, dummy 9, agents 10..13;
      * flame codes have the top bit set -> 4), then cells outside the window are overwritten with 5 (fog) */
     const uint32_t* bw = reinterpret_cast<const uint32_t*>(r + R_BOARD);
     int x = 0, y = 0;
-    for(int w = 0; w < 31; w++)
+    uint32_t litWords = 0u;                                    /* bit w: board word w holds a visible flame cell */
+    POM_LOOP
+    for(int q = 0; q < 8; q++)
     {
+        uint32_t word[4];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for(int k = 0; k < 4; k++)
+        {
+            const int w = 4 * q + k;
+            uint32_t ids = 0u;
+            if(w < 31)
+            {
+                const uint32_t codes = bw[w];
+                uint32_t vis = 0u;                             /* 0xFF in the bytes of visible cells */
+                for(int j = 0; j < 4; j++)
+                {
+                    const bool cell = w < 30 || j == 0;        /* word 30: only its first byte is a board cell */
+                    if(cell && x >= x0 && x <= x1 && y >= y0 && y <= y1) vis |= 0xFFu << (8 * j);
+                    if(++x == POM_BOARD_SIZE) { x = 0; y++; }
+                }
+                const uint32_t l = codes & 0x7F7F7F7Fu, flame = codes & 0x80808080u, plain = ~codes & 0x80808080u;
+                const uint32_t ge2 = (l + 0x7E7E7E7Eu) & 0x80808080u, ge7 = (l + 0x79797979u) & 0x80808080u, ge8 = (l + 0x78787878u) & 0x80808080u;
+                const uint32_t keep = ((plain & ~ge2) >> 7) * 0xFFu, wood = ((plain & ge2 & ~ge7) >> 7) * 0xFFu;
+                const uint32_t bomb = ((plain & ge7 & ~ge8) >> 7) * 0xFFu, high = ((plain & ge8) >> 7) * 0xFFu, burn = (flame >> 7) * 0xFFu;
+                const uint32_t minus3 = ((l | 0x80808080u) - 0x03030303u) & 0x7F7F7F7Fu;       /* per byte, no borrow between bytes */
+                ids = (codes & keep) | (0x02020202u & wood) | (0x03030303u & bomb) | (minus3 & high) | (0x04040404u & burn);
+                ids = (ids & vis) | (0x05050505u & ~vis);
+                if(w == 30) ids &= 0xFFu;                      /* bytes 121..123: the first cells of the bomb-strength plane */
+                if(burn & vis) litWords |= 1u << w;
+            }
+            word[k] = ids;
+        }
+        obs_store16(out, q, word[0], word[1], word[2], word[3]);
+    }
+    {
+        const int ammo = int(r[R_AMAX + agent]) - int(int8_t(r[R_ABCNT + agent]));
+        uint32_t alive = 0;
+        for(int i = 0; i < 4; i++) alive |= (r[R_AFLAGS + i] & AF_DEAD) ? 0u : (1u << i);
+        obs_store16(out, 30, 0u,
+                    uint32_t(ax) | (uint32_t(ay) << 8) | (uint32_t(ammo < 0 ? 0 : (ammo > 255 ? 255 : ammo)) << 16) | (uint32_t(r[R_ASTR + agent]) << 24),
+                    ((r[R_AFLAGS + agent] & AF_CANKICK) ? 1u : 0u) | (alive << 8) | (uint32_t(r[R_TIME]) << 16) | (uint32_t(r[R_TIME + 1]) << 24),
+                    (alive >> agent) & 1u);
+    }
+    /* visible flame cells: how long they still burn */
+    POM_LOOP
+    while(litWords)
+    {
+        int w = 0;
+        while(!((litWords >> w) & 1u)) w++;
+        litWords &= litWords - 1u;
         const uint32_t codes = bw[w];
-        uint32_t vis = 0u;                                     /* 0xFF in the bytes of visible cells */
+        const int fc = r[R_FCOUNT];
         for(int j = 0; j < 4; j++)
         {
-            const bool cell = w < 30 || j == 0;                /* word 30: only its first byte is a board cell */
-            if(cell && x >= x0 && x <= x1 && y >= y0 && y <= y1) vis |= 0xFFu << (8 * j);
-            if(++x == POM_BOARD_SIZE) { x = 0; y++; }
-        }
-        const uint32_t l = codes & 0x7F7F7F7Fu, flame = codes & 0x80808080u, plain = ~codes & 0x80808080u;
-        const uint32_t ge2 = (l + 0x7E7E7E7Eu) & 0x80808080u, ge7 = (l + 0x79797979u) & 0x80808080u, ge8 = (l + 0x78787878u) & 0x80808080u;
-        const uint32_t keep = ((plain & ~ge2) >> 7) * 0xFFu, wood = ((plain & ge2 & ~ge7) >> 7) * 0xFFu;
-        const uint32_t bomb = ((plain & ge7 & ~ge8) >> 7) * 0xFFu, high = ((plain & ge8) >> 7) * 0xFFu, burn = (flame >> 7) * 0xFFu;
-        const uint32_t minus3 = ((l | 0x80808080u) - 0x03030303u) & 0x7F7F7F7Fu;       /* per byte, no borrow between bytes */
-        uint32_t ids = (codes & keep) | (0x02020202u & wood) | (0x03030303u & bomb) | (minus3 & high) | (0x04040404u & burn);
-        ids = (ids & vis) | (0x05050505u & ~vis);
-        if(w == 30) ids &= 0xFFu;                              /* bytes 121..123: the first cells of the bomb-strength plane */
-        ow[w] = ids;
-        uint32_t lit = burn & vis;                             /* visible flame cells: how long they still burn */
-        if(lit)
-        {
-            const int fc = r[R_FCOUNT];
-            for(int j = 0; j < 4; j++)
+            const int c = 4 * w + j;
+            if(c >= POM_BOARD_CELLS || !((codes >> (8 * j)) & 0x80u)) continue;
+            const int cx = c % POM_BOARD_SIZE, cy = c / POM_BOARD_SIZE;
+            if(cx < x0 || cx > x1 || cy < y0 || cy > y1) continue;
+            /* the flame-queue entry the cell belongs to: the first one, in queue order, with the cell's origin
+             * (the rule State::PopFlame matches cells by, bboard.cpp:160-176) */
+            const uint32_t origin = flame_origin(r, (codes >> (8 * j)) & 0xFFu);
+            uint32_t slot = r[R_FINDEX];
+            for(int k = 0; k < fc && k < 20; k++, slot = ring_next(slot))
             {
-                if(!((lit >> (8 * j)) & 0xFFu)) continue;
-                /* the flame-queue entry the cell belongs to: the first one, in queue order, with the cell's origin
-                 * (the rule State::PopFlame matches cells by, bboard.cpp:160-176) */
-                const uint32_t origin = flame_origin(r, (codes >> (8 * j)) & 0xFFu);
-                uint32_t slot = r[R_FINDEX];
-                for(int k = 0; k < fc && k < 20; k++, slot = ring_next(slot))
+                if(r[R_FPOS + slot] == origin)
                 {
-                    if(r[R_FPOS + slot] == origin)
-                    {
-                        const int t = int(int8_t(r[R_FTIME + slot]));
-                        out[363 + 4 * w + j] = uint8_t(t < 0 ? 0 : t);
-                        break;
-                    }
+                    const int t = int(int8_t(r[R_FTIME + slot]));
+                    out[363 + c] = uint8_t(t < 0 ? 0 : t);
+                    break;
                 }
             }
         }
@@ -1613,12 +1660,6 @@ POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out) 
             out[242 + bx + 11 * by] = uint8_t((b >> 16) & 15u);
         }
     }
-    const int ammo = int(r[R_AMAX + agent]) - int(int8_t(r[R_ABCNT + agent]));
-    uint32_t alive = 0;
-    for(int i = 0; i < 4; i++) alive |= (r[R_AFLAGS + i] & AF_DEAD) ? 0u : (1u << i);
-    ow[121] = uint32_t(ax) | (uint32_t(ay) << 8) | (uint32_t(ammo < 0 ? 0 : (ammo > 255 ? 255 : ammo)) << 16) | (uint32_t(r[R_ASTR + agent]) << 24);
-    ow[122] = ((r[R_AFLAGS + agent] & AF_CANKICK) ? 1u : 0u) | (alive << 8) | (uint32_t(r[R_TIME]) << 16) | (uint32_t(r[R_TIME + 1]) << 24);
-    ow[123] = (alive >> agent) & 1u;
 }
 
 /* the shared stateless action source (same arithmetic as oracle/pom_oracle.c pom_oracle_rng_moves) */

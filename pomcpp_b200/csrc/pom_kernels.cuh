@@ -423,8 +423,15 @@ struct StepIO {
     uint32_t*   done_bits;     /* one word per slice: bit l = env 32 s + l ended an episode this tick, or null */
     uint32_t*   fin_env;       /* compacted list of those envs ...            (null: no list) */
     uint8_t*    fin_status;    /* ... and their status bytes (as in status_out) */
-    uint32_t*   fin_counter;   /* DEVICE counter the list is appended through */
+    uint32_t*   fin_counter;   /* DEVICE words: [0] the counter the list is appended through, [1] CTAs that are done */
+    uint32_t*   fin_count_out; /* where the last CTA publishes the list length (device or mapped host memory) */
     uint32_t    fin_capacity;
+    uint8_t*    obs;           /* observation planes of the agents in obs_mask, written from the resident record at the
+                                  end of the tick (after an auto-reset): slab k (k-th agent of the mask) at
+                                  obs + k * obs_stride * POM_OBS_BYTES; null = none */
+    uint64_t    obs_stride;
+    uint32_t    obs_mask;
+    int         obs_view;
 };
 
 /* four moves from a joint action index */
@@ -463,7 +470,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
     if(threadIdx.x == 0)
     {
         for(int b = 0; b < NBUF; b++) { mbar_init(full + b, 1); mbar_init(empty + b, 1); }
-        *ticket = 0u;
+        ticket[0] = 0u;
+        ticket[1] = 0u;                                               /* compute warps that have finished */
         fence_barrier_init();
     }
     __syncthreads();
@@ -545,23 +553,48 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
         }
         fence_proxy_async();
         __syncwarp();
+        if(lane == 0) bulk_s2g(P.recs + s * R::SLICE_BYTES, sslice, R::SLICE_BYTES);
+        if(io.obs && active)
+        {
+            /* what the agents see now: built from the record while it is still in shared memory (the bulk store above
+             * only reads it), written straight to HBM in 16-byte pieces - no second pass over the 306 MB record array */
+            uint32_t k = 0u;
+            for(int a = 0; a < 4; a++)
+            {
+                if(!((io.obs_mask >> a) & 1u)) continue;
+                pomcore::observe_planes(rec, a, io.obs_view, io.obs + (uint64_t(k) * io.obs_stride + env) * POM_OBS_BYTES);
+                k++;
+            }
+        }
+        __syncwarp();
         if(lane == 0)
         {
-            bulk_s2g(P.recs + s * R::SLICE_BYTES, sslice, R::SLICE_BYTES);
             bulk_wait_read_all();
             mbar_arrive(empty + b);
         }
         __syncwarp();
     }
     acc_flush(P.stats, acc, (flags & POM_STEP_COUNT) != 0u);
-}
-
-/* hands the length of the finished-env list to the caller (host-mapped or device word) and clears the device counter */
-__global__ void k_publish_count(uint32_t* counter, uint32_t* out, uint32_t capacity)
-{
-    const uint32_t n = *counter;
-    *out = n < capacity ? n : capacity;
-    *counter = 0u;
+    if(io.fin_env)
+    {
+        /* the last warp of the last CTA hands the list length to the caller and clears the counters for the next launch
+         * (no second kernel): every warp makes its list entries visible, then counts itself off */
+        __threadfence();
+        uint32_t* warps_done = ticket + 1;
+        bool last = false;
+        if(lane == 0) last = atomicAdd(warps_done, 1u) == uint32_t(NW - 1);
+        if(last)
+        {
+            __threadfence();
+            if(atomicAdd(io.fin_counter + 1, 1u) == gridDim.x - 1u)
+            {
+                __threadfence();
+                const uint32_t count = atomicExch(io.fin_counter, 0u);
+                *io.fin_count_out = count < io.fin_capacity ? count : io.fin_capacity;
+                io.fin_counter[1] = 0u;
+            }
+        }
+    }
 }
 
 /* ---------------------------------------------------------------- K7: agent memories of the SimpleAgent policy */
@@ -863,13 +896,9 @@ __global__ void k_observe(const uint8_t* __restrict__ recs, pom_state* aos, uint
 
 /* observation planes (pomcore::observe_planes) for the agents in `mask`, written as POM_OBS_BYTES records into one slab
  * per agent: out[((k * stride) + env) * POM_OBS_BYTES], k = rank of the agent within the mask.  Same per-warp staging as
- * k_step: the warp's 32 records come in with one bulk load; every lane writes its env's observation into the warp's
- * 32 x 496-byte tile in shared memory, which leaves with ONE bulk store per agent (15.9 KB, contiguous in the slab). */
-template<int TPB> struct ObsScratch {
-    static constexpr uint32_t OFF_OBS = (TileScratch<TPB>::BYTES + 127u) / 128u * 128u;
-    static constexpr uint32_t BYTES = OFF_OBS + uint32_t(TPB) * POM_OBS_BYTES;
-};
-
+ * k_step: the warp's 32 records come in with one bulk load; every lane then writes its env's observation straight to
+ * the slab.  (Round 1 staged the 32 x 496 bytes in shared memory and bulk-stored them: 25 KB per warp, 8 warps per SM,
+ * 53 % of the HBM peak; without the tile the kernel runs at 24 warps per SM.)  The fused form is StepIO::obs. */
 template<int TPB>
 __global__ void __launch_bounds__(TPB) k_observe_planes(BatchParams P, uint8_t* __restrict__ out, uint64_t stride, uint32_t mask, int view)
 {
@@ -879,7 +908,6 @@ __global__ void __launch_bounds__(TPB) k_observe_planes(BatchParams P, uint8_t* 
     const uint64_t env0 = uint64_t(blockIdx.x) * TPB + warp * 32u;            /* first env of this warp's slice */
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR) + warp;
     uint8_t* sslice = smem + warp * SLICE_BYTES;
-    uint8_t* otile = smem + ObsScratch<TPB>::OFF_OBS + warp * (32u * POM_OBS_BYTES);
     if(lane == 0)
     {
         mbar_init(bar, 1);
@@ -890,20 +918,13 @@ __global__ void __launch_bounds__(TPB) k_observe_planes(BatchParams P, uint8_t* 
     __syncwarp();
     mbar_wait(bar, 0);
     const uint8_t* rec = sslice + lane * POM_REC_BYTES;
+    if(env0 + lane >= P.n_envs) return;
     uint32_t k = 0;
     for(int a = 0; a < 4; a++)
     {
         if(!((mask >> a) & 1u)) continue;
-        /* lanes past n_envs read the zeroed tail of the record array and write into the padded tail of the slab */
-        pomcore::observe_planes(rec, a, view, otile + lane * POM_OBS_BYTES);
-        fence_proxy_async();
-        __syncwarp();
-        if(lane == 0)
-        {
-            bulk_s2g(out + (uint64_t(k) * stride + env0) * POM_OBS_BYTES, otile, 32u * POM_OBS_BYTES);
-            bulk_wait_read_all();                                 /* the tile is rewritten for the next agent */
-        }
-        __syncwarp();
+        /* every lane writes its env's 496 bytes straight to the slab, 16 bytes per store (pomcore::observe_planes) */
+        pomcore::observe_planes(rec, a, view, out + (uint64_t(k) * stride + env0 + lane) * POM_OBS_BYTES);
         k++;
     }
 }

@@ -11,6 +11,16 @@ def shard_plan(rank, world, envs_per_gpu):
     return {"first": rank * envs_per_gpu, "count": envs_per_gpu, "total": world * envs_per_gpu}
 
 
+def strong_plan(rank, world, total):
+    """Global env range owned by `rank` when a FIXED total is split over the ranks (strong scaling): contiguous ranges,
+    sizes differ by at most one."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world %d" % (rank, world))
+    base, extra = divmod(total, world)
+    first = rank * base + min(rank, extra)
+    return {"first": first, "count": base + (1 if rank < extra else 0), "total": total}
+
+
 def reduce_counters(counters, dist=None, device="cpu"):
     """Sum of the POM_STATS_WORDS episode counters over all ranks (the one collective of a run)."""
     c = np.ascontiguousarray(counters, dtype=np.int64)

@@ -193,3 +193,38 @@ def test_expand_partial_last_slice_keeps_neighbours(pb, orc):
         assert orc.diff_batch(after[c:c + 1], s)[0] == -1 and sa[c] == st[0]
     src.close()
     dst.close()
+
+
+@pytest.mark.parametrize("mask,view", [(1, 4), (0b1010, 2)])
+def test_step_observe_fused_equals_step_then_observe(pb, orc, mask, view):
+    """pom_batch_step_observe: the planes written by the step kernel itself == pom_batch_observe_planes after the step
+    == the definition in the oracle, with auto-reset (the planes show the re-initialised env)"""
+    n = 20011
+    a = pb.Batch(n, n_templates=64, max_ticks=25)
+    c = pb.Batch(n, n_templates=64, max_ticks=25)
+    k = bin(mask).count("1")
+    stride = int(pb.lib().pom_batch_obs_stride(a.h))
+    obs = a.alloc(k * stride * pb.OBS_BYTES)
+    mv, mv2 = a.alloc(4 * n), c.alloc(4 * n)      # one buffer per handle: the two handles run on different streams
+    flags = pb.STEP_AUTORESET | pb.STEP_COUNT
+    for t in range(40):
+        a.generate_moves(mv, 5, t, 6)
+        a.step_observe(mv, obs, mask, view, flags)
+        c.generate_moves(mv2, 5, t, 6)
+        c.step(mv2, flags)
+        if t % 13 == 12 or t == 39:
+            a.sync()
+            fused = np.zeros((k, stride, pb.OBS_BYTES), np.uint8)
+            pb.lib().pom_device_copy(0, fused.ctypes.data_as(__import__("ctypes").c_void_p), obs, fused.nbytes)
+            plain = c.observe_planes(mask, view)
+            assert (fused[:, :n] == plain).all(), "tick %d" % t
+            S, _ = c.download()
+            agents = [i for i in range(4) if (mask >> i) & 1]
+            for j, ag in enumerate(agents):
+                want = orc.observe_planes_batch(S[:3000], ag, view)
+                assert (fused[j, :3000] == want).all(), "agent %d tick %d" % (ag, t)
+    A, sa = a.download()
+    Cc, sc = c.download()
+    assert A.tobytes() == Cc.tobytes() and (sa == sc).all()
+    a.free(obs); a.free(mv); c.free(mv2)
+    a.close(); c.close()

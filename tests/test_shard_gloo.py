@@ -55,3 +55,13 @@ def test_single_rank_passthrough():
     assert shard.shard_plan(0, 1, 7) == {"first": 0, "count": 7, "total": 7}
     with pytest.raises(ValueError):
         shard.shard_plan(2, 2, 7)
+
+
+def test_strong_plan_partitions_a_fixed_total():
+    from pomcpp_b200 import shard
+    for total, world in ((1 << 20, 8), (1000, 3), (5, 8)):
+        plans = [shard.strong_plan(r, world, total) for r in range(world)]
+        assert plans[0]["first"] == 0 and sum(p["count"] for p in plans) == total
+        for a, b in zip(plans, plans[1:]):
+            assert a["first"] + a["count"] == b["first"]
+        assert max(p["count"] for p in plans) - min(p["count"] for p in plans) <= 1
