@@ -151,6 +151,12 @@ def load_profile(name, key):
         return None
 
 
+def traffic_per_tick(n):
+    """DRAM bytes per tick of n envs from the committed ncu capture of k_step_ws (which stepped envs_per_launch envs)"""
+    t, e = load_profile("k_step_ncu_summary_r2.json", "dram_bytes_per_launch"), load_profile("k_step_ncu_summary_r2.json", "envs_per_launch")
+    return None if not t or not e else float(t) * n / float(e)
+
+
 def profile_metric(name, metric):
     try:
         v = json.load(open(os.path.join(ROOT, "profiles", name)))["metrics"][metric]["values"][0]
@@ -557,12 +563,12 @@ def run_own(args):
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_nominal_8tbs": achieved / NOMINAL_HBM_GBS,
-                         "traffic": load_profile("k_step_ncu_summary_r2.json", "dram_bytes_per_launch"),
+                         "traffic": traffic_per_tick(n),
                          "algorithmic_bytes_per_env_step": ALGO_BYTES,
                          "peak_source": peak_src, "kernel": "k_step_ws<20,24>", "step_ms": ms / K,
                          "launches_per_step": 2,
                          "note": "achieved = 582 B x envs / time per tick over the timed region (CUDA events bracket both streams); traffic = DRAM "
-                                 "bytes per tick from the ncu capture of one whole-batch launch",
+                                 "bytes per tick, scaled from the ncu capture of one half-batch launch (profiles/k_step_ncu_summary_r2.json)",
                          "single_launch": {"launch_ms": single_ms, "achieved": single_achieved, "frac": single_achieved / peak,
                                            "frac_nominal_8tbs": single_achieved / NOMINAL_HBM_GBS, "steps": SINGLE_STEPS,
                                            "what": "one launch per tick over the whole batch, no overlap between ticks"}},

@@ -46,6 +46,13 @@ enum {
                                  step without this flag) is not stepped and therefore stays frozen: use pom_batch_reset,
                                  or upload a running state */
     POM_STEP_COUNT     = 0x4, /* add the number of envs stepped to stats.env_steps                       */
+    POM_STEP_CONTINUE_UNDEFINED = 0x10, /* Where the reference dereferences a null bomb (step.cpp:167, a kicker walks onto a
+                                 BOMB cell without queue entry) or recurses without end (step_utility.cpp:89-92, the
+                                 reversion chain reaches an agent that did not move), the env is by default marked
+                                 POM_STATUS_INVALID and frozen (counted in stats.invalid).  With this flag it keeps
+                                 running with the canonical result instead: the kicker moves and no bomb gets a
+                                 direction; the chain stops at that agent.  Queue overflows and values the record cannot
+                                 carry still invalidate.  The reference has no behaviour to compare with here. */
     POM_STEP_OVERLAP   = 0x8  /* pom_batch_step only: step the two halves of the batch on two internal streams so that
                                  consecutive ticks overlap at their edges.  Every other call on the handle first waits
                                  for both halves; work the caller enqueues DIRECTLY on pom_batch_stream() is ordered after
@@ -58,6 +65,7 @@ enum {
 enum {
     POM_ROLL_HARMLESS  = 0x1,
     POM_ROLL_NO_RESET  = 0x2, /* finished envs freeze (Environment::Step, environment.cpp:125-128) instead of auto-resetting */
+    POM_ROLL_CONTINUE_UNDEFINED = 0x4, /* as POM_STEP_CONTINUE_UNDEFINED */
     /* bits 8..11: agent a plays the reference's heuristic SimpleAgent (simple_agent.cpp:12-141) instead of drawing
      * uniformly; the reference's own benchmark runs four of them (performance_test.cpp:38,59-63) */
     POM_ROLL_SIMPLE_SHIFT = 8

@@ -68,6 +68,10 @@ class Restatement:
         for f in ("pom_oracle_step", "pom_oracle_env_step"):
             getattr(L, f).restype = C.c_int
 
+    def set_continue_undefined(self, on):
+        """D3 / D5 ticks keep the env running with the canonical result (POM_STEP_CONTINUE_UNDEFINED)"""
+        self.lib.pom_oracle_set_continue_undefined(int(bool(on)))
+
     # --- single-state helpers (fixtures) ---
     def zero_state(self, n=None):
         s = np.zeros(1 if n is None else n, dtype=STATE_DT)

@@ -559,6 +559,15 @@ int pom_oracle_step(pom_state* s, const uint8_t moves_in[4])
     return flags;
 }
 
+/* POM_STEP_CONTINUE_UNDEFINED (include/pom_batch.h): where the reference dereferences null (D3) or recurses for ever
+ * (D5) the restatement already computes the canonical continuation (the kicker moves and no direction is set; the
+ * reversion chain stops); with this switch on such a tick no longer takes the env out of the game. */
+static int g_invalid_mask = POM_ORC_INVALID_MASK;
+void pom_oracle_set_continue_undefined(int on)
+{
+    g_invalid_mask = on ? (POM_ORC_INVALID_MASK & ~(POM_ORC_D3_NULL_BOMB | POM_ORC_D5_REVERT_LOOP)) : POM_ORC_INVALID_MASK;
+}
+
 int pom_oracle_env_step(pom_state* s, uint8_t* status, const uint8_t moves[4])   /* environment.cpp:125-128,149-168 */
 {
     if (*status & (POM_STATUS_DONE | POM_STATUS_INVALID)) return 0;   /* invalid envs freeze: the reference would have crashed */
@@ -570,7 +579,7 @@ int pom_oracle_env_step(pom_state* s, uint8_t* status, const uint8_t moves[4])  
         *status = (uint8_t)((*status & POM_STATUS_INVALID) | POM_STATUS_DONE | (w << POM_STATUS_WINNER_SHIFT));
     }
     if (s->aliveAgents == 0) *status = (uint8_t)((*status & POM_STATUS_INVALID) | POM_STATUS_DONE | POM_STATUS_DRAW);
-    if (flags & POM_ORC_INVALID_MASK) *status |= POM_STATUS_INVALID;
+    if (flags & g_invalid_mask) *status |= POM_STATUS_INVALID;
     return flags;
 }
 

@@ -42,6 +42,7 @@ int pom_oracle_step(pom_state* s, const uint8_t moves[4]);
 
 /* Environment::Step on a bare state + status byte (environment.cpp:125-128,149-168) */
 int pom_oracle_env_step(pom_state* s, uint8_t* status, const uint8_t moves[4]);
+void pom_oracle_set_continue_undefined(int on);   /* D3 / D5 ticks keep the env running (canonical continuation) */
 
 /* State primitives used by fixtures (bboard.cpp) */
 void pom_oracle_put_agent(pom_state* s, int x, int y, int id);                 /* :313-320 */

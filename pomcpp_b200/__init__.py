@@ -18,8 +18,8 @@ OBS_BYTES = 496
 ALGO_BYTES_PER_ENV_STEP = 2 * 289 + 4      # packed PAYLOAD in + out + 4 move bytes (what the roofline credits)
 MOVED_BYTES_PER_ENV_STEP = 2 * 292 + 4     # what actually crosses HBM: the record is padded to 292 B
 
-STEP_RAW, STEP_AUTORESET, STEP_COUNT, STEP_OVERLAP = 1, 2, 4, 8
-ROLL_HARMLESS, ROLL_NO_RESET = 1, 2
+STEP_RAW, STEP_AUTORESET, STEP_COUNT, STEP_OVERLAP, STEP_CONTINUE_UNDEFINED = 1, 2, 4, 8, 16
+ROLL_HARMLESS, ROLL_NO_RESET, ROLL_CONTINUE_UNDEFINED = 1, 2, 4
 
 
 def ROLL_SIMPLE(agent_mask):

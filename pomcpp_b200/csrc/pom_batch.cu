@@ -285,7 +285,7 @@ int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t*
 template<int TPB>
 int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, uint32_t flags, const uint8_t* move_seq = nullptr)
 {
-    const uint32_t n_actions = (flags & POM_ROLL_HARMLESS) ? 5u : 6u, no_reset = (flags & POM_ROLL_NO_RESET) ? 1u : 0u;
+    const uint32_t n_actions = (flags & POM_ROLL_HARMLESS) ? 5u : 6u, no_reset = flags & (POM_ROLL_NO_RESET | POM_ROLL_CONTINUE_UNDEFINED);
     const uint32_t mask = (flags >> POM_ROLL_SIMPLE_SHIFT) & 0xFu;
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
     if(mask)
@@ -793,7 +793,7 @@ int pom_batch_step_seq(pom_batch* b, const uint8_t* moves_dev, uint32_t ticks, u
 {
     int rc = use(b); if(rc) return rc;
     if(!moves_dev) return fail(POM_E_ARG, "pom_batch_step_seq: null moves");
-    if(flags & ~uint32_t(POM_ROLL_NO_RESET)) return fail(POM_E_ARG, "pom_batch_step_seq: only POM_ROLL_NO_RESET is accepted");
+    if(flags & ~uint32_t(POM_ROLL_NO_RESET | POM_ROLL_CONTINUE_UNDEFINED)) return fail(POM_E_ARG, "pom_batch_step_seq: only POM_ROLL_NO_RESET and POM_ROLL_CONTINUE_UNDEFINED are accepted");
     POM_DISPATCH(b, launch_rollout, b, ticks, 0, 0, flags, moves_dev);
 }
 

@@ -44,9 +44,12 @@ enum {
     F_D4_BOMB_OVF    = 0x04,
     F_FLAME_OVF      = 0x08,
     F_BAD_MOVE       = 0x10,
-    F_LOOP_GUARD     = 0x20,   /* D5: AgentBombChainReversion would recurse forever (also: internal loop guards) */
+    F_LOOP_GUARD     = 0x20,   /* D5: AgentBombChainReversion would recurse forever (canonical: the chain stops) */
     F_RANGE          = 0x40,   /* device only: a field left what the packed record can carry (maxBombCount / bombStrength > 255) */
-    F_INVALID_MASK   = 0x7E
+    F_INTERNAL       = 0x80,   /* device only: a guard of the explosion machine tripped (depth / iteration bound) */
+    F_INVALID_MASK   = 0xFE,
+    /* POM_STEP_CONTINUE_UNDEFINED: D3 and D5 have a canonical continuation and do not stop the env */
+    F_INVALID_MASK_CONTINUE = F_INVALID_MASK & ~(F_D3_NULL_BOMB | F_LOOP_GUARD)
 };
 
 /* the four agents, one byte per agent in each word */
@@ -361,7 +364,7 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
             const int jj = bomb_index(r, cp);
             if(jj >= 0)
             {
-                if(sp >= 24) { flags |= F_LOOP_GUARD; return; }
+                if(sp >= 24) { flags |= F_INTERNAL; return; }
                 stack[sp++] = slot | (d << 5) | (rem << 7) | (ci << 11) | (j << 18);
                 const uint32_t b = bomb_at(r, jj);
                 p = cp;
@@ -373,7 +376,7 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
         }
         *cell = uint8_t(C_FLAME | (slot << 2));
     }
-    flags |= F_LOOP_GUARD;
+    flags |= F_INTERNAL;
 }
 
 /* util::AgentBombChainReversion, step_utility.cpp:62-128 (tail recursion -> loop).
@@ -1348,11 +1351,11 @@ POM_HD void env_post(uint8_t* r)
 
 /* Environment::Step on the record (environment.cpp:125-128,149-168): skip finished envs, Step,
  * timeStep++, winner / draw.  Returns F_* flags (0 for a skipped env). */
-POM_HD int env_step(uint8_t* r, uint32_t moves)
+POM_HD int env_step(uint8_t* r, uint32_t moves, int invalid_mask = F_INVALID_MASK)
 {
     if(r[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_INVALID)) return 0;   /* invalid envs freeze: the reference would have crashed */
     const int flags = step(r, moves);
-    if(flags & F_INVALID_MASK) r[R_STATUS] |= POM_STATUS_INVALID;
+    if(flags & invalid_mask) r[R_STATUS] |= POM_STATUS_INVALID;
     env_post(r);
     return flags;
 }

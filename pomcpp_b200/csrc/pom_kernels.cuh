@@ -328,7 +328,8 @@ __device__ __forceinline__ void warp_explode_due(uint8_t* sslice, uint8_t* rec, 
 }
 
 /* bboard::Step (+ Environment::Step's bookkeeping unless raw) for the env of every lane with `step` set */
-__device__ __forceinline__ void warp_tick(uint8_t* sslice, uint8_t* rec, uint32_t m, bool step, bool raw, uint8_t* wlist)
+__device__ __forceinline__ void warp_tick(uint8_t* sslice, uint8_t* rec, uint32_t m, bool step, bool raw, uint8_t* wlist,
+                                          int invalid_mask = pomcore::F_INVALID_MASK)
 {
     const bool pops = step && pomcore::flames_age(rec);       /* TickFlames, step.cpp:15 */
     warp_pop_due(sslice, rec, pops, wlist);
@@ -338,7 +339,7 @@ __device__ __forceinline__ void warp_tick(uint8_t* sslice, uint8_t* rec, uint32_
     warp_explode_due(sslice, rec, due, flags, wlist);
     if(step)
     {
-        if(flags & pomcore::F_INVALID_MASK) rec[R_STATUS] |= POM_STATUS_INVALID;
+        if(flags & invalid_mask) rec[R_STATUS] |= POM_STATUS_INVALID;
         if(!raw) pomcore::env_post(rec);
     }
 }
@@ -382,7 +383,8 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
     uint8_t* rec = sslice + lane * POM_REC_BYTES;
     /* finished envs are skipped (environment.cpp:125) unless raw; invalid envs always freeze */
     const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
-    warp_tick(sslice, rec, m, stepped, raw, smem + TileScratch<TPB>::OFF_LIST + 8u * warp);
+    warp_tick(sslice, rec, m, stepped, raw, smem + TileScratch<TPB>::OFF_LIST + 8u * warp,
+              (flags & POM_STEP_CONTINUE_UNDEFINED) ? pomcore::F_INVALID_MASK_CONTINUE : pomcore::F_INVALID_MASK);
     EpisodeAcc acc;
     acc.steps = stepped ? 1u : 0u;
     uint32_t st_end = active ? rec[R_STATUS] : 0u;
@@ -447,7 +449,13 @@ template<int NBUF> struct RingScratch {
     static constexpr uint32_t OFF_FULL = NBUF * SLOT;
     static constexpr uint32_t OFF_EMPTY = OFF_FULL + 8 * NBUF;
     static constexpr uint32_t OFF_TICKET = OFF_EMPTY + 8 * NBUF;
-    static constexpr uint32_t BYTES = OFF_TICKET + 16;
+    /* finished-env list of this CTA, handed to the global list in one piece when the CTA is done: word [0] = entries
+     * reserved, word [1] = position of the first reservation that did not fit (0xFFFFFFFF: all fit) */
+    static constexpr uint32_t FIN_CAP = 480;
+    static constexpr uint32_t OFF_FIN = OFF_TICKET + 16;
+    static constexpr uint32_t OFF_FIN_ENV = OFF_FIN + 16;
+    static constexpr uint32_t OFF_FIN_ST = OFF_FIN_ENV + 4 * FIN_CAP;
+    static constexpr uint32_t BYTES = OFF_FIN_ST + FIN_CAP;
 };
 
 template<int NW, int NBUF>
@@ -472,6 +480,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
         for(int b = 0; b < NBUF; b++) { mbar_init(full + b, 1); mbar_init(empty + b, 1); }
         ticket[0] = 0u;
         ticket[1] = 0u;                                               /* compute warps that have finished */
+        reinterpret_cast<uint32_t*>(smem + R::OFF_FIN)[0] = 0u;
+        reinterpret_cast<uint32_t*>(smem + R::OFF_FIN)[1] = 0xFFFFFFFFu;
         fence_barrier_init();
     }
     __syncthreads();
@@ -524,7 +534,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
 
         uint8_t* rec = sslice + lane * POM_REC_BYTES;
         const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
-        warp_tick(sslice, rec, m, stepped, raw, sslice + R::SLICE_BYTES + 128u);
+        warp_tick(sslice, rec, m, stepped, raw, sslice + R::SLICE_BYTES + 128u,
+                  (flags & POM_STEP_CONTINUE_UNDEFINED) ? pomcore::F_INVALID_MASK_CONTINUE : pomcore::F_INVALID_MASK);
         acc.steps += stepped ? 1u : 0u;
         uint32_t st_end = active ? rec[R_STATUS] : 0u;
         if(flags & POM_STEP_AUTORESET)
@@ -541,13 +552,34 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
             if(io.done_bits && lane == 0) io.done_bits[s] = em;
             if(io.fin_env && em)
             {
-                uint32_t base = 0u;
-                if(lane == 0) base = atomicAdd(io.fin_counter, uint32_t(__popc(em)));
-                base = __shfl_sync(FULL_WARP, base, 0) + uint32_t(__popc(em & ((1u << lane) - 1u)));
-                if(ended && base < io.fin_capacity)
+                /* appended to the CTA's list in shared memory (one shared-memory atomic per slice); 148 CTAs x 1 global
+                 * atomic per launch instead of one per slice - 11 k atomics on ONE address per tick serialise in the L2
+                 * and cost the 0.5 Mi-env step 20 us.  A CTA whose list is full appends to the global list directly. */
+                uint32_t* fin = reinterpret_cast<uint32_t*>(smem + R::OFF_FIN);
+                const uint32_t k = uint32_t(__popc(em));
+                uint32_t pos = 0u;
+                if(lane == 0) pos = atomicAdd(fin, k);
+                pos = __shfl_sync(FULL_WARP, pos, 0);
+                const uint32_t mine = uint32_t(__popc(em & ((1u << lane) - 1u)));
+                if(pos + k <= R::FIN_CAP)
                 {
-                    io.fin_env[base] = uint32_t(env);
-                    io.fin_status[base] = uint8_t(st_end);
+                    if(ended)
+                    {
+                        reinterpret_cast<uint32_t*>(smem + R::OFF_FIN_ENV)[pos + mine] = uint32_t(env);
+                        smem[R::OFF_FIN_ST + pos + mine] = uint8_t(st_end);
+                    }
+                }
+                else
+                {
+                    /* the shared-memory counter only grows: from the first reservation that does not fit, every later
+                     * one fails too, so the entries below that position are exactly the ones written (fin[1]) */
+                    if(lane == 0) { atomicMin(fin + 1, pos); pos = atomicAdd(io.fin_counter, k); }
+                    pos = __shfl_sync(FULL_WARP, pos, 0) + mine;
+                    if(ended && pos < io.fin_capacity)
+                    {
+                        io.fin_env[pos] = uint32_t(env);
+                        io.fin_status[pos] = uint8_t(st_end);
+                    }
                 }
             }
         }
@@ -583,9 +615,29 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
         uint32_t* warps_done = ticket + 1;
         bool last = false;
         if(lane == 0) last = atomicAdd(warps_done, 1u) == uint32_t(NW - 1);
+        last = __shfl_sync(FULL_WARP, last ? 1 : 0, 0) != 0;
         if(last)
         {
+            /* this CTA's list -> the global list, one reservation, coalesced copies by the whole warp */
+            const uint32_t* fin = reinterpret_cast<const uint32_t*>(smem + R::OFF_FIN);
             __threadfence();
+            const uint32_t k = fin[1] != 0xFFFFFFFFu ? fin[1] : fin[0];
+            uint32_t base = 0u;
+            if(lane == 0 && k) base = atomicAdd(io.fin_counter, k);
+            base = __shfl_sync(FULL_WARP, base, 0);
+            for(uint32_t i = lane; i < k; i += 32u)
+            {
+                if(base + i < io.fin_capacity)
+                {
+                    io.fin_env[base + i] = reinterpret_cast<const uint32_t*>(smem + R::OFF_FIN_ENV)[i];
+                    io.fin_status[base + i] = smem[R::OFF_FIN_ST + i];
+                }
+            }
+            __threadfence();
+            __syncwarp();
+        }
+        if(last && lane == 0)
+        {
             if(atomicAdd(io.fin_counter + 1, 1u) == gridDim.x - 1u)
             {
                 __threadfence();
@@ -668,9 +720,11 @@ __global__ void __launch_bounds__(TPB) k_policy_moves(BatchParams P, uint32_t* _
  * POLICY = true : the agents in `policy_mask` play SimpleAgent, the others stay uniform random. */
 template<int TPB, bool POLICY>
 __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, uint64_t seed, uint32_t tick0,
-                                                uint32_t n_actions, uint32_t no_reset, uint32_t policy_mask,
+                                                uint32_t n_actions, uint32_t roll_flags, uint32_t policy_mask,
                                                 const uint32_t* __restrict__ move_seq)
 {
+    const uint32_t no_reset = (roll_flags & POM_ROLL_NO_RESET) ? 1u : 0u;
+    const int invalid_mask = (roll_flags & POM_ROLL_CONTINUE_UNDEFINED) ? pomcore::F_INVALID_MASK_CONTINUE : pomcore::F_INVALID_MASK;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
     const bool active = env < P.n_envs;
@@ -725,7 +779,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(BatchParams P, uint32_t ticks, 
             }
             acc.steps++;
         }
-        warp_tick(sslice, rec, m, stepped, false, smem + TileScratch<TPB>::OFF_LIST + 8u * warp);
+        warp_tick(sslice, rec, m, stepped, false, smem + TileScratch<TPB>::OFF_LIST + 8u * warp, invalid_mask);
         const uint32_t st = finish_and_reset(sslice, rec, P, env, active && stepped, !no_reset, ep_now, acc);
         /* a new episode starts with four new agents */
         if(POLICY && stepped && !no_reset && (st & (POM_STATUS_DONE | POM_STATUS_TRUNCATED | POM_STATUS_INVALID))) agents.clear(ep_now);
@@ -840,7 +894,8 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
     {
         for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = 0u;
     }
-    warp_tick(sslice, rec, m, stepped, raw, smem + TileScratch<TPB>::OFF_LIST + 8u * warp);
+    warp_tick(sslice, rec, m, stepped, raw, smem + TileScratch<TPB>::OFF_LIST + 8u * warp,
+              (flags & POM_STEP_CONTINUE_UNDEFINED) ? pomcore::F_INVALID_MASK_CONTINUE : pomcore::F_INVALID_MASK);
     const uint64_t c0 = uint64_t(blockIdx.x) * TPB + warp * 32u;      /* first child of this warp's slice */
     if(c0 + 32u <= n_children)
     {

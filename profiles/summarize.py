@@ -115,7 +115,11 @@ def main():
             wr = [float(v.replace(",", "")) for v in r["dram__bytes_write.sum"]["values"]]
             scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[r["dram__bytes_read.sum"]["unit"]]
             summ["dram_bytes_per_launch"] = (sum(rd) + sum(wr)) / len(rd) * scale
-            summ["algorithmic_bytes_per_launch"] = 582 * (1 << 20)
+            # r1 captured whole-batch launches of k_step (1 Mi envs); r2 captures k_step_ws in the bench's POM_STEP_OVERLAP
+            # phase, where one launch steps half of the batch
+            envs = (1 << 20) if tag == "r1" else (1 << 19)
+            summ["envs_per_launch"] = envs
+            summ["algorithmic_bytes_per_launch"] = 582 * envs
         json.dump(summ, open(os.path.join(OUT, "k_%s_ncu_summary%s.json" % (kern[1:], "" if tag == "r1" and kern == "kstep" else "_" + tag)), "w"), indent=1)
         open(os.path.join(OUT, "k_%s_by_function_%s.txt" % (kern[1:], tag)), "w").write("\n".join(by_function(rep)) + "\n")
     print("profiles written for", tag)

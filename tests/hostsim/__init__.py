@@ -46,6 +46,10 @@ class HostSim:
         L.hostsim_move_towards_safe_place.argtypes = [vp, C.c_int, C.c_int]
         assert L.hostsim_record_bytes() == REC
 
+    def set_continue_undefined(self, on):
+        """True: D3 / D5 ticks keep the env running with the canonical result (POM_STEP_CONTINUE_UNDEFINED)"""
+        self.lib.hostsim_set_continue_undefined(int(bool(on)))
+
     def set_by_rays(self, on):
         """True: step_records runs the tick in the warp-cooperative kernels' decomposition (pomcore::step_by_rays)"""
         self.lib.hostsim_set_by_rays(int(bool(on)))

@@ -39,6 +39,9 @@ void hostsim_unpack_batch(const uint8_t* recs, long n, pom_state* S, uint8_t* st
  * pops: the lanes' work done one after the other), so that the scan / commit decomposition itself is checked on the CPU */
 static int g_by_rays = 0;
 void hostsim_set_by_rays(int on) { g_by_rays = on; }
+/* POM_STEP_CONTINUE_UNDEFINED: D3 / D5 ticks continue with the canonical result instead of freezing the env */
+static int g_invalid_mask = pomcore::F_INVALID_MASK;
+void hostsim_set_continue_undefined(int on) { g_invalid_mask = on ? pomcore::F_INVALID_MASK_CONTINUE : pomcore::F_INVALID_MASK; }
 
 void hostsim_step_records(uint8_t* recs, long n, const uint8_t* moves, int raw, uint8_t* flags_out)
 {
@@ -48,13 +51,13 @@ void hostsim_step_records(uint8_t* recs, long n, const uint8_t* moves, int raw, 
         std::memcpy(&m, moves + 4 * e, 4);
         uint8_t* r = recs + e * POM_REC_BYTES;
         int f = 0;
-        if(!g_by_rays) f = raw ? pomcore::step(r, m) : pomcore::env_step(r, m);
+        if(!g_by_rays) f = raw ? pomcore::step(r, m) : pomcore::env_step(r, m, g_invalid_mask);
         else if(raw || !(r[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_INVALID)))
         {
             f = pomcore::step_by_rays(r, m);
             if(!raw)
             {
-                if(f & pomcore::F_INVALID_MASK) r[R_STATUS] |= POM_STATUS_INVALID;
+                if(f & g_invalid_mask) r[R_STATUS] |= POM_STATUS_INVALID;
                 pomcore::env_post(r);
             }
         }

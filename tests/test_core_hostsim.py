@@ -53,7 +53,7 @@ def test_pack_rejects_unrepresentable(orc, hs):
     assert (status[:3] & 0x10).all() and status[3] == 0
 
 
-def _trace(orc, hs, n, ticks, nact, stress, seed, restart=True, ring_start=None):
+def _trace(orc, hs, n, ticks, nact, stress, seed, restart=True, ring_start=None, count_invalid=None):
     seeds = oracle.clean_seeds(128)
     B = orc.zero_state(n)
     for e in range(n):
@@ -92,6 +92,9 @@ def _trace(orc, hs, n, ticks, nact, stress, seed, restart=True, ring_start=None)
         assert ((fo & 0x1F) == (fc & 0x1F)).all(), "flags differ at tick %d" % t
         fin = (sb & 0x11) != 0
         steps += int((~fin).sum())
+        if count_invalid is not None:
+            count_invalid[0] += int(((sb & 0x10) != 0).sum())
+            count_invalid[1] += int(((fo & 0x22) != 0).sum())
         if restart:
             idx = np.nonzero(fin)[0]
             B[idx] = B0[idx]
@@ -154,6 +157,27 @@ def test_scenarios_core_by_rays(orc, fn):
         fn(b)
     finally:
         b.h.set_by_rays(False)
+
+
+def test_core_continue_undefined(orc, hs):
+    """POM_STEP_CONTINUE_UNDEFINED: D3 (kicker onto a BOMB cell without queue entry) and D5 (reversion chain reaches an
+    agent that did not move) keep the env running with the canonical result; kernel body == restatement on the stress
+    regime, where such ticks are frequent - and now no env is lost to them"""
+    hs.set_continue_undefined(True)
+    orc.set_continue_undefined(True)
+    try:
+        inv = [0, 0]
+        assert _trace(orc, hs, 4096, 300, 6, 1, 2021, count_invalid=inv) > 500000
+        assert inv[1] > 20, "the regime must actually hit D3 / D5 ticks"
+        inv2 = [0, 0]
+        _trace(orc, hs, 2048, 200, 6, 2, 2022, count_invalid=inv2)
+    finally:
+        hs.set_continue_undefined(False)
+        orc.set_continue_undefined(False)
+    # the same run without the flag loses envs to those ticks
+    inv3 = [0, 0]
+    _trace(orc, hs, 4096, 300, 6, 1, 2021, count_invalid=inv3)
+    assert inv3[0] > inv[0]
 
 
 def test_core_rng_matches_oracle(orc, hs):

@@ -228,3 +228,44 @@ def test_step_observe_fused_equals_step_then_observe(pb, orc, mask, view):
     assert A.tobytes() == Cc.tobytes() and (sa == sc).all()
     a.free(obs); a.free(mv); c.free(mv2)
     a.close(); c.close()
+
+
+def test_continue_undefined_on_gpu(pb, orc):
+    """POM_STEP_CONTINUE_UNDEFINED through the C ABI: the stress regime step by step against the restatement running the
+    same rule, and a four-SimpleAgent soak that ends with invalid == 0"""
+    n, ticks, seed = 8192, 200, 3003
+    b = pb.Batch(n, n_templates=256)
+    S, _ = b.download()
+    S["agents"]["canKick"] = 1
+    S["agents"]["maxBombCount"] = 5
+    S["agents"]["bombStrength"] = 4
+    b.upload(S)
+    status = np.zeros(n, np.uint8)
+    mv_dev = b.alloc(4 * n)
+    hits = 0
+    orc.set_continue_undefined(True)
+    try:
+        for t in range(ticks):
+            b.generate_moves(mv_dev, seed, t, 6)
+            b.step(mv_dev, pb.STEP_CONTINUE_UNDEFINED)
+            fl = np.zeros(n, np.uint8)
+            orc.env_step_batch(S, status, orc.rng_moves(seed, 0, n, t, 6), fl)
+            hits += int(((fl & 0x22) != 0).sum())
+            if t % 10 == 9 or t == ticks - 1:
+                G, gst = b.download()
+                e, why = orc.diff_batch(G, S)
+                assert e == -1, "tick %d env %d field group %d" % (t, e, why)
+                assert (gst == status).all()
+    finally:
+        orc.set_continue_undefined(False)
+    assert hits > 10
+    b.free(mv_dev)
+    b.close()
+    # soak: four SimpleAgents kick and chain bombs far more than random agents do (3e-4 of their episodes used to abort)
+    s = pb.Batch(65536, n_templates=512, max_ticks=800)
+    s.rollout(800, 17, 0, pb.ROLL_SIMPLE(15) | pb.ROLL_CONTINUE_UNDEFINED)
+    st = s.stats().as_dict()
+    assert st["env_steps"] == 65536 * 800 and st["episodes"] > 50000
+    assert st["invalid"] == 0, st
+    assert st["episodes"] == sum(st["wins"]) + st["draws"] + st["truncated"]
+    s.close()
