@@ -252,6 +252,7 @@ int launch_step_io(pom_batch* b, const pomk::BatchParams& P, pomk::StepIO io, ui
     case 14: return launch_step_ws<14>(b, P, io, flags, on);
     case 16: return launch_step_ws<16>(b, P, io, flags, on);
     case 18: return launch_step_ws<18>(b, P, io, flags, on);
+    case 22: return launch_step_ws<22>(b, P, io, flags, on);
     default: return launch_step_ws<WS_NW>(b, P, io, flags, on);
     }
 }

@@ -1570,16 +1570,35 @@ POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
     const int x0 = ax - view, x1 = ax + view, y0 = ay - view, y1 = ay + view;
     /* planes 1-3 start out empty: bytes 128..479 = chunks 8..29 (bytes 121..127 leave with board chunk 7) */
     for(int q = 8; q < 30; q++) obs_store16(out, q, 0u, 0u, 0u, 0u);
+    /* which of the 121 cells lie in the window, one bit per cell (bit = x + 11 y), built row by row; four scalars, not
+     * an array: a dynamically indexed array would live in local memory */
+    uint32_t seen0 = 0u, seen1 = 0u, seen2 = 0u, seen3 = 0u;
+    {
+        const int cx0 = x0 < 0 ? 0 : x0, cx1 = x1 > 10 ? 10 : x1, cy0 = y0 < 0 ? 0 : y0, cy1 = y1 > 10 ? 10 : y1;
+        const uint32_t cols = ((2u << cx1) - 1u) & ~((1u << cx0) - 1u);          /* columns cx0..cx1 */
+        POM_LOOP
+        for(int yy = cy0; yy <= cy1; yy++)
+        {
+            const int pos = 11 * yy, wi = pos >> 5, sh = pos & 31;
+            const uint64_t wide = uint64_t(cols) << sh;
+            const uint32_t lo = uint32_t(wide), hi = uint32_t(wide >> 32);
+            seen0 |= wi == 0 ? lo : 0u;
+            seen1 |= wi == 1 ? lo : (wi == 0 ? hi : 0u);
+            seen2 |= wi == 2 ? lo : (wi == 1 ? hi : 0u);
+            seen3 |= wi == 3 ? lo : (wi == 2 ? hi : 0u);
+        }
+    }
     /* board plane, four cells per word: the item ids come from byte-parallel range tests on the cell codes
      * (0,1 keep; 2..6 wood -> 2; 7 bomb -> 3; 8.. -> code - 3, i.e. fog 5, powerups 6..8, dummy 9, agents 10..13;
      * flame codes have the top bit set -> 4), then cells outside the window are overwritten with 5 (fog) */
     const uint32_t* bw = reinterpret_cast<const uint32_t*>(r + R_BOARD);
-    int x = 0, y = 0;
     uint32_t litWords = 0u;                                    /* bit w: board word w holds a visible flame cell */
     POM_LOOP
     for(int q = 0; q < 8; q++)
     {
         uint32_t word[4];
+        const uint32_t seenw = q < 4 ? (q < 2 ? seen0 : seen1) : (q < 6 ? seen2 : seen3);
+        const uint32_t bits16 = (seenw >> (16 * (q & 1))) & 0xFFFFu;              /* the 16 cells of this chunk */
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -1589,23 +1608,23 @@ POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
             uint32_t ids = 0u;
             if(w < 31)
             {
-                const uint32_t codes = bw[w];
-                uint32_t vis = 0u;                             /* 0xFF in the bytes of visible cells */
-                for(int j = 0; j < 4; j++)
+                const uint32_t b4 = (bits16 >> (4 * k)) & 15u;
+                /* four bits -> 0xFF in the bytes of visible cells (bit j lands in bit 8j, then every byte is widened) */
+                const uint32_t vis = ((b4 * 0x00204081u) & 0x01010101u) * 0xFFu;
+                ids = 0x05050505u;                             /* out of sight: fog */
+                if(vis)
                 {
-                    const bool cell = w < 30 || j == 0;        /* word 30: only its first byte is a board cell */
-                    if(cell && x >= x0 && x <= x1 && y >= y0 && y <= y1) vis |= 0xFFu << (8 * j);
-                    if(++x == POM_BOARD_SIZE) { x = 0; y++; }
+                    const uint32_t codes = bw[w];
+                    const uint32_t l = codes & 0x7F7F7F7Fu, flame = codes & 0x80808080u, plain = ~codes & 0x80808080u;
+                    const uint32_t ge2 = (l + 0x7E7E7E7Eu) & 0x80808080u, ge7 = (l + 0x79797979u) & 0x80808080u, ge8 = (l + 0x78787878u) & 0x80808080u;
+                    const uint32_t keep = ((plain & ~ge2) >> 7) * 0xFFu, wood = ((plain & ge2 & ~ge7) >> 7) * 0xFFu;
+                    const uint32_t bomb = ((plain & ge7 & ~ge8) >> 7) * 0xFFu, high = ((plain & ge8) >> 7) * 0xFFu, burn = (flame >> 7) * 0xFFu;
+                    const uint32_t minus3 = ((l | 0x80808080u) - 0x03030303u) & 0x7F7F7F7Fu;       /* per byte, no borrow between bytes */
+                    ids = (codes & keep) | (0x02020202u & wood) | (0x03030303u & bomb) | (minus3 & high) | (0x04040404u & burn);
+                    ids = (ids & vis) | (0x05050505u & ~vis);
+                    if(burn & vis) litWords |= 1u << w;
                 }
-                const uint32_t l = codes & 0x7F7F7F7Fu, flame = codes & 0x80808080u, plain = ~codes & 0x80808080u;
-                const uint32_t ge2 = (l + 0x7E7E7E7Eu) & 0x80808080u, ge7 = (l + 0x79797979u) & 0x80808080u, ge8 = (l + 0x78787878u) & 0x80808080u;
-                const uint32_t keep = ((plain & ~ge2) >> 7) * 0xFFu, wood = ((plain & ge2 & ~ge7) >> 7) * 0xFFu;
-                const uint32_t bomb = ((plain & ge7 & ~ge8) >> 7) * 0xFFu, high = ((plain & ge8) >> 7) * 0xFFu, burn = (flame >> 7) * 0xFFu;
-                const uint32_t minus3 = ((l | 0x80808080u) - 0x03030303u) & 0x7F7F7F7Fu;       /* per byte, no borrow between bytes */
-                ids = (codes & keep) | (0x02020202u & wood) | (0x03030303u & bomb) | (minus3 & high) | (0x04040404u & burn);
-                ids = (ids & vis) | (0x05050505u & ~vis);
                 if(w == 30) ids &= 0xFFu;                      /* bytes 121..123: the first cells of the bomb-strength plane */
-                if(burn & vis) litWords |= 1u << w;
             }
             word[k] = ids;
         }

@@ -408,9 +408,10 @@ __global__ void __launch_bounds__(TPB) k_step(BatchParams P, const uint32_t* __r
 /* One CTA per SM for the whole launch.  Shared memory is a ring of NBUF slice buffers (32 records + the slice's 32 x 4
  * move bytes each); warp NW is the PRODUCER: it keeps every free buffer filled with the CTA's next slice (TMA bulk load,
  * completion on the buffer's `full` mbarrier).  Warps 0..NW-1 COMPUTE: a warp takes the next ticket (shared-memory
- * counter), waits for that buffer to be full, runs the tick on it in place, bulk-stores it and hands the buffer back
- * (`empty` mbarrier) once the store has read it.  NBUF > NW, so NBUF - NW loads are always in flight ahead of the
- * compute warps: they never wait for HBM, and nothing is relaunched or drained between slices.
+ * counter), reads from the ticket's mail slot which buffer its slice is landing in, waits for that buffer's `full`
+ * barrier, runs the tick on it in place, bulk-stores it and returns the buffer to the free mask once the store has read
+ * it.  NBUF > NW, so NBUF - NW loads are always in flight ahead of the compute warps, and nothing is relaunched or
+ * drained between slices.
  * With k_step every warp did load -> tick -> store itself; once the tick got cheap (vectorised movement, shared-out
  * explosions) ncu showed 4 long-scoreboard stall cycles per issue and 45 % issue utilisation: the 24 resident warps
  * spent 40 % of their time waiting for their own loads (profiles/k_step_ncu_summary_r2b.json).
@@ -447,8 +448,11 @@ template<int NBUF> struct RingScratch {
     static constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
     static constexpr uint32_t SLOT = SLICE_BYTES + 128 + 16;      /* records, the slice's moves, the warp's due list */
     static constexpr uint32_t OFF_FULL = NBUF * SLOT;
-    static constexpr uint32_t OFF_EMPTY = OFF_FULL + 8 * NBUF;
-    static constexpr uint32_t OFF_TICKET = OFF_EMPTY + 8 * NBUF;
+    /* mail[t % MAIL]: which buffer holds the slice of ticket t, written by the producer: (t + 1) << 8 | buffer << 1 |
+     * phase parity of the buffer's `full` barrier */
+    static constexpr uint32_t MAIL = 256;
+    static constexpr uint32_t OFF_MAIL = OFF_FULL + 8 * NBUF;
+    static constexpr uint32_t OFF_TICKET = OFF_MAIL + 4 * MAIL;    /* [0] next ticket, [1] warps done, [2] free-buffer mask */
     /* finished-env list of this CTA, handed to the global list in one piece when the CTA is done: word [0] = entries
      * reserved, word [1] = position of the first reservation that did not fit (0xFFFFFFFF: all fit) */
     static constexpr uint32_t FIN_CAP = 480;
@@ -469,36 +473,50 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
     extern __shared__ __align__(128) uint8_t smem[];
     typedef RingScratch<NBUF> R;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + R::OFF_FULL);
-    uint64_t* empty = reinterpret_cast<uint64_t*>(smem + R::OFF_EMPTY);
+    volatile uint32_t* mail = reinterpret_cast<volatile uint32_t*>(smem + R::OFF_MAIL);
     uint32_t* ticket = reinterpret_cast<uint32_t*>(smem + R::OFF_TICKET);
+    uint32_t* free_mask = ticket + 2;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint64_t n_slices = (P.n_envs + 31u) / 32u;
     /* this CTA's slices: blockIdx.x, blockIdx.x + gridDim.x, ... */
     const uint32_t T = blockIdx.x < n_slices ? uint32_t((n_slices - blockIdx.x + gridDim.x - 1u) / gridDim.x) : 0u;
     if(threadIdx.x == 0)
     {
-        for(int b = 0; b < NBUF; b++) { mbar_init(full + b, 1); mbar_init(empty + b, 1); }
+        for(int b = 0; b < NBUF; b++) mbar_init(full + b, 1);
         ticket[0] = 0u;
         ticket[1] = 0u;                                               /* compute warps that have finished */
+        *free_mask = (NBUF >= 32) ? 0xFFFFFFFFu : ((1u << NBUF) - 1u);
         reinterpret_cast<uint32_t*>(smem + R::OFF_FIN)[0] = 0u;
         reinterpret_cast<uint32_t*>(smem + R::OFF_FIN)[1] = 0xFFFFFFFFu;
         fence_barrier_init();
     }
+    for(uint32_t i = threadIdx.x; i < R::MAIL; i += blockDim.x) mail[i] = 0u;
     __syncthreads();
 
     if(warp == NW)
     {
+        /* PRODUCER.  Buffers are handed out from a free mask, not in ring order: a slice that takes long (a chained
+         * explosion, many resets) keeps its own buffer busy and nothing else - with an in-order ring everything 24
+         * tickets behind it waited (15 % of the compute warps' time, profiles/k_step_ncu_summary_r2.json). */
         if(lane != 0) return;
+        uint32_t parity = 0u;                                         /* bit b: phase parity of full[b]'s next use */
         for(uint32_t t = 0; t < T; t++)
         {
-            const uint32_t b = t % NBUF, use = t / NBUF;
-            if(use) mbar_wait(empty + b, (use - 1u) & 1u);               /* the buffer's previous slice has been stored */
+            uint32_t fm;
+            while((fm = *reinterpret_cast<volatile uint32_t*>(free_mask)) == 0u) __nanosleep(40);
+            const uint32_t b = uint32_t(__ffs(int(fm))) - 1u;
+            atomicAnd(free_mask, ~(1u << b));
             const uint64_t s = blockIdx.x + uint64_t(t) * gridDim.x;
             const bool whole = (s + 1u) * 32u <= P.n_envs;                /* the last slice's moves may end early: per-lane loads */
             const uint32_t mbytes = (moves_bulk && whole) ? mv_bytes : 0u;
             mbar_expect_tx(full + b, R::SLICE_BYTES + mbytes);
             bulk_g2s(smem + b * R::SLOT, P.recs + s * R::SLICE_BYTES, R::SLICE_BYTES, full + b);
             if(mbytes) bulk_g2s(smem + b * R::SLOT + R::SLICE_BYTES, static_cast<const uint8_t*>(io.moves) + s * mv_bytes, mbytes, full + b);
+            /* tell the warp that holds (or will hold) ticket t where its slice lands.  The buffer was free, so its
+             * previous load had completed: `full[b]` is in the phase this load completes - a parity wait on it cannot
+             * mistake an older phase for this one. */
+            mail[t % R::MAIL] = ((t + 1u) << 8) | (b << 1) | ((parity >> b) & 1u);
+            parity ^= 1u << b;
         }
         return;
     }
@@ -511,22 +529,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
         if(lane == 0) t = atomicAdd(ticket, 1u);
         t = __shfl_sync(FULL_WARP, t, 0);
         if(t >= T) break;
-        const uint32_t b = t % NBUF, use = t / NBUF;
         const uint64_t s = blockIdx.x + uint64_t(t) * gridDim.x;
         const uint64_t env = s * 32u + lane;
         const bool active = env < P.n_envs;
         const bool whole = (s + 1u) * 32u <= P.n_envs;
-        uint8_t* sslice = smem + b * R::SLOT;
         uint32_t m = 0u;
         if(!(moves_bulk && whole) && active) m = io.joint ? uint32_t(__ldg(joint + env)) : __ldg(moves + env);   /* overlaps the wait below */
         uint32_t ep_now = (active && (flags & POM_STEP_AUTORESET)) ? P.episodes[env] : 0u;
-        /* A parity wait can only tell the current phase from the one before it.  In quiet ticks the compute warps are
-         * faster than HBM: with one slow load outstanding they can take 24 further tickets and come back to the same
-         * buffer while its barrier is still in the phase of that load - the parity of the NEXT use then reads as
-         * "complete".  So a warp first waits until the buffer's previous user has handed it back (the producer cannot
-         * have re-armed `full` before that); from then on `full` is at most one phase behind. */
-        if(use) mbar_wait(empty + b, (use - 1u) & 1u);
-        mbar_wait(full + b, use & 1u);
+        /* where is my slice?  (The mail slot of ticket t is rewritten for ticket t + 256; by then this warp has long read
+         * it: the producer is never more than the 24 buffers ahead of the warps.) */
+        uint32_t v;
+        while(((v = mail[t % R::MAIL]) >> 8) != t + 1u) __nanosleep(20);
+        const uint32_t b = (v >> 1) & 31u;
+        uint8_t* sslice = smem + b * R::SLOT;
+        mbar_wait(full + b, v & 1u);
         if(moves_bulk && whole)
             m = io.joint ? uint32_t(reinterpret_cast<const uint16_t*>(sslice + R::SLICE_BYTES)[lane])
                          : reinterpret_cast<const uint32_t*>(sslice + R::SLICE_BYTES)[lane];
@@ -602,7 +618,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
         if(lane == 0)
         {
             bulk_wait_read_all();
-            mbar_arrive(empty + b);
+            __threadfence_block();
+            atomicOr(free_mask, 1u << b);                             /* the buffer may be loaded into again */
         }
         __syncwarp();
     }

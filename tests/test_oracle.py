@@ -162,6 +162,17 @@ def test_differential_stress(orc, ref):
     assert _differential(orc, ref, 2048, 200, 6, 1, 1003) > 300000
 
 
+@pytest.mark.slow
+def test_differential_twenty_million_steps(orc, ref):
+    """the long differential behind DESIGN §0's figure, committed: >= 2 x 10^7 env-steps of restatement vs the compiled
+    reference, every field after every tick, over the three regimes (random, harmless, all-kick stress)"""
+    total = 0
+    total += _differential(orc, ref, 32768, 240, 6, 0, 5001)
+    total += _differential(orc, ref, 16384, 400, 5, 0, 5002)
+    total += _differential(orc, ref, 32768, 260, 6, 1, 5003)
+    assert total >= 20_000_000, total
+
+
 def test_defect_d1_three_on_one_is_canonical_and_fenced(orc, ref):
     """Three agents converge on one occupied cell: two agents are unreachable in the dependency walk and the
     reference continues with i = dependency[-1] (a stack word; -O0 segfaults, -O3 returns a non-canonical board).
