@@ -586,7 +586,7 @@ def run_own(args):
             "e2e_obs": {"value": world * n * (E2E_STEPS // 2) / e2e_obs_max, "unit": "env-steps/s", "steps": E2E_STEPS // 2,
                         "ms_per_1Mi_env_steps": 1e3 * e2e_obs_max / (E2E_STEPS // 2) * (1 << 20) / n,
                         "clocks": obs_clocks.result(),
-                        "api": "the e2e loop with obs_dev set: the step kernel also writes agent 0's observation planes (view 4, 496 B per "
+                        "api": "the e2e loop with obs_dev set: the step kernel also writes agent 0's observation planes (view 4, 512 B per "
                                "env) from the resident record; they stay on the device"},
             "legs": {
                 "rollout": {"value": float(roll_total[0]) / (roll_max * 1e-3), "unit": "env-steps/s", "ms": roll_max,

@@ -119,7 +119,8 @@ int  pom_batch_download(pom_batch* b, uint64_t first, uint64_t count, pom_state*
  * never implements it.  The result is what Agent::act(const State*) is meant to receive. */
 int  pom_batch_observe(pom_batch* b, uint64_t first, uint64_t count, int agent, int view, pom_state* states, uint8_t* status);
 /* The same view as byte planes for a network input, written on the device (nothing crosses PCIe).
- * One observation = POM_OBS_BYTES (496) bytes:
+ * One observation = POM_OBS_BYTES (512) bytes, 496 of content and 16 of zero padding, so that every record is 32-byte
+ * aligned and a thread can write it with sixteen 256-bit stores (full 32-byte sectors):
  *     0..120   board: the game's item ids in the reference's Item order (bboard.hpp:54-71): 0 passage, 1 rigid, 2 wood,
  *              3 bomb, 4 flames, 5 fog, 6 extra bomb, 7 incr range, 8 kick, 9 agent dummy, 10 + i agent i; index x + 11*y;
  *              powerups hidden in wood / carried by flames are not shown
@@ -127,12 +128,12 @@ int  pom_batch_observe(pom_batch* b, uint64_t first, uint64_t count, int agent, 
  *   242..362   its timer (1..10)
  *   363..483   ticks the visible flame on the cell still burns (timeLeft of its flame-queue entry)
  *   484 x  485 y  486 ammo = maxBombCount - bombCount (clamped to 0..255)  487 blast strength  488 can kick
- *   489 alive mask (bit i = agent i alive; public)  490..491 timeStep (little endian)  492 observer alive  493..495 zero
+ *   489 alive mask (bit i = agent i alive; public)  490..491 timeStep (little endian)  492 observer alive  493..511 zero
  * Cells outside the window hold 5 (fog) in the board plane and 0 elsewhere.
  * obs_dev: DEVICE buffer of popcount(agent_mask) slabs of pom_batch_obs_stride(b) observations each; the observation of
  * env e for the k-th agent of the mask (in agent order) starts at ((k * stride) + e) * POM_OBS_BYTES.  The stride is
  * n_envs rounded up to a multiple of 256; the tail of each slab is scratch. */
-#define POM_OBS_BYTES 496
+#define POM_OBS_BYTES 512
 uint64_t pom_batch_obs_stride(const pom_batch* b);
 int  pom_batch_observe_planes(pom_batch* b, uint8_t* obs_dev, uint32_t agent_mask, int view);
 int  pom_batch_reset(pom_batch* b);   /* all envs back to their template, counters and episode numbers cleared */

@@ -151,7 +151,7 @@ class Restatement:
         return S
 
     def observe_planes_batch(self, S, agent, view=4):
-        out = np.zeros((S.shape[0], 496), np.uint8)
+        out = np.zeros((S.shape[0], 512), np.uint8)
         self.lib.pom_oracle_observe_planes_batch(_ptr(S), C.c_long(S.shape[0]), agent, view, _ptr(out))
         return out
 

@@ -866,11 +866,11 @@ void pom_oracle_fog_batch(pom_state* S, long n, int agent, int view)
 
 /* ---- observation planes: the DEFINITION the device code is checked against (the reference has no counterpart).
  * Built from the AoS State through pom_oracle_fog, i.e. independently of the packed record. */
-void pom_oracle_observe_planes(const pom_state* full, int agent, int view, uint8_t out[496])
+void pom_oracle_observe_planes(const pom_state* full, int agent, int view, uint8_t out[512])
 {
     pom_state s = *full;
     pom_oracle_fog(&s, agent, view);
-    memset(out, 0, 496);
+    memset(out, 0, 512);
     for (int y = 0; y < BS; y++)
         for (int x = 0; x < BS; x++) {
             int v = s.board[y][x], id;
@@ -905,5 +905,5 @@ void pom_oracle_observe_planes(const pom_state* full, int agent, int view, uint8
 
 void pom_oracle_observe_planes_batch(const pom_state* S, long n, int agent, int view, uint8_t* out)
 {
-    for (long e = 0; e < n; e++) pom_oracle_observe_planes(&S[e], agent, view, out + 496 * e);
+    for (long e = 0; e < n; e++) pom_oracle_observe_planes(&S[e], agent, view, out + 512 * e);
 }

@@ -93,7 +93,7 @@ void pom_oracle_fog(pom_state* s, int agent, int view);
 void pom_oracle_fog_batch(pom_state* S, long n, int agent, int view);
 
 /* observation planes of agent `agent` (layout: include/pom_batch.h POM_OBS_BYTES); a definition like pom_oracle_fog */
-void pom_oracle_observe_planes(const pom_state* s, int agent, int view, uint8_t out[496]);
+void pom_oracle_observe_planes(const pom_state* s, int agent, int view, uint8_t out[512]);
 void pom_oracle_observe_planes_batch(const pom_state* S, long n, int agent, int view, uint8_t* out);
 
 /* ---- agents::SimpleAgent + bboard::strategy (pom_oracle_agent.c) ----

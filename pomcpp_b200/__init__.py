@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpom_b200.so")
 
 REC_BYTES = 292
-OBS_BYTES = 496
+OBS_BYTES = 512
 ALGO_BYTES_PER_ENV_STEP = 2 * 289 + 4      # packed PAYLOAD in + out + 4 move bytes (what the roofline credits)
 MOVED_BYTES_PER_ENV_STEP = 2 * 292 + 4     # what actually crosses HBM: the record is padded to 292 B
 
@@ -224,7 +224,7 @@ class Batch:
 
     def observe_planes(self, agent_mask=15, view=4, obs_dev=None):
         """observation planes of the agents in agent_mask, computed and kept on the device; returns a host copy
-        [n_agents, n_envs, 496] (and leaves obs_dev filled if the caller passed its own buffer)"""
+        [n_agents, n_envs, 512] (and leaves obs_dev filled if the caller passed its own buffer)"""
         k = bin(agent_mask & 15).count("1")
         stride = int(lib().pom_batch_obs_stride(self.h))
         own = obs_dev is None

@@ -83,7 +83,7 @@ class HostSim:
         return self.lib.hostsim_move_towards_safe_place(_p(rec), agent, radius)
 
     def observe_planes(self, recs, agent, view):
-        out = np.zeros((recs.shape[0], 496), np.uint8)
+        out = np.zeros((recs.shape[0], 512), np.uint8)
         self.lib.hostsim_observe_planes(_p(recs), recs.shape[0], agent, view, _p(out))
         return out
 

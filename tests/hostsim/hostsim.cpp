@@ -133,7 +133,7 @@ void hostsim_fog_batch(pom_state* S, long n, int agent, int view)
 /* the device observation code (pomcore::observe_planes) on packed records */
 void hostsim_observe_planes(const uint8_t* recs, long n, int agent, int view, uint8_t* out)
 {
-    for(long e = 0; e < n; e++) pomcore::observe_planes(recs + e * POM_REC_BYTES, agent, view, out + 496 * e);
+    for(long e = 0; e < n; e++) pomcore::observe_planes(recs + e * POM_REC_BYTES, agent, view, out + 512 * e);
 }
 
 uint32_t hostsim_rng_moves(uint64_t seed, uint64_t env, uint32_t tick, uint32_t n_actions)

@@ -108,12 +108,12 @@ def test_observation_planes_on_gpu(orc, mask, view):
     full, _ = b.download()
     obs = b.observe_planes(mask, view)
     agents = [a for a in range(4) if (mask >> a) & 1]
-    assert obs.shape == (len(agents), n, 496)
+    assert obs.shape == (len(agents), n, 512)
     for k, a in enumerate(agents):
         want = orc.observe_planes_batch(full, a, view)
         assert (obs[k] == want).all(), (a, np.argwhere(obs[k] != want)[:4])
     L = pb.lib()
-    dev = b.alloc(496 * 256)
+    dev = b.alloc(512 * 256)
     assert L.pom_batch_observe_planes(b.h, None, 1, 4) == -1
     assert L.pom_batch_observe_planes(b.h, dev, 0, 4) == -1
     assert L.pom_batch_observe_planes(b.h, dev, 16, 4) == -1
@@ -130,7 +130,7 @@ def test_observation_planes_throughput_smoke():
     n = 1 << 20
     b = pb.Batch(n, n_templates=256)
     stride = int(pb.lib().pom_batch_obs_stride(b.h))
-    dev = b.alloc(4 * stride * 496)
+    dev = b.alloc(4 * stride * 512)
     pb._ck(pb.lib().pom_batch_observe_planes(b.h, dev, 15, 4))
     b.sync()
     b.event(0)
@@ -139,7 +139,7 @@ def test_observation_planes_throughput_smoke():
     b.event(1)
     b.sync()
     ms = b.elapsed_ms() / 5
-    print("observe_planes: %.3f ms per 1 Mi envs x 4 agents, %.0f GB/s written" % (ms, 4 * n * 496 / ms / 1e6))
+    print("observe_planes: %.3f ms per 1 Mi envs x 4 agents, %.0f GB/s written" % (ms, 4 * n * 512 / ms / 1e6))
     assert ms < 20
     b.free(dev)
     b.close()
