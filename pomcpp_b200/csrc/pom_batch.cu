@@ -61,6 +61,8 @@ struct pom_batch {
     int       n_sms = 1;
     int       ws_nw = 20;
     uint32_t  attr_ws = 0;
+    uint32_t  walk = 0;                        /* whole-batch per-tick launches so far: odd ones walk the batch backwards (StepIO::reverse) */
+    int       pingpong = 1;                    /* POM_STEP_PINGPONG=0 switches the alternation off (experiments) */
     int       step_kernel = 0;                 /* 0 = k_step_ws (persistent, warp-specialised), 1 = k_step (one CTA per tile); POM_STEP_KERNEL=tile */
     uint8_t*  recs = nullptr;
     uint8_t*  templates = nullptr;
@@ -74,6 +76,8 @@ struct pom_batch {
     uint32_t* fin_counter = nullptr;           /* device word behind the finished-env list of pom_batch_step_compact */
     uint32_t* policy = nullptr;                /* 9 x n_alloc words: SimpleAgent memories (allocated on first use) */
     void*     flush_buf = nullptr;
+    uint32_t* idx_buf = nullptr;               /* root / source indices of pom_batch_expand_step on the device (grow-only) */
+    uint64_t  idx_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = { nullptr, nullptr };
     /* pom_batch_step_host pipelines chunks of the batch: H2D of chunk c+1 and D2H of chunk c-1 overlap the
@@ -245,6 +249,8 @@ int launch_step_ws(pom_batch* b, const pomk::BatchParams& P, const pomk::StepIO&
 int launch_step_io(pom_batch* b, const pomk::BatchParams& P, pomk::StepIO io, uint32_t flags, cudaStream_t on)
 {
     io.bulk = (reinterpret_cast<uintptr_t>(io.moves) & 15u) == 0u ? 1u : 0u;   /* TMA needs 16-byte alignment */
+    /* whole-batch launches alternate the direction of the walk (L2 reuse between ticks, see StepIO::reverse) */
+    if(P.n_envs == b->n_envs && b->pingpong) io.reverse = (b->walk++) & 1u;
     /* persistent, warp-specialised: one CTA per SM; POM_WS_NW picks the number of compute warps (experiments) */
     switch(b->ws_nw)
     {
@@ -426,6 +432,7 @@ int pom_batch_init(pom_batch** out, int device, uint64_t n_envs, const pom_init_
     if(b->n_sms < 1) b->n_sms = 1;
     if(const char* e = std::getenv("POM_STEP_KERNEL")) b->step_kernel = std::strcmp(e, "tile") == 0 ? 1 : 0;
     if(const char* e = std::getenv("POM_WS_NW")) b->ws_nw = std::atoi(e);
+    if(const char* e = std::getenv("POM_STEP_PINGPONG")) b->pingpong = std::atoi(e) != 0;
     if(const char* e = std::getenv("POM_TPB"))
     {
         const int t = std::atoi(e);
@@ -485,7 +492,7 @@ int pom_batch_destroy(pom_batch* b)
     if(b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->recs); cudaFree(b->templates); cudaFree(b->episodes); cudaFree(b->stats);
     cudaFree(b->moves_buf); cudaFree(b->status_buf); cudaFree(b->aos_stage); cudaFree(b->st_stage);
-    cudaFree(b->bad_count); cudaFree(b->flush_buf); cudaFree(b->policy); cudaFree(b->fin_counter);
+    cudaFree(b->bad_count); cudaFree(b->flush_buf); cudaFree(b->idx_buf); cudaFree(b->policy); cudaFree(b->fin_counter);
     if(b->ev[0]) cudaEventDestroy(b->ev[0]);
     if(b->ev[1]) cudaEventDestroy(b->ev[1]);
     for(int i = 0; i < pom_batch::MAX_CHUNKS; i++) { if(b->ev_in[i]) cudaEventDestroy(b->ev_in[i]); if(b->ev_done[i]) cudaEventDestroy(b->ev_done[i]); }
@@ -920,14 +927,24 @@ int pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* 
     if(n_children > dst->n_envs) return fail(POM_E_RANGE, "pom_batch_expand_step: destination too small");
     for(uint64_t i = 0; i < n_roots; i++) if(src_idx[i] >= src->n_envs) return fail(POM_E_RANGE, "pom_batch_expand_step: root index outside the batch");
     if(n_roots == 0) return POM_OK;
-    DevBuf idx_b;
-    CK(idx_b.alloc(n_roots * sizeof(uint32_t)));
-    uint32_t* idx_dev = idx_b.as<uint32_t>();
+    /* the index array lives in a buffer of the handle that only grows: a cudaMalloc / cudaFree pair per call cost more
+     * than the kernel of a small expansion, and the call no longer has to wait for the kernel before returning */
+    if(dst->idx_cap < n_roots)
+    {
+        CK(cudaStreamSynchronize(dst->stream));
+        if(dst->idx_buf) CK(cudaFree(dst->idx_buf));
+        dst->idx_buf = nullptr; dst->idx_cap = 0;
+        if(cudaMalloc(reinterpret_cast<void**>(&dst->idx_buf), n_roots * sizeof(uint32_t)) != cudaSuccess)
+            return fail(POM_E_NOMEM, "pom_batch_expand_step: index buffer");
+        dst->idx_cap = n_roots;
+    }
+    uint32_t* idx_dev = dst->idx_buf;
+    /* pageable source: the runtime has read src_idx when this returns; the copy itself is ordered on dst's stream,
+     * behind the kernel of a previous expansion that may still be reading the buffer */
     CK(cudaMemcpyAsync(idx_dev, src_idx, n_roots * sizeof(uint32_t), cudaMemcpyHostToDevice, dst->stream));
     CK(cudaStreamSynchronize(src->stream));
     rc = [&]() -> int { POM_DISPATCH(dst, launch_expand, dst, src, idx_dev, n_children, fanout, flags); }();
     if(rc) return rc;
-    CK(cudaStreamSynchronize(dst->stream));             /* idx_dev must outlive the kernel */
     return POM_OK;
 }
 

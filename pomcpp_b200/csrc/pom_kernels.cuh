@@ -422,6 +422,9 @@ struct StepIO {
     const void* moves;         /* n_envs x 4 move bytes (uint32 per env), or n_envs joint actions (uint16 per env) when joint != 0 */
     uint32_t    joint;         /* j = a0 + 6 a1 + 36 a2 + 216 a3 (the encoding of pom_batch_expand_step) */
     uint32_t    bulk;          /* moves are 16-byte aligned: fetch them with the slice's TMA load */
+    uint32_t    reverse;       /* walk the batch from its last slice to its first.  The host alternates the direction tick by
+                                  tick: a tick then STARTS with the records the previous tick touched last, which are still in
+                                  the 126 MB L2 (read hits, and their write-backs are merged with this tick's stores) */
     uint8_t*    status_out;    /* one end-of-tick status byte per env, or null */
     uint32_t*   done_bits;     /* one word per slice: bit l = env 32 s + l ended an episode this tick, or null */
     uint32_t*   fin_env;       /* compacted list of those envs ...            (null: no list) */
@@ -506,7 +509,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
             while((fm = *reinterpret_cast<volatile uint32_t*>(free_mask)) == 0u) __nanosleep(40);
             const uint32_t b = uint32_t(__ffs(int(fm))) - 1u;
             atomicAnd(free_mask, ~(1u << b));
-            const uint64_t s = blockIdx.x + uint64_t(t) * gridDim.x;
+            const uint64_t s0 = blockIdx.x + uint64_t(t) * gridDim.x;
+            const uint64_t s = io.reverse ? n_slices - 1u - s0 : s0;
             const bool whole = (s + 1u) * 32u <= P.n_envs;                /* the last slice's moves may end early: per-lane loads */
             const uint32_t mbytes = (moves_bulk && whole) ? mv_bytes : 0u;
             mbar_expect_tx(full + b, R::SLICE_BYTES + mbytes);
@@ -529,7 +533,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
         if(lane == 0) t = atomicAdd(ticket, 1u);
         t = __shfl_sync(FULL_WARP, t, 0);
         if(t >= T) break;
-        const uint64_t s = blockIdx.x + uint64_t(t) * gridDim.x;
+        const uint64_t s0 = blockIdx.x + uint64_t(t) * gridDim.x;
+        const uint64_t s = io.reverse ? n_slices - 1u - s0 : s0;
         const uint64_t env = s * 32u + lane;
         const bool active = env < P.n_envs;
         const bool whole = (s + 1u) * 32u <= P.n_envs;
@@ -626,22 +631,26 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
     acc_flush(P.stats, acc, (flags & POM_STEP_COUNT) != 0u);
     if(io.fin_env)
     {
-        /* the last warp of the last CTA hands the list length to the caller and clears the counters for the next launch
-         * (no second kernel): every warp makes its list entries visible, then counts itself off */
-        __threadfence();
+        /* The last warp of a CTA hands the CTA's list to the global list; the last CTA publishes the length and clears the
+         * counters for the next launch (no second kernel).  ONE global round trip per CTA: a 64-bit atomic adds the CTA's
+         * entries to the low word (the list position) and 1 to the high word (CTAs done).  No device-wide fences: the
+         * caller reads the list after the launch has completed, and the CTA that finds itself last knows the total from
+         * the value the atomic returned.  (Reservation, fence, a second atomic for the CTA count and another fence, one
+         * after the other at the end of every CTA, cost 3.5 us per launch - tools/e2e_probe.py.) */
+        __threadfence_block();
         uint32_t* warps_done = ticket + 1;
         bool last = false;
         if(lane == 0) last = atomicAdd(warps_done, 1u) == uint32_t(NW - 1);
         last = __shfl_sync(FULL_WARP, last ? 1 : 0, 0) != 0;
         if(last)
         {
-            /* this CTA's list -> the global list, one reservation, coalesced copies by the whole warp */
-            const uint32_t* fin = reinterpret_cast<const uint32_t*>(smem + R::OFF_FIN);
-            __threadfence();
+            __threadfence_block();
+            const volatile uint32_t* fin = reinterpret_cast<const volatile uint32_t*>(smem + R::OFF_FIN);
             const uint32_t k = fin[1] != 0xFFFFFFFFu ? fin[1] : fin[0];
-            uint32_t base = 0u;
-            if(lane == 0 && k) base = atomicAdd(io.fin_counter, k);
-            base = __shfl_sync(FULL_WARP, base, 0);
+            unsigned long long old = 0ull;
+            if(lane == 0) old = atomicAdd(reinterpret_cast<unsigned long long*>(io.fin_counter), (1ull << 32) | k);
+            old = __shfl_sync(FULL_WARP, old, 0);
+            const uint32_t base = uint32_t(old);
             for(uint32_t i = lane; i < k; i += 32u)
             {
                 if(base + i < io.fin_capacity)
@@ -650,17 +659,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
                     io.fin_status[base + i] = smem[R::OFF_FIN_ST + i];
                 }
             }
-            __threadfence();
-            __syncwarp();
-        }
-        if(last && lane == 0)
-        {
-            if(atomicAdd(io.fin_counter + 1, 1u) == gridDim.x - 1u)
+            if(lane == 0 && uint32_t(old >> 32) == gridDim.x - 1u)
             {
-                __threadfence();
-                const uint32_t count = atomicExch(io.fin_counter, 0u);
+                /* every other CTA has made its reservations (also those that went past a full CTA list): base + k is the total */
+                const uint32_t count = base + k;
                 *io.fin_count_out = count < io.fin_capacity ? count : io.fin_capacity;
-                io.fin_counter[1] = 0u;
+                *reinterpret_cast<volatile unsigned long long*>(io.fin_counter) = 0ull;
             }
         }
     }
@@ -881,7 +885,12 @@ __global__ void k_fill_from_templates(BatchParams P)
 
 /* ---------------------------------------------------------------- K4: tree-search expansion */
 /* child c = root_i * fanout + j: copy the root's record into the tile, apply joint action j
- * (a_k = (j / 6^k) % 6), Step once, bulk-store the tile. */
+ * (a_k = (j / 6^k) % 6), Step once, bulk-store the tile.
+ * The tile is filled by the whole warp: the 32 children of a slice share one root (two where a slice straddles a root
+ * boundary; fanout >= 32 in a tree search), so the lanes fetch the root's 73 words ONCE with three coalesced loads and
+ * replicate them from registers into the 32 records - 96 conflict-free shared-memory stores per lane, no load between
+ * them.  (The first form had every lane copy its own record word by word: 73 dependent load -> store pairs per lane,
+ * one in flight at a time, 0.55 of the HBM write peak.) */
 template<int TPB>
 __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
                                                     const uint32_t* __restrict__ src_idx, uint64_t n_children,
@@ -890,31 +899,53 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint64_t c = uint64_t(blockIdx.x) * TPB + threadIdx.x;
+    const uint64_t c0 = uint64_t(blockIdx.x) * TPB + warp * 32u;      /* first child of this warp's slice */
+    if(c0 >= n_children) return;
+    const uint64_t c = c0 + lane;
     uint8_t* sslice = smem + warp * SLICE_BYTES;
     uint8_t* rec = sslice + lane * POM_REC_BYTES;
-    uint32_t* rw = reinterpret_cast<uint32_t*>(rec);
+    uint32_t* sw = reinterpret_cast<uint32_t*>(sslice);
     const bool raw = (flags & POM_STEP_RAW) != 0u;
+
+    const uint64_t root0 = c0 / fanout;
+    const uint32_t j0 = uint32_t(c0 - root0 * fanout);
+    const uint32_t n_here = uint32_t(n_children - c0 < 32u ? n_children - c0 : 32u);
+    {
+        uint64_t root = root0;
+        uint32_t j = j0, w0 = 0u, w1 = 0u, w2 = 0u;
+        bool have = false;
+#pragma unroll 4
+        for(uint32_t r = 0; r < 32u; r++)
+        {
+            if(r >= n_here) { w0 = w1 = w2 = 0u; have = true; }       /* lanes behind the last child hold empty records */
+            else if(!have)
+            {
+                const uint32_t* s = reinterpret_cast<const uint32_t*>(src + size_t(__ldg(src_idx + root)) * POM_REC_BYTES);
+                w0 = __ldg(s + lane);
+                w1 = __ldg(s + lane + 32u);
+                w2 = lane < uint32_t(POM_REC_WORDS - 64) ? __ldg(s + lane + 64u) : 0u;
+                have = true;
+            }
+            uint32_t* d = sw + r * POM_REC_WORDS;
+            d[lane] = w0;
+            d[lane + 32u] = w1;
+            if(lane < uint32_t(POM_REC_WORDS - 64)) d[lane + 64u] = w2;
+            if(++j == fanout) { j = 0u; root++; have = false; }      /* warp-uniform */
+        }
+    }
+    __syncwarp();
     uint32_t m = 0u;
     bool stepped = false;
     if(c < n_children)
     {
-        const uint64_t root = c / fanout;
-        const uint32_t j = uint32_t(c - root * fanout);
-        const uint32_t* s = reinterpret_cast<const uint32_t*>(src + size_t(src_idx[root]) * POM_REC_BYTES);
-#pragma unroll 1
-        for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = __ldg(s + w);
-        m = (j % 6u) | (((j / 6u) % 6u) << 8) | (((j / 36u) % 6u) << 16) | (((j / 216u) % 6u) << 24);
+        uint32_t j = j0 + lane;
+        while(j >= fanout) j -= fanout;                               /* fanout may be smaller than 32 */
+        m = moves_of_joint(j);
         stepped = !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
-    }
-    else
-    {
-        for(int w = 0; w < POM_REC_WORDS; w++) rw[w] = 0u;
     }
     warp_tick(sslice, rec, m, stepped, raw, smem + TileScratch<TPB>::OFF_LIST + 8u * warp,
               (flags & POM_STEP_CONTINUE_UNDEFINED) ? pomcore::F_INVALID_MASK_CONTINUE : pomcore::F_INVALID_MASK);
-    const uint64_t c0 = uint64_t(blockIdx.x) * TPB + warp * 32u;      /* first child of this warp's slice */
-    if(c0 + 32u <= n_children)
+    if(n_here == 32u)
     {
         fence_proxy_async();
         __syncwarp();
@@ -924,13 +955,13 @@ __global__ void __launch_bounds__(TPB) k_expand_step(uint8_t* __restrict__ dst, 
             bulk_wait_read_all();
         }
     }
-    else if(c < n_children)
+    else
     {
         /* the last, partly filled slice: only the children's own records are written - dst envs behind n_children keep
          * their contents (a bulk store of the whole slice would overwrite up to 31 of them) */
-        uint32_t* out = reinterpret_cast<uint32_t*>(dst + c * POM_REC_BYTES);
-#pragma unroll 1
-        for(int w = 0; w < POM_REC_WORDS; w++) out[w] = rw[w];
+        __syncwarp();
+        uint32_t* out = reinterpret_cast<uint32_t*>(dst + c0 * POM_REC_BYTES);
+        for(uint32_t w = lane; w < n_here * uint32_t(POM_REC_WORDS); w += 32u) out[w] = sw[w];
     }
 }
 

@@ -195,6 +195,31 @@ def test_expand_partial_last_slice_keeps_neighbours(pb, orc):
     dst.close()
 
 
+@pytest.mark.parametrize("fanout,n_roots", [(1, 77), (6, 301), (7, 64), (31, 33), (36, 100), (216, 9), (1296, 3)])
+def test_expand_any_fanout_every_child(pb, orc, fanout, n_roots):
+    """the warp-cooperative tile fill of k_expand_step: slices that hold one root, two roots (a boundary inside the slice)
+    or many roots (fanout < 32); every child against the oracle; two calls in a row reuse the handle's index buffer"""
+    src = pb.Batch(512, n_templates=64)
+    src.rollout(14, 3, 0, pb.ROLL_NO_RESET)
+    R, rst = src.download()
+    rng = np.random.default_rng(fanout)
+    dst = pb.Batch(n_roots * fanout + 40, n_templates=4)
+    for rep in range(2):
+        roots = rng.integers(0, 512, n_roots).astype(np.uint32)
+        dst.expand_step_from(src, roots, fanout, 0)
+        G, gst = dst.download(0, n_roots * fanout)
+        E = np.repeat(R[roots], fanout)
+        est = np.repeat(rst[roots], fanout)
+        j = np.tile(np.arange(fanout), n_roots)
+        mv = np.stack([j % 6, (j // 6) % 6, (j // 36) % 6, (j // 216) % 6], axis=1).astype(np.uint8)
+        orc.env_step_batch(E, est, np.ascontiguousarray(mv))
+        e, why = orc.diff_batch(G, E)
+        assert e == -1, "child %d field group %d" % (e, why)
+        assert (gst == est).all()
+    src.close()
+    dst.close()
+
+
 @pytest.mark.parametrize("mask,view", [(1, 4), (0b1010, 2)])
 def test_step_observe_fused_equals_step_then_observe(pb, orc, mask, view):
     """pom_batch_step_observe: the planes written by the step kernel itself == pom_batch_observe_planes after the step
