@@ -1560,46 +1560,64 @@ POM_HD void obs_store32(uint8_t* out, int chunk, uint32_t a, uint32_t b, uint32_
 #endif
 }
 
+/* per byte: 0xFF where the top bit is set, else 0.  One PRMT on the device: selector nibble 8 + k = "byte k, its sign
+ * replicated over the eight bits" (PTX prmt, default mode; __byte_perm masks that bit away, hence the asm) */
+POM_HD uint32_t msb_fill(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(d) : "r"(x));
+    return d;
+#else
+    return ((x >> 7) & 0x01010101u) * 0xFFu;
+#endif
+}
+/* per bit: a where m is set, else b (one LOP3) */
+POM_HD uint32_t sel_bits(uint32_t m, uint32_t a, uint32_t b) { return (m & a) | (~m & b); }
+
+/* the window [x0v, x1v] x [y0v, y1v] (every bound replicated into the four bytes of its word; the upper bounds already
+ * carry 0x80 per byte) against four cells whose coordinates sit in the bytes of xs / ys: 0xFF per visible cell.  All
+ * values are < 0x80, so (a | 0x80) - b keeps the top bit of a byte exactly when a >= b and never borrows from the
+ * byte above. */
+POM_HD uint32_t window_mask(uint32_t xs, uint32_t ys, uint32_t x0v, uint32_t x1h, uint32_t y0v, uint32_t y1h)
+{
+    const uint32_t H = 0x80808080u;
+    return msb_fill(((xs | H) - x0v) & (x1h - xs) & ((ys | H) - y0v) & (y1h - ys));
+}
+
 /* `out` is GLOBAL memory, 32-byte aligned (POM_OBS_BYTES = 512): the record is written in 16 chunks of 32 bytes (whole
  * sectors, nothing is read back), then the few bytes of visible bombs and flames are patched in by the same thread.  So
  * a lane writes its env's observation straight to its place in HBM from the record it holds in shared memory, and no
  * staging tile is needed.  (With 16-byte pieces of a 496-byte record the L1 / L2 saw 32 M half-written sectors per
- * 1 Mi envs and the kernel ran at 1.5 TB/s.) */
+ * 1 Mi envs and the kernel ran at 1.5 TB/s.)
+ * Everything the 32 lanes do together is straight-line, byte-parallel code: per board word one load, the window test on
+ * the four cells' (compile-time) coordinates, the item ids by range masks, selects - no branch.  Only the patches loop,
+ * and they loop flat: once per board word that shows a flame, once per bomb.  (The first form branched per word on
+ * "anything visible here?", walked the window row by row to build a bit mask and nested three loops for the flame
+ * lives: 2700 warp-instructions per 32 envs at 15 lanes, profiles/k_observe_lines_r2.txt.) */
 POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
 {
+    const uint32_t H = 0x80808080u;
     const uint32_t ap = r[R_APOS + agent];
     const int ax = int(ap & 15u), ay = int(ap >> 4);
+    if(view > 16) view = 16;                                   /* anything past the board is the whole board */
     const int x0 = ax - view, x1 = ax + view, y0 = ay - view, y1 = ay + view;
+    /* the window, clamped to the board and replicated per byte */
+    const uint32_t x0v = uint32_t(x0 < 0 ? 0 : x0) * 0x01010101u, x1h = uint32_t(x1 > 10 ? 10 : x1) * 0x01010101u | H;
+    const uint32_t y0v = uint32_t(y0 < 0 ? 0 : y0) * 0x01010101u, y1h = uint32_t(y1 > 10 ? 10 : y1) * 0x01010101u | H;
     /* planes 1-3 start out empty: bytes 128..479 = chunks 4..14 (bytes 121..127 leave with board chunk 3) */
     for(int q = 4; q < 15; q++) obs_store32(out, q, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
-    /* which of the 121 cells lie in the window, one bit per cell (bit = x + 11 y), built row by row; four scalars, not
-     * an array: a dynamically indexed array would live in local memory */
-    uint32_t seen0 = 0u, seen1 = 0u, seen2 = 0u, seen3 = 0u;
-    {
-        const int cx0 = x0 < 0 ? 0 : x0, cx1 = x1 > 10 ? 10 : x1, cy0 = y0 < 0 ? 0 : y0, cy1 = y1 > 10 ? 10 : y1;
-        const uint32_t cols = ((2u << cx1) - 1u) & ~((1u << cx0) - 1u);          /* columns cx0..cx1 */
-        POM_LOOP
-        for(int yy = cy0; yy <= cy1; yy++)
-        {
-            const int pos = 11 * yy, wi = pos >> 5, sh = pos & 31;
-            const uint64_t wide = uint64_t(cols) << sh;
-            const uint32_t lo = uint32_t(wide), hi = uint32_t(wide >> 32);
-            seen0 |= wi == 0 ? lo : 0u;
-            seen1 |= wi == 1 ? lo : (wi == 0 ? hi : 0u);
-            seen2 |= wi == 2 ? lo : (wi == 1 ? hi : 0u);
-            seen3 |= wi == 3 ? lo : (wi == 2 ? hi : 0u);
-        }
-    }
     /* board plane, four cells per word: the item ids come from byte-parallel range tests on the cell codes
      * (0,1 keep; 2..6 wood -> 2; 7 bomb -> 3; 8.. -> code - 3, i.e. fog 5, powerups 6..8, dummy 9, agents 10..13;
      * flame codes have the top bit set -> 4), then cells outside the window are overwritten with 5 (fog) */
     const uint32_t* bw = reinterpret_cast<const uint32_t*>(r + R_BOARD);
     uint32_t litWords = 0u;                                    /* bit w: board word w holds a visible flame cell */
-    POM_LOOP
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
     for(int q = 0; q < 4; q++)
     {
         uint32_t word[8];
-        const uint32_t seenw = q < 2 ? (q < 1 ? seen0 : seen1) : (q < 3 ? seen2 : seen3);       /* the 32 cells of this chunk */
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -1609,22 +1627,26 @@ POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
             uint32_t ids = 0u;
             if(w < 31)
             {
-                const uint32_t b4 = (seenw >> (4 * k)) & 15u;
-                /* four bits -> 0xFF in the bytes of visible cells (bit j lands in bit 8j, then every byte is widened) */
-                const uint32_t vis = ((b4 * 0x00204081u) & 0x01010101u) * 0xFFu;
-                ids = 0x05050505u;                             /* out of sight: fog */
-                if(vis)
+                /* coordinates of cells 4w .. 4w+3: constants once the loops are unrolled (cells 121..123 of word 30 get a
+                 * row the window never reaches) */
+                uint32_t xs = 0u, ys = 0u;
+                for(int j = 0; j < 4; j++)
                 {
-                    const uint32_t codes = bw[w];
-                    const uint32_t l = codes & 0x7F7F7F7Fu, flame = codes & 0x80808080u, plain = ~codes & 0x80808080u;
-                    const uint32_t ge2 = (l + 0x7E7E7E7Eu) & 0x80808080u, ge7 = (l + 0x79797979u) & 0x80808080u, ge8 = (l + 0x78787878u) & 0x80808080u;
-                    const uint32_t keep = ((plain & ~ge2) >> 7) * 0xFFu, wood = ((plain & ge2 & ~ge7) >> 7) * 0xFFu;
-                    const uint32_t bomb = ((plain & ge7 & ~ge8) >> 7) * 0xFFu, high = ((plain & ge8) >> 7) * 0xFFu, burn = (flame >> 7) * 0xFFu;
-                    const uint32_t minus3 = ((l | 0x80808080u) - 0x03030303u) & 0x7F7F7F7Fu;       /* per byte, no borrow between bytes */
-                    ids = (codes & keep) | (0x02020202u & wood) | (0x03030303u & bomb) | (minus3 & high) | (0x04040404u & burn);
-                    ids = (ids & vis) | (0x05050505u & ~vis);
-                    if(burn & vis) litWords |= 1u << w;
+                    const int c = 4 * w + j;
+                    xs |= uint32_t(c % POM_BOARD_SIZE) << (8 * j);
+                    ys |= uint32_t(c < POM_BOARD_CELLS ? c / POM_BOARD_SIZE : 0x7F) << (8 * j);
                 }
+                const uint32_t vis = window_mask(xs, ys, x0v, x1h, y0v, y1h);
+                const uint32_t codes = bw[w];
+                const uint32_t l = codes & 0x7F7F7F7Fu, burn = msb_fill(codes);
+                const uint32_t ge2 = msb_fill(l + 0x7E7E7E7Eu), ge7 = msb_fill(l + 0x79797979u), ge8 = msb_fill(l + 0x78787878u);
+                const uint32_t minus3 = ((l | H) - 0x03030303u) & 0x7F7F7F7Fu;           /* per byte, no borrow between bytes */
+                ids = sel_bits(ge2, 0x02020202u, l);
+                ids = sel_bits(ge7, 0x03030303u, ids);
+                ids = sel_bits(ge8, minus3, ids);
+                ids = sel_bits(burn, 0x04040404u, ids);
+                ids = sel_bits(vis, ids, 0x05050505u);
+                litWords |= ((burn & vis) != 0u ? 1u : 0u) << w;
                 if(w == 30) ids &= 0xFFu;                      /* bytes 121..123: the first cells of the bomb-strength plane */
             }
             word[k] = ids;
@@ -1633,49 +1655,62 @@ POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
     }
     {
         const int ammo = int(r[R_AMAX + agent]) - int(int8_t(r[R_ABCNT + agent]));
+        const uint32_t deadw = *reinterpret_cast<const uint32_t*>(r + R_AFLAGS) & (uint32_t(AF_DEAD) * 0x01010101u);
         uint32_t alive = 0;
-        for(int i = 0; i < 4; i++) alive |= (r[R_AFLAGS + i] & AF_DEAD) ? 0u : (1u << i);
+        for(int i = 0; i < 4; i++) alive |= ((deadw >> (8 * i)) & 0xFFu) ? 0u : (1u << i);
         /* chunk 15 = bytes 480..511: the last flame-plane cells, the twelve scalar bytes, the padding */
         obs_store32(out, 15, 0u,
                     uint32_t(ax) | (uint32_t(ay) << 8) | (uint32_t(ammo < 0 ? 0 : (ammo > 255 ? 255 : ammo)) << 16) | (uint32_t(r[R_ASTR + agent]) << 24),
                     ((r[R_AFLAGS + agent] & AF_CANKICK) ? 1u : 0u) | (alive << 8) | (uint32_t(r[R_TIME]) << 16) | (uint32_t(r[R_TIME + 1]) << 24),
                     (alive >> agent) & 1u, 0u, 0u, 0u, 0u);
     }
-    /* visible flame cells: how long they still burn */
-    POM_LOOP
-    while(litWords)
+    /* visible flame cells: how long they still burn.  One turn per board word that shows a flame. */
+    if(litWords)
     {
-        int w = 0;
-        while(!((litWords >> w) & 1u)) w++;
-        litWords &= litWords - 1u;
-        const uint32_t codes = bw[w];
-        const int fc = r[R_FCOUNT];
-        for(int j = 0; j < 4; j++)
+        const int fc = r[R_FCOUNT] < 20 ? r[R_FCOUNT] : 20;
+        const uint32_t first = r[R_FINDEX];
+        POM_LOOP
+        while(litWords)
         {
-            const int c = 4 * w + j;
-            if(c >= POM_BOARD_CELLS || !((codes >> (8 * j)) & 0x80u)) continue;
-            const int cx = c % POM_BOARD_SIZE, cy = c / POM_BOARD_SIZE;
-            if(cx < x0 || cx > x1 || cy < y0 || cy > y1) continue;
-            /* the flame-queue entry the cell belongs to: the first one, in queue order, with the cell's origin
-             * (the rule State::PopFlame matches cells by, bboard.cpp:160-176) */
-            const uint32_t origin = flame_origin(r, (codes >> (8 * j)) & 0xFFu);
-            uint32_t slot = r[R_FINDEX];
-            for(int k = 0; k < fc && k < 20; k++, slot = ring_next(slot))
+#if defined(__CUDA_ARCH__)
+            const int w = __ffs(int(litWords)) - 1;
+#else
+            const int w = __builtin_ctz(litWords);
+#endif
+            litWords &= litWords - 1u;
+            const uint32_t codes = bw[w];
+            /* coordinates of the word's four cells: a row ends inside the word when x0 + j reaches 11 */
+            const int c0 = 4 * w, cy = c0 / POM_BOARD_SIZE, cx = c0 - POM_BOARD_SIZE * cy;
+            const uint32_t xr = uint32_t(cx) * 0x01010101u + 0x03020100u;
+            const uint32_t wrap = msb_fill(xr + 0x75757575u);                           /* x >= 11 */
+            const uint32_t xs = xr - (wrap & 0x0B0B0B0Bu), ys = uint32_t(cy) * 0x01010101u + (wrap & 0x01010101u);
+            const uint32_t lit = msb_fill(codes) & window_mask(xs, ys, x0v, x1h, y0v, y1h);
+            for(int j = 0; j < 4; j++)
             {
-                if(r[R_FPOS + slot] == origin)
+                if(!((lit >> (8 * j)) & 1u) || c0 + j >= POM_BOARD_CELLS) continue;
+                /* the flame-queue entry the cell belongs to: the first one, in queue order, with the cell's origin
+                 * (the rule State::PopFlame matches cells by, bboard.cpp:160-176) */
+                const uint32_t origin = flame_origin(r, (codes >> (8 * j)) & 0xFFu);
+                uint32_t slot = first;
+                POM_LOOP
+                for(int k = 0; k < fc; k++, slot = ring_next(slot))
                 {
-                    const int t = int(int8_t(r[R_FTIME + slot]));
-                    out[363 + c] = uint8_t(t < 0 ? 0 : t);
-                    break;
+                    if(r[R_FPOS + slot] == origin)
+                    {
+                        const int t = int(int8_t(r[R_FTIME + slot]));
+                        out[363 + c0 + j] = uint8_t(t < 0 ? 0 : t);
+                        break;
+                    }
                 }
             }
         }
     }
     /* visible bombs: blast strength and timer at their cell; a later queue entry on the same cell overwrites an earlier one */
     {
-        const int bc = r[R_BCOUNT];
+        const int bc = r[R_BCOUNT] < 20 ? r[R_BCOUNT] : 20;
         uint32_t slot = r[R_BINDEX];
-        for(int k = 0; k < bc && k < 20; k++, slot = ring_next(slot))
+        POM_LOOP
+        for(int k = 0; k < bc; k++, slot = ring_next(slot))
         {
             const uint32_t b = reinterpret_cast<const uint32_t*>(r + R_BOMBS)[slot];
             const int bx = int(b & 15u), by = int((b >> 4) & 15u);

@@ -41,8 +41,12 @@ fenv_d = [H[i].alloc(4 * h).value for i in range(2)]
 fst_d = [H[i].alloc(h).value for i in range(2)]
 fcnt_d = [H[i].alloc(4).value for i in range(2)]
 
-def loop(name, jin, outs, wait=True, steps=K):
-    ios = [[H[i].compact_io(jin[i][k], *(outs[i] if outs else (None, None, None, None))) for k in range(RING)] for i in range(2)]
+stride = int(pb.lib().pom_batch_obs_stride(H[0].h))
+obs_d = [H[i].alloc(stride * pb.OBS_BYTES) for i in range(2)]
+
+def loop(name, jin, outs, wait=True, steps=K, obs=False):
+    ios = [[H[i].compact_io(jin[i][k], *(outs[i] if outs else (None, None, None, None)), obs_d[i] if obs else None, 1 if obs else 0, 4)
+            for k in range(RING)] for i in range(2)]
     if outs and outs[0][1] is not None:
         for i in range(2):
             for io in ios[i]:
@@ -76,3 +80,38 @@ loop("device joint, no outputs, wait per half", joint_d, None)
 loop("pinned joint, pinned outputs, no waits (queue runs ahead)", joint_h, outs_h, wait=False)
 loop("device joint, device outputs, no waits", joint_d, outs_d, wait=False)
 loop("device joint, no outputs, no waits", joint_d, None, wait=False)
+loop("OBS: pinned joint, pinned outputs, wait per half (= bench e2e_obs)", joint_h, outs_h, obs=True, steps=K // 2)
+loop("OBS: device joint, no outputs, wait per half", joint_d, None, obs=True, steps=K // 2)
+loop("OBS: device joint, no outputs, no waits", joint_d, None, wait=False, obs=True, steps=K // 2)
+loop("OBS: pinned joint, pinned outputs, no waits", joint_h, outs_h, wait=False, obs=True, steps=K // 2)
+# one handle alone, compact path, with and without observation planes (is it the alternation or the path?)
+for obs in (False, True):
+    ios = [H[0].compact_io(joint_d[0][k], None, None, None, None, obs_d[0] if obs else None, 1 if obs else 0, 4) for k in range(RING)]
+    for k in range(10):
+        H[0].step_compact_io(ios[k % RING], fl)
+    H[0].sync()
+    H[0].event(0)
+    for k in range(100):
+        H[0].step_compact_io(ios[k % RING], fl)
+    H[0].event(1)
+    H[0].sync()
+    print("one half alone, compact, obs=%s: %.1f us per launch" % (obs, H[0].elapsed_ms() * 10), flush=True)
+# the same actions as 4 move bytes per env
+mv4_d = []
+for k in range(RING):
+    j = joint_h[0][k].astype(np.uint32)
+    m4 = np.stack([j % 6, (j // 6) % 6, (j // 36) % 6, (j // 216) % 6], axis=1).astype(np.uint8)
+    p4 = H[0].alloc(4 * h)
+    pb._ck(pb.lib().pom_device_copy(0, p4, np.ascontiguousarray(m4).ctypes.data_as(C.c_void_p), 4 * h))
+    mv4_d.append(p4)
+for obs in (False, True):
+    f = (lambda k: H[0].step_observe(mv4_d[k % RING], obs_d[0], 1, 4, fl)) if obs else (lambda k: H[0].step(mv4_d[k % RING], fl))
+    for k in range(10):
+        f(k)
+    H[0].sync()
+    H[0].event(0)
+    for k in range(100):
+        f(k)
+    H[0].event(1)
+    H[0].sync()
+    print("one half alone, 4-byte moves (same actions), obs=%s: %.1f us per launch" % (obs, H[0].elapsed_ms() * 10), flush=True)
