@@ -63,6 +63,8 @@ struct pom_batch {
     uint32_t  attr_ws = 0;
     uint32_t  walk = 0;                        /* whole-batch per-tick launches so far: odd ones walk the batch backwards (StepIO::reverse) */
     int       pingpong = 1;                    /* POM_STEP_PINGPONG=0 switches the alternation off (experiments) */
+    int       obs_fused = 0;                   /* POM_OBS_FUSED=1: pom_batch_step_observe / pom_step_compact_io::obs_dev write the planes
+                                                  from inside the step kernel instead of launching k_observe_planes behind it */
     int       step_kernel = 0;                 /* 0 = k_step_ws (persistent, warp-specialised), 1 = k_step (one CTA per tile); POM_STEP_KERNEL=tile */
     uint8_t*  recs = nullptr;
     uint8_t*  templates = nullptr;
@@ -229,18 +231,19 @@ int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, c
 /* geometry of the persistent per-tick kernel (k_step_ws): compute warps and slice buffers per CTA (= per SM) */
 constexpr int WS_NW = 20, WS_NBUF = 24;
 
-template<int NW>
+template<int NW, bool OBS>
 int launch_step_ws(pom_batch* b, const pomk::BatchParams& P, const pomk::StepIO& io, uint32_t flags, cudaStream_t on)
 {
     typedef pomk::RingScratch<WS_NBUF> R;
-    if(!(b->attr_ws & (1u << NW)))
+    const uint32_t bit = 1u << (NW + (OBS ? 1 : 0));                    /* NW is even */
+    if(!(b->attr_ws & bit))
     {
-        CK(cudaFuncSetAttribute(pomk::k_step_ws<NW, WS_NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(R::BYTES)));
-        b->attr_ws |= 1u << NW;
+        CK(cudaFuncSetAttribute(pomk::k_step_ws<NW, WS_NBUF, OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(R::BYTES)));
+        b->attr_ws |= bit;
     }
     const uint64_t n_slices = (P.n_envs + 31) / 32;
     const unsigned grid = unsigned(n_slices < uint64_t(b->n_sms) ? n_slices : uint64_t(b->n_sms));
-    pomk::k_step_ws<NW, WS_NBUF><<<grid, (NW + 1) * 32, R::BYTES, on ? on : b->stream>>>(P, io, flags);
+    pomk::k_step_ws<NW, WS_NBUF, OBS><<<grid, (NW + 1) * 32, R::BYTES, on ? on : b->stream>>>(P, io, flags);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -251,15 +254,16 @@ int launch_step_io(pom_batch* b, const pomk::BatchParams& P, pomk::StepIO io, ui
     io.bulk = (reinterpret_cast<uintptr_t>(io.moves) & 15u) == 0u ? 1u : 0u;   /* TMA needs 16-byte alignment */
     /* whole-batch launches alternate the direction of the walk (L2 reuse between ticks, see StepIO::reverse) */
     if(P.n_envs == b->n_envs && b->pingpong) io.reverse = (b->walk++) & 1u;
+    if(io.obs) return launch_step_ws<WS_NW, true>(b, P, io, flags, on);
     /* persistent, warp-specialised: one CTA per SM; POM_WS_NW picks the number of compute warps (experiments) */
     switch(b->ws_nw)
     {
-    case 12: return launch_step_ws<12>(b, P, io, flags, on);
-    case 14: return launch_step_ws<14>(b, P, io, flags, on);
-    case 16: return launch_step_ws<16>(b, P, io, flags, on);
-    case 18: return launch_step_ws<18>(b, P, io, flags, on);
-    case 22: return launch_step_ws<22>(b, P, io, flags, on);
-    default: return launch_step_ws<WS_NW>(b, P, io, flags, on);
+    case 12: return launch_step_ws<12, false>(b, P, io, flags, on);
+    case 14: return launch_step_ws<14, false>(b, P, io, flags, on);
+    case 16: return launch_step_ws<16, false>(b, P, io, flags, on);
+    case 18: return launch_step_ws<18, false>(b, P, io, flags, on);
+    case 22: return launch_step_ws<22, false>(b, P, io, flags, on);
+    default: return launch_step_ws<WS_NW, false>(b, P, io, flags, on);
     }
 }
 
@@ -327,7 +331,9 @@ int launch_observe_planes(pom_batch* b, uint8_t* obs_dev, uint32_t mask, int vie
 {
     { int rc = set_smem(b, ATTR_OBS, pomk::k_observe_planes<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
-    pomk::k_observe_planes<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), obs_dev, b->n_alloc, mask, view);
+    /* start where the last whole-batch step ended (its records are still in L2): a forward walk ended at the last tile */
+    const uint32_t reverse = (b->pingpong && b->walk && ((b->walk - 1u) & 1u) == 0u) ? 1u : 0u;
+    pomk::k_observe_planes<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), obs_dev, b->n_alloc, mask, view, reverse);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -433,6 +439,7 @@ int pom_batch_init(pom_batch** out, int device, uint64_t n_envs, const pom_init_
     if(const char* e = std::getenv("POM_STEP_KERNEL")) b->step_kernel = std::strcmp(e, "tile") == 0 ? 1 : 0;
     if(const char* e = std::getenv("POM_WS_NW")) b->ws_nw = std::atoi(e);
     if(const char* e = std::getenv("POM_STEP_PINGPONG")) b->pingpong = std::atoi(e) != 0;
+    if(const char* e = std::getenv("POM_OBS_FUSED")) b->obs_fused = std::atoi(e) != 0;
     if(const char* e = std::getenv("POM_TPB"))
     {
         const int t = std::atoi(e);
@@ -751,8 +758,17 @@ int pom_batch_step_observe(pom_batch* b, const uint8_t* moves_dev, uint32_t flag
     if(b->step_kernel != 0) return fail(POM_E_ARG, "pom_batch_step_observe needs the persistent step kernel (unset POM_STEP_KERNEL)");
     pomk::StepIO k{};
     k.moves = moves_dev;
-    k.obs = obs_dev; k.obs_stride = b->n_alloc; k.obs_mask = agent_mask; k.obs_view = view;
-    return launch_step_io(b, b->params(), k, flags, b->stream);
+    if(b->obs_fused)
+    {
+        k.obs = obs_dev; k.obs_stride = b->n_alloc; k.obs_mask = agent_mask; k.obs_view = view;
+        return launch_step_io(b, b->params(), k, flags, b->stream);
+    }
+    /* Two launches, the second one starting with the records the first one wrote last.  Writing the planes from inside
+     * the step kernel saves the second read of the records, but the slice buffers are then held for twice as long and 24
+     * of them per SM no longer cover the latency: 0.267 ms per 1 Mi envs against 0.104 + 0.135 ms. */
+    rc = launch_step_io(b, b->params(), k, flags, b->stream);
+    if(rc) return rc;
+    POM_DISPATCH(b, launch_observe_planes, b, obs_dev, agent_mask, view);
 }
 
 int pom_batch_step_compact(pom_batch* b, const pom_step_compact_io* io, uint32_t flags)
@@ -776,7 +792,7 @@ int pom_batch_step_compact(pom_batch* b, const pom_step_compact_io* io, uint32_t
     if(io->obs_dev)
     {
         if(io->obs_agent_mask == 0 || io->obs_agent_mask > 0xFu || io->obs_view < 0) return fail(POM_E_ARG, "pom_batch_step_compact: obs_agent_mask must be 1..15 and obs_view >= 0");
-        k.obs = io->obs_dev; k.obs_stride = b->n_alloc; k.obs_mask = io->obs_agent_mask; k.obs_view = io->obs_view;
+        if(b->obs_fused) { k.obs = io->obs_dev; k.obs_stride = b->n_alloc; k.obs_mask = io->obs_agent_mask; k.obs_view = io->obs_view; }
     }
     if(k.fin_env)
     {
@@ -788,7 +804,9 @@ int pom_batch_step_compact(pom_batch* b, const pom_step_compact_io* io, uint32_t
         k.fin_counter = b->fin_counter;
         k.fin_count_out = count;
     }
-    return launch_step_io(b, b->params(), k, flags, b->stream);
+    rc = launch_step_io(b, b->params(), k, flags, b->stream);
+    if(rc || !io->obs_dev || b->obs_fused) return rc;
+    POM_DISPATCH(b, launch_observe_planes, b, io->obs_dev, io->obs_agent_mask, io->obs_view);
 }
 
 int pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t tick0, uint32_t flags)

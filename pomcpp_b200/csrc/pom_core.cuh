@@ -1585,109 +1585,128 @@ POM_HD uint32_t window_mask(uint32_t xs, uint32_t ys, uint32_t x0v, uint32_t x1h
     return msb_fill(((xs | H) - x0v) & (x1h - xs) & ((ys | H) - y0v) & (y1h - ys));
 }
 
-/* `out` is GLOBAL memory, 32-byte aligned (POM_OBS_BYTES = 512): the record is written in 16 chunks of 32 bytes (whole
- * sectors, nothing is read back), then the few bytes of visible bombs and flames are patched in by the same thread.  So
- * a lane writes its env's observation straight to its place in HBM from the record it holds in shared memory, and no
- * staging tile is needed.  (With 16-byte pieces of a 496-byte record the L1 / L2 saw 32 M half-written sectors per
- * 1 Mi envs and the kernel ran at 1.5 TB/s.)
- * Everything the 32 lanes do together is straight-line, byte-parallel code: per board word one load, the window test on
- * the four cells' (compile-time) coordinates, the item ids by range masks, selects - no branch.  Only the patches loop,
- * and they loop flat: once per board word that shows a flame, once per bomb.  (The first form branched per word on
- * "anything visible here?", walked the window row by row to build a bit mask and nested three loops for the flame
- * lives: 2700 warp-instructions per 32 envs at 15 lanes, profiles/k_observe_lines_r2.txt.) */
-POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
+/* An observation is written by FOUR parts (i = 0..3; on the device the four lanes of a quad, in tests/hostsim one after
+ * the other).  `out` is GLOBAL memory, 32-byte aligned (POM_OBS_BYTES = 512), written as 16 chunks of 32 bytes (whole
+ * sectors, nothing is read back); part i writes chunks i, i + 4, i + 8 and i + 12, so one store instruction of a quad
+ * covers 128 contiguous bytes and a warp's store touches 8 full lines.  (With one lane per env every lane's 32-byte
+ * store was a line of its own: 16 x 32 lines per warp and agent, and the L1 data pipe - 67 % busy - bounded the kernel,
+ * not HBM: profiles/k_observe_lines_r2.txt.)  Then the few bytes of visible bombs and flames are patched in.
+ * Everything the lanes do together is straight-line, byte-parallel code: per board word one load, the window test on
+ * the four cells' coordinates, the item ids by range masks, selects - no branch.  Only the patches loop: once per board
+ * word that shows a flame (shared out over the four parts), once per bomb. */
+struct ObsWindow {
+    int x0, x1, y0, y1;                     /* the window, not clamped */
+    uint32_t x0v, x1h, y0v, y1h;            /* clamped to the board, replicated per byte; the upper bounds carry 0x80 per byte */
+};
+
+POM_HD ObsWindow obs_window(const uint8_t* r, int agent, int view)
 {
     const uint32_t H = 0x80808080u;
     const uint32_t ap = r[R_APOS + agent];
     const int ax = int(ap & 15u), ay = int(ap >> 4);
     if(view > 16) view = 16;                                   /* anything past the board is the whole board */
-    const int x0 = ax - view, x1 = ax + view, y0 = ay - view, y1 = ay + view;
-    /* the window, clamped to the board and replicated per byte */
-    const uint32_t x0v = uint32_t(x0 < 0 ? 0 : x0) * 0x01010101u, x1h = uint32_t(x1 > 10 ? 10 : x1) * 0x01010101u | H;
-    const uint32_t y0v = uint32_t(y0 < 0 ? 0 : y0) * 0x01010101u, y1h = uint32_t(y1 > 10 ? 10 : y1) * 0x01010101u | H;
-    /* planes 1-3 start out empty: bytes 128..479 = chunks 4..14 (bytes 121..127 leave with board chunk 3) */
-    for(int q = 4; q < 15; q++) obs_store32(out, q, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
-    /* board plane, four cells per word: the item ids come from byte-parallel range tests on the cell codes
-     * (0,1 keep; 2..6 wood -> 2; 7 bomb -> 3; 8.. -> code - 3, i.e. fog 5, powerups 6..8, dummy 9, agents 10..13;
-     * flame codes have the top bit set -> 4), then cells outside the window are overwritten with 5 (fog) */
+    ObsWindow W;
+    W.x0 = ax - view; W.x1 = ax + view; W.y0 = ay - view; W.y1 = ay + view;
+    W.x0v = uint32_t(W.x0 < 0 ? 0 : W.x0) * 0x01010101u; W.x1h = uint32_t(W.x1 > 10 ? 10 : W.x1) * 0x01010101u | H;
+    W.y0v = uint32_t(W.y0 < 0 ? 0 : W.y0) * 0x01010101u; W.y1h = uint32_t(W.y1 > 10 ? 10 : W.y1) * 0x01010101u | H;
+    return W;
+}
+
+/* coordinates of the four cells c0 .. c0+3 (c0 = x + 11 y), one per byte; a row ends inside the word when x + j reaches 11 */
+POM_HD void obs_cell_coords(int x, int y, uint32_t& xs, uint32_t& ys)
+{
+    const uint32_t xr = uint32_t(x) * 0x01010101u + 0x03020100u;
+    const uint32_t wrap = msb_fill(xr + 0x75757575u);                               /* x >= 11 */
+    xs = xr - (wrap & 0x0B0B0B0Bu);
+    ys = uint32_t(y) * 0x01010101u + (wrap & 0x01010101u);
+}
+
+/* part i, the chunks: board chunk i (cells 32 i .. 32 i + 31; the item ids come from byte-parallel range tests on the
+ * cell codes - 0,1 keep; 2..6 wood -> 2; 7 bomb -> 3; 8.. -> code - 3, i.e. fog 5, powerups 6..8, dummy 9, agents
+ * 10..13; flame codes have the top bit set -> 4 - then cells outside the window are overwritten with 5, fog), the empty
+ * chunks i + 4 and i + 8 of planes 1-3, and chunk i + 12 (part 3: the scalars).  Returns bit w for every board word w
+ * of this chunk that shows a visible flame cell. */
+POM_HD uint32_t observe_part_chunks(const uint8_t* r, int agent, const ObsWindow& W, uint8_t* out, int i)
+{
+    const uint32_t H = 0x80808080u;
     const uint32_t* bw = reinterpret_cast<const uint32_t*>(r + R_BOARD);
-    uint32_t litWords = 0u;                                    /* bit w: board word w holds a visible flame cell */
+    uint32_t litWords = 0u;
+    uint32_t word[8];
+    int y = (32 * i) / POM_BOARD_SIZE, x = 32 * i - POM_BOARD_SIZE * y;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for(int q = 0; q < 4; q++)
+    for(int k = 0; k < 8; k++)
     {
-        uint32_t word[8];
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-        for(int k = 0; k < 8; k++)
-        {
-            const int w = 8 * q + k;
-            uint32_t ids = 0u;
-            if(w < 31)
-            {
-                /* coordinates of cells 4w .. 4w+3: constants once the loops are unrolled (cells 121..123 of word 30 get a
-                 * row the window never reaches) */
-                uint32_t xs = 0u, ys = 0u;
-                for(int j = 0; j < 4; j++)
-                {
-                    const int c = 4 * w + j;
-                    xs |= uint32_t(c % POM_BOARD_SIZE) << (8 * j);
-                    ys |= uint32_t(c < POM_BOARD_CELLS ? c / POM_BOARD_SIZE : 0x7F) << (8 * j);
-                }
-                const uint32_t vis = window_mask(xs, ys, x0v, x1h, y0v, y1h);
-                const uint32_t codes = bw[w];
-                const uint32_t l = codes & 0x7F7F7F7Fu, burn = msb_fill(codes);
-                const uint32_t ge2 = msb_fill(l + 0x7E7E7E7Eu), ge7 = msb_fill(l + 0x79797979u), ge8 = msb_fill(l + 0x78787878u);
-                const uint32_t minus3 = ((l | H) - 0x03030303u) & 0x7F7F7F7Fu;           /* per byte, no borrow between bytes */
-                ids = sel_bits(ge2, 0x02020202u, l);
-                ids = sel_bits(ge7, 0x03030303u, ids);
-                ids = sel_bits(ge8, minus3, ids);
-                ids = sel_bits(burn, 0x04040404u, ids);
-                ids = sel_bits(vis, ids, 0x05050505u);
-                litWords |= ((burn & vis) != 0u ? 1u : 0u) << w;
-                if(w == 30) ids &= 0xFFu;                      /* bytes 121..123: the first cells of the bomb-strength plane */
-            }
-            word[k] = ids;
-        }
-        obs_store32(out, q, word[0], word[1], word[2], word[3], word[4], word[5], word[6], word[7]);
+        const int w = 8 * i + k;
+        uint32_t xs, ys;
+        obs_cell_coords(x, y, xs, ys);
+        x += 4;
+        if(x >= POM_BOARD_SIZE) { x -= POM_BOARD_SIZE; y++; }
+        const uint32_t vis = window_mask(xs, ys, W.x0v, W.x1h, W.y0v, W.y1h);    /* cells 121.. sit in row 11: never visible */
+        const uint32_t codes = bw[w < 31 ? w : 30];
+        const uint32_t l = codes & 0x7F7F7F7Fu, burn = msb_fill(codes);
+        const uint32_t ge2 = msb_fill(l + 0x7E7E7E7Eu), ge7 = msb_fill(l + 0x79797979u), ge8 = msb_fill(l + 0x78787878u);
+        const uint32_t minus3 = ((l | H) - 0x03030303u) & 0x7F7F7F7Fu;               /* per byte, no borrow between bytes */
+        uint32_t ids = sel_bits(ge2, 0x02020202u, l);
+        ids = sel_bits(ge7, 0x03030303u, ids);
+        ids = sel_bits(ge8, minus3, ids);
+        ids = sel_bits(burn, 0x04040404u, ids);
+        ids = sel_bits(vis, ids, 0x05050505u);
+        /* bytes 121..127 are the first cells of the bomb-strength plane */
+        word[k] = w < 30 ? ids : (w == 30 ? (ids & 0xFFu) : 0u);
+        litWords |= ((burn & vis) != 0u && w < 31 ? 1u : 0u) << w;
     }
+    obs_store32(out, i, word[0], word[1], word[2], word[3], word[4], word[5], word[6], word[7]);
+    obs_store32(out, i + 4, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+    obs_store32(out, i + 8, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+    uint32_t s1 = 0u, s2 = 0u, s3 = 0u;
+    if(i == 3)
     {
+        /* chunk 15 = bytes 480..511: the last flame-plane cells, the twelve scalar bytes, the padding */
         const int ammo = int(r[R_AMAX + agent]) - int(int8_t(r[R_ABCNT + agent]));
         const uint32_t deadw = *reinterpret_cast<const uint32_t*>(r + R_AFLAGS) & (uint32_t(AF_DEAD) * 0x01010101u);
         uint32_t alive = 0;
-        for(int i = 0; i < 4; i++) alive |= ((deadw >> (8 * i)) & 0xFFu) ? 0u : (1u << i);
-        /* chunk 15 = bytes 480..511: the last flame-plane cells, the twelve scalar bytes, the padding */
-        obs_store32(out, 15, 0u,
-                    uint32_t(ax) | (uint32_t(ay) << 8) | (uint32_t(ammo < 0 ? 0 : (ammo > 255 ? 255 : ammo)) << 16) | (uint32_t(r[R_ASTR + agent]) << 24),
-                    ((r[R_AFLAGS + agent] & AF_CANKICK) ? 1u : 0u) | (alive << 8) | (uint32_t(r[R_TIME]) << 16) | (uint32_t(r[R_TIME + 1]) << 24),
-                    (alive >> agent) & 1u, 0u, 0u, 0u, 0u);
+        for(int a = 0; a < 4; a++) alive |= ((deadw >> (8 * a)) & 0xFFu) ? 0u : (1u << a);
+        const uint32_t ap = r[R_APOS + agent];
+        s1 = (ap & 15u) | ((ap >> 4) << 8) | (uint32_t(ammo < 0 ? 0 : (ammo > 255 ? 255 : ammo)) << 16) | (uint32_t(r[R_ASTR + agent]) << 24);
+        s2 = ((r[R_AFLAGS + agent] & AF_CANKICK) ? 1u : 0u) | (alive << 8) | (uint32_t(r[R_TIME]) << 16) | (uint32_t(r[R_TIME + 1]) << 24);
+        s3 = (alive >> agent) & 1u;
     }
-    /* visible flame cells: how long they still burn.  One turn per board word that shows a flame. */
-    if(litWords)
+    obs_store32(out, i + 12, 0u, s1, s2, s3, 0u, 0u, 0u, 0u);
+    return litWords;
+}
+
+/* part i, the patches; `litWords` = the OR of the four parts' observe_part_chunks results.  The caller orders the four
+ * parts' chunk stores before any part's patches (__syncwarp on the device): a flame byte may lie in another part's chunk.
+ * Bomb bytes are written by the part that owns their chunk, every part walking the whole queue: a later queue entry on
+ * the same cell overwrites an earlier one, which one thread's program order guarantees. */
+POM_HD void observe_part_patches(const uint8_t* r, const ObsWindow& W, uint8_t* out, int i, uint32_t litWords)
+{
+    const uint32_t* bw = reinterpret_cast<const uint32_t*>(r + R_BOARD);
+    /* visible flame cells: how long they still burn.  Board word w is looked after by part w % 4. */
+    uint32_t mine = litWords & (0x11111111u << i);
+    if(mine)
     {
         const int fc = r[R_FCOUNT] < 20 ? r[R_FCOUNT] : 20;
         const uint32_t first = r[R_FINDEX];
         POM_LOOP
-        while(litWords)
+        while(mine)
         {
 #if defined(__CUDA_ARCH__)
-            const int w = __ffs(int(litWords)) - 1;
+            const int w = __ffs(int(mine)) - 1;
 #else
-            const int w = __builtin_ctz(litWords);
+            const int w = __builtin_ctz(mine);
 #endif
-            litWords &= litWords - 1u;
+            mine &= mine - 1u;
             const uint32_t codes = bw[w];
-            /* coordinates of the word's four cells: a row ends inside the word when x0 + j reaches 11 */
             const int c0 = 4 * w, cy = c0 / POM_BOARD_SIZE, cx = c0 - POM_BOARD_SIZE * cy;
-            const uint32_t xr = uint32_t(cx) * 0x01010101u + 0x03020100u;
-            const uint32_t wrap = msb_fill(xr + 0x75757575u);                           /* x >= 11 */
-            const uint32_t xs = xr - (wrap & 0x0B0B0B0Bu), ys = uint32_t(cy) * 0x01010101u + (wrap & 0x01010101u);
-            const uint32_t lit = msb_fill(codes) & window_mask(xs, ys, x0v, x1h, y0v, y1h);
+            uint32_t xs, ys;
+            obs_cell_coords(cx, cy, xs, ys);
+            const uint32_t lit = msb_fill(codes) & window_mask(xs, ys, W.x0v, W.x1h, W.y0v, W.y1h);
             for(int j = 0; j < 4; j++)
             {
-                if(!((lit >> (8 * j)) & 1u) || c0 + j >= POM_BOARD_CELLS) continue;
+                if(!((lit >> (8 * j)) & 1u)) continue;
                 /* the flame-queue entry the cell belongs to: the first one, in queue order, with the cell's origin
                  * (the rule State::PopFlame matches cells by, bboard.cpp:160-176) */
                 const uint32_t origin = flame_origin(r, (codes >> (8 * j)) & 0xFFu);
@@ -1705,7 +1724,7 @@ POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
             }
         }
     }
-    /* visible bombs: blast strength and timer at their cell; a later queue entry on the same cell overwrites an earlier one */
+    /* visible bombs: blast strength and timer at their cell */
     {
         const int bc = r[R_BCOUNT] < 20 ? r[R_BCOUNT] : 20;
         uint32_t slot = r[R_BINDEX];
@@ -1714,11 +1733,21 @@ POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
         {
             const uint32_t b = reinterpret_cast<const uint32_t*>(r + R_BOMBS)[slot];
             const int bx = int(b & 15u), by = int((b >> 4) & 15u);
-            if(bx > 10 || by > 10 || bx < x0 || bx > x1 || by < y0 || by > y1) continue;
-            out[121 + bx + 11 * by] = uint8_t((b >> 12) & 15u);
-            out[242 + bx + 11 * by] = uint8_t((b >> 16) & 15u);
+            if(bx > 10 || by > 10 || bx < W.x0 || bx > W.x1 || by < W.y0 || by > W.y1) continue;
+            const int o1 = 121 + bx + 11 * by, o2 = o1 + 121;
+            if(((o1 >> 5) & 3) == i) out[o1] = uint8_t((b >> 12) & 15u);
+            if(((o2 >> 5) & 3) == i) out[o2] = uint8_t((b >> 16) & 15u);
         }
     }
+}
+
+/* the four parts one after the other (tests/hostsim; not used by the kernels) */
+POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
+{
+    const ObsWindow W = obs_window(r, agent, view);
+    uint32_t lit = 0u;
+    for(int i = 0; i < 4; i++) lit |= observe_part_chunks(r, agent, W, out, i);
+    for(int i = 0; i < 4; i++) observe_part_patches(r, W, out, i, lit);
 }
 
 /* the shared stateless action source (same arithmetic as oracle/pom_oracle.c pom_oracle_rng_moves) */

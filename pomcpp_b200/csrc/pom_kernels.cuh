@@ -14,7 +14,7 @@
  *  K3 k_make_templates / k_fill_from_templates   board generation on the device and env (re)initialisation.
  *  K4 k_gather_records / k_expand_step           state copy (pom_batch_clone) and tree-search fan-out (+ one Step, fused).
  *  K5 k_pack / k_unpack / k_observe              AoS bboard::State <-> packed record; the State as one agent sees it (fog).
- *     k_observe_planes                            the same view as byte planes for a network input, written with bulk stores.
+ *     k_observe_planes                            the same view as byte planes for a network input, four lanes per env.
  *  K7 k_policy_moves / k_rollout<TPB, true>   the reference's SimpleAgent (pom_policy.cuh) as the action source: per tick
  *                                                 into a moves buffer, or inside the fused rollout; the agents' 8-byte
  *                                                 memories live in global memory, word-major (coalesced, L1/L2-resident).
@@ -344,6 +344,35 @@ __device__ __forceinline__ void warp_tick(uint8_t* sslice, uint8_t* rec, uint32_
     }
 }
 
+/* observation planes of agent `agent` for the warp's 32 resident records: every quad of lanes writes the observations
+ * of four envs (quad q: envs q, q + 8, q + 16, q + 24 of the slice), lane i of the quad the chunks i, i + 4, i + 8, i + 12
+ * (pomcore::observe_part_chunks), so that every store instruction of the warp covers eight full 128-byte lines.
+ * `out0` = the observation of the slice's first env, `n_valid` = envs of the slice inside the batch.  All 32 lanes call. */
+__device__ __forceinline__ void warp_observe_slice(const uint8_t* sslice, int agent, int view, uint8_t* out0, uint32_t n_valid)
+{
+    const uint32_t lane = threadIdx.x & 31u, quad = lane >> 2;
+    const int part = int(lane & 3u);
+#pragma unroll 1
+    for(uint32_t m = 0; m < 4u; m++)
+    {
+        const uint32_t e = quad + 8u * m;
+        const bool valid = e < n_valid;
+        const uint8_t* r = sslice + e * POM_REC_BYTES;
+        uint8_t* out = out0 + size_t(e) * POM_OBS_BYTES;
+        pomcore::ObsWindow W{};
+        uint32_t lit = 0u;
+        if(valid)
+        {
+            W = pomcore::obs_window(r, agent, view);
+            lit = pomcore::observe_part_chunks(r, agent, W, out, part);
+        }
+        lit |= __shfl_xor_sync(FULL_WARP, lit, 1);
+        lit |= __shfl_xor_sync(FULL_WARP, lit, 2);
+        __syncwarp();                                         /* the quad's chunk stores are ordered before its patches */
+        if(valid) pomcore::observe_part_patches(r, W, out, part, lit);
+    }
+}
+
 /* dynamic shared memory of the tile kernels: TPB records + one mbarrier per warp */
 template<int TPB> struct TileScratch {
     static constexpr uint32_t OFF_BAR = TPB * POM_REC_BYTES;
@@ -465,7 +494,9 @@ template<int NBUF> struct RingScratch {
     static constexpr uint32_t BYTES = OFF_FIN_ST + FIN_CAP;
 };
 
-template<int NW, int NBUF>
+/* OBS: the kernel image with the observation code (StepIO::obs); the plain step runs the image without it - 1200
+ * instructions less in the loop body of a kernel whose warps are spread all over the instruction cache */
+template<int NW, int NBUF, bool OBS>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, StepIO io, uint32_t flags)
 {
     const uint32_t* __restrict__ moves = static_cast<const uint32_t*>(io.moves);
@@ -607,15 +638,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
         fence_proxy_async();
         __syncwarp();
         if(lane == 0) bulk_s2g(P.recs + s * R::SLICE_BYTES, sslice, R::SLICE_BYTES);
-        if(io.obs && active)
+        if(OBS && io.obs)
         {
-            /* what the agents see now: built from the record while it is still in shared memory (the bulk store above
-             * only reads it), written straight to HBM in 16-byte pieces - no second pass over the 306 MB record array */
+            /* what the agents see now: built from the records while they are still in shared memory (the bulk store above
+             * only reads them), written straight to HBM - no second pass over the 306 MB record array */
+            const uint32_t n_valid = whole ? 32u : uint32_t(P.n_envs - s * 32u);
             uint32_t k = 0u;
             for(int a = 0; a < 4; a++)
             {
                 if(!((io.obs_mask >> a) & 1u)) continue;
-                pomcore::observe_planes(rec, a, io.obs_view, io.obs + (uint64_t(k) * io.obs_stride + env) * POM_OBS_BYTES);
+                warp_observe_slice(sslice, a, io.obs_view, io.obs + (uint64_t(k) * io.obs_stride + s * 32u) * POM_OBS_BYTES, n_valid);
                 k++;
             }
         }
@@ -997,18 +1029,24 @@ __global__ void k_observe(const uint8_t* __restrict__ recs, pom_state* aos, uint
     if(status) status[i] = st;
 }
 
-/* observation planes (pomcore::observe_planes) for the agents in `mask`, written as POM_OBS_BYTES records into one slab
- * per agent: out[((k * stride) + env) * POM_OBS_BYTES], k = rank of the agent within the mask.  Same per-warp staging as
- * k_step: the warp's 32 records come in with one bulk load; every lane then writes its env's observation straight to
- * the slab.  (Round 1 staged the 32 x 496 bytes in shared memory and bulk-stored them: 25 KB per warp, 8 warps per SM,
- * 53 % of the HBM peak; without the tile the kernel runs at 24 warps per SM.)  The fused form is StepIO::obs. */
+/* observation planes for the agents in `mask`, written as POM_OBS_BYTES records into one slab per agent:
+ * out[((k * stride) + env) * POM_OBS_BYTES], k = rank of the agent within the mask.  Same per-warp staging as k_step: the
+ * warp's 32 records come in with one bulk load; the quads of the warp then write the observations straight to the slab
+ * (warp_observe_slice).  History: round 1 staged the 32 x 496 bytes in shared memory and bulk-stored them (25 KB per
+ * warp, 8 warps per SM, 0.53 of the HBM peak); one lane per env with 32-byte stores needs no tile but makes every
+ * lane's store a line of its own (L1 data pipe 67 % busy, 0.164 ms per 1 Mi envs on the bench's states); four lanes
+ * per env store whole lines.  The fused form is StepIO::obs. */
 template<int TPB>
-__global__ void __launch_bounds__(TPB) k_observe_planes(BatchParams P, uint8_t* __restrict__ out, uint64_t stride, uint32_t mask, int view)
+__global__ void __launch_bounds__(TPB) k_observe_planes(BatchParams P, uint8_t* __restrict__ out, uint64_t stride, uint32_t mask, int view,
+                                                       uint32_t reverse)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint64_t env0 = uint64_t(blockIdx.x) * TPB + warp * 32u;            /* first env of this warp's slice */
+    /* `reverse`: the tiles are taken from the end of the batch - right after a step that walked forwards, its last
+     * records are still in L2 */
+    const uint64_t tile = reverse ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    const uint64_t env0 = tile * TPB + warp * 32u;                              /* first env of this warp's slice */
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TileScratch<TPB>::OFF_BAR) + warp;
     uint8_t* sslice = smem + warp * SLICE_BYTES;
     if(lane == 0)
@@ -1020,14 +1058,13 @@ __global__ void __launch_bounds__(TPB) k_observe_planes(BatchParams P, uint8_t* 
     }
     __syncwarp();
     mbar_wait(bar, 0);
-    const uint8_t* rec = sslice + lane * POM_REC_BYTES;
-    if(env0 + lane >= P.n_envs) return;
+    if(env0 >= P.n_envs) return;
+    const uint32_t n_valid = P.n_envs - env0 < 32u ? uint32_t(P.n_envs - env0) : 32u;
     uint32_t k = 0;
     for(int a = 0; a < 4; a++)
     {
         if(!((mask >> a) & 1u)) continue;
-        /* every lane writes its env's 496 bytes straight to the slab, 16 bytes per store (pomcore::observe_planes) */
-        pomcore::observe_planes(rec, a, view, out + (uint64_t(k) * stride + env0 + lane) * POM_OBS_BYTES);
+        warp_observe_slice(sslice, a, view, out + (uint64_t(k) * stride + env0) * POM_OBS_BYTES, n_valid);
         k++;
     }
 }

@@ -220,12 +220,16 @@ def test_expand_any_fanout_every_child(pb, orc, fanout, n_roots):
     dst.close()
 
 
+@pytest.mark.parametrize("fused_kernel", [0, 1])
 @pytest.mark.parametrize("mask,view", [(1, 4), (0b1010, 2)])
-def test_step_observe_fused_equals_step_then_observe(pb, orc, mask, view):
-    """pom_batch_step_observe: the planes written by the step kernel itself == pom_batch_observe_planes after the step
-    == the definition in the oracle, with auto-reset (the planes show the re-initialised env)"""
+def test_step_observe_fused_equals_step_then_observe(pb, orc, mask, view, fused_kernel, monkeypatch):
+    """pom_batch_step_observe == pom_batch_step followed by pom_batch_observe_planes == the definition in the oracle, with
+    auto-reset (the planes show the re-initialised env); both forms of the call: the observe kernel launched behind the
+    step (default) and the planes written by the step kernel itself (POM_OBS_FUSED=1, read when the handle is made)"""
     n = 20011
+    monkeypatch.setenv("POM_OBS_FUSED", str(fused_kernel))
     a = pb.Batch(n, n_templates=64, max_ticks=25)
+    monkeypatch.delenv("POM_OBS_FUSED")
     c = pb.Batch(n, n_templates=64, max_ticks=25)
     k = bin(mask).count("1")
     stride = int(pb.lib().pom_batch_obs_stride(a.h))
@@ -253,6 +257,35 @@ def test_step_observe_fused_equals_step_then_observe(pb, orc, mask, view):
     assert A.tobytes() == Cc.tobytes() and (sa == sc).all()
     a.free(obs); a.free(mv); c.free(mv2)
     a.close(); c.close()
+
+
+@pytest.mark.parametrize("fused_kernel", [0, 1])
+def test_step_compact_with_observation_planes(pb, orc, fused_kernel, monkeypatch):
+    """pom_step_compact_io::obs_dev: the compact step also leaves the observation planes of the chosen agents on the device"""
+    import ctypes as C
+    n = 4999
+    monkeypatch.setenv("POM_OBS_FUSED", str(fused_kernel))
+    a = pb.Batch(n, n_templates=64, max_ticks=30)
+    monkeypatch.delenv("POM_OBS_FUSED")
+    mask, view = 0b0110, 3
+    stride = int(pb.lib().pom_batch_obs_stride(a.h))
+    obs = a.alloc(2 * stride * pb.OBS_BYTES)
+    joint, o1 = pb.pinned_array((n,), np.uint16)
+    rng = np.random.default_rng(5)
+    flags = pb.STEP_AUTORESET | pb.STEP_COUNT
+    for t in range(33):
+        joint[:] = rng.integers(0, 1296, n, dtype=np.uint16)
+        a.step_compact(joint, flags=flags, obs_dev=obs, obs_agent_mask=mask, obs_view=view)
+        a.sync()
+    got = np.zeros((2, stride, pb.OBS_BYTES), np.uint8)
+    pb.lib().pom_device_copy(0, got.ctypes.data_as(C.c_void_p), obs, got.nbytes)
+    S, _ = a.download()
+    for j, ag in enumerate((1, 2)):
+        want = orc.observe_planes_batch(S, ag, view)
+        assert (got[j, :n] == want).all(), "agent %d" % ag
+    a.free(obs)
+    pb.pinned_free(o1)
+    a.close()
 
 
 def test_continue_undefined_on_gpu(pb, orc):
