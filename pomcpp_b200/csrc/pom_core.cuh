@@ -80,8 +80,10 @@ POM_HD uint32_t with_byte(uint32_t w, int i, uint32_t v)
     return (w & ~(0xFFu << s)) | ((v & 0xFFu) << s);
 #endif
 }
-/* (index + i) % 20 for the FixedQueue rings; the common operands are < 40 */
-POM_HD uint32_t ring20(uint32_t a) { return a < 20u ? a : (a < 40u ? a - 20u : a % 20u); }
+/* (index + i) % 20 for the FixedQueue rings: multiply-high, shift, multiply-subtract - three instructions without a branch
+ * at every one of the ~40 places the ring arithmetic is inlined (the three-way form "a < 20 ? a : a < 40 ? a - 20 : a % 20"
+ * was 474 instructions of the step kernel's image, and the image size is felt: see k_step_ws) */
+POM_HD uint32_t ring20(uint32_t a) { return a % 20u; }
 POM_HD uint32_t ring_next(uint32_t slot) { return slot == 19u ? 0u : slot + 1u; }
 /* byte-wise equality of the four bytes of w with the byte v: 0x80 in every byte that matches */
 POM_HD uint32_t bytes_equal(uint32_t w, uint32_t v)
@@ -273,7 +275,7 @@ POM_HD void tick_flames(uint8_t* r)
  * frame is 32 bits on an explicit stack; the spawn's strength is read back from its flame-queue entry.
  * ExplodeBombAt's epilogue re-reads bombs[j] AFTER the nested explosions.
  */
-POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint32_t j0, int& flags)
+POM_HD_COLD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint32_t j0, int& flags)
 {
     uint32_t stack[24];
     int sp = 0;
@@ -381,7 +383,7 @@ POM_HD void explode(uint8_t* r, Agents& A, uint32_t p0, uint32_t strength0, uint
 
 /* util::AgentBombChainReversion, step_utility.cpp:62-128 (tail recursion -> loop).
  * bd[k] = biased destination of bomb k snapshotted before the pre-pass (step.cpp:191-192). */
-POM_HD void revert_chain(uint8_t* r, Agents& A, uint32_t moves, const uint8_t* bd, int agentID, int& flags)
+POM_HD_COLD void revert_chain(uint8_t* r, Agents& A, uint32_t moves, const uint8_t* bd, int agentID, int& flags)
 {
     POM_LOOP
     for(int guard = 0; guard < 64; guard++)
