@@ -491,13 +491,38 @@ def run_own(args):
     eb.expand_step_from(b, roots, EXPAND_FANOUT, 0)
     barrier(eb)
     with clocks_during(local_rank) as exp_clocks:
-        t0 = time.perf_counter()
-        EXP_REPS = 5
+        EXP_REPS = 10
+        eb.event(0)
         for _ in range(EXP_REPS):
-            eb.expand_step_from(b, roots, EXPAND_FANOUT, 0)           # synchronises (host index array)
-        exp_s = (time.perf_counter() - t0) / EXP_REPS
+            eb.expand_step_from(b, roots, EXPAND_FANOUT, 0)           # enqueues: index upload + one kernel
+        eb.event(1)
+        exp_s = eb.elapsed_ms() / 1e3 / EXP_REPS
         barrier(eb)
     eb.close()
+
+    # ---- roofline.big_batch: the same kernel on 4 Mi envs per GPU (1.2 GB of records): a launch's fill and drain
+    #      (about 10 us: the first loads before any store, the last slices of every CTA) is 10 % of a 1 Mi-env tick
+    #      and 2.5 % of this one - what the kernel sustains, as opposed to what one configs[2] tick costs
+    BIG = 4 * (1 << 20)
+    bb = pb.Batch(BIG, device=local_rank, env_offset=plan["first"] * 4, n_templates=N_TEMPLATES, max_ticks=800)
+    bb.rollout(PREROLL_TICKS, RNG_SEED, 0, 0)
+    big_ring = 6
+    big_moves = bb.alloc(4 * BIG * big_ring)
+    for t in range(big_ring):
+        bb.generate_moves(big_moves.value + 4 * BIG * t, RNG_SEED, 200000 + t, 6)
+    big_flags = pb.STEP_AUTORESET | pb.STEP_COUNT
+    for w in range(4):
+        bb.step(big_moves.value + 4 * BIG * (w % big_ring), big_flags)
+    barrier(bb)
+    BIG_STEPS = 20
+    bb.event(0)
+    for k in range(BIG_STEPS):
+        bb.step(big_moves.value + 4 * BIG * (k % big_ring), big_flags)
+    bb.event(1)
+    big_ms = bb.elapsed_ms() / BIG_STEPS
+    barrier(bb)
+    bb.free(big_moves)
+    bb.close()
 
     # ---- legs.strong: 1 Mi envs in TOTAL split over the ranks, per-tick kernel
     sp = shard.strong_plan(rank, world, STRONG_TOTAL)
@@ -569,6 +594,9 @@ def run_own(args):
                          "launches_per_step": 2,
                          "note": "achieved = 582 B x envs / time per tick over the timed region (CUDA events bracket both streams); traffic = DRAM "
                                  "bytes per tick, scaled from the ncu capture of one half-batch launch (profiles/k_step_ncu_summary_r2.json)",
+                         "big_batch": {"envs_per_gpu": 4 * (1 << 20), "launch_ms": big_ms, "achieved": ALGO_BYTES * 4 * (1 << 20) / (big_ms * 1e-3) / 1e9,
+                                       "frac": ALGO_BYTES * 4 * (1 << 20) / (big_ms * 1e-3) / 1e9 / peak, "steps": 20,
+                                       "what": "one launch per tick over 4 Mi envs per GPU: the per-launch fill and drain amortised (this rank)"},
                          "single_launch": {"launch_ms": single_ms, "achieved": single_achieved, "frac": single_achieved / peak,
                                            "frac_nominal_8tbs": single_achieved / NOMINAL_HBM_GBS, "steps": SINGLE_STEPS,
                                            "what": "one launch per tick over the whole batch, no overlap between ticks"}},
@@ -586,8 +614,9 @@ def run_own(args):
             "e2e_obs": {"value": world * n * (E2E_STEPS // 2) / e2e_obs_max, "unit": "env-steps/s", "steps": E2E_STEPS // 2,
                         "ms_per_1Mi_env_steps": 1e3 * e2e_obs_max / (E2E_STEPS // 2) * (1 << 20) / n,
                         "clocks": obs_clocks.result(),
-                        "api": "the e2e loop with obs_dev set: the step kernel also writes agent 0's observation planes (view 4, 512 B per "
-                               "env) from the resident record; they stay on the device"},
+                        "api": "the e2e loop with obs_dev set: every step also leaves agent 0's observation planes (view 4, 512 B per env) on "
+                               "the device, where a policy network would read them (k_observe_planes queued behind the step kernel by the "
+                               "same call; POM_OBS_FUSED=1 selects the fused kernel, which is slower)"},
             "legs": {
                 "rollout": {"value": float(roll_total[0]) / (roll_max * 1e-3), "unit": "env-steps/s", "ms": roll_max,
                             "envs_per_gpu": ROLLOUT_ENVS_PER_GPU, "ticks": ROLLOUT_TICKS,
@@ -601,8 +630,8 @@ def run_own(args):
                            "roots": EXPAND_ROOTS, "fanout": EXPAND_FANOUT,
                            "write_gbs": EXPAND_ROOTS * EXPAND_FANOUT * 289 / exp_max / 1e9,
                            "write_frac_of_peak": EXPAND_ROOTS * EXPAND_FANOUT * 289 / exp_max / 1e9 / peak,
-                           "what": "configs[4]: pom_batch_expand_step, clone + one Step per child in one kernel; wall time of the call "
-                                   "incl. the upload of the root index array", "clocks": exp_clocks.result()},
+                           "what": "configs[4]: pom_batch_expand_step, clone + one Step per child in one kernel; CUDA events around 10 calls "
+                                   "back to back, incl. the upload of the root index array", "clocks": exp_clocks.result()},
                 "strong": {"value": STRONG_TOTAL * K / (strong_max * 1e-3), "unit": "env-steps/s", "ms_per_step": strong_max / K,
                            "envs_total": STRONG_TOTAL, "envs_per_gpu": STRONG_TOTAL // world, "scaling": "strong",
                            "what": "configs[2] with 1 Mi envs in total split over the GPUs, per-tick kernel, one launch per tick",

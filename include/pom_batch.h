@@ -167,11 +167,13 @@ int  pom_batch_step_host_async(pom_batch* b, const uint8_t* moves_host, uint8_t*
  *              ones are dropped: size the list for the worst case n_envs, or poll done_bits).  fin_env may be NULL.
  * Every pointer may be device memory or page-locked mapped host memory (pom_host_alloc / pom_host_alloc_near): the
  * kernel reads and writes host memory directly.  Enqueues only: results are valid after pom_batch_sync(b). */
-/* pom_batch_step and pom_batch_observe_planes in ONE kernel: at the end of the tick (after an auto-reset, so that the
- * planes show the state the next action applies to) every env's observation for the agents in agent_mask is written
- * from the record the kernel still holds in shared memory - the 306 MB record array of a 1 Mi-env batch is not read a
- * second time and no second launch is needed.  obs_dev, agent_mask, view and the layout are those of
- * pom_batch_observe_planes.  Envs that are frozen (done / invalid, no auto-reset) are observed as they are. */
+/* pom_batch_step and pom_batch_observe_planes in ONE call: at the end of the tick (after an auto-reset, so that the
+ * planes show the state the next action applies to) every env's observation for the agents in agent_mask is written.
+ * obs_dev, agent_mask, view and the layout are those of pom_batch_observe_planes.  Envs that are frozen (done / invalid,
+ * no auto-reset) are observed as they are.  The call queues the step kernel and, behind it, the observation kernel, which
+ * starts with the records the step wrote last.  With POM_OBS_FUSED=1 in the environment when the handle is made, the
+ * step kernel writes the planes itself from the records it still holds in shared memory (no second read of the record
+ * array, no second launch) - measured slower on a B200: the slice buffers are held twice as long. */
 int  pom_batch_step_observe(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* obs_dev, uint32_t agent_mask, int view);
 typedef struct pom_step_compact_io {
     const uint16_t* joint;
@@ -180,7 +182,7 @@ typedef struct pom_step_compact_io {
     uint8_t*        fin_status;
     uint32_t*       fin_count;
     uint32_t        fin_capacity;
-    /* optional: observation planes written by the same kernel (see pom_batch_step_observe): DEVICE buffer, agents, window */
+    /* optional: observation planes written by the same call (see pom_batch_step_observe): DEVICE buffer, agents, window */
     uint8_t*        obs_dev;
     uint32_t        obs_agent_mask;
     int32_t         obs_view;
@@ -223,7 +225,8 @@ int  pom_batch_policy_upload(pom_batch* b, uint64_t first, uint64_t count, const
 int  pom_batch_clone(pom_batch* dst, uint64_t first_dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_dst);
 /* tree-search expansion: child c = i * fanout + j of root src_idx[i] gets joint action j with
  * a_k = (j / 6^k) % 6 and is stepped once (clone + Step fused, one HBM write per child).
- * fanout <= 1296; dst needs n_roots * fanout envs; dst envs behind the last child are left untouched.  */
+ * fanout <= 1296; dst needs n_roots * fanout envs; dst envs behind the last child are left untouched.
+ * Enqueues on dst's stream (src_idx has been read when the call returns); work queued on src afterwards waits for it. */
 int  pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* src_idx, uint64_t n_roots, uint32_t fanout, uint32_t flags);
 
 /* ---- State primitives on ONE env, executed by the device code of the step path (fixtures, the

@@ -80,6 +80,7 @@ struct pom_batch {
     void*     flush_buf = nullptr;
     uint32_t* idx_buf = nullptr;               /* root / source indices of pom_batch_expand_step on the device (grow-only) */
     uint64_t  idx_cap = 0;
+    cudaEvent_t ev_expand = nullptr;           /* end of the last expansion INTO this handle: the source handle's stream waits for it */
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = { nullptr, nullptr };
     /* pom_batch_step_host pipelines chunks of the batch: H2D of chunk c+1 and D2H of chunk c-1 overlap the
@@ -499,7 +500,7 @@ int pom_batch_destroy(pom_batch* b)
     if(b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->recs); cudaFree(b->templates); cudaFree(b->episodes); cudaFree(b->stats);
     cudaFree(b->moves_buf); cudaFree(b->status_buf); cudaFree(b->aos_stage); cudaFree(b->st_stage);
-    cudaFree(b->bad_count); cudaFree(b->flush_buf); cudaFree(b->idx_buf); cudaFree(b->policy); cudaFree(b->fin_counter);
+    cudaFree(b->bad_count); cudaFree(b->flush_buf); cudaFree(b->idx_buf); if(b->ev_expand) cudaEventDestroy(b->ev_expand); cudaFree(b->policy); cudaFree(b->fin_counter);
     if(b->ev[0]) cudaEventDestroy(b->ev[0]);
     if(b->ev[1]) cudaEventDestroy(b->ev[1]);
     for(int i = 0; i < pom_batch::MAX_CHUNKS; i++) { if(b->ev_in[i]) cudaEventDestroy(b->ev_in[i]); if(b->ev_done[i]) cudaEventDestroy(b->ev_done[i]); }
@@ -963,6 +964,11 @@ int pom_batch_expand_step(pom_batch* dst, const pom_batch* src, const uint32_t* 
     CK(cudaStreamSynchronize(src->stream));
     rc = [&]() -> int { POM_DISPATCH(dst, launch_expand, dst, src, idx_dev, n_children, fanout, flags); }();
     if(rc) return rc;
+    /* the call returns with the kernel queued: whatever is queued on the SOURCE handle from now on (a step that rewrites
+     * the roots) must wait until the expansion has read them */
+    if(!dst->ev_expand) CK(cudaEventCreateWithFlags(&dst->ev_expand, cudaEventDisableTiming));
+    CK(cudaEventRecord(dst->ev_expand, dst->stream));
+    CK(cudaStreamWaitEvent(src->stream, dst->ev_expand, 0));
     return POM_OK;
 }
 

@@ -74,8 +74,10 @@ int main(int argc, char** argv)
         std::vector<uint32_t> idx(a.roots);
         for(uint64_t i = 0; i < a.roots; i++) idx[i] = uint32_t(i);
         for(int w = 0; w < a.warmup; w++) if(pom_batch_expand_step(dst, src, idx.data(), a.roots, 1296, 0)) die("expand");
+        if(pom_batch_sync(dst)) die("sync");
         auto t0 = std::chrono::steady_clock::now();
         for(int k = 0; k < a.steps; k++) if(pom_batch_expand_step(dst, src, idx.data(), a.roots, 1296, 0)) die("expand");
+        if(pom_batch_sync(dst)) die("sync");                         /* the calls only enqueue */
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         const double children = double(a.roots) * 1296.0 * a.steps;
         std::printf("{\"metric\": \"env-steps/sec\", \"mode\": \"expand\", \"value\": %.6g, \"unit\": \"children (clone+Step)/s\", \"roots\": %llu, "
