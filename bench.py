@@ -153,7 +153,7 @@ def load_profile(name, key):
 
 def traffic_per_tick(n):
     """DRAM bytes per tick of n envs from the committed ncu capture of k_step_ws (which stepped envs_per_launch envs)"""
-    t, e = load_profile("k_step_ncu_summary_r2.json", "dram_bytes_per_launch"), load_profile("k_step_ncu_summary_r2.json", "envs_per_launch")
+    t, e = load_profile("k_step_ncu_summary_r2f.json", "dram_bytes_per_launch"), load_profile("k_step_ncu_summary_r2f.json", "envs_per_launch")
     return None if not t or not e else float(t) * n / float(e)
 
 
@@ -593,7 +593,7 @@ def run_own(args):
                          "peak_source": peak_src, "kernel": "k_step_ws<20,24>", "step_ms": ms / K,
                          "launches_per_step": 2,
                          "note": "achieved = 582 B x envs / time per tick over the timed region (CUDA events bracket both streams); traffic = DRAM "
-                                 "bytes per tick, scaled from the ncu capture of one half-batch launch (profiles/k_step_ncu_summary_r2.json)",
+                                 "bytes per tick, scaled from the ncu capture of one half-batch launch (profiles/k_step_ncu_summary_r2f.json)",
                          "big_batch": {"envs_per_gpu": 4 * (1 << 20), "launch_ms": big_ms, "achieved": ALGO_BYTES * 4 * (1 << 20) / (big_ms * 1e-3) / 1e9,
                                        "frac": ALGO_BYTES * 4 * (1 << 20) / (big_ms * 1e-3) / 1e9 / peak, "steps": 20,
                                        "what": "one launch per tick over 4 Mi envs per GPU: the per-launch fill and drain amortised (this rank)"},
@@ -623,8 +623,8 @@ def run_own(args):
                             "what": "configs[3]: fused %d-tick rollout, in-kernel counter RNG, auto-reset, counters all-reduced" % ROLLOUT_TICKS,
                             "episodes": int(roll_total[1]), "wins": [int(x) for x in roll_total[2:6]], "draws": int(roll_total[6]),
                             "invalid": int(roll_total[9]),
-                            "issue_slot_pct": profile_metric("k_rollout_ncu_summary_r2.json", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                            "smem_wavefront_pct": profile_metric("k_rollout_ncu_summary_r2.json", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                            "issue_slot_pct": profile_metric("k_rollout_ncu_summary_r2f.json", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                            "smem_wavefront_pct": profile_metric("k_rollout_ncu_summary_r2f.json", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
                             "clocks": roll_clocks.result()},
                 "expand": {"value": world * EXPAND_ROOTS * EXPAND_FANOUT / exp_max, "unit": "children/s", "ms": 1e3 * exp_max,
                            "roots": EXPAND_ROOTS, "fanout": EXPAND_FANOUT,

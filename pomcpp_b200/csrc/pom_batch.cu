@@ -63,6 +63,7 @@ struct pom_batch {
     uint32_t  attr_ws = 0;
     uint32_t  walk = 0;                        /* whole-batch per-tick launches so far: odd ones walk the batch backwards (StepIO::reverse) */
     int       pingpong = 1;                    /* POM_STEP_PINGPONG=0 switches the alternation off (experiments) */
+    int       policy_pertick = 1;              /* POM_ROLL_POLICY=fused: pom_batch_rollout with SimpleAgents always uses the fused kernel */
     int       obs_fused = 0;                   /* POM_OBS_FUSED=1: pom_batch_step_observe / pom_step_compact_io::obs_dev write the planes
                                                   from inside the step kernel instead of launching k_observe_planes behind it */
     int       step_kernel = 0;                 /* 0 = k_step_ws (persistent, warp-specialised), 1 = k_step (one CTA per tile); POM_STEP_KERNEL=tile */
@@ -317,11 +318,11 @@ int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, 
 }
 
 template<int TPB>
-int launch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_t tick, uint32_t mask)
+int launch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_t tick, uint32_t mask, uint32_t gen_actions = 0, uint32_t freeze_truncated = 0)
 {
     { int rc = set_smem(b, ATTR_POLICY_MOVES, pomk::k_policy_moves<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
-    pomk::k_policy_moves<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), reinterpret_cast<uint32_t*>(moves_dev), seed, tick, mask);
+    pomk::k_policy_moves<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), reinterpret_cast<uint32_t*>(moves_dev), seed, tick, mask, gen_actions, freeze_truncated);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -441,6 +442,7 @@ int pom_batch_init(pom_batch** out, int device, uint64_t n_envs, const pom_init_
     if(const char* e = std::getenv("POM_WS_NW")) b->ws_nw = std::atoi(e);
     if(const char* e = std::getenv("POM_STEP_PINGPONG")) b->pingpong = std::atoi(e) != 0;
     if(const char* e = std::getenv("POM_OBS_FUSED")) b->obs_fused = std::atoi(e) != 0;
+    if(const char* e = std::getenv("POM_ROLL_POLICY")) b->policy_pertick = std::strcmp(e, "fused") != 0;
     if(const char* e = std::getenv("POM_TPB"))
     {
         const int t = std::atoi(e);
@@ -813,6 +815,28 @@ int pom_batch_step_compact(pom_batch* b, const pom_step_compact_io* io, uint32_t
 int pom_batch_rollout(pom_batch* b, uint32_t ticks, uint64_t rng_seed, uint32_t tick0, uint32_t flags)
 {
     int rc = use(b); if(rc) return rc;
+    const uint32_t mask = (flags >> POM_ROLL_SIMPLE_SHIFT) & 0xFu;
+    if(mask && !(flags & POM_ROLL_NO_RESET) && b->policy_pertick && b->step_kernel == 0 && b->n_envs >= (uint64_t(1) << 16))
+    {
+        /* A large batch with SimpleAgents runs tick by tick: k_policy_moves (which also draws the other agents' random
+         * moves) and the per-tick step kernel, two launches per tick on the records in HBM - the same moves, states and
+         * counters as the fused kernel, 1.26 against 0.94 x 10^9 env-steps/s with four SimpleAgents on 1 Mi envs.  The
+         * fused image (policy + tick, 7200 instructions, warps spread over both halves of it) is the slower one whatever
+         * its register budget; policy work dwarfs the HBM traffic of a tick here. */
+        rc = ensure_policy(b); if(rc) return rc;
+        const uint32_t n_actions = (flags & POM_ROLL_HARMLESS) ? 5u : 6u;
+        const uint32_t sflags = POM_STEP_AUTORESET | POM_STEP_COUNT | pomk::STEP_FREEZE_TRUNCATED |
+                                ((flags & POM_ROLL_CONTINUE_UNDEFINED) ? uint32_t(POM_STEP_CONTINUE_UNDEFINED) : 0u);
+        uint8_t* mv = reinterpret_cast<uint8_t*>(b->moves_buf);
+        for(uint32_t k = 0; k < ticks; k++)
+        {
+            rc = [&]() -> int { POM_DISPATCH(b, launch_policy_moves, b, mv, rng_seed, tick0 + k, mask, n_actions, 1u); }();
+            if(rc) return rc;
+            rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, mv, sflags, nullptr); }();
+            if(rc) return rc;
+        }
+        return POM_OK;
+    }
     POM_DISPATCH(b, launch_rollout, b, ticks, rng_seed, tick0, flags);
 }
 

@@ -33,6 +33,10 @@
 namespace pomk
 {
 
+/* internal flag of the per-tick kernels (not part of the ABI): envs whose status carries TRUNCATED are frozen too, as in
+ * the fused rollout (pom_batch_rollout run tick by tick) */
+constexpr uint32_t STEP_FREEZE_TRUNCATED = 0x40000000u;
+
 enum { ST_STEPS = 0, ST_EPISODES = 1, ST_WIN0 = 2, ST_DRAWS = 6, ST_TRUNC = 7, ST_SUMLEN = 8, ST_INVALID = 9 };
 
 struct BatchParams {
@@ -585,7 +589,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
         if(io.joint) m = moves_of_joint(m);
 
         uint8_t* rec = sslice + lane * POM_REC_BYTES;
-        const bool stepped = active && !(rec[R_STATUS] & (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)));
+        const uint32_t frozen = (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)) |
+                                ((flags & STEP_FREEZE_TRUNCATED) ? POM_STATUS_TRUNCATED : 0u);
+        const bool stepped = active && !(rec[R_STATUS] & frozen);
         warp_tick(sslice, rec, m, stepped, raw, sslice + R::SLICE_BYTES + 128u,
                   (flags & POM_STEP_CONTINUE_UNDEFINED) ? pomcore::F_INVALID_MASK_CONTINUE : pomcore::F_INVALID_MASK);
         acc.steps += stepped ? 1u : 0u;
@@ -736,7 +742,8 @@ struct GlobalAgentStore {
 /* per-tick mode: moves[env] byte a <- SimpleAgent::act for every agent a in `mask` of every running env (IDLE for a dead
  * agent); the other bytes are kept.  Records are staged read-only with the same per-warp bulk load as k_step. */
 template<int TPB>
-__global__ void __launch_bounds__(TPB) k_policy_moves(BatchParams P, uint32_t* __restrict__ moves, uint64_t seed, uint32_t tick, uint32_t mask)
+__global__ void __launch_bounds__(TPB) k_policy_moves(BatchParams P, uint32_t* __restrict__ moves, uint64_t seed, uint32_t tick, uint32_t mask,
+                                                     uint32_t gen_actions, uint32_t freeze_truncated)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint64_t env = uint64_t(blockIdx.x) * TPB + threadIdx.x;
@@ -753,19 +760,22 @@ __global__ void __launch_bounds__(TPB) k_policy_moves(BatchParams P, uint32_t* _
         mbar_expect_tx(bar, SLICE_BYTES);
         bulk_g2s(sslice, gslice, SLICE_BYTES, bar);
     }
-    uint32_t m = active ? moves[env] : 0u;
+    /* gen_actions != 0: the agents outside the mask play uniform random moves from the shared counter RNG (what the fused
+     * rollout does); else their bytes are the caller's */
+    uint32_t m = !active ? 0u : (gen_actions ? pomcore::rng_moves(seed, P.env_offset + env, tick, gen_actions) : moves[env]);
     const uint32_t ep = active ? P.episodes[env] : 0u;
     const uint32_t draws = pomcore::rng_moves(seed, P.env_offset + env, tick, 5u);
     __syncwarp();
     mbar_wait(bar, 0);
     const uint8_t* rec = sslice + lane * POM_REC_BYTES;
-    if(active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_INVALID)))
+    if(active && !(rec[R_STATUS] & (POM_STATUS_DONE | POM_STATUS_INVALID | (freeze_truncated ? POM_STATUS_TRUNCATED : 0u))))
     {
         GlobalAgentStore S{ P.policy + env, P.policy_stride };
         S.claim(ep);
         m = pompolicy::simple_moves(rec, mask, m, draws, S);
         moves[env] = m;
     }
+    else if(active && gen_actions) moves[env] = m;
 }
 
 /* ---------------------------------------------------------------- K2: fused K-tick rollout */

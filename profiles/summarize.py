@@ -101,27 +101,44 @@ def by_function(rep):
     return lines
 
 
+def by_line(rep, top=45):
+    """top source lines by warp-instructions (tools/ncu_lines.py)"""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "0", str(top)],
+                         capture_output=True, text=True).stdout
+    return out.splitlines()
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
-    launches(tag)
-    for kern in ("kstep", "krollout"):
+    if os.path.exists(os.path.join(G, "launches_%s.csv" % tag)):
+        launches(tag)
+    for kern in ("kstep", "krollout", "kexpand", "kobs"):
         rep = os.path.join(G, "prof_%s_%s.ncu-rep" % (kern, tag))
         if not os.path.exists(rep):
             continue
         r = raw(rep)
         summ = {"source": "ncu --set full --clock-control none --import-source on, " + os.path.basename(rep), "metrics": r}
-        if kern == "kstep":
+        if kern in ("kstep", "kexpand", "kobs"):
             rd = [float(v.replace(",", "")) for v in r["dram__bytes_read.sum"]["values"]]
             wr = [float(v.replace(",", "")) for v in r["dram__bytes_write.sum"]["values"]]
-            scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[r["dram__bytes_read.sum"]["unit"]]
-            summ["dram_bytes_per_launch"] = (sum(rd) + sum(wr)) / len(rd) * scale
+            unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
+            summ["dram_bytes_per_launch"] = (sum(rd) * unit[r["dram__bytes_read.sum"]["unit"]] +
+                                             sum(wr) * unit[r["dram__bytes_write.sum"]["unit"]]) / len(rd)
+        if kern == "kstep":
             # r1 captured whole-batch launches of k_step (1 Mi envs); r2 captures k_step_ws in the bench's POM_STEP_OVERLAP
             # phase, where one launch steps half of the batch
             envs = (1 << 20) if tag == "r1" else (1 << 19)
             summ["envs_per_launch"] = envs
             summ["algorithmic_bytes_per_launch"] = 582 * envs
+        if kern == "kexpand":
+            summ["children_per_launch"] = 4096 * 1296
+            summ["algorithmic_bytes_per_launch"] = 289 * 4096 * 1296
+        if kern == "kobs":
+            summ["envs_per_launch"] = 1 << 20
+            summ["algorithmic_bytes_per_launch"] = (289 + 496) * (1 << 20)
         json.dump(summ, open(os.path.join(OUT, "k_%s_ncu_summary%s.json" % (kern[1:], "" if tag == "r1" and kern == "kstep" else "_" + tag)), "w"), indent=1)
-        open(os.path.join(OUT, "k_%s_by_function_%s.txt" % (kern[1:], tag)), "w").write("\n".join(by_function(rep)) + "\n")
+        lines = by_function(rep) + ["", "# top source lines"] + by_line(rep)
+        open(os.path.join(OUT, "k_%s_by_function_%s.txt" % (kern[1:], tag)), "w").write("\n".join(lines) + "\n")
     print("profiles written for", tag)
 
 

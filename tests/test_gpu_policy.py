@@ -240,3 +240,29 @@ def test_rollout_with_simple_agents_at_scale(pb, orc):
     assert (gst == status).all()
     assert _same_agents(b.policy_download(lo, cnt), A)
     b.close()
+
+
+@pytest.mark.parametrize("mask,harmless", [(0b1011, 0), (15, 1)])
+def test_rollout_with_simple_agents_fused_equals_tick_by_tick(pb, orc, mask, harmless, monkeypatch):
+    """pom_batch_rollout with SimpleAgents on a large batch runs k_policy_moves + the per-tick step kernel; with
+    POM_ROLL_POLICY=fused (read when the handle is made) the fused kernel: same states, status bytes, counters and agent
+    memories.  Envs that carry TRUNCATED without having been reset (a NO_RESET rollout before) stay frozen in both."""
+    n, seed = (1 << 16) + 4099, 77
+    monkeypatch.setenv("POM_ROLL_POLICY", "fused")
+    a = pb.Batch(n, n_templates=128, max_ticks=60)
+    monkeypatch.delenv("POM_ROLL_POLICY")
+    c = pb.Batch(n, n_templates=128, max_ticks=60)
+    flags = pb.ROLL_SIMPLE(mask) | (pb.ROLL_HARMLESS if harmless else 0)
+    for x in (a, c):
+        x.rollout(70, seed, 0, pb.ROLL_NO_RESET | (pb.ROLL_HARMLESS if harmless else 0))   # leaves truncated / done envs behind
+        x.clear_stats()
+        l0 = x.launch_count()
+        x.rollout(45, seed, 70, flags)
+        x.launches = x.launch_count() - l0
+    assert a.launches == 1 and c.launches == 90
+    A, sa = a.download()
+    Cc, sc = c.download()
+    assert A.tobytes() == Cc.tobytes() and (sa == sc).all()
+    assert a.stats().as_dict() == c.stats().as_dict()
+    assert _same_agents(a.policy_download(), c.policy_download())
+    a.close(); c.close()
