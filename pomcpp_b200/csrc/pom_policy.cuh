@@ -108,7 +108,12 @@ POM_HD bool safe_condition(uint32_t danger, uint32_t min) { return danger == 0u 
 typedef unsigned __int128 bb_t;
 
 POM_HD bb_t bb_make(uint64_t hi, uint64_t lo) { return (bb_t(hi) << 64) | bb_t(lo); }
-POM_HD bb_t bb_bit(int cell) { return bb_t(1) << cell; }
+/* (a generic 128-bit shift by a variable amount is a dozen instructions and a branch; the two 64-bit halves are not) */
+POM_HD bb_t bb_bit(int cell)
+{
+    const uint64_t one = 1ull << (cell & 63);
+    return (cell & 64) ? bb_make(one, 0ull) : bb_make(0ull, one);
+}
 POM_HD int bb_lowest(bb_t b)           /* index of the lowest set bit, b != 0 */
 {
     const uint64_t lo = uint64_t(b), hi = uint64_t(b >> 64);
@@ -345,7 +350,11 @@ POM_HD Plan plan_agent(const uint8_t* r, int id, const SimpleSt& st, uint32_t dr
  *   job B         MoveTowardsPosition (strategy.cpp:101-124): grow a set from the target through walkable cells
  *                 until it touches a neighbour of the source; the neighbours touched first are the nearest to the
  *                 target, and the first of them in the order down, up, right, left is where FillRMap's path starts. */
-POM_HD bool bb_test(bb_t b, int cell) { return (uint32_t(b >> (cell & 96)) >> (cell & 31)) & 1u; }
+POM_HD bool bb_test(bb_t b, int cell)
+{
+    const uint64_t half = (cell & 64) ? uint64_t(b >> 64) : uint64_t(b);
+    return ((half >> (cell & 63)) & 1ull) != 0ull;
+}
 
 POM_HD void run_floods(const uint8_t* r, const Boards& B, Plan* pl, uint32_t jobs)
 {
