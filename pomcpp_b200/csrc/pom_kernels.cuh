@@ -1,16 +1,17 @@
 /*
  * pom_kernels.cuh — sm_100a kernels of the batched step path.
  *
- *  K1 k_step        per-tick mode: every WARP stages its own 32 consecutive 292-byte records (9344 B) in
- *                   shared memory with ONE 1-D TMA bulk copy (cp.async.bulk + its own mbarrier), every thread
- *                   runs the tick (pom_core.cuh) on its own record in place, and the slice goes back with one
- *                   bulk store.  No CTA-wide barrier.  HBM traffic per env-step = 292 B in + 292 B out + 4 B of
- *                   moves (+ 1 status byte when asked for); no thread issues a global load/store for state.
- *                   The record stride of 73 words is odd, so same-field accesses of the 32 lanes are
- *                   bank-conflict free.
- *  K2 k_rollout     fused K-tick mode: same staging, then K ticks on the resident record with actions
- *                   from the stateless counter RNG, truncation, episode statistics and auto-reset from the
- *                   template pool inside the kernel.
+ *  K1 k_step_ws     per-tick mode, persistent and warp-specialised: one CTA per SM, a ring of 24 slice buffers in shared
+ *                   memory (32 consecutive 292-byte records + the slice's move bytes each), a producer warp that keeps
+ *                   them filled with 1-D TMA bulk copies (cp.async.bulk + mbarrier), 20 compute warps that run the tick
+ *                   (pom_core.cuh) in place and bulk-store the slice.  HBM traffic per env-step = 292 B in + 292 B out +
+ *                   4 B of moves (2 B as a joint action); no thread issues a global load/store for state.  The record
+ *                   stride of 73 words is odd, so same-field accesses of the 32 lanes are bank-conflict free.
+ *     k_step        round 1's form (one CTA per tile, every warp loads -> ticks -> stores its own slice), kept as
+ *                   POM_STEP_KERNEL=tile and as the oracle of test_persistent_kernel_equals_tile_kernel.
+ *  K2 k_rollout     fused K-tick mode: per-warp staging once, then K ticks on the resident record with actions
+ *                   from the stateless counter RNG (or the caller's tick-major moves), truncation, episode statistics
+ *                   and auto-reset from the template pool inside the kernel.
  *  K3 k_make_templates / k_fill_from_templates   board generation on the device and env (re)initialisation.
  *  K4 k_gather_records / k_expand_step           state copy (pom_batch_clone) and tree-search fan-out (+ one Step, fused).
  *  K5 k_pack / k_unpack / k_observe              AoS bboard::State <-> packed record; the State as one agent sees it (fog).
@@ -18,8 +19,8 @@
  *  K7 k_policy_moves / k_rollout<TPB, true>   the reference's SimpleAgent (pom_policy.cuh) as the action source: per tick
  *                                                 into a moves buffer, or inside the fused rollout; the agents' 8-byte
  *                                                 memories live in global memory, word-major (coalesced, L1/L2-resident).
- *  K6 stats                                      nine counters packed into three warp reductions, then one atomicAdd
- *                                                 per warp and non-zero counter; warp-cooperative reset (cp.async).
+ *  K6 stats                                      episode counters gathered per lane in registers, one warp reduction and
+ *                                                 one atomicAdd per counter, warp and launch; warp-cooperative reset (cp.async).
  */
 #ifndef POM_KERNELS_CUH_
 #define POM_KERNELS_CUH_
