@@ -2,7 +2,8 @@
  * sanitize_main.cpp — TEST-ONLY.  Runs the kernel body (pom_core.cuh, host build) and the plain-C restatement side by
  * side under AddressSanitizer + UndefinedBehaviorSanitizer on seeded random traces (random agents, the all-kick stress
  * regime, and games in which agents 1-3 are played by the device policy code, pom_policy.cuh, against the oracle's
- * SimpleAgent), comparing every field after every tick.  compute-sanitizer is not available on the GPU pool,
+ * SimpleAgent), comparing every field after every tick, and every 16th env-tick the observation planes of one agent with
+ * the oracle's definition.  compute-sanitizer is not available on the GPU pool,
  * so this is the memory-safety check of the exact code the CUDA kernels run: every record access of the tick
  * happens inside a 292-byte heap block of its own, so an out-of-bounds ring / board / stack index trips ASan.
  *
@@ -78,6 +79,18 @@ int main(int argc, char** argv)
                 {
                     std::printf("MISMATCH stress %d tick %d env %d\n", stress, t, e);
                     return 1;
+                }
+                if(((t + e) & 15) == 0)
+                {
+                    /* the observation code on the packed record, into an exact-size block, against the definition */
+                    const int agent = (t + e) >> 4 & 3, view = 1 + ((t >> 2) & 7);
+                    uint8_t* obs = static_cast<uint8_t*>(std::aligned_alloc(32, 512));
+                    uint8_t want[512];
+                    pomcore::observe_planes(recs[size_t(e)], agent, view, obs);
+                    pom_oracle_observe_planes(&S[size_t(e)], agent, view, want);
+                    const bool same = std::memcmp(obs, want, 496) == 0;
+                    std::free(obs);
+                    if(!same) { std::printf("OBSERVATION MISMATCH stress %d tick %d env %d\n", stress, t, e); return 1; }
                 }
                 if(st[size_t(e)] & 0x11)
                 {
