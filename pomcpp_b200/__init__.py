@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpom_b200.so")
+LIB_PATH = os.environ.get("POM_B200_LIB") or os.path.join(HERE, "libpom_b200.so")   # POM_B200_LIB: A/B runs of two builds
 
 REC_BYTES = 292
 OBS_BYTES = 512

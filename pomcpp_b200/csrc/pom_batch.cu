@@ -233,19 +233,19 @@ int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, c
 /* geometry of the persistent per-tick kernel (k_step_ws): compute warps and slice buffers per CTA (= per SM) */
 constexpr int WS_NW = 20, WS_NBUF = 24;
 
-template<int NW, bool OBS>
+template<int NW, bool OBS, bool FREEZE = false>
 int launch_step_ws(pom_batch* b, const pomk::BatchParams& P, const pomk::StepIO& io, uint32_t flags, cudaStream_t on)
 {
     typedef pomk::RingScratch<WS_NBUF> R;
-    const uint32_t bit = 1u << (NW + (OBS ? 1 : 0));                    /* NW is even */
+    const uint32_t bit = FREEZE ? 1u : (1u << (NW + (OBS ? 1 : 0)));    /* NW is even and >= 12 */
     if(!(b->attr_ws & bit))
     {
-        CK(cudaFuncSetAttribute(pomk::k_step_ws<NW, WS_NBUF, OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(R::BYTES)));
+        CK(cudaFuncSetAttribute(pomk::k_step_ws<NW, WS_NBUF, OBS, FREEZE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(R::BYTES)));
         b->attr_ws |= bit;
     }
     const uint64_t n_slices = (P.n_envs + 31) / 32;
     const unsigned grid = unsigned(n_slices < uint64_t(b->n_sms) ? n_slices : uint64_t(b->n_sms));
-    pomk::k_step_ws<NW, WS_NBUF, OBS><<<grid, (NW + 1) * 32, R::BYTES, on ? on : b->stream>>>(P, io, flags);
+    pomk::k_step_ws<NW, WS_NBUF, OBS, FREEZE><<<grid, (NW + 1) * 32, R::BYTES, on ? on : b->stream>>>(P, io, flags);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -256,6 +256,7 @@ int launch_step_io(pom_batch* b, const pomk::BatchParams& P, pomk::StepIO io, ui
     io.bulk = (reinterpret_cast<uintptr_t>(io.moves) & 15u) == 0u ? 1u : 0u;   /* TMA needs 16-byte alignment */
     /* whole-batch launches alternate the direction of the walk (L2 reuse between ticks, see StepIO::reverse) */
     if(P.n_envs == b->n_envs && b->pingpong) io.reverse = (b->walk++) & 1u;
+    if(flags & pomk::STEP_FREEZE_TRUNCATED) return launch_step_ws<WS_NW, false, true>(b, P, io, flags, on);
     if(io.obs) return launch_step_ws<WS_NW, true>(b, P, io, flags, on);
     /* persistent, warp-specialised: one CTA per SM; POM_WS_NW picks the number of compute warps (experiments) */
     switch(b->ws_nw)

@@ -501,7 +501,8 @@ template<int NBUF> struct RingScratch {
 
 /* OBS: the kernel image with the observation code (StepIO::obs); the plain step runs the image without it - 1200
  * instructions less in the loop body of a kernel whose warps are spread all over the instruction cache */
-template<int NW, int NBUF, bool OBS>
+/* FREEZE: envs whose status carries TRUNCATED are frozen too, as in the fused rollout (pom_batch_rollout run tick by tick) */
+template<int NW, int NBUF, bool OBS, bool FREEZE>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, StepIO io, uint32_t flags)
 {
     const uint32_t* __restrict__ moves = static_cast<const uint32_t*>(io.moves);
@@ -590,9 +591,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) k_step_ws(BatchParams P, Ste
         if(io.joint) m = moves_of_joint(m);
 
         uint8_t* rec = sslice + lane * POM_REC_BYTES;
-        const uint32_t frozen = (raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)) |
-                                ((flags & STEP_FREEZE_TRUNCATED) ? POM_STATUS_TRUNCATED : 0u);
-        const bool stepped = active && !(rec[R_STATUS] & frozen);
+        /* (FREEZE as a run-time mask - an expression of `flags`, or a word of StepIO - cost the kernel 17 % of its speed,
+         * 0.127 against 0.109 ms per 1 Mi-env tick, with the same instruction and register counts: the mask must be a
+         * compile-time constant per branch of `raw`.  tools/ab keeps the builds of that A/B.) */
+        const bool stepped = active && !(rec[R_STATUS] & ((raw ? POM_STATUS_INVALID : (POM_STATUS_DONE | POM_STATUS_INVALID)) |
+                                                          (FREEZE ? POM_STATUS_TRUNCATED : 0)));
         warp_tick(sslice, rec, m, stepped, raw, sslice + R::SLICE_BYTES + 128u,
                   (flags & POM_STEP_CONTINUE_UNDEFINED) ? pomcore::F_INVALID_MASK_CONTINUE : pomcore::F_INVALID_MASK);
         acc.steps += stepped ? 1u : 0u;

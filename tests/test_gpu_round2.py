@@ -327,3 +327,33 @@ def test_continue_undefined_on_gpu(pb, orc):
     assert st["invalid"] == 0, st
     assert st["episodes"] == sum(st["wins"]) + st["draws"] + st["truncated"]
     s.close()
+
+
+def test_persistent_kernel_is_not_slower_than_the_tile_kernel(pb, monkeypatch):
+    """A guard against code-generation cliffs in the headline kernel.  k_step_ws runs a 1 Mi-env tick about 10 % faster than
+    round 1's tile kernel; twice in round 2 an innocent-looking edit (the observation code in the loop body; the mask of
+    frozen status bits as a run-time value) cost it 4 % and 17 % with unchanged instruction and register counts, which
+    only a timing shows.  Both kernels are timed here on the same box and the same states."""
+    n, ring = 1 << 20, 8
+    ms = {}
+    for kern in ("ws", "tile"):
+        monkeypatch.setenv("POM_STEP_KERNEL", kern)
+        b = pb.Batch(n, n_templates=1024, max_ticks=800)
+        b.rollout(96, 5, 0, 0)
+        mv = b.alloc(4 * n * ring).value
+        for k in range(ring):
+            b.generate_moves(mv + 4 * n * k, 1, k, 6)
+        flags = pb.STEP_AUTORESET | pb.STEP_COUNT
+        for k in range(10):
+            b.step(mv + 4 * n * (k % ring), flags)
+        b.sync()
+        best = 1e9
+        for rep in range(3):
+            b.event(0)
+            for k in range(40):
+                b.step(mv + 4 * n * (k % ring), flags)
+            b.event(1)
+            best = min(best, b.elapsed_ms() / 40)
+        ms[kern] = best
+        b.close()
+    assert ms["ws"] <= 1.03 * ms["tile"], ms
