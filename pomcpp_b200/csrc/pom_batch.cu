@@ -63,6 +63,7 @@ struct pom_batch {
     uint32_t  attr_ws = 0;
     uint32_t  walk = 0;                        /* whole-batch per-tick launches so far: odd ones walk the batch backwards (StepIO::reverse) */
     int       pingpong = 1;                    /* POM_STEP_PINGPONG=0 switches the alternation off (experiments) */
+    int       no_spec = 0;                     /* POM_WS_NOSPEC=1: always the generic image of k_step_ws / k_rollout */
     int       policy_pertick = 1;              /* POM_ROLL_POLICY=fused: pom_batch_rollout with SimpleAgents always uses the fused kernel */
     int       obs_fused = 0;                   /* POM_OBS_FUSED=1: pom_batch_step_observe / pom_step_compact_io::obs_dev write the planes
                                                   from inside the step kernel instead of launching k_observe_planes behind it */
@@ -128,7 +129,7 @@ int use(const pom_batch* cb, bool join = true)
 
 /* The dynamic shared-memory limit of a kernel is a per-device attribute: remember it per handle (one handle = one
  * device), not in a process-wide flag, so that handles on other GPUs and other host threads set it for themselves. */
-enum { ATTR_STEP = 1, ATTR_ROLLOUT = 2, ATTR_ROLLOUT_POLICY = 4, ATTR_POLICY_MOVES = 8, ATTR_EXPAND = 16, ATTR_OBS = 32 };
+enum { ATTR_STEP = 1, ATTR_ROLLOUT = 2, ATTR_ROLLOUT_POLICY = 4, ATTR_POLICY_MOVES = 8, ATTR_EXPAND = 16, ATTR_OBS = 32, ATTR_ROLLOUT_SPEC = 64 };
 
 template<typename K>
 int set_smem(pom_batch* b, uint32_t which, K kernel, uint32_t bytes)
@@ -233,19 +234,19 @@ int pack_into(pom_batch* b, uint8_t* dst_recs, uint64_t first, uint64_t count, c
 /* geometry of the persistent per-tick kernel (k_step_ws): compute warps and slice buffers per CTA (= per SM) */
 constexpr int WS_NW = 20, WS_NBUF = 24;
 
-template<int NW, bool OBS, bool FREEZE = false>
+template<int NW, bool OBS, bool FREEZE = false, bool SPEC = false>
 int launch_step_ws(pom_batch* b, const pomk::BatchParams& P, const pomk::StepIO& io, uint32_t flags, cudaStream_t on)
 {
     typedef pomk::RingScratch<WS_NBUF> R;
-    const uint32_t bit = FREEZE ? 1u : (1u << (NW + (OBS ? 1 : 0)));    /* NW is even and >= 12 */
+    const uint32_t bit = SPEC ? 2u : (FREEZE ? 1u : (1u << (NW + (OBS ? 1 : 0))));    /* NW is even and >= 12 */
     if(!(b->attr_ws & bit))
     {
-        CK(cudaFuncSetAttribute(pomk::k_step_ws<NW, WS_NBUF, OBS, FREEZE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(R::BYTES)));
+        CK(cudaFuncSetAttribute(pomk::k_step_ws<NW, WS_NBUF, OBS, FREEZE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(R::BYTES)));
         b->attr_ws |= bit;
     }
     const uint64_t n_slices = (P.n_envs + 31) / 32;
     const unsigned grid = unsigned(n_slices < uint64_t(b->n_sms) ? n_slices : uint64_t(b->n_sms));
-    pomk::k_step_ws<NW, WS_NBUF, OBS, FREEZE><<<grid, (NW + 1) * 32, R::BYTES, on ? on : b->stream>>>(P, io, flags);
+    pomk::k_step_ws<NW, WS_NBUF, OBS, FREEZE, SPEC><<<grid, (NW + 1) * 32, R::BYTES, on ? on : b->stream>>>(P, io, flags);
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -257,6 +258,10 @@ int launch_step_io(pom_batch* b, const pomk::BatchParams& P, pomk::StepIO io, ui
     /* whole-batch launches alternate the direction of the walk (L2 reuse between ticks, see StepIO::reverse) */
     if(P.n_envs == b->n_envs && b->pingpong) io.reverse = (b->walk++) & 1u;
     if(flags & pomk::STEP_FREEZE_TRUNCATED) return launch_step_ws<WS_NW, false, true>(b, P, io, flags, on);
+    /* the specialised image (k_step_ws, SPEC) for the plain loop */
+    if(b->ws_nw == WS_NW && (flags & ~uint32_t(POM_STEP_OVERLAP)) == uint32_t(POM_STEP_AUTORESET | POM_STEP_COUNT) && io.bulk &&
+       !io.status_out && !io.obs && !io.joint && !io.done_bits && !io.fin_env && !b->no_spec)
+        return launch_step_ws<WS_NW, false, false, true>(b, P, io, flags, on);
     if(io.obs) return launch_step_ws<WS_NW, true>(b, P, io, flags, on);
     /* persistent, warp-specialised: one CTA per SM; POM_WS_NW picks the number of compute warps (experiments) */
     switch(b->ws_nw)
@@ -307,6 +312,11 @@ int launch_rollout(pom_batch* b, uint32_t ticks, uint64_t seed, uint32_t tick0, 
         int rc = set_smem(b, ATTR_ROLLOUT_POLICY, pomk::k_rollout<TPB, true>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc;
         rc = ensure_policy(b); if(rc) return rc;
         pomk::k_rollout<TPB, true><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, n_actions, no_reset, mask, nullptr);
+    }
+    else if(n_actions == 6u && no_reset == 0u && !move_seq && !b->no_spec)
+    {
+        int rc = set_smem(b, ATTR_ROLLOUT_SPEC, pomk::k_rollout<TPB, false, true>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc;
+        pomk::k_rollout<TPB, false, true><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), ticks, seed, tick0, 6u, 0u, 0u, nullptr);
     }
     else
     {
@@ -443,6 +453,7 @@ int pom_batch_init(pom_batch** out, int device, uint64_t n_envs, const pom_init_
     if(const char* e = std::getenv("POM_WS_NW")) b->ws_nw = std::atoi(e);
     if(const char* e = std::getenv("POM_STEP_PINGPONG")) b->pingpong = std::atoi(e) != 0;
     if(const char* e = std::getenv("POM_OBS_FUSED")) b->obs_fused = std::atoi(e) != 0;
+    if(const char* e = std::getenv("POM_WS_NOSPEC")) b->no_spec = std::atoi(e) != 0;
     if(const char* e = std::getenv("POM_ROLL_POLICY")) b->policy_pertick = std::strcmp(e, "fused") != 0;
     if(const char* e = std::getenv("POM_TPB"))
     {
