@@ -345,6 +345,7 @@ def run_own(args):
     #      one launch drains, the other fills
     if os.environ.get("POM_BENCH_OVERLAP", "1") != "0":
         flags |= pb.STEP_OVERLAP
+    flags_main = flags
     for w in range(W):
         b.step(moves_dev.value + 4 * n * (w % ring), flags)
     barrier()
@@ -510,7 +511,7 @@ def run_own(args):
     big_moves = bb.alloc(4 * BIG * big_ring)
     for t in range(big_ring):
         bb.generate_moves(big_moves.value + 4 * BIG * t, RNG_SEED, 200000 + t, 6)
-    big_flags = pb.STEP_AUTORESET | pb.STEP_COUNT
+    big_flags = flags_main            # as in the timed region (POM_STEP_OVERLAP unless POM_BENCH_OVERLAP=0)
     for w in range(4):
         bb.step(big_moves.value + 4 * BIG * (w % big_ring), big_flags)
     barrier(bb)
@@ -596,7 +597,7 @@ def run_own(args):
                                  "bytes per tick, scaled from the ncu capture of one half-batch launch (profiles/k_step_ncu_summary_r2f.json)",
                          "big_batch": {"envs_per_gpu": 4 * (1 << 20), "launch_ms": big_ms, "achieved": ALGO_BYTES * 4 * (1 << 20) / (big_ms * 1e-3) / 1e9,
                                        "frac": ALGO_BYTES * 4 * (1 << 20) / (big_ms * 1e-3) / 1e9 / peak, "steps": 20,
-                                       "what": "one launch per tick over 4 Mi envs per GPU: the per-launch fill and drain amortised (this rank)"},
+                                       "what": "the timed region's call on 4 Mi envs per GPU: the per-launch fill and drain amortised (this rank)"},
                          "single_launch": {"launch_ms": single_ms, "achieved": single_achieved, "frac": single_achieved / peak,
                                            "frac_nominal_8tbs": single_achieved / NOMINAL_HBM_GBS, "steps": SINGLE_STEPS,
                                            "what": "one launch per tick over the whole batch, no overlap between ticks"}},
