@@ -10,6 +10,7 @@
  * mode rollout : K launches of the fused kernel (pom_batch_rollout), T ticks each, in-kernel RNG + auto-reset
  * mode expand  : tree-search expansion (BASELINE config 5): --roots R root states (taken from a 16-tick pre-roll)
  *                x 6^4 joint actions, one Step each, K repetitions of pom_batch_expand_step (GPU 0 only)
+ * mode hostc   : mode host with compact I/O (pom_batch_step_compact: uint16 joint actions in, done bits + finished-env list out)
  * mode host    : end to end from host buffers (GPU 0): the envs as two half-batches stepped alternately with
  *                pom_batch_step_host_async + pom_batch_sync from pinned move / status buffers (what bench.py reports as e2e)
  * --no-overlap  : mode step without POM_STEP_OVERLAP (one launch per tick; default: two half-batch launches on two streams)
@@ -132,6 +133,81 @@ int main(int argc, char** argv)
                     double(2 * h) * a.steps / s, (unsigned long long)(2 * h), a.steps, 1e6 * s / a.steps,
                     (unsigned long long)(8 * h), (unsigned long long)(2 * h), done_seen);
         for(int i = 0; i < 2; i++) { pom_batch_destroy(B[i]); pom_host_free(mv[i]); pom_host_free(st[i]); }
+        return 0;
+    }
+    if(a.mode == "hostc")
+    {
+        /* the same loop with compact I/O (pom_batch_step_compact): per env a uint16 joint action in; a done bit per env and
+         * the list of finished envs (index + status byte) out; the host waits for every half-batch every tick and reads
+         * the list.  Pinned buffers on the GPU's NUMA node, the calling thread bound there too. */
+        const uint64_t h = a.envs / 2;
+        const int ring = 16;
+        pom_bind_thread_near(0);
+        pom_batch* B[2] = { nullptr, nullptr };
+        uint16_t* jt[2]; uint32_t* bits[2]; uint32_t* fenv[2]; uint8_t* fst[2]; uint32_t* fcnt[2];
+        pom_step_compact_io io[2][16];
+        for(int i = 0; i < 2; i++)
+        {
+            pom_init_desc d;
+            std::memset(&d, 0, sizeof(d));
+            d.env_offset = uint64_t(i) * h; d.n_templates = 4096; d.first_seed = 0x1337; d.max_ticks = 800;
+            if(pom_batch_init(&B[i], 0, h, &d)) die("pom_batch_init");
+            if(pom_batch_rollout(B[i], 96, 20240229, 0, 0)) die("preroll");
+            if(pom_host_alloc_near(0, 2 * h * ring, reinterpret_cast<void**>(&jt[i])) ||
+               pom_host_alloc_near(0, 4 * ((h + 31) / 32), reinterpret_cast<void**>(&bits[i])) ||
+               pom_host_alloc_near(0, 4 * h, reinterpret_cast<void**>(&fenv[i])) ||
+               pom_host_alloc_near(0, h, reinterpret_cast<void**>(&fst[i])) ||
+               pom_host_alloc_near(0, 64, reinterpret_cast<void**>(&fcnt[i]))) die("pom_host_alloc_near");
+            for(int t = 0; t < ring; t++)
+                for(uint64_t e = 0; e < h; e++)
+                {
+                    const uint32_t m = pom_rng_moves(77, uint64_t(i) * h + e, uint32_t(t), 6);
+                    jt[i][size_t(t) * h + e] = uint16_t((m & 0xFF) + 6 * ((m >> 8) & 0xFF) + 36 * ((m >> 16) & 0xFF) + 216 * (m >> 24));
+                }
+            for(int t = 0; t < ring; t++)
+            {
+                std::memset(&io[i][t], 0, sizeof(pom_step_compact_io));
+                io[i][t].joint = jt[i] + size_t(t) * h; io[i][t].done_bits = bits[i]; io[i][t].fin_env = fenv[i];
+                io[i][t].fin_status = fst[i]; io[i][t].fin_count = fcnt[i]; io[i][t].fin_capacity = uint32_t(h);
+            }
+            if(pom_batch_sync(B[i])) die("sync");
+        }
+        unsigned long long fin_seen = 0, wins0 = 0;
+        const uint32_t fl = POM_STEP_AUTORESET | POM_STEP_COUNT;
+        auto consume = [&](int i)
+        {
+            const uint32_t n = *fcnt[i];
+            fin_seen += n;
+            for(uint32_t k = 0; k < n; k += 64) wins0 += (fst[i][k] >> 2) & 1u;      /* the host reads the results */
+        };
+        auto run = [&](int steps)
+        {
+            if(pom_batch_step_compact(B[0], &io[0][0], fl)) die("step_compact");
+            for(int k = 0; k < steps; k++)
+            {
+                if(pom_batch_step_compact(B[1], &io[1][k % ring], fl)) die("step_compact");
+                if(pom_batch_sync(B[0])) die("sync");
+                consume(0);
+                if(k + 1 < steps && pom_batch_step_compact(B[0], &io[0][(k + 1) % ring], fl)) die("step_compact");
+                if(pom_batch_sync(B[1])) die("sync");
+                consume(1);
+            }
+        };
+        run(a.warmup);
+        fin_seen = 0;
+        auto t0 = std::chrono::steady_clock::now();
+        run(a.steps);
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("{\"metric\": \"env-steps/sec\", \"mode\": \"hostc\", \"value\": %.6g, \"unit\": \"env-steps/s\", \"envs\": %llu, \"steps\": %d, "
+                    "\"us_per_step\": %.4g, \"h2d_bytes_per_step\": %llu, \"d2h_bytes_per_step\": %llu, \"finished_envs_seen\": %llu}\n",
+                    double(2 * h) * a.steps / s, (unsigned long long)(2 * h), a.steps, 1e6 * s / a.steps,
+                    (unsigned long long)(4 * h), (unsigned long long)(2 * (4 * ((h + 31) / 32) + 4) + 5 * fin_seen / (unsigned long long)a.steps), fin_seen);
+        (void)wins0;
+        for(int i = 0; i < 2; i++)
+        {
+            pom_batch_destroy(B[i]);
+            pom_host_free(jt[i]); pom_host_free(bits[i]); pom_host_free(fenv[i]); pom_host_free(fst[i]); pom_host_free(fcnt[i]);
+        }
         return 0;
     }
     if(a.gpus < 1 || a.gpus > pom_device_count()) { std::fprintf(stderr, "pom_bench: %d GPUs requested, %d present\n", a.gpus, pom_device_count()); return 2; }
