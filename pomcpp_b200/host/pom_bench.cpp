@@ -4,7 +4,7 @@
  * sharded contiguously over the GPUs with no collective on the data path; the only collective is one
  * ncclAllReduce of the episode counters after the run.
  *
- *   pom_bench [--gpus N] [--envs-per-gpu E] [--steps K] [--warmup W] [--mode step|rollout|expand|host] [--ticks T] [--simple MASK]
+ *   pom_bench [--gpus N] [--envs-per-gpu E] [--steps K] [--warmup W] [--mode step|rollout|expand|host|hostc] [--ticks T] [--simple MASK]
  *
  * mode step    : K launches of the per-tick kernel (pom_batch_step, auto-reset), moves pre-generated on device
  * mode rollout : K launches of the fused kernel (pom_batch_rollout), T ticks each, in-kernel RNG + auto-reset

@@ -349,6 +349,7 @@ def test_cpp_bench_driver_runs(pb):
     for extra in (["--mode", "rollout", "--simple", "14", "--ticks", "50", "--steps", "2", "--warmup", "1"],
                   ["--mode", "step", "--simple", "15", "--steps", "10", "--warmup", "2"],
                   ["--mode", "host", "--steps", "10", "--warmup", "2"],
+                  ["--mode", "hostc", "--steps", "10", "--warmup", "2"],
                   ["--mode", "expand", "--roots", "64", "--steps", "2", "--warmup", "1"]):
         out = subprocess.run([exe, "--gpus", "1", "--envs-per-gpu", "65536"] + extra, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, " ".join(extra) + "\n" + out.stdout + out.stderr
