@@ -276,7 +276,8 @@ int launch_step_io(pom_batch* b, const pomk::BatchParams& P, pomk::StepIO io, ui
 }
 
 template<int TPB>
-int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* status_dev, uint64_t first = 0, uint64_t count = 0, cudaStream_t on = nullptr)
+int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* status_dev, uint64_t first = 0, uint64_t count = 0, cudaStream_t on = nullptr,
+                bool tile_kernel = false)
 {
     /* envs [first, first + count) only (first is a multiple of TPB); count == 0 means the whole batch */
     pomk::BatchParams P = b->params();
@@ -286,7 +287,7 @@ int launch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t*
         moves_dev += 4 * first;
         if(status_dev) status_dev += first;
     }
-    if(b->step_kernel == 0)
+    if(b->step_kernel == 0 && !tile_kernel)
     {
         pomk::StepIO io{};
         io.moves = moves_dev;
@@ -647,13 +648,18 @@ int pom_batch_step(pom_batch* b, const uint8_t* moves_dev, uint32_t flags)
     static int parts = -1;
     if(parts < 0) { const char* e = std::getenv("POM_STEP_PARTS"); parts = e ? std::atoi(e) : 2; if(parts < 2 || parts > 16) parts = 2; }
     const uint64_t per = ((b->n_envs + parts - 1) / parts + 1023) / 1024 * 1024;
+    /* Up to 0.5 Mi envs the two parts run on the tile kernel: its small CTAs let the two launches share every SM (the
+     * persistent kernel takes a whole SM per CTA, so its two launches can only follow each other), and with 60 slices or
+     * fewer per SM the persistent launch is mostly fill and drain: 0.047 against 0.057 ms per tick at 0.5 Mi envs, 0.031
+     * against 0.034 at 0.25 Mi (tools/prof_step.py).  Same tick code, same results. */
+    const bool tile_parts = b->n_envs <= (uint64_t(1) << 19) && !b->no_spec;
     CK(cudaEventRecord(b->ev_begin, b->stream));
     CK(cudaStreamWaitEvent(b->s_k2, b->ev_begin, 0));
     int c = 0;
     for(uint64_t first = 0; first < b->n_envs; first += per, c++)
     {
         const uint64_t count = first + per <= b->n_envs ? per : b->n_envs - first;
-        rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, moves_dev, flags, nullptr, first, count, (c & 1) ? b->s_k2 : b->stream); }();
+        rc = [&]() -> int { POM_DISPATCH(b, launch_step, b, moves_dev, flags, nullptr, first, count, (c & 1) ? b->s_k2 : b->stream, tile_parts); }();
         if(rc) return rc;
     }
     b->forked = true;

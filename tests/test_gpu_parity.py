@@ -539,10 +539,12 @@ def test_step_host_large_batches(pb, orc, n, pinned):
             pb.pinned_free(o2)
 
 
-def test_step_overlap_flag_matches_oracle(pb, orc):
+@pytest.mark.parametrize("n", [(1 << 18) + 1500, (1 << 19) + 1500])
+def test_step_overlap_flag_matches_oracle(pb, orc, n):
     """POM_STEP_OVERLAP: the two halves of the batch are stepped on two internal streams, ticks overlap at their edges;
-    results, status bytes and counters must be those of the plain per-tick path (auto-reset rule included)"""
-    n, ticks, seed = (1 << 18) + 1500, 36, 13
+    results, status bytes and counters must be those of the plain per-tick path (auto-reset rule included).  Up to 0.5 Mi
+    envs the halves run on the tile kernel, above on the persistent kernel: one size for each."""
+    ticks, seed = 36, 13
     b = pb.Batch(n, n_templates=32, max_ticks=0)
     T, _ = b.templates()
     S, _ = b.download()
