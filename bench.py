@@ -530,12 +530,12 @@ def run_own(args):
     sb = pb.Batch(sp["count"], device=local_rank, env_offset=sp["first"], n_templates=N_TEMPLATES, max_ticks=800)
     sb.rollout(PREROLL_TICKS, RNG_SEED, 0, 0)
     for w in range(5):
-        sb.step(moves_dev.value + 4 * n * (w % ring), flags)
+        sb.step(moves_dev.value + 4 * n * (w % ring), flags_main)
     barrier(sb)
     with clocks_during(local_rank) as strong_clocks:
         sb.event(0)
         for k in range(K):
-            sb.step(moves_dev.value + 4 * n * (k % ring), flags)
+            sb.step(moves_dev.value + 4 * n * (k % ring), flags_main)
         sb.event(1)
         strong_ms = sb.elapsed_ms()
         barrier(sb)
@@ -635,7 +635,7 @@ def run_own(args):
                                    "back to back, incl. the upload of the root index array", "clocks": exp_clocks.result()},
                 "strong": {"value": STRONG_TOTAL * K / (strong_max * 1e-3), "unit": "env-steps/s", "ms_per_step": strong_max / K,
                            "envs_total": STRONG_TOTAL, "envs_per_gpu": STRONG_TOTAL // world, "scaling": "strong",
-                           "what": "configs[2] with 1 Mi envs in total split over the GPUs, per-tick kernel, one launch per tick",
+                           "what": "configs[2] with 1 Mi envs in total split over the GPUs, the timed region's call (pom_batch_step with POM_STEP_OVERLAP; it applies from 0.25 Mi envs per GPU up)",
                            "clocks": strong_clocks.result()}},
             "parity_sampled": {"envs": int(parity[0]), "ticks": PARITY_TICKS, "mismatches": int(parity[1]),
                                "what": "every rank: strided envs of its shard after %d per-tick auto-reset steps vs the oracle's replay "
