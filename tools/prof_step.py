@@ -3,6 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pomcpp_b200 as pb
 n = int(os.environ.get("POM_PROF_ENVS", 1 << 20))
+if os.environ.get("POM_PROF_HOLDER"):
+    holder = pb.Batch(int(os.environ["POM_PROF_HOLDER"]), n_templates=16)      # another handle's allocations first
 b = pb.Batch(n, n_templates=4096, max_ticks=800)
 b.rollout(96, 5, 0, 0)
 ring = 23
