@@ -136,6 +136,15 @@ int  pom_batch_observe(pom_batch* b, uint64_t first, uint64_t count, int agent, 
 #define POM_OBS_BYTES 512
 uint64_t pom_batch_obs_stride(const pom_batch* b);
 int  pom_batch_observe_planes(pom_batch* b, uint8_t* obs_dev, uint32_t agent_mask, int view);
+/* The CROPPED layout of the same observation: only the window.  With W = 2 * view + 1 (view 0..5) one observation is
+ * pom_obs_cropped_bytes(view) = 4 * W * W + 12 bytes rounded up to a multiple of 32 (view 4: 352 instead of 512):
+ *     p * W * W + row * W + col   plane p (0 board ids, 1 blast strength, 2 bomb timer, 3 flame life, as above) of board
+ *                                 cell (x - view + col, y - view + row), (x, y) = the observer's position; window cells
+ *                                 that lie off the board hold 5 (fog) in the board plane and 0 elsewhere
+ *     4 * W * W ... + 11          the twelve scalar bytes 484..495 of the full layout, then zero padding
+ * Slabs as for pom_batch_observe_planes, with pom_obs_cropped_bytes(view) in place of POM_OBS_BYTES. */
+uint32_t pom_obs_cropped_bytes(int view);   /* 0 for a view outside 0..5 */
+int  pom_batch_observe_planes_cropped(pom_batch* b, uint8_t* obs_dev, uint32_t agent_mask, int view);
 int  pom_batch_reset(pom_batch* b);   /* all envs back to their template, counters and episode numbers cleared */
 int  pom_batch_templates(pom_batch* b, pom_state* out /* n_templates */, int32_t* seeds_out /* may be NULL */);
 

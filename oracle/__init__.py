@@ -155,6 +155,15 @@ class Restatement:
         self.lib.pom_oracle_observe_planes_batch(_ptr(S), C.c_long(S.shape[0]), agent, view, _ptr(out))
         return out
 
+    def obs_cropped_bytes(self, view=4):
+        self.lib.pom_oracle_obs_cropped_bytes.restype = C.c_long
+        return int(self.lib.pom_oracle_obs_cropped_bytes(view))
+
+    def observe_cropped_batch(self, S, agent, view=4):
+        out = np.zeros((S.shape[0], self.obs_cropped_bytes(view)), np.uint8)
+        self.lib.pom_oracle_observe_cropped_batch(_ptr(S), C.c_long(S.shape[0]), agent, view, _ptr(out))
+        return out
+
     # --- agents::SimpleAgent / bboard::strategy (oracle/pom_oracle_agent.c) ---
     def simple_agents(self, n_envs):
         return np.zeros((n_envs, 4), dtype=SIMPLE_DT)

@@ -903,6 +903,34 @@ void pom_oracle_observe_planes(const pom_state* full, int agent, int view, uint8
     out[492] = (uint8_t)((alive >> agent) & 1);
 }
 
+/* the cropped layout (include/pom_batch.h, pom_batch_observe_planes_cropped): the window of the full planes, row-major,
+ * plane after plane, then the twelve scalar bytes; window cells off the board hold 5 (fog) in the board plane, 0 elsewhere.
+ * Defined THROUGH the full-layout definition above, so that the two layouts cannot drift apart. */
+long pom_oracle_obs_cropped_bytes(int view) { long w = 2 * view + 1; return (4 * w * w + 12 + 31) & ~31L; }
+
+void pom_oracle_observe_cropped(const pom_state* full, int agent, int view, uint8_t* out)
+{
+    uint8_t planes[512];
+    const int W = 2 * view + 1, W2 = W * W;
+    const int ax = full->agents[agent].x, ay = full->agents[agent].y;
+    pom_oracle_observe_planes(full, agent, view, planes);
+    memset(out, 0, (size_t)pom_oracle_obs_cropped_bytes(view));
+    for (int p = 0; p < 4; p++)
+        for (int row = 0; row < W; row++)
+            for (int col = 0; col < W; col++) {
+                int x = ax - view + col, y = ay - view + row;
+                int inb = x >= 0 && x < BS && y >= 0 && y < BS;
+                out[p * W2 + row * W + col] = inb ? planes[p * BS * BS + x + BS * y] : (uint8_t)(p == 0 ? 5 : 0);
+            }
+    memcpy(out + 4 * W2, planes + 484, 12);
+}
+
+void pom_oracle_observe_cropped_batch(const pom_state* S, long n, int agent, int view, uint8_t* out)
+{
+    const long rb = pom_oracle_obs_cropped_bytes(view);
+    for (long e = 0; e < n; e++) pom_oracle_observe_cropped(&S[e], agent, view, out + rb * e);
+}
+
 void pom_oracle_observe_planes_batch(const pom_state* S, long n, int agent, int view, uint8_t* out)
 {
     for (long e = 0; e < n; e++) pom_oracle_observe_planes(&S[e], agent, view, out + 512 * e);

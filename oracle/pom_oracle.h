@@ -95,6 +95,9 @@ void pom_oracle_fog_batch(pom_state* S, long n, int agent, int view);
 /* observation planes of agent `agent` (layout: include/pom_batch.h POM_OBS_BYTES); a definition like pom_oracle_fog */
 void pom_oracle_observe_planes(const pom_state* s, int agent, int view, uint8_t out[512]);
 void pom_oracle_observe_planes_batch(const pom_state* S, long n, int agent, int view, uint8_t* out);
+long pom_oracle_obs_cropped_bytes(int view);
+void pom_oracle_observe_cropped(const pom_state* s, int agent, int view, uint8_t* out);
+void pom_oracle_observe_cropped_batch(const pom_state* S, long n, int agent, int view, uint8_t* out);
 
 /* ---- agents::SimpleAgent + bboard::strategy (pom_oracle_agent.c) ----
  * act() of the reference's heuristic agent `id` on state s (simple_agent.cpp:128-141); `st` holds the

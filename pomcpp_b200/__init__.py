@@ -103,6 +103,9 @@ def lib():
         L.pom_batch_obs_stride.restype = u64
         L.pom_batch_obs_stride.argtypes = [vp]
         L.pom_batch_observe_planes.argtypes = [vp, vp, u32, i32]
+        L.pom_batch_observe_planes_cropped.argtypes = [vp, vp, u32, i32]
+        L.pom_obs_cropped_bytes.argtypes = [i32]
+        L.pom_obs_cropped_bytes.restype = u32
         L.pom_device_copy.argtypes = [i32, vp, vp, u64]
         L.pom_batch_reset.argtypes = [vp]
         L.pom_batch_templates.argtypes = [vp, vp, vp]
@@ -233,6 +236,22 @@ class Batch:
         _ck(lib().pom_batch_observe_planes(self.h, obs_dev, agent_mask, view))
         self.sync()
         host = np.zeros((k, stride, OBS_BYTES), np.uint8)
+        _ck(lib().pom_device_copy(self.device, _p(host), obs_dev, host.nbytes))
+        if own:
+            self.free(obs_dev)
+        return host[:, :self.n]
+
+    def observe_planes_cropped(self, agent_mask=15, view=4, obs_dev=None):
+        """the cropped layout (pom_batch_observe_planes_cropped): returns a host copy [n_agents, n_envs, pom_obs_cropped_bytes(view)]"""
+        k = bin(agent_mask & 15).count("1")
+        stride = int(lib().pom_batch_obs_stride(self.h))
+        rb = int(lib().pom_obs_cropped_bytes(view))
+        own = obs_dev is None
+        if own:
+            obs_dev = self.alloc(k * stride * max(rb, 32))
+        _ck(lib().pom_batch_observe_planes_cropped(self.h, obs_dev, agent_mask, view))
+        self.sync()
+        host = np.zeros((k, stride, rb), np.uint8)
         _ck(lib().pom_device_copy(self.device, _p(host), obs_dev, host.nbytes))
         if own:
             self.free(obs_dev)

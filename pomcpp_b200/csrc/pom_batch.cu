@@ -129,7 +129,7 @@ int use(const pom_batch* cb, bool join = true)
 
 /* The dynamic shared-memory limit of a kernel is a per-device attribute: remember it per handle (one handle = one
  * device), not in a process-wide flag, so that handles on other GPUs and other host threads set it for themselves. */
-enum { ATTR_STEP = 1, ATTR_ROLLOUT = 2, ATTR_ROLLOUT_POLICY = 4, ATTR_POLICY_MOVES = 8, ATTR_EXPAND = 16, ATTR_OBS = 32, ATTR_ROLLOUT_SPEC = 64 };
+enum { ATTR_STEP = 1, ATTR_ROLLOUT = 2, ATTR_ROLLOUT_POLICY = 4, ATTR_POLICY_MOVES = 8, ATTR_EXPAND = 16, ATTR_OBS = 32, ATTR_ROLLOUT_SPEC = 64, ATTR_OBS_CROPPED = 128 };
 
 template<typename K>
 int set_smem(pom_batch* b, uint32_t which, K kernel, uint32_t bytes)
@@ -341,13 +341,21 @@ int launch_policy_moves(pom_batch* b, uint8_t* moves_dev, uint64_t seed, uint32_
 }
 
 template<int TPB>
-int launch_observe_planes(pom_batch* b, uint8_t* obs_dev, uint32_t mask, int view)
+int launch_observe_planes(pom_batch* b, uint8_t* obs_dev, uint32_t mask, int view, uint32_t cropped_bytes = 0)
 {
-    { int rc = set_smem(b, ATTR_OBS, pomk::k_observe_planes<TPB>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc; }
     const unsigned grid = unsigned((b->n_envs + TPB - 1) / TPB);
     /* start where the last whole-batch step ended (its records are still in L2): a forward walk ended at the last tile */
     const uint32_t reverse = (b->pingpong && b->walk && ((b->walk - 1u) & 1u) == 0u) ? 1u : 0u;
-    pomk::k_observe_planes<TPB><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), obs_dev, b->n_alloc, mask, view, reverse);
+    if(cropped_bytes)
+    {
+        int rc = set_smem(b, ATTR_OBS_CROPPED, pomk::k_observe_planes<TPB, true>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc;
+        pomk::k_observe_planes<TPB, true><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), obs_dev, b->n_alloc, mask, view, reverse, cropped_bytes);
+    }
+    else
+    {
+        int rc = set_smem(b, ATTR_OBS, pomk::k_observe_planes<TPB, false>, pomk::TileScratch<TPB>::BYTES); if(rc) return rc;
+        pomk::k_observe_planes<TPB, false><<<grid, TPB, pomk::TileScratch<TPB>::BYTES, b->stream>>>(b->params(), obs_dev, b->n_alloc, mask, view, reverse, 0u);
+    }
     b->launches++;
     CK(cudaGetLastError());
     return POM_OK;
@@ -768,6 +776,16 @@ int pom_batch_step_host(pom_batch* b, const uint8_t* moves_host, uint8_t* status
     if(rc) return rc;
     CK(cudaStreamSynchronize(b->stream));
     return POM_OK;
+}
+
+uint32_t pom_obs_cropped_bytes(int view) { return (view < 0 || view > 5) ? 0u : pomcore::obs_cropped_bytes(view); }
+
+int pom_batch_observe_planes_cropped(pom_batch* b, uint8_t* obs_dev, uint32_t agent_mask, int view)
+{
+    int rc = use(b); if(rc) return rc;
+    if(!obs_dev) return fail(POM_E_ARG, "pom_batch_observe_planes_cropped: null output");
+    if(agent_mask == 0 || agent_mask > 0xFu || view < 0 || view > 5) return fail(POM_E_ARG, "pom_batch_observe_planes_cropped: agent_mask must be 1..15 and view 0..5");
+    POM_DISPATCH(b, launch_observe_planes, b, obs_dev, agent_mask, view, pomcore::obs_cropped_bytes(view));
 }
 
 int pom_batch_step_observe(pom_batch* b, const uint8_t* moves_dev, uint32_t flags, uint8_t* obs_dev, uint32_t agent_mask, int view)

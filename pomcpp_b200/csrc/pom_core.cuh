@@ -1752,6 +1752,162 @@ POM_HD void observe_planes(const uint8_t* r, int agent, int view, uint8_t* out)
     for(int i = 0; i < 4; i++) observe_part_patches(r, W, out, i, lit);
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * The CROPPED layout of the same observation (pom_batch_observe_planes_cropped): only the window, four planes of
+ * W x W bytes (W = 2 view + 1, view <= 5) centred on the observer - plane cell (row, col) is board cell
+ * (x - view + col, y - view + row) - followed by the twelve scalar bytes, padded to a multiple of 32 bytes
+ * (view 4: 4 x 81 + 12 = 336 -> 352 bytes instead of 512).  Window cells that lie off the board hold 5 (fog) in the board
+ * plane and 0 elsewhere.  Written by the same four parts as the full layout: part i owns the 32-byte chunks i, i + 4, ...
+ * ------------------------------------------------------------------------------------------- */
+POM_HD uint32_t obs_cropped_bytes(int view) { const uint32_t w = uint32_t(2 * view + 1); return (4u * w * w + 12u + 31u) & ~31u; }
+
+/* the game's item id of a cell code (see observe_part_chunks) */
+POM_HD uint32_t obs_item_id(uint32_t code)
+{
+    return (code & 0x80u) ? 4u : (code >= 8u ? code - 3u : (code == 7u ? 3u : (code >= 2u ? 2u : code)));
+}
+
+/* part i, the chunks.  Returns the mask of this part's board-plane bytes (bit b = byte 32 i + b) that show a flame. */
+POM_HD uint32_t observe_cropped_part_chunks(const uint8_t* r, int agent, int view, uint8_t* out, int i)
+{
+    const int W = 2 * view + 1, W2 = W * W;
+    const uint32_t nchunks = obs_cropped_bytes(view) >> 5;
+    const uint32_t ap = r[R_APOS + agent];
+    const int x0 = int(ap & 15u) - view, y0 = int(ap >> 4) - view;
+    uint32_t flames = 0u;
+    /* the twelve scalar bytes as three words (the layout of the full record's bytes 484..495) */
+    uint32_t sc0 = 0u, sc1 = 0u, sc2 = 0u;
+    {
+        const int ammo = int(r[R_AMAX + agent]) - int(int8_t(r[R_ABCNT + agent]));
+        const uint32_t deadw = *reinterpret_cast<const uint32_t*>(r + R_AFLAGS) & (uint32_t(AF_DEAD) * 0x01010101u);
+        uint32_t alive = 0;
+        for(int a = 0; a < 4; a++) alive |= ((deadw >> (8 * a)) & 0xFFu) ? 0u : (1u << a);
+        sc0 = (ap & 15u) | ((ap >> 4) << 8) | (uint32_t(ammo < 0 ? 0 : (ammo > 255 ? 255 : ammo)) << 16) | (uint32_t(r[R_ASTR + agent]) << 24);
+        sc1 = ((r[R_AFLAGS + agent] & AF_CANKICK) ? 1u : 0u) | (alive << 8) | (uint32_t(r[R_TIME]) << 16) | (uint32_t(r[R_TIME + 1]) << 24);
+        sc2 = (alive >> agent) & 1u;
+    }
+    POM_LOOP
+    for(uint32_t q = uint32_t(i); q < nchunks; q += 4u)
+    {
+        uint32_t word[8] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u };
+        const int o0 = int(32u * q);
+        if(o0 < W2)
+        {
+            /* board plane: walk the window cells of this chunk, row-major, four to an output word.  No branch per cell: a
+             * cell off the board reads a clamped address and its code is replaced by 8, the code of FOG, which maps to the
+             * id 5; then the byte-parallel mapping of observe_part_chunks turns the four codes into ids, and bytes behind
+             * the plane's last cell are cleared. */
+            int row = o0 / W, col = o0 - W * row;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for(int k = 0; k < 8; k++)
+            {
+                uint32_t codes = 0u, inplane = 0u;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                for(int j = 0; j < 4; j++)
+                {
+                    const int x = x0 + col, y = y0 + row;
+                    const bool onboard = uint32_t(x) < 11u && uint32_t(y) < 11u;
+                    const int cell = onboard ? x + 11 * y : 0;
+                    const uint32_t c = onboard ? uint32_t(r[R_BOARD + cell]) : 8u;
+                    codes |= c << (8 * j);
+                    inplane |= (o0 + 4 * k + j < W2 ? 0xFFu : 0u) << (8 * j);
+                    if(++col == W) { col = 0; row++; }
+                }
+                const uint32_t H = 0x80808080u;
+                const uint32_t l = codes & 0x7F7F7F7Fu, burn = msb_fill(codes);
+                const uint32_t ge2 = msb_fill(l + 0x7E7E7E7Eu), ge7 = msb_fill(l + 0x79797979u), ge8 = msb_fill(l + 0x78787878u);
+                const uint32_t minus3 = ((l | H) - 0x03030303u) & 0x7F7F7F7Fu;
+                uint32_t ids = sel_bits(ge2, 0x02020202u, l);
+                ids = sel_bits(ge7, 0x03030303u, ids);
+                ids = sel_bits(ge8, minus3, ids);
+                ids = sel_bits(burn, 0x04040404u, ids);
+                word[k] = ids & inplane;
+                /* one bit per flame byte of this word: bits 7, 15, 23, 31 -> bits 0..3 */
+                const uint32_t fb = burn & inplane & H;
+                flames |= ((((fb >> 7) * 0x01020408u) >> 24) & 0x0Fu) << (4 * k);
+            }
+        }
+        /* the scalars: bytes 4 W2 .. 4 W2 + 11, anywhere in (at most two) chunks */
+        {
+            const int s0 = 4 * W2 - o0;                                /* position of scalar byte 0 within this chunk (W2 is odd: s0 % 4 == 0) */
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for(int k = 0; k < 8; k++)
+            {
+                const int t = 4 * k - s0;                               /* scalar byte held by byte 0 of word k */
+                if(t == 0) word[k] |= sc0; else if(t == 4) word[k] |= sc1; else if(t == 8) word[k] |= sc2;
+            }
+        }
+        obs_store32(out, int(q), word[0], word[1], word[2], word[3], word[4], word[5], word[6], word[7]);
+    }
+    return flames;
+}
+
+/* part i, the patches: the lives of this part's flame cells (their bytes may lie in another part's chunk: the caller
+ * orders all chunk stores before any patch), and the bomb bytes that fall into this part's chunks */
+POM_HD void observe_cropped_part_patches(const uint8_t* r, int agent, int view, uint8_t* out, int i, uint32_t flames)
+{
+    const int W = 2 * view + 1, W2 = W * W;
+    const uint32_t ap = r[R_APOS + agent];
+    const int x0 = int(ap & 15u) - view, y0 = int(ap >> 4) - view;
+    if(flames)
+    {
+        const int fc = r[R_FCOUNT] < 20 ? r[R_FCOUNT] : 20;
+        const uint32_t first = r[R_FINDEX];
+        POM_LOOP
+        while(flames)
+        {
+#if defined(__CUDA_ARCH__)
+            const int b = __ffs(int(flames)) - 1;
+#else
+            const int b = __builtin_ctz(flames);
+#endif
+            flames &= flames - 1u;
+            const int o = 32 * i + b, row = o / W, col = o - W * row;
+            const uint32_t origin = flame_origin(r, r[R_BOARD + (x0 + col) + 11 * (y0 + row)]);
+            uint32_t slot = first;
+            POM_LOOP
+            for(int k = 0; k < fc; k++, slot = ring_next(slot))
+            {
+                if(r[R_FPOS + slot] == origin)
+                {
+                    const int t = int(int8_t(r[R_FTIME + slot]));
+                    out[3 * W2 + o] = uint8_t(t < 0 ? 0 : t);
+                    break;
+                }
+            }
+        }
+    }
+    {
+        const int bc = r[R_BCOUNT] < 20 ? r[R_BCOUNT] : 20;
+        uint32_t slot = r[R_BINDEX];
+        POM_LOOP
+        for(int k = 0; k < bc; k++, slot = ring_next(slot))
+        {
+            const uint32_t b = reinterpret_cast<const uint32_t*>(r + R_BOMBS)[slot];
+            const int bx = int(b & 15u), by = int((b >> 4) & 15u);
+            const int col = bx - x0, row = by - y0;
+            if(bx > 10 || by > 10 || uint32_t(col) >= uint32_t(W) || uint32_t(row) >= uint32_t(W)) continue;
+            const int o1 = W2 + row * W + col, o2 = o1 + W2;
+            if(((o1 >> 5) & 3) == i) out[o1] = uint8_t((b >> 12) & 15u);
+            if(((o2 >> 5) & 3) == i) out[o2] = uint8_t((b >> 16) & 15u);
+        }
+    }
+}
+
+/* the four parts one after the other (tests/hostsim; not used by the kernels) */
+POM_HD void observe_cropped(const uint8_t* r, int agent, int view, uint8_t* out)
+{
+    uint32_t fl[4];
+    for(int i = 0; i < 4; i++) fl[i] = observe_cropped_part_chunks(r, agent, view, out, i);
+    for(int i = 0; i < 4; i++) observe_cropped_part_patches(r, agent, view, out, i, fl[i]);
+}
+
 /* the shared stateless action source (same arithmetic as oracle/pom_oracle.c pom_oracle_rng_moves) */
 POM_HD uint64_t splitmix64(uint64_t z)
 {

@@ -353,6 +353,25 @@ __device__ __forceinline__ void warp_tick(uint8_t* sslice, uint8_t* rec, uint32_
  * of four envs (quad q: envs q, q + 8, q + 16, q + 24 of the slice), lane i of the quad the chunks i, i + 4, i + 8, i + 12
  * (pomcore::observe_part_chunks), so that every store instruction of the warp covers eight full 128-byte lines.
  * `out0` = the observation of the slice's first env, `n_valid` = envs of the slice inside the batch.  All 32 lanes call. */
+/* the cropped layout (pomcore::observe_cropped_part_*): records of `rec_bytes`; every lane patches its own flame cells */
+__device__ __forceinline__ void warp_observe_slice_cropped(const uint8_t* sslice, int agent, int view, uint8_t* out0, uint32_t n_valid, uint32_t rec_bytes)
+{
+    const uint32_t lane = threadIdx.x & 31u, quad = lane >> 2;
+    const int part = int(lane & 3u);
+#pragma unroll 1
+    for(uint32_t m = 0; m < 4u; m++)
+    {
+        const uint32_t e = quad + 8u * m;
+        const bool valid = e < n_valid;
+        const uint8_t* r = sslice + e * POM_REC_BYTES;
+        uint8_t* out = out0 + size_t(e) * rec_bytes;
+        uint32_t flames = 0u;
+        if(valid) flames = pomcore::observe_cropped_part_chunks(r, agent, view, out, part);
+        __syncwarp();                                         /* the quad's chunk stores are ordered before its patches */
+        if(valid) pomcore::observe_cropped_part_patches(r, agent, view, out, part, flames);
+    }
+}
+
 __device__ __forceinline__ void warp_observe_slice(const uint8_t* sslice, int agent, int view, uint8_t* out0, uint32_t n_valid)
 {
     const uint32_t lane = threadIdx.x & 31u, quad = lane >> 2;
@@ -1066,9 +1085,11 @@ __global__ void k_observe(const uint8_t* __restrict__ recs, pom_state* aos, uint
  * warp, 8 warps per SM, 0.53 of the HBM peak); one lane per env with 32-byte stores needs no tile but makes every
  * lane's store a line of its own (L1 data pipe 67 % busy, 0.164 ms per 1 Mi envs on the bench's states); four lanes
  * per env store whole lines.  The fused form is StepIO::obs. */
-template<int TPB>
-__global__ void __launch_bounds__(TPB) k_observe_planes(BatchParams P, uint8_t* __restrict__ out, uint64_t stride, uint32_t mask, int view,
-                                                       uint32_t reverse)
+/* CROPPED: the image for the cropped layout (with both layouts in one image the kernel needed 127 registers and the full
+ * layout lost a third of its speed) */
+template<int TPB, bool CROPPED = false>
+__global__ void __launch_bounds__(TPB, CROPPED ? 768 / TPB : 0) k_observe_planes(BatchParams P, uint8_t* __restrict__ out, uint64_t stride, uint32_t mask, int view,
+                                                                  uint32_t reverse, uint32_t cropped_bytes)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr uint32_t SLICE_BYTES = 32 * POM_REC_BYTES;
@@ -1094,7 +1115,8 @@ __global__ void __launch_bounds__(TPB) k_observe_planes(BatchParams P, uint8_t* 
     for(int a = 0; a < 4; a++)
     {
         if(!((mask >> a) & 1u)) continue;
-        warp_observe_slice(sslice, a, view, out + (uint64_t(k) * stride + env0) * POM_OBS_BYTES, n_valid);
+        if(CROPPED) warp_observe_slice_cropped(sslice, a, view, out + (uint64_t(k) * stride + env0) * cropped_bytes, n_valid, cropped_bytes);
+        else warp_observe_slice(sslice, a, view, out + (uint64_t(k) * stride + env0) * POM_OBS_BYTES, n_valid);
         k++;
     }
 }

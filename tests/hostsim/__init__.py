@@ -87,6 +87,13 @@ class HostSim:
         self.lib.hostsim_observe_planes(_p(recs), recs.shape[0], agent, view, _p(out))
         return out
 
+    def observe_cropped(self, recs, agent, view):
+        self.lib.hostsim_obs_cropped_bytes.restype = C.c_long
+        rb = int(self.lib.hostsim_obs_cropped_bytes(view))
+        out = np.zeros((recs.shape[0], rb), np.uint8)
+        self.lib.hostsim_observe_cropped(_p(recs), C.c_long(recs.shape[0]), agent, view, _p(out))
+        return out
+
     def fog_batch(self, S, agent, view):
         self.lib.hostsim_fog_batch(_p(S), S.shape[0], agent, view)
         return S

@@ -136,6 +136,14 @@ void hostsim_observe_planes(const uint8_t* recs, long n, int agent, int view, ui
     for(long e = 0; e < n; e++) pomcore::observe_planes(recs + e * POM_REC_BYTES, agent, view, out + 512 * e);
 }
 
+/* the cropped layout (pomcore::observe_cropped) */
+long hostsim_obs_cropped_bytes(int view) { return long(pomcore::obs_cropped_bytes(view)); }
+void hostsim_observe_cropped(const uint8_t* recs, long n, int agent, int view, uint8_t* out)
+{
+    const long rb = long(pomcore::obs_cropped_bytes(view));
+    for(long e = 0; e < n; e++) pomcore::observe_cropped(recs + e * POM_REC_BYTES, agent, view, out + rb * e);
+}
+
 uint32_t hostsim_rng_moves(uint64_t seed, uint64_t env, uint32_t tick, uint32_t n_actions)
 {
     return pomcore::rng_moves(seed, env, tick, n_actions);

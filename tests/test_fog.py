@@ -98,6 +98,30 @@ def test_observation_planes_device_code_on_host(orc, agent, view):
     assert a[:, 363:484].any() or view < 10     # flame lives show up once bombs have gone off
 
 
+@pytest.mark.parametrize("agent,view", [(0, 4), (3, 4), (1, 2), (2, 5), (1, 0), (0, 1), (2, 3)])
+def test_cropped_observation_device_code_on_host(orc, agent, view):
+    """pomcore::observe_cropped on packed records vs the oracle's definition (the window of the full planes), on mid-game
+    states and on the mutually inconsistent states of tests/test_fuzz_states.py; and the definition's own properties"""
+    from hostsim import HostSim
+    from test_fuzz_states import mutated_states
+    hs = HostSim()
+    W = 2 * view + 1
+    for S in (mutated_states(orc, 31 + agent, 1500), _mid_game_states(orc)):
+        recs, bad = hs.pack(S, np.zeros(S.shape[0], np.uint8))
+        S, recs = S[bad == 0].copy(), recs[bad == 0].copy()
+        a = orc.observe_cropped_batch(S, agent, view)
+        b = hs.observe_cropped(recs, agent, view)
+        assert a.shape == b.shape == (S.shape[0], (4 * W * W + 12 + 31) // 32 * 32)
+        assert (a == b).all(), np.argwhere(a != b)[:5]
+        full = orc.observe_planes_batch(S, agent, view)
+        # the centre of the window is the observer's own cell, the scalars are the full layout's
+        centre = view * W + view
+        ax, ay = S["agents"]["x"][:, agent], S["agents"]["y"][:, agent]
+        assert (a[:, centre] == full[np.arange(S.shape[0]), ax + 11 * ay]).all()
+        assert (a[:, 4 * W * W:4 * W * W + 12] == full[:, 484:496]).all()
+        assert (a[:, 4 * W * W + 12:] == 0).all()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mask,view", [(15, 4), (0b0101, 2)])
 def test_observation_planes_on_gpu(orc, mask, view):
@@ -118,6 +142,33 @@ def test_observation_planes_on_gpu(orc, mask, view):
     assert L.pom_batch_observe_planes(b.h, dev, 0, 4) == -1
     assert L.pom_batch_observe_planes(b.h, dev, 16, 4) == -1
     assert L.pom_batch_observe_planes(b.h, dev, 1, -1) == -1
+    b.free(dev)
+    b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mask,view", [(15, 4), (0b0110, 2), (0b1000, 5), (0b0001, 0)])
+def test_cropped_observation_planes_on_gpu(orc, mask, view):
+    """pom_batch_observe_planes_cropped against the oracle's definition, ragged batch size, every agent of the mask"""
+    import pomcpp_b200 as pb
+    n = 5000 + 19
+    b = pb.Batch(n, n_templates=64)
+    b.rollout(45, 3, 0, pb.ROLL_NO_RESET)
+    full, _ = b.download()
+    obs = b.observe_planes_cropped(mask, view)
+    agents = [a for a in range(4) if (mask >> a) & 1]
+    rb = int(pb.lib().pom_obs_cropped_bytes(view))
+    assert rb == orc.obs_cropped_bytes(view) and obs.shape == (len(agents), n, rb)
+    for k, a in enumerate(agents):
+        want = orc.observe_cropped_batch(full, a, view)
+        assert (obs[k] == want).all(), (a, np.argwhere(obs[k] != want)[:4])
+    L = pb.lib()
+    dev = b.alloc(512 * 256)
+    assert L.pom_batch_observe_planes_cropped(b.h, None, 1, 4) == -1
+    assert L.pom_batch_observe_planes_cropped(b.h, dev, 0, 4) == -1
+    assert L.pom_batch_observe_planes_cropped(b.h, dev, 1, 6) == -1
+    assert L.pom_batch_observe_planes_cropped(b.h, dev, 1, -1) == -1
+    assert L.pom_obs_cropped_bytes(4) == 352 and L.pom_obs_cropped_bytes(6) == 0
     b.free(dev)
     b.close()
 

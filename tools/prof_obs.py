@@ -20,7 +20,8 @@ def moves():
     tick[0] += 1
     return mv + 4 * n * (tick[0] % RING)
 for name, fn in (("step", lambda: b.step(moves(), flags)), ("step_observe(1 agent)", lambda: b.step_observe(moves(), obs, 1, 4, flags)),
-                 ("observe_planes(1 agent)", lambda: pb._ck(pb.lib().pom_batch_observe_planes(b.h, obs, 1, 4)))):
+                 ("observe_planes(1 agent)", lambda: pb._ck(pb.lib().pom_batch_observe_planes(b.h, obs, 1, 4))),
+                 ("observe_planes_cropped(1 agent)", lambda: pb._ck(pb.lib().pom_batch_observe_planes_cropped(b.h, obs, 1, 4)))):
     for _ in range(30):
         fn()
     b.sync()
